@@ -1,0 +1,571 @@
+// oracle/oracle_port.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Stand-alone CPU restatement ("port") of the reference algorithms on the ray-casting hot path, written
+// for clarity, not speed, with no dependency on /root/reference, glm, or the product library.  Every
+// function cites the reference lines it follows.  Parity status: PINNED -- tests/test_oracle_pinning.py
+// compares this port with oracle/_ref/libref.so (the reference's own translation units compiled in
+// place) wherever the reference has real code (octree build, BFS flatten, octreeRaySkip, localMC mesh,
+// BVH build/query, Camera) and against the golden vectors under tests/golden/ generated from it.
+// For the pieces the reference does not have (Moller-Trumbore closest hit, shadow rays, GLSL traversal
+// on a CPU) the written-down rules of SURVEY.md section 8c are the specification; both this port and
+// oracle/ref_harness.cpp (which uses real glm types) implement them and must agree bit for bit.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use this.
+// Build: oracle/Makefile `port` (-O2 -ffp-contract=off: x86-64 SSE2 scalar, no FMA).
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../ray_tracing_octrees_b200/csrc/mc_tables.h"   // packed public-domain MC table (data only)
+
+namespace {
+
+// ---- glm-order fp32 helpers (thirdparty/glm-0.9.9.7/glm/detail/func_geometric.inl:48-90) -------------
+struct V3 { float x, y, z; float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); } };
+inline V3 v3(float a, float b, float c) { return V3{ a, b, c }; }
+inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+inline V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+inline V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+inline V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+inline V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+inline float dot(V3 a, V3 b) { V3 t = a * b; return t.x + t.y + t.z; }                       // :48-55
+inline V3 cross(V3 x, V3 y) { return v3(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }  // :68-79
+inline V3 normalize(V3 v) { return v * (1.0f / std::sqrt(dot(v, v))); }                      // :82-90 + func_exponential.inl:136-139
+inline float fmin2(float a, float b) { return (b < a) ? b : a; }   // glm::min / std::min / GLSL min
+inline float fmax2(float a, float b) { return (a < b) ? b : a; }   // glm::max / std::max / GLSL max
+
+// ---- reference-compatible PODs -----------------------------------------------------------------------
+struct Grid {                        // VoxelGrid, OctreeVoxel.h:28-42 (x-fastest index)
+	int dx = 0, dy = 0, dz = 0; float minX = 0, minY = 0, minZ = 0, voxel = 1; std::vector<uint8_t> data;
+	uint8_t safe(int x, int y, int z) const {      // getVoxelSafe, OctreeVoxel.cpp:692-701 (OOB => EMPTY)
+		if (x < 0 || y < 0 || z < 0 || x >= dx || y >= dy || z >= dz) return 0;
+		return data[(size_t)x + (size_t)y * dx + (size_t)z * ((size_t)dx * dy)];
+	}
+};
+struct ONode { int x, y, z, size; bool leaf, solid, uniform; ONode* child[8]; };   // OctreeNode, OctreeVoxel.h:45-62
+struct GNode { int32_t x, y, z, size, isLeaf, isSolid, isUniform, child[8]; };     // GPUNodes, RayTracerBVH.h:21-26
+static_assert(sizeof(GNode) == 60, "GPUNodes is 15 x int32");
+struct Tri { V3 v0, v1, v2; };                                                       // Triangle, BVH.h:7-11
+struct Box { V3 mn, mx; };                                                           // AABB, BVH.h:14-34
+struct BNode { Box b; BNode* l = nullptr; BNode* r = nullptr; std::vector<const Tri*> tris; };   // BVHNode, BVH.h:37-42
+
+struct Cam {                         // same layout as RtoCamera (include/rto_c.h)
+	float camPos[3]; float invView[16]; float tanHalfFov; float aspect; int width, height;
+};
+
+// ---- octree build: buildOctreeRec, OctreeVoxel.cpp:704-762 -----------------------------------------
+ONode* buildRec(const Grid& g, int x0, int y0, int z0, int size) {
+	ONode* n = new ONode{ x0, y0, z0, size, false, false, false, {} };
+	if (size == 1) { n->leaf = true; n->solid = g.safe(x0, y0, z0) == 1; n->uniform = true; return n; }
+	uint8_t first = g.safe(x0, y0, z0);
+	bool same = true;
+	for (int z = z0; z < z0 + size && same; z++)
+		for (int y = y0; y < y0 + size && same; y++)
+			for (int x = x0; x < x0 + size; x++)
+				if (g.safe(x, y, z) != first) { same = false; break; }
+	if (same) { n->leaf = true; n->uniform = true; n->solid = first == 1; return n; }
+	int half = size / 2;
+	for (int i = 0; i < 8; i++)    // bit0 = x, bit1 = y, bit2 = z (:749-757)
+		n->child[i] = buildRec(g, x0 + ((i & 1) ? half : 0), y0 + ((i & 2) ? half : 0), z0 + ((i & 4) ? half : 0), half);
+	return n;
+}
+void freeRec(ONode* n) { if (!n) return; for (auto* c : n->child) freeRec(c); delete n; }
+
+struct Octree {
+	Grid g; ONode* root = nullptr; std::vector<GNode> flat; std::unordered_map<const ONode*, int> index;
+	~Octree() { freeRec(root); }
+	void build() {                   // createOctreeFromVoxelGrid, OctreeVoxel.cpp:765-778
+		if (g.dx == 0 || g.dy == 0 || g.dz == 0) return;
+		int maxDim = std::max({ g.dx, g.dy, g.dz });
+		int p2 = 1; while (p2 < maxDim) p2 <<= 1;
+		root = buildRec(g, 0, 0, 0, p2);
+		flatten();
+	}
+	void flatten() {                 // RayTracerBVH::setOctree BFS, RayTracerBVH.cpp:443-490
+		flat.clear(); index.clear();
+		std::queue<const ONode*> q; q.push(root); index[root] = 0;
+		flat.push_back(GNode{ 0, 0, 0, 0, 0, 0, 0, { -1, -1, -1, -1, -1, -1, -1, -1 } });
+		while (!q.empty()) {
+			const ONode* nd = q.front(); q.pop();
+			int idx = index[nd];
+			flat[idx].x = nd->x; flat[idx].y = nd->y; flat[idx].z = nd->z; flat[idx].size = nd->size;
+			flat[idx].isLeaf = nd->leaf; flat[idx].isSolid = nd->solid; flat[idx].isUniform = nd->uniform;
+			for (int i = 0; i < 8; i++) flat[idx].child[i] = -1;
+			if (nd->leaf) continue;
+			for (int i = 0; i < 8; i++) if (nd->child[i]) {
+				if (!index.count(nd->child[i])) {
+					index[nd->child[i]] = (int)flat.size();
+					flat.push_back(GNode{ 0, 0, 0, 0, 0, 0, 0, { -1, -1, -1, -1, -1, -1, -1, -1 } });
+				}
+				flat[idx].child[i] = index[nd->child[i]];
+				q.push(nd->child[i]);
+			}
+		}
+	}
+};
+
+// ---- marching cubes: localMC, OctreeVoxel.cpp:780-879; vertexInterp :633-640; render order Renderer.cpp:14-36
+inline V3 vertexInterp(V3 p1, V3 p2, float a, float b) {
+	if (std::fabs(0.0f - a) < 0.00001f) return p1;
+	if (std::fabs(0.0f - b) < 0.00001f) return p2;
+	if (std::fabs(a - b) < 0.00001f) return p1;
+	float mu = (0.0f - a) / (b - a);
+	return p1 + mu * (p2 - p1);
+}
+void localMC(const Grid& g, int x0, int y0, int z0, int size, std::vector<Tri>& out) {
+	float vx = g.voxel;
+	auto scalar = [&](int x, int y, int z) -> float {       // FILLED => -1, else (incl. OOB) +1 (:787-792)
+		if (x < 0 || y < 0 || z < 0 || x >= g.dx || y >= g.dy || z >= g.dz) return 1.0f;
+		return g.data[(size_t)x + (size_t)y * g.dx + (size_t)z * ((size_t)g.dx * g.dy)] == 1 ? -1.0f : 1.0f;
+	};
+	static const int off[8][3] = { {0,0,0},{1,0,0},{1,1,0},{0,1,0},{0,0,1},{1,0,1},{1,1,1},{0,1,1} };   // corner order :802-817
+	for (int z = z0; z < z0 + size && z < g.dz - 1; z++)
+		for (int y = y0; y < y0 + size && y < g.dy - 1; y++)
+			for (int x = x0; x < x0 + size && x < g.dx - 1; x++) {
+				V3 pos[8]; float val[8]; int cube = 0;
+				for (int c = 0; c < 8; c++) {
+					pos[c] = v3(g.minX + (x + off[c][0]) * vx, g.minY + (y + off[c][1]) * vx, g.minZ + (z + off[c][2]) * vx);
+					val[c] = scalar(x + off[c][0], y + off[c][1], z + off[c][2]);
+					if (val[c] < 0) cube |= 1 << c;
+				}
+				int flags = mc_edge_flags(cube);
+				if (flags == 0) continue;
+				V3 vert[12];
+				for (int e = 0; e < 12; e++) if (flags & (1 << e)) {
+					int a = kMcEdgeCorner[e][0], b = kMcEdgeCorner[e][1];
+					vert[e] = vertexInterp(pos[a], pos[b], val[a], val[b]);
+				}
+				for (int i = 0; mc_tri_edge(cube, i) != -1; i += 3)
+					out.push_back(Tri{ vert[mc_tri_edge(cube, i)], vert[mc_tri_edge(cube, i + 1)], vert[mc_tri_edge(cube, i + 2)] });
+			}
+}
+void mcRender(const Grid& g, const ONode* n, int x0, int y0, int z0, int size, std::vector<Tri>& out) {
+	if (!n) return;
+	if (n->leaf) { localMC(g, x0, y0, z0, size, out); return; }
+	int half = size / 2;
+	for (int i = 0; i < 8; i++)
+		mcRender(g, n->child[i], x0 + ((i & 1) ? half : 0), y0 + ((i & 2) ? half : 0), z0 + ((i & 4) ? half : 0), half, out);
+}
+
+// ---- BVH: BVH.cpp:19-113 ----------------------------------------------------------------------------
+inline V3 vmin(V3 a, V3 b) { return v3(fmin2(a.x, b.x), fmin2(a.y, b.y), fmin2(a.z, b.z)); }
+inline V3 vmax(V3 a, V3 b) { return v3(fmax2(a.x, b.x), fmax2(a.y, b.y), fmax2(a.z, b.z)); }
+inline void expand(Box& b, V3 p) { b.mn = vmin(b.mn, p); b.mx = vmax(b.mx, p); }           // AABB::expand, BVH.h:24-27
+inline Box emptyBox() { float m = std::numeric_limits<float>::max(); return Box{ v3(m, m, m), v3(-m, -m, -m) }; }
+inline V3 centroid(const Tri* t) { return (t->v0 + t->v1 + t->v2) / 3.0f; }                // BVH.cpp:15-17
+
+BNode* bvhBuild(std::vector<const Tri*>& tris) {      // BVH::build, BVH.cpp:33-71
+	BNode* node = new BNode();
+	Box bounds = emptyBox();
+	for (const Tri* t : tris) {
+		Box tb = emptyBox(); expand(tb, t->v0); expand(tb, t->v1); expand(tb, t->v2);
+		expand(bounds, tb.mn); expand(bounds, tb.mx);
+	}
+	node->b = bounds;
+	if (tris.size() <= 2) { node->tris = tris; return node; }
+	V3 ext = bounds.mx - bounds.mn;
+	int axis = 0;
+	if (ext.y > ext.x) axis = 1;
+	if (ext.z > ext[axis]) axis = 2;
+	std::sort(tris.begin(), tris.end(), [axis](const Tri* a, const Tri* b) { return centroid(a)[axis] < centroid(b)[axis]; });
+	size_t mid = tris.size() / 2;
+	std::vector<const Tri*> L(tris.begin(), tris.begin() + mid), R(tris.begin() + mid, tris.end());
+	node->l = bvhBuild(L);
+	node->r = bvhBuild(R);
+	return node;
+}
+void bvhFree(BNode* n) { if (!n) return; bvhFree(n->l); bvhFree(n->r); delete n; }
+
+inline bool slab(const Box& box, V3 o, V3 inv, const int neg[3], float tmin, float tmax) {   // intersectAABB, BVH.cpp:76-87
+	for (int i = 0; i < 3; i++) {
+		float t0 = ((neg[i] ? box.mx[i] : box.mn[i]) - o[i]) * inv[i];
+		float t1 = ((neg[i] ? box.mn[i] : box.mx[i]) - o[i]) * inv[i];
+		tmin = t0 > tmin ? t0 : tmin;
+		tmax = t1 < tmax ? t1 : tmax;
+		if (tmax < tmin) return false;
+	}
+	return true;
+}
+void queryNode(const BNode* n, V3 o, V3 inv, const int neg[3], std::vector<const Tri*>& out, uint64_t* boxes) {   // BVH.cpp:89-105
+	if (!n) return;
+	if (boxes) (*boxes)++;
+	if (!slab(n->b, o, inv, neg, 0.0f, std::numeric_limits<float>::max())) return;
+	if (!n->l && !n->r) { for (auto* t : n->tris) out.push_back(t); return; }
+	queryNode(n->l, o, inv, neg, out, boxes);
+	queryNode(n->r, o, inv, neg, out, boxes);
+}
+struct Mesh {
+	std::vector<Tri> tris; BNode* root = nullptr;
+	~Mesh() { bvhFree(root); }
+	void build() { std::vector<const Tri*> p; p.reserve(tris.size()); for (auto& t : tris) p.push_back(&t); root = bvhBuild(p); }   // BVH.cpp:19-27
+	void query(V3 o, V3 d, std::vector<const Tri*>& out, uint64_t* boxes = nullptr) const {     // BVH::query, BVH.cpp:107-113
+		V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+		int neg[3] = { inv.x < 0, inv.y < 0, inv.z < 0 };
+		queryNode(root, o, inv, neg, out, boxes);
+	}
+};
+
+// ---- ray generation: GLSL generateRay, RayTracerBVH.cpp:338-355 (inverse(view), tan hoisted to host) -----
+inline void genRay(const Cam& c, int px, int py, V3& o, V3& d) {
+	float nx = (float(px) + 0.5f) / float(c.width) * 2.0f - 1.0f;
+	float ny = 1.0f - (float(py) + 0.5f) / float(c.height) * 2.0f;
+	nx *= c.aspect; nx *= c.tanHalfFov; ny *= c.tanHalfFov;
+	// normalize(vec4(nx,ny,-1,0)): dot4 = (x*x + y*y) + (z*z + w*w)   (func_geometric.inl:58-66)
+	float len2 = (nx * nx + ny * ny) + ((-1.0f) * (-1.0f) + 0.0f * 0.0f);
+	float il = 1.0f / std::sqrt(len2);
+	float vx = nx * il, vy = ny * il, vz = -1.0f * il, vw = 0.0f * il;
+	// mat4 * vec4 = (m0*v0 + m1*v1) + (m2*v2 + m3*v3)   (type_mat4x4.inl:561-572), column-major m
+	const float* m = c.invView;
+	float w[3];
+	for (int r = 0; r < 3; r++) w[r] = (m[0 + r] * vx + m[4 + r] * vy) + (m[8 + r] * vz + m[12 + r] * vw);
+	o = v3(c.camPos[0], c.camPos[1], c.camPos[2]);
+	d = normalize(v3(w[0], w[1], w[2]));
+}
+
+inline V3 shadeLambert(V3 n) {       // GLSL shade, RayTracerBVH.cpp:331-336
+	V3 lightDir = normalize(v3(-1.0f, -1.0f, -1.0f));
+	float ndotl = fmax2(0.0f, dot(n, -lightDir));
+	return v3(1.0f, 0.8f, 0.6f) * ndotl + v3(0.1f, 0.1f, 0.1f);
+}
+
+// Moller-Trumbore, SURVEY.md 8c rule; all comparisons reject NaN.
+inline bool mollerTrumbore(const Tri& tri, V3 o, V3 d, float& tOut) {
+	V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
+	V3 p = cross(d, e2);
+	float det = dot(e1, p);
+	if (!(std::fabs(det) >= 1e-8f)) return false;
+	float inv = 1.0f / det;
+	V3 s = o - tri.v0;
+	float u = dot(s, p) * inv;
+	if (!(u >= 0.0f && u <= 1.0f)) return false;
+	V3 q = cross(s, e1);
+	float v = dot(d, q) * inv;
+	if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+	float t = dot(e2, q) * inv;
+	if (!(t > 1e-4f)) return false;
+	tOut = t; return true;
+}
+
+// ---- octree traversal mode A: octreeRaySkip, VolumeRaycastRenderer.cpp:50-155 ------------------------
+float raySkip(const ONode* node, V3 ro, V3 rd, float tMin, float tMax, const Grid& g, const ONode*& leafOut, uint64_t& visits) {
+	if (!node) return 1e30f;
+	visits++;
+	float vx = g.voxel;
+	float wx0 = g.minX + node->x * vx, wy0 = g.minY + node->y * vx, wz0 = g.minZ + node->z * vx;   // :70-74
+	float wSize = node->size * vx;
+	V3 bmin = v3(wx0, wy0, wz0), bmax = v3(wx0 + wSize, wy0 + wSize, wz0 + wSize);
+	V3 inv = v3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+	const float small = 1e-10f;                                                                      // :84-87
+	if (std::fabs(rd.x) < small) inv.x = rd.x >= 0 ? 1e10f : -1e10f;
+	if (std::fabs(rd.y) < small) inv.y = rd.y >= 0 ? 1e10f : -1e10f;
+	if (std::fabs(rd.z) < small) inv.z = rd.z >= 0 ? 1e10f : -1e10f;
+	V3 t1 = (bmin - ro) * inv, t2 = (bmax - ro) * inv;
+	V3 tN = vmin(t1, t2), tF = vmax(t1, t2);
+	float enterT = fmax2(fmax2(tN.x, tN.y), fmax2(tN.z, tMin));                                     // :96
+	float exitT = fmin2(fmin2(tF.x, tF.y), fmin2(tF.z, tMax));                                      // :97
+	if (enterT > exitT) return 1e30f;
+	if (node->leaf) { if (!node->solid) return 1e30f; leafOut = node; return enterT; }               // :105-110
+	int dirMask = ((rd.x > 0) ? 1 : 0) | ((rd.y > 0) ? 2 : 0) | ((rd.z > 0) ? 4 : 0);               // :114-116
+	float bestT = 1e30f;
+	for (int dist = 0; dist <= 3; dist++)
+		for (int oct = 0; oct < 8; oct++) {
+			if (__builtin_popcount(oct ^ dirMask) != dist) continue;
+			const ONode* c = node->child[oct];
+			if (!c) continue;
+			float ct = raySkip(c, ro, rd, enterT, exitT, g, leafOut, visits);
+			if (ct < bestT) { bestT = ct; if (ct < 1e30f) return ct; }                               // :143-149
+		}
+	return bestT;
+}
+
+// ---- octree traversal mode B: GLSL intersectAABB + intersectOctreeIterative, RayTracerBVH.cpp:226-327 ------
+struct HitB { bool hit; float t; int id; V3 normal; int steps; };
+HitB traverseGLSL(const std::vector<GNode>& nodes, V3 gridMin, float voxel, V3 o, V3 d) {
+	HitB r{ false, 1e30f, -1, v3(0, 0, 0), 0 };
+	float closestT = 1e30f;
+	int stack[128]; int sp = 0; stack[sp++] = 0;
+	while (sp > 0 && r.steps < 512) {
+		int idx = stack[--sp];
+		if (idx < 0) continue;
+		r.steps++;
+		const GNode& n = nodes[idx];
+		V3 nmin = gridMin + v3((float)n.x, (float)n.y, (float)n.z) * voxel;
+		V3 nmax = nmin + v3((float)n.size, (float)n.size, (float)n.size) * voxel;
+		V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+		V3 t1 = (nmin - o) * inv, t2 = (nmax - o) * inv;
+		V3 tMn = vmin(t1, t2), tMx = vmax(t1, t2);
+		float tNear = fmax2(fmax2(tMn.x, tMn.y), tMn.z);
+		float tFar = fmin2(fmin2(tMx.x, tMx.y), tMx.z);
+		if (!(tNear <= tFar && tFar > 0.0f)) continue;
+		if (tNear >= closestT) continue;
+		if (n.isUniform == 1 || n.isLeaf == 1) {       // the two GLSL branches (:271-306) are identical
+			if (n.isSolid == 1) {
+				float tHit = fmax2(0.0f, tNear);
+				if (tHit < closestT && tHit <= tFar) {
+					closestT = tHit; r.hit = true; r.id = idx;
+					V3 center = 0.5f * (nmin + nmax);
+					V3 p = o + d * tHit;
+					r.normal = normalize(p - center);
+					break;
+				}
+			}
+			continue;
+		}
+		for (int i = 0; i < 8; i++) if (n.child[i] >= 0) stack[sp++] = n.child[i];
+	}
+	r.t = closestT;
+	return r;
+}
+
+// ---- camera: Camera.cpp:11-29, glm::lookAtRH (gtc/matrix_transform.inl), glm::inverse (func_matrix.inl) ----
+void lookAtRH(V3 eye, V3 center, V3 up, float* m /*col-major*/) {
+	V3 f = normalize(center - eye);
+	V3 s = normalize(cross(f, up));
+	V3 u = cross(s, f);
+	float r[16] = { s.x, u.x, -f.x, 0,  s.y, u.y, -f.y, 0,  s.z, u.z, -f.z, 0,  -dot(s, eye), -dot(u, eye), dot(f, eye), 1 };
+	std::memcpy(m, r, 64);
+}
+void inverse4(const float* mm, float* out) {      // glm compute_inverse<4,4>, func_matrix.inl
+	auto m = [&](int c, int r) { return mm[c * 4 + r]; };
+	float c00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3), c02 = m(1, 2) * m(3, 3) - m(3, 2) * m(1, 3), c03 = m(1, 2) * m(2, 3) - m(2, 2) * m(1, 3);
+	float c04 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3), c06 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3), c07 = m(1, 1) * m(2, 3) - m(2, 1) * m(1, 3);
+	float c08 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2), c10 = m(1, 1) * m(3, 2) - m(3, 1) * m(1, 2), c11 = m(1, 1) * m(2, 2) - m(2, 1) * m(1, 2);
+	float c12 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3), c14 = m(1, 0) * m(3, 3) - m(3, 0) * m(1, 3), c15 = m(1, 0) * m(2, 3) - m(2, 0) * m(1, 3);
+	float c16 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2), c18 = m(1, 0) * m(3, 2) - m(3, 0) * m(1, 2), c19 = m(1, 0) * m(2, 2) - m(2, 0) * m(1, 2);
+	float c20 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1), c22 = m(1, 0) * m(3, 1) - m(3, 0) * m(1, 1), c23 = m(1, 0) * m(2, 1) - m(2, 0) * m(1, 1);
+	float F0[4] = { c00, c00, c02, c03 }, F1[4] = { c04, c04, c06, c07 }, F2[4] = { c08, c08, c10, c11 };
+	float F3[4] = { c12, c12, c14, c15 }, F4[4] = { c16, c16, c18, c19 }, F5[4] = { c20, c20, c22, c23 };
+	float V0[4] = { m(1, 0), m(0, 0), m(0, 0), m(0, 0) }, V1[4] = { m(1, 1), m(0, 1), m(0, 1), m(0, 1) };
+	float V2[4] = { m(1, 2), m(0, 2), m(0, 2), m(0, 2) }, V3_[4] = { m(1, 3), m(0, 3), m(0, 3), m(0, 3) };
+	const float sA[4] = { +1, -1, +1, -1 }, sB[4] = { -1, +1, -1, +1 };
+	float inv[16];
+	for (int i = 0; i < 4; i++) {
+		float i0 = (V1[i] * F0[i] - V2[i] * F1[i]) + V3_[i] * F2[i];
+		float i1 = (V0[i] * F0[i] - V2[i] * F3[i]) + V3_[i] * F4[i];
+		float i2 = (V0[i] * F1[i] - V1[i] * F3[i]) + V3_[i] * F5[i];
+		float i3 = (V0[i] * F2[i] - V1[i] * F4[i]) + V2[i] * F5[i];
+		inv[0 * 4 + i] = i0 * sA[i]; inv[1 * 4 + i] = i1 * sB[i]; inv[2 * 4 + i] = i2 * sA[i]; inv[3 * 4 + i] = i3 * sB[i];
+	}
+	// Dot0 = m[0] * row0 ; Dot1 = (x + y) + (z + w)
+	float d0 = m(0, 0) * inv[0 * 4 + 0], d1 = m(0, 1) * inv[1 * 4 + 0], d2 = m(0, 2) * inv[2 * 4 + 0], d3 = m(0, 3) * inv[3 * 4 + 0];
+	float det = (d0 + d1) + (d2 + d3);
+	float ood = 1.0f / det;
+	for (int i = 0; i < 16; i++) out[i] = inv[i] * ood;
+}
+
+} // namespace
+
+#define RTO_FLAG_SHADOWS 1u
+
+extern "C" {
+
+// ---- camera -----------------------------------------------------------------------------------------
+void orc_camera_consts(float theta, float phi, float radius, const float* target, float fovDeg, float aspect,
+	int w, int h, Cam* out, float* view16) {
+	V3 tgt = v3(target[0], target[1], target[2]);
+	V3 eye = radius * v3(std::cos(theta) * std::sin(phi), std::sin(theta), std::cos(theta) * std::cos(phi)) + tgt;   // Camera.cpp:13-17
+	float view[16];
+	lookAtRH(eye, tgt, v3(0, 1, 0), view);
+	inverse4(view, out->invView);
+	out->camPos[0] = eye.x; out->camPos[1] = eye.y; out->camPos[2] = eye.z;
+	float fovRad = fovDeg * 0.01745329251994329576923690768489f;    // glm::radians
+	out->tanHalfFov = std::tan(fovRad * 0.5f);
+	out->aspect = aspect; out->width = w; out->height = h;
+	if (view16) std::memcpy(view16, view, 64);
+}
+
+// ---- octree -----------------------------------------------------------------------------------------
+void* orc_grid_create(int dx, int dy, int dz, float minX, float minY, float minZ, float voxel, const uint8_t* data) {
+	Octree* o = new Octree();
+	o->g.dx = dx; o->g.dy = dy; o->g.dz = dz; o->g.minX = minX; o->g.minY = minY; o->g.minZ = minZ; o->g.voxel = voxel;
+	o->g.data.assign(data, data + (size_t)dx * dy * dz);
+	return o;
+}
+void* orc_grid_load(const char* path) {     // sceneCache.bin format, CacheUtils.cpp:33-59
+	FILE* f = std::fopen(path, "rb");
+	if (!f) return nullptr;
+	Octree* o = new Octree();
+	size_t n = 0; bool ok = true;
+	ok &= std::fread(&o->g.dx, 4, 1, f) == 1; ok &= std::fread(&o->g.dy, 4, 1, f) == 1; ok &= std::fread(&o->g.dz, 4, 1, f) == 1;
+	ok &= std::fread(&o->g.minX, 4, 1, f) == 1; ok &= std::fread(&o->g.minY, 4, 1, f) == 1; ok &= std::fread(&o->g.minZ, 4, 1, f) == 1;
+	ok &= std::fread(&o->g.voxel, 4, 1, f) == 1; ok &= std::fread(&n, sizeof(size_t), 1, f) == 1;
+	if (ok) { o->g.data.resize(n); ok = std::fread(o->g.data.data(), 1, n, f) == n; }
+	std::fclose(f);
+	if (!ok) { delete o; return nullptr; }
+	return o;
+}
+void orc_grid_info(void* h, int* dims, float* minVoxel) {
+	Octree* o = (Octree*)h;
+	dims[0] = o->g.dx; dims[1] = o->g.dy; dims[2] = o->g.dz;
+	minVoxel[0] = o->g.minX; minVoxel[1] = o->g.minY; minVoxel[2] = o->g.minZ; minVoxel[3] = o->g.voxel;
+}
+void orc_grid_data(void* h, uint8_t* out) { Octree* o = (Octree*)h; std::memcpy(out, o->g.data.data(), o->g.data.size()); }
+int orc_octree_build(void* h) { Octree* o = (Octree*)h; o->build(); return (int)o->flat.size(); }
+void orc_octree_flat(void* h, int32_t* out15) { Octree* o = (Octree*)h; std::memcpy(out15, o->flat.data(), o->flat.size() * 60); }
+void orc_octree_free(void* h) { delete (Octree*)h; }
+
+double orc_render_octree(void* h, const Cam* cam, int mode, int y0, int y1, float* rgba, int32_t* leafId, float* tOut,
+	uint64_t* stats, int nthreads) {
+	Octree* oc = (Octree*)h;
+	const int W = cam->width;
+	V3 gridMin = v3(oc->g.minX, oc->g.minY, oc->g.minZ);
+	uint64_t sVisits = 0;
+#ifdef _OPENMP
+	if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+	auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 4) reduction(+:sVisits)
+	for (int py = y0; py < y1; py++)
+		for (int px = 0; px < W; px++) {
+			size_t pix = (size_t)(py - y0) * W + px;
+			V3 o, d; genRay(*cam, px, py, o, d);
+			float tRes = 1e30f; int id = -1; V3 color = v3(0, 0, 0);
+			if (mode == 0) {
+				const ONode* leaf = nullptr; uint64_t visits = 0;
+				tRes = raySkip(oc->root, o, d, 0.0f, 1e30f, oc->g, leaf, visits);
+				sVisits += visits;
+				if (leaf) {     // extension: box-centre normal + Lambert, same formulas as the GLSL hit (:279-283)
+					id = oc->index[leaf];
+					V3 nmin = gridMin + v3((float)leaf->x, (float)leaf->y, (float)leaf->z) * oc->g.voxel;
+					V3 nmax = nmin + v3((float)leaf->size, (float)leaf->size, (float)leaf->size) * oc->g.voxel;
+					V3 center = 0.5f * (nmin + nmax);
+					V3 p = o + d * tRes;
+					color = shadeLambert(normalize(p - center));
+				}
+			}
+			else {
+				HitB r = traverseGLSL(oc->flat, gridMin, oc->g.voxel, o, d);
+				sVisits += (uint64_t)r.steps;
+				if (r.hit) { tRes = r.t; id = r.id; color = shadeLambert(r.normal); }
+			}
+			if (rgba) { rgba[4 * pix] = color.x; rgba[4 * pix + 1] = color.y; rgba[4 * pix + 2] = color.z; rgba[4 * pix + 3] = 1.0f; }
+			if (leafId) leafId[pix] = id;
+			if (tOut) tOut[pix] = tRes;
+		}
+	double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (stats) { stats[0] = sVisits; stats[1] = 0; }
+	return sec;
+}
+
+void orc_octree_rayskip(void* h, const float* o3, const float* d3, size_t n, float tMin, float tMax, float* tOut, int32_t* idOut) {
+	Octree* oc = (Octree*)h;
+	for (size_t i = 0; i < n; i++) {
+		const ONode* leaf = nullptr; uint64_t visits = 0;
+		tOut[i] = raySkip(oc->root, v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]), tMin, tMax, oc->g, leaf, visits);
+		if (idOut) idOut[i] = leaf ? oc->index[leaf] : -1;
+	}
+}
+
+// ---- mesh + BVH -------------------------------------------------------------------------------------
+void* orc_mesh_from_octree(void* h) {
+	Octree* oc = (Octree*)h; Mesh* m = new Mesh();
+	mcRender(oc->g, oc->root, 0, 0, 0, oc->root->size, m->tris);
+	return m;
+}
+void* orc_mesh_from_tris(const float* xyz9, size_t n) { Mesh* m = new Mesh(); m->tris.resize(n); std::memcpy((void*)m->tris.data(), xyz9, n * 36); return m; }
+size_t orc_mesh_count(void* mv) { return ((Mesh*)mv)->tris.size(); }
+void orc_mesh_tris(void* mv, float* out9) { Mesh* m = (Mesh*)mv; std::memcpy(out9, m->tris.data(), m->tris.size() * 36); }
+double orc_bvh_build(void* mv) {
+	auto t0 = std::chrono::steady_clock::now();
+	((Mesh*)mv)->build();
+	return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+void orc_mesh_free(void* mv) { delete (Mesh*)mv; }
+
+static void exportNode(const Mesh* m, const BNode* n, std::vector<float>& boxes, std::vector<int32_t>& meta) {
+	for (int i = 0; i < 3; i++) boxes.push_back(n->b.mn[i]);
+	for (int i = 0; i < 3; i++) boxes.push_back(n->b.mx[i]);
+	bool leaf = !n->l && !n->r;
+	meta.push_back(leaf); meta.push_back((int32_t)n->tris.size());
+	for (int i = 0; i < 2; i++) meta.push_back(i < (int)n->tris.size() ? (int32_t)(n->tris[i] - &m->tris[0]) : -1);
+	if (!leaf) { exportNode(m, n->l, boxes, meta); exportNode(m, n->r, boxes, meta); }
+}
+size_t orc_bvh_export(void* mv, float* boxes6, int32_t* meta4, size_t cap) {
+	Mesh* m = (Mesh*)mv; std::vector<float> b; std::vector<int32_t> me;
+	exportNode(m, m->root, b, me);
+	size_t n = me.size() / 4;
+	if (boxes6 && meta4 && n <= cap) { std::memcpy(boxes6, b.data(), b.size() * 4); std::memcpy(meta4, me.data(), me.size() * 4); }
+	return n;
+}
+size_t orc_bvh_query(void* mv, const float* o3, const float* d3, size_t nrays, int64_t* offsets, int32_t* ids, size_t cap) {
+	Mesh* m = (Mesh*)mv; std::vector<const Tri*> cand; size_t total = 0;
+	for (size_t r = 0; r < nrays; r++) {
+		cand.clear();
+		m->query(v3(o3[3 * r], o3[3 * r + 1], o3[3 * r + 2]), v3(d3[3 * r], d3[3 * r + 1], d3[3 * r + 2]), cand);
+		offsets[r] = (int64_t)total;
+		for (auto* t : cand) { if (ids && total < cap) ids[total] = (int32_t)(t - &m->tris[0]); total++; }
+	}
+	offsets[nrays] = (int64_t)total;
+	return total;
+}
+
+double orc_render_bvh(void* mv, const Cam* cam, unsigned flags, float shadowBias, int y0, int y1,
+	float* rgba, int32_t* hitId, float* tOut, uint64_t* stats, int nthreads) {
+	Mesh* m = (Mesh*)mv;
+	const int W = cam->width;
+	uint64_t sB = 0, sC = 0, sBs = 0, sCs = 0, nShadow = 0;
+#ifdef _OPENMP
+	if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+	auto tstart = std::chrono::steady_clock::now();
+#pragma omp parallel reduction(+:sB,sC,sBs,sCs,nShadow)
+	{
+		std::vector<const Tri*> cand;
+#pragma omp for schedule(dynamic, 4)
+		for (int py = y0; py < y1; py++)
+			for (int px = 0; px < W; px++) {
+				size_t pix = (size_t)(py - y0) * W + px;
+				V3 o, d; genRay(*cam, px, py, o, d);
+				cand.clear();
+				m->query(o, d, cand, stats ? &sB : nullptr);
+				sC += cand.size();
+				float best = 1e30f; const Tri* bestTri = nullptr;
+				for (const Tri* tri : cand) { float t; if (mollerTrumbore(*tri, o, d, t) && t < best) { best = t; bestTri = tri; } }
+				V3 color = v3(0, 0, 0);
+				if (bestTri) {
+					V3 e1 = bestTri->v1 - bestTri->v0, e2 = bestTri->v2 - bestTri->v0;
+					V3 n = normalize(cross(e1, e2));
+					if (dot(n, d) > 0.0f) n = -n;
+					V3 hit = o + d * best;
+					bool shadowed = false;
+					if (flags & RTO_FLAG_SHADOWS) {
+						V3 so = hit + n * shadowBias;
+						V3 sd = normalize(v3(1.0f, 1.0f, 1.0f));
+						cand.clear();
+						m->query(so, sd, cand, stats ? &sBs : nullptr);
+						sCs += cand.size(); nShadow++;
+						for (const Tri* tri : cand) { float t; if (mollerTrumbore(*tri, so, sd, t)) { shadowed = true; break; } }
+					}
+					color = shadowed ? v3(0.1f, 0.1f, 0.1f) : shadeLambert(n);
+				}
+				if (rgba) { rgba[4 * pix] = color.x; rgba[4 * pix + 1] = color.y; rgba[4 * pix + 2] = color.z; rgba[4 * pix + 3] = 1.0f; }
+				if (hitId) hitId[pix] = bestTri ? (int32_t)(bestTri - &m->tris[0]) : -1;
+				if (tOut) tOut[pix] = best;
+			}
+	}
+	double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - tstart).count();
+	if (stats) { stats[0] = sB; stats[1] = sC; stats[2] = sBs; stats[3] = sCs; stats[4] = nShadow; }
+	return sec;
+}
+
+int orc_num_threads() {
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+} // extern "C"
