@@ -1,0 +1,191 @@
+/* rto_c.h -- C ABI of the B200-native ray-casting core (librto.so).
+ *
+ * This is the drop-in boundary for the reference's ray-casting hot path.  The reference
+ * (abodthedude25/Ray_Tracing_Octrees) has no FFI layer: the path is reached through C++ class calls
+ *   BVH::BVH / BVH::query                              453-skeleton/BVH.h:44-63, BVH.cpp:19-113
+ *   createOctreeFromVoxelGrid / freeOctree             453-skeleton/OctreeVoxel.h:66-69, OctreeVoxel.cpp:765-778
+ *   RayTracerBVH::setOctree / renderSceneCompute       453-skeleton/RayTracerBVH.h:30-50, RayTracerBVH.cpp:430-505, 614-704
+ *   static octreeRaySkip (VolumeRaycastRenderer)       453-skeleton/VolumeRaycastRenderer.cpp:50-155
+ *   MarchingCubesRenderer::render / localMC            453-skeleton/Renderer.cpp:14-36, OctreeVoxel.cpp:780-879
+ *   Camera::getView / getPos                           453-skeleton/Camera.cpp:11-29
+ * Each entry point below names the reference interface it replaces.  C++ shims that keep the
+ * reference's class names on top of this ABI live in ray_tracing_octrees_b200/csrc/shim/.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an RtoStatus (0 = OK) unless
+ * stated; nothing throws across the boundary; rto_last_error() gives a thread-local message.
+ * All ray work runs on the GPU (sm_100a).  There is NO CPU fallback: without a usable CUDA device
+ * every rto_scene_* / rto_render* / rto_trace* call fails with RTO_ERR_NO_DEVICE.
+ * Host-side builders (rto_host_*) are CPU code exactly where the reference's are (tree construction).
+ */
+#ifndef RTO_C_H
+#define RTO_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTO_API __attribute__((visibility("default")))
+
+typedef enum RtoStatus {
+	RTO_OK = 0,
+	RTO_ERR_INVALID = 1,      /* bad argument */
+	RTO_ERR_NO_DEVICE = 2,    /* CUDA device missing / wrong architecture */
+	RTO_ERR_CUDA = 3,         /* CUDA runtime error; see rto_last_error() */
+	RTO_ERR_ALLOC = 4,
+	RTO_ERR_IO = 5,
+	RTO_ERR_UNSUPPORTED = 6
+} RtoStatus;
+
+/* ---- reference-compatible plain data ------------------------------------------------------------- */
+
+/* GPUNodes, RayTracerBVH.h:21-26: 15 x int32, std430 stride 60.  Index in the array == node id. */
+typedef struct RtoGpuNode {
+	int32_t x, y, z, size;
+	int32_t isLeaf, isSolid, isUniform;
+	int32_t child[8];
+} RtoGpuNode;
+
+/* Triangle, BVH.h:7-11: 9 floats (v0, v1, v2), 36 bytes. */
+typedef struct RtoTriangle { float v0[3], v1[3], v2[3]; } RtoTriangle;
+
+/* Per-frame camera constants.  The GLSL generateRay (RayTracerBVH.cpp:338-355) recomputes inverse(view)
+ * and tan(fov/2) per pixel; here they are computed once on the host (rto_host_camera_orbit, or by the
+ * caller with glm) so libm never runs on the GPU.  invView is column-major like glm::mat4. */
+typedef struct RtoCamera {
+	float   camPos[3];
+	float   invView[16];
+	float   tanHalfFov;
+	float   aspect;
+	int32_t width, height;
+} RtoCamera;
+
+/* Output planes of one render call.  Any pointer may be NULL (plane not wanted).  Row 0 is the top row
+ * (gl_GlobalInvocationID.y == 0).  Pointers are host or device addresses according to `memory`. */
+typedef enum RtoMemory { RTO_MEM_HOST = 0, RTO_MEM_DEVICE = 1 } RtoMemory;
+typedef struct RtoFrame {
+	float*   rgba;     /* 4 floats / pixel: Lambert colour of RayTracerBVH.cpp:331-336, alpha 1, miss = 0,0,0,1 */
+	int32_t* hitId;    /* BVH scenes: index of the hit triangle in the caller's array; octree scenes: node index
+	                      (== leaf id of RayTracerBVH::setOctree's BFS numbering); -1 on miss */
+	float*   t;        /* hit distance along the (unit) ray; 1e30f on miss */
+	int32_t  memory;   /* RtoMemory */
+} RtoFrame;
+
+/* Traversal semantics selector. */
+typedef enum RtoMode {
+	RTO_MODE_BVH = 0,           /* BVH::query candidate set + Moller-Trumbore closest hit (SURVEY.md 8c rule) */
+	RTO_MODE_OCTREE_SKIP = 1,   /* octreeRaySkip semantics, VolumeRaycastRenderer.cpp:50-155 ("mode A") */
+	RTO_MODE_OCTREE_GLSL = 2    /* intersectOctreeIterative semantics, RayTracerBVH.cpp:239-327 ("mode B") */
+} RtoMode;
+
+#define RTO_FLAG_SHADOWS      1u   /* BVH scenes: one shadow ray per primary hit towards normalize(1,1,1) */
+#define RTO_FLAG_NO_PRUNE     2u   /* BVH scenes: visit every box the reference's queryNode visits (no t-pruning) */
+
+typedef struct RtoScene RtoScene;          /* device-resident scene (BVH or octree), one CUDA stream each */
+typedef struct RtoHostBvh RtoHostBvh;      /* host BVH identical in shape to the reference's BVH */
+
+/* ---- library ----------------------------------------------------------------------------------------- */
+RTO_API const char* rto_version(void);
+RTO_API const char* rto_last_error(void);
+/* Select the CUDA device for this thread (cudaSetDevice) and check it is sm_100. */
+RTO_API int rto_init(int device);
+RTO_API int rto_device_info(int* smCount, int* ccMajor, int* ccMinor, size_t* l2Bytes, size_t* totalMem);
+
+/* ---- host-side builders (CPU, like the reference's own) ---------------------------------------------- */
+
+/* createOctreeFromVoxelGrid (OctreeVoxel.cpp:765-778) followed by RayTracerBVH::setOctree's BFS flatten
+ * (RayTracerBVH.cpp:443-490): voxels are x-fastest uint8 (0 EMPTY, 1 FILLED), dims in voxels.
+ * Returns a malloc'ed array of *numNodes RtoGpuNode in the reference's BFS numbering; free with rto_host_free. */
+RTO_API int rto_host_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	RtoGpuNode** nodesOut, size_t* numNodes);
+
+/* MarchingCubesRenderer::render(root, grid, 0,0,0, root->size) (Renderer.cpp:14-36 over localMC,
+ * OctreeVoxel.cpp:780-879): triangle soup in the reference's emission order.  malloc'ed; rto_host_free. */
+RTO_API int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
+	RtoTriangle** trisOut, size_t* numTris);
+
+/* BVH::BVH(const std::vector<Triangle>&) (BVH.cpp:19-71): same tree (median split, longest axis, std::sort
+ * by centroid, leaves <= 2 triangles).  The triangle array must outlive the handle (the reference keeps raw
+ * pointers too, BVH.cpp:21-25). */
+RTO_API int rto_host_bvh_build(const RtoTriangle* tris, size_t numTris, RtoHostBvh** out);
+RTO_API void rto_host_bvh_free(RtoHostBvh* bvh);
+RTO_API size_t rto_host_bvh_num_nodes(const RtoHostBvh* bvh);
+/* Pre-order export (left before right): boxes6 = min xyz, max xyz; meta4 = isLeaf, triCount, tri0, tri1. */
+RTO_API int rto_host_bvh_export(const RtoHostBvh* bvh, float* boxes6, int32_t* meta4, size_t capacity);
+
+/* Camera(theta, phi, radius) with target (Camera.cpp:8-29), view = lookAt(eye, target, +Y), plus the two
+ * host constants of generateRay: inverse(view) and tan(radians(fovDeg)/2).  Angles in radians. */
+RTO_API int rto_host_camera_orbit(float theta, float phi, float radius, const float target[3],
+	float fovDeg, float aspect, int width, int height, RtoCamera* out, float* view16 /* may be NULL */);
+
+/* loadVoxelGrid / saveVoxelGrid, CacheUtils.cpp:5-59 (sceneCache.bin: 3 x int32 dims, 4 x float, size_t n, bytes). */
+RTO_API int rto_host_grid_load(const char* path, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut);
+RTO_API int rto_host_grid_save(const char* path, const int dims[3], const float minAndVoxel[4], const uint8_t* voxels);
+
+RTO_API void rto_host_free(void* p);
+
+/* ---- device scenes ----------------------------------------------------------------------------------- */
+
+/* Replaces RayTracerBVH::setOctree's SSBO upload (RayTracerBVH.cpp:492-504).  `nodes` is any GPUNodes array
+ * with root at index 0 (normally rto_host_octree_build's).  The scene is linearised on upload into a
+ * pointer-free array; arrays produced by the reference builder (every internal node has 8 contiguous
+ * children) take the compact 4-byte-per-node path, anything else the general 64-byte-per-node path. */
+RTO_API int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3],
+	float voxelSize, RtoScene** out);
+
+/* Replaces "build a BVH, keep it for queries": builds the reference-shaped tree on the host
+ * (or takes `prebuilt`), flattens it to the GPU layout and uploads triangles + nodes once. */
+RTO_API int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt /* may be NULL */,
+	RtoScene** out);
+
+RTO_API void rto_scene_destroy(RtoScene* scene);
+RTO_API int rto_scene_info(const RtoScene* scene, int* kind /* RtoMode of a BVH or octree scene */,
+	size_t* numPrims, size_t* numNodes, size_t* deviceBytes, int* compactLayout);
+/* The CUDA stream all work of this scene is enqueued on (cudaStream_t as void*). */
+RTO_API void* rto_scene_stream(const RtoScene* scene);
+
+/* ---- rendering (replaces RayTracerBVH::renderSceneCompute, RayTracerBVH.cpp:614-704) -------------------- */
+
+/* Trace rows [y0, y1) of the camera's image.  Planes in `frame` are indexed from row y0 (size (y1-y0)*width).
+ * mode must match the scene kind (BVH scene: RTO_MODE_BVH; octree scene: either octree mode).
+ * shadowBias: offset of the shadow-ray origin along the shading normal (rule: 1e-3f * scene scale).
+ * With RTO_MEM_HOST the call copies results to the host and synchronises; with RTO_MEM_DEVICE it only
+ * enqueues on rto_scene_stream() (use rto_scene_sync or your own event). */
+RTO_API int rto_render(RtoScene* scene, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias,
+	int y0, int y1, const RtoFrame* frame);
+
+/* Many cameras in one submission (frame f writes planes at offset f*(y1-y0)*width). */
+RTO_API int rto_render_batch(RtoScene* scene, const RtoCamera* cams, int numCams, int mode, uint32_t flags,
+	float shadowBias, int y0, int y1, const RtoFrame* frame);
+
+/* Explicit ray list (origins/directions 3 floats each, directions need not be unit), for edge cases and as the
+ * batched counterpart of single-ray calls: octree scenes return what octreeRaySkip(root, ro, rd, tMin, tMax, grid)
+ * returns (mode A) or the GLSL traversal's closestT (mode B); BVH scenes the closest MT hit. */
+RTO_API int rto_trace_rays(RtoScene* scene, int mode, uint32_t flags, const float* origins, const float* dirs, size_t numRays,
+	float tMin, float tMax, float* tOut, int32_t* idOut, int memory);
+
+/* BVH::query for many rays (BVH.cpp:107-113): candidate triangle ids per ray in the reference's order.
+ * offsets has numRays+1 entries (host memory).  Call with ids == NULL to get the total in *totalOut first. */
+RTO_API int rto_bvh_query(RtoScene* scene, const float* origins, const float* dirs, size_t numRays,
+	int64_t* offsets, int32_t* ids, size_t idsCapacity, size_t* totalOut);
+
+/* Work counters of the reference algorithm for the image rows [y0,y1), measured on the GPU by replaying the
+ * reference's visit pattern: BVH scenes: {box tests primary, candidates primary, box tests shadow, candidates shadow,
+ * shadow rays}; octree scenes: {nodes visited, 0, 0, 0, 0}.  Used for the algorithmic bytes/flops of SURVEY.md 8d. */
+RTO_API int rto_render_stats(RtoScene* scene, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias,
+	int y0, int y1, uint64_t stats[5]);
+
+RTO_API int rto_scene_sync(RtoScene* scene);
+/* Device time in milliseconds of the most recent rto_render / rto_render_batch on this scene
+ * (CUDA events on the scene's stream around the kernels only).  Synchronises. */
+RTO_API int rto_scene_last_kernel_ms(RtoScene* scene, float* ms);
+/* Number of kernel launches issued by this library on this scene so far. */
+RTO_API uint64_t rto_scene_launch_count(const RtoScene* scene);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTO_C_H */

@@ -1,0 +1,339 @@
+"""Python mirror of the reference's interface for the ray-casting hot path, on top of the C ABI (librto.so).
+
+Names follow the reference (abodthedude25/Ray_Tracing_Octrees):
+  VoxelGrid                         OctreeVoxel.h:28-42
+  create_octree_from_voxel_grid     createOctreeFromVoxelGrid (OctreeVoxel.cpp:765-778) + RayTracerBVH::setOctree's
+                                    BFS numbering (RayTracerBVH.cpp:443-490) -> (n, 15) int32 GPUNodes array
+  marching_cubes_mesh               MarchingCubesRenderer::render(root, grid, 0,0,0, root->size) (Renderer.cpp:14-36)
+  BVH                               BVH.h:44-63 (build on the host, query on the GPU)
+  Camera                            Camera.h:5-44 (orbit camera; angles in radians)
+  RayTracerBVH                      RayTracerBVH.h:28-80: set_octree / render_scene_compute, plus the mesh path
+                                    (set_mesh) that BASELINE.json's north_star adds.
+Everything that traces a ray runs in CUDA; nothing here computes a pixel on the CPU.
+"""
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import (FLAG_NO_PRUNE, FLAG_SHADOWS, MEM_DEVICE, MEM_HOST, MODE_BVH, MODE_OCTREE_GLSL, MODE_OCTREE_SKIP,
+                   RtoCamera, RtoError, RtoFrame, check, lib)
+
+MISS_T = np.float32(1e30)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _take(ptr, count, dtype, shape):
+    """Copy a malloc'ed C array into numpy and free it."""
+    if not ptr or count == 0:
+        return np.zeros((0,) + tuple(shape[1:]), dtype)
+    n = int(np.prod(shape))
+    buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy().reshape(shape)
+    lib().rto_host_free(ptr)
+    return buf
+
+
+class VoxelGrid:
+    """VoxelGrid (OctreeVoxel.h:28-42): x-fastest uint8 occupancy, world min corner, voxel size."""
+
+    def __init__(self, dims, gmin, voxel_size, data):
+        self.dims = tuple(int(d) for d in dims)
+        self.min = np.asarray(gmin, np.float32).copy()
+        self.voxel_size = float(np.float32(voxel_size))
+        self.data = np.ascontiguousarray(data, np.uint8).ravel()
+        if self.data.size != self.dims[0] * self.dims[1] * self.dims[2]:
+            raise ValueError("voxel data size does not match dims")
+
+    @staticmethod
+    def load(path):
+        """loadVoxelGrid (CacheUtils.cpp:33-59); also accepts a gzip-compressed sceneCache.bin."""
+        if path.endswith(".gz"):
+            raw = gzip.open(path, "rb").read()
+            dims = np.frombuffer(raw, np.int32, 3, 0)
+            mv = np.frombuffer(raw, np.float32, 4, 12)
+            n = int(np.frombuffer(raw, np.uint64, 1, 28)[0])
+            data = np.frombuffer(raw, np.uint8, n, 36)
+            if n != int(dims[0]) * int(dims[1]) * int(dims[2]):
+                raise IOError("inconsistent voxel cache " + path)
+            return VoxelGrid(dims, mv[:3], mv[3], data)
+        dims = np.zeros(3, np.int32)
+        mv = np.zeros(4, np.float32)
+        ptr = C.c_void_p()
+        check(lib().rto_host_grid_load(path.encode(), _p(dims), _p(mv), C.byref(ptr)))
+        n = int(dims[0]) * int(dims[1]) * int(dims[2])
+        data = _take(ptr, n, np.uint8, (n,))
+        return VoxelGrid(dims, mv[:3], mv[3], data)
+
+    def save(self, path):
+        dims = np.asarray(self.dims, np.int32)
+        mv = np.concatenate([self.min, [np.float32(self.voxel_size)]]).astype(np.float32)
+        check(lib().rto_host_grid_save(path.encode(), _p(dims), _p(mv), _p(self.data)))
+
+
+def create_octree_from_voxel_grid(grid):
+    """-> (n, 15) int32 array of GPUNodes in the reference's BFS numbering (row index == node / leaf id)."""
+    ptr = C.c_void_p()
+    n = C.c_size_t()
+    check(lib().rto_host_octree_build(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], C.byref(ptr), C.byref(n)))
+    return _take(ptr, n.value, np.int32, (n.value, 15))
+
+
+def marching_cubes_mesh(grid, nodes):
+    """-> (m, 9) float32 triangle soup (v0, v1, v2) in the reference's emission order."""
+    nodes = np.ascontiguousarray(nodes, np.int32)
+    ptr = C.c_void_p()
+    n = C.c_size_t()
+    check(lib().rto_host_mc_mesh(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min), grid.voxel_size,
+                                 _p(nodes), len(nodes), C.byref(ptr), C.byref(n)))
+    return _take(ptr, n.value, np.float32, (n.value, 9))
+
+
+class Camera:
+    """Orbit camera (Camera.h:5-44): theta / phi in radians, radius, target."""
+
+    def __init__(self, theta, phi, radius, target=(0.0, 0.0, 0.0)):
+        self.theta, self.phi, self.radius = float(theta), float(phi), float(radius)
+        self.target = np.asarray(target, np.float32).copy()
+
+    @staticmethod
+    def from_degrees(theta_deg, phi_deg, radius, target=(0.0, 0.0, 0.0)):
+        return Camera(float(np.deg2rad(np.float32(theta_deg))), float(np.deg2rad(np.float32(phi_deg))), radius, target)
+
+    def consts(self, fov_deg, aspect, width, height):
+        """getView/getPos + the per-frame constants of generateRay -> (RtoCamera, view matrix as 16 floats)."""
+        cam = RtoCamera()
+        view = np.zeros(16, np.float32)
+        check(lib().rto_host_camera_orbit(self.theta, self.phi, self.radius, _p(self.target), fov_deg, aspect,
+                                          width, height, C.byref(cam), _p(view)))
+        return cam, view
+
+
+class HostBVH:
+    """BVH::BVH(triangles) on the host (BVH.cpp:19-71).  Keeps the triangle array alive like the caller must."""
+
+    def __init__(self, tris):
+        self.tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        self.h = C.c_void_p()
+        check(lib().rto_host_bvh_build(_p(self.tris), len(self.tris), C.byref(self.h)))
+
+    @property
+    def num_nodes(self):
+        return lib().rto_host_bvh_num_nodes(self.h)
+
+    def export(self):
+        n = self.num_nodes
+        boxes = np.zeros((n, 6), np.float32)
+        meta = np.zeros((n, 4), np.int32)
+        check(lib().rto_host_bvh_export(self.h, _p(boxes), _p(meta), n))
+        return boxes, meta
+
+    def close(self):
+        if self.h:
+            lib().rto_host_bvh_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scene:
+    """A device-resident scene (RtoScene*)."""
+
+    def __init__(self, handle, keep=()):
+        self.h = handle
+        self._keep = keep
+
+    @staticmethod
+    def octree(nodes, grid_min, voxel_size):
+        nodes = np.ascontiguousarray(nodes, np.int32).reshape(-1, 15)
+        gm = np.asarray(grid_min, np.float32)
+        h = C.c_void_p()
+        check(lib().rto_scene_create_octree(_p(nodes), len(nodes), _p(gm), float(voxel_size), C.byref(h)))
+        return Scene(h)
+
+    @staticmethod
+    def bvh(tris, prebuilt=None):
+        tris = prebuilt.tris if prebuilt is not None else np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        h = C.c_void_p()
+        check(lib().rto_scene_create_bvh(_p(tris), len(tris), prebuilt.h if prebuilt is not None else None, C.byref(h)))
+        return Scene(h, keep=(tris,))
+
+    def info(self):
+        kind, compact = C.c_int(), C.c_int()
+        prims, nodes, nbytes = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(lib().rto_scene_info(self.h, C.byref(kind), C.byref(prims), C.byref(nodes), C.byref(nbytes), C.byref(compact)))
+        return dict(kind=kind.value, prims=prims.value, nodes=nodes.value, device_bytes=nbytes.value, compact=compact.value)
+
+    @property
+    def stream(self):
+        return lib().rto_scene_stream(self.h)
+
+    def sync(self):
+        check(lib().rto_scene_sync(self.h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(lib().rto_scene_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launch_count(self):
+        return int(lib().rto_scene_launch_count(self.h))
+
+    def render(self, cam, mode, flags=0, shadow_bias=0.0, y0=0, y1=None, want=("rgba", "id", "t")):
+        """Host-memory render of rows [y0, y1): returns dict(rgba (n,4) f32, id (n,) i32, t (n,) f32)."""
+        y1 = cam.height if y1 is None else y1
+        n = (y1 - y0) * cam.width
+        out = dict(rgba=np.empty((n, 4), np.float32) if "rgba" in want else None,
+                   id=np.empty(n, np.int32) if "id" in want else None,
+                   t=np.empty(n, np.float32) if "t" in want else None)
+        fr = RtoFrame(_p(out["rgba"]), _p(out["id"]), _p(out["t"]), MEM_HOST)
+        check(lib().rto_render(self.h, C.byref(cam), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
+        return out
+
+    def render_device(self, cams, mode, flags=0, shadow_bias=0.0, y0=0, y1=None, rgba_ptr=None, id_ptr=None, t_ptr=None):
+        """Enqueue a render of one camera or a list of cameras writing to device pointers (asynchronous)."""
+        if isinstance(cams, RtoCamera):
+            cams = [cams]
+        arr = (RtoCamera * len(cams))(*cams)
+        y1 = cams[0].height if y1 is None else y1
+        fr = RtoFrame(rgba_ptr, id_ptr, t_ptr, MEM_DEVICE)
+        check(lib().rto_render_batch(self.h, arr, len(cams), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
+
+    def render_host_ptrs(self, cams, mode, flags, shadow_bias, y0, y1, rgba_ptr, id_ptr, t_ptr):
+        """Synchronous render into caller-owned HOST pointers (e.g. pinned torch tensors)."""
+        if isinstance(cams, RtoCamera):
+            cams = [cams]
+        arr = (RtoCamera * len(cams))(*cams)
+        fr = RtoFrame(rgba_ptr, id_ptr, t_ptr, MEM_HOST)
+        check(lib().rto_render_batch(self.h, arr, len(cams), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
+
+    def stats(self, cam, mode, flags=0, shadow_bias=0.0, y0=0, y1=None):
+        y1 = cam.height if y1 is None else y1
+        st = np.zeros(5, np.uint64)
+        check(lib().rto_render_stats(self.h, C.byref(cam), mode, flags, shadow_bias, y0, y1, _p(st)))
+        return st
+
+    def trace_rays(self, origins, dirs, mode, flags=0, tmin=0.0, tmax=1e30):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        t = np.empty(len(o), np.float32)
+        ids = np.empty(len(o), np.int32)
+        check(lib().rto_trace_rays(self.h, mode, flags, _p(o), _p(d), len(o), tmin, tmax, _p(t), _p(ids), MEM_HOST))
+        return t, ids
+
+    def query(self, origins, dirs):
+        """BVH::query for many rays -> (offsets int64 (n+1,), triangle ids int32) in the reference's candidate order."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        off = np.zeros(len(o) + 1, np.int64)
+        total = C.c_size_t()
+        check(lib().rto_bvh_query(self.h, _p(o), _p(d), len(o), _p(off), None, 0, C.byref(total)))
+        ids = np.zeros(total.value, np.int32)
+        if total.value:
+            check(lib().rto_bvh_query(self.h, _p(o), _p(d), len(o), _p(off), _p(ids), total.value, C.byref(total)))
+        return off, ids
+
+    def close(self):
+        if self.h:
+            lib().rto_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BVH:
+    """BVH(triangles) + query(origin, direction) (BVH.h:44-63): tree built on the host, queries run on the GPU."""
+
+    def __init__(self, tris):
+        self.host = HostBVH(tris)
+        self.scene = Scene.bvh(None, prebuilt=self.host)
+
+    def query(self, origin, direction):
+        off, ids = self.scene.query(np.asarray(origin, np.float32).reshape(1, 3), np.asarray(direction, np.float32).reshape(1, 3))
+        return ids
+
+    def query_batch(self, origins, dirs):
+        return self.scene.query(origins, dirs)
+
+
+class RayTracerBVH:
+    """RayTracerBVH (RayTracerBVH.h:28-80) without OpenGL: scenes live in HBM, frames come back as arrays."""
+
+    def __init__(self):
+        self.scene = None
+        self.mode = MODE_OCTREE_GLSL
+        self.shadow_bias = 0.0
+
+    def set_octree(self, nodes, grid):
+        """setOctree(root, grid): `nodes` is the flattened octree (create_octree_from_voxel_grid)."""
+        if self.scene is not None:
+            self.scene.close()
+        self.scene = None if nodes is None or len(nodes) == 0 else Scene.octree(nodes, grid.min, grid.voxel_size)
+        self.mode = MODE_OCTREE_GLSL
+
+    def set_mesh(self, tris, scene_scale=1.0):
+        """Extension: ray-cast the triangle soup through the reference-shaped BVH (north_star's mesh path)."""
+        if self.scene is not None:
+            self.scene.close()
+        self.scene = Scene.bvh(tris)
+        self.mode = MODE_BVH
+        self.shadow_bias = float(np.float32(1e-3) * np.float32(scene_scale))
+
+    def ensure_compute_initialized(self):
+        check(lib().rto_init(0))
+
+    def render_scene_compute(self, camera, width, height, aspect, fov_deg, mode=None, flags=0):
+        """renderSceneCompute(camera, w, h, aspect, fovDeg) -> dict(rgba, id, t) as (h, w, ...) arrays.
+        Like the reference (RayTracerBVH.cpp:624-627) an empty scene renders nothing: returns None."""
+        if self.scene is None:
+            return None
+        cam, _ = camera.consts(fov_deg, aspect, width, height)
+        out = self.scene.render(cam, self.mode if mode is None else mode, flags, self.shadow_bias)
+        return dict(rgba=out["rgba"].reshape(height, width, 4), id=out["id"].reshape(height, width), t=out["t"].reshape(height, width))
+
+
+def generate_test_volume(dim):
+    """Multi-shell sphere of generateTestVolume (main.cpp:337-372) as a VoxelGrid set up like main.cpp:1050-1070:
+    FILLED iff rInner <= |p - c| <= rOuter, grid min -0.5, voxel 1/dim."""
+    c = np.float32(0.5) * np.float32(dim - 1)
+    r_out = np.float32(0.4) * np.float32(dim)
+    r_in = np.float32(0.2) * np.float32(dim)
+    ax = np.arange(dim, dtype=np.float32) - c
+    dz, dy, dx = np.meshgrid(ax, ax, ax, indexing="ij")
+    dist = np.sqrt(dx * dx + dy * dy + dz * dz)
+    filled = ~((dist < r_in) | (dist > r_out))
+    return VoxelGrid((dim, dim, dim), (-0.5, -0.5, -0.5), np.float32(1.0) / np.float32(dim), filled.astype(np.uint8).ravel())
+
+
+def city_block_grid(dim, seed, blocks, max_height=None):
+    """Synthetic city-block voxel grid: `blocks` x `blocks` lots on the x-z ground plane,
+    a building on a lot with p = 0.7, footprint inset U{1..4} voxels, height U{8..max_height} voxels (y up), voxel 1.0,
+    grid min = -dim/2.  Deterministic for a given (dim, seed, blocks) via numpy's PCG64."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lot = dim // blocks
+    max_height = (3 * dim) // 4 if max_height is None else max_height
+    vol = np.zeros((dim, dim, dim), np.uint8)            # [z, y, x]
+    for bz in range(blocks):
+        for bx in range(blocks):
+            present = rng.random() < 0.7
+            inset = int(rng.integers(1, 5))
+            height = int(rng.integers(8, max_height + 1))
+            if not present or lot - 2 * inset <= 0:
+                continue
+            x0, z0 = bx * lot + inset, bz * lot + inset
+            vol[z0:z0 + lot - 2 * inset, 0:height, x0:x0 + lot - 2 * inset] = 1
+    h = np.float32(dim) * np.float32(0.5)
+    return VoxelGrid((dim, dim, dim), (-h, -h, -h), 1.0, vol.ravel())

@@ -1,0 +1,374 @@
+// host_builders.cpp -- CPU-side scene construction of the product library (librto.so).
+//
+// These are the host halves of the reference's hot path, re-implemented for speed but producing the SAME
+// data the reference produces (node sets, numbering, triangle order, tree shape), because hit ids are
+// indices into those arrays:
+//   rto_host_octree_build  == createOctreeFromVoxelGrid (OctreeVoxel.cpp:704-778) + setOctree BFS flatten
+//                             (RayTracerBVH.cpp:443-490); built bottom-up from an occupancy pyramid instead
+//                             of the reference's top-down full-region rescans.
+//   rto_host_mc_mesh       == MarchingCubesRenderer::render over localMC (Renderer.cpp:14-36,
+//                             OctreeVoxel.cpp:780-879); only the outer cell layers of a uniform leaf can
+//                             straddle a sign change, so interior cells are skipped without changing order.
+//   rto_host_bvh_build     == BVH::BVH / BVH::build (BVH.cpp:19-71); index-based, pre-order node array,
+//                             subtrees built on worker threads, identical std::sort call sequence per range.
+//   rto_host_camera_orbit  == Camera::getView/getPos (Camera.cpp:11-29) + glm::lookAtRH + glm::inverse.
+// Compiled with -ffp-contract=off; arithmetic follows rto_math.h (glm operation order).
+#include "rto_internal.h"
+#include "mc_tables.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+using namespace rto;
+
+// =================================================================================================
+// Octree: bottom-up uniformity pyramid + BFS emission
+// =================================================================================================
+namespace {
+
+constexpr uint8_t kMixed = 0xFF;
+
+struct Pyramid {
+	// level l holds cells of edge 2^l voxels, clipped to the grid: dims ceil(dim / 2^l). Level 0 aliases the voxels.
+	std::vector<std::vector<uint8_t>> store;
+	std::vector<const uint8_t*> data;
+	std::vector<int> nx, ny, nz;
+	// state of the cell of edge 2^l at voxel origin (x, y, z); outside the grid everything is EMPTY (getVoxelSafe, OctreeVoxel.cpp:692-701)
+	inline uint8_t at(int l, int x, int y, int z) const {
+		int cx = x >> l, cy = y >> l, cz = z >> l;
+		if (cx >= nx[l] || cy >= ny[l] || cz >= nz[l]) return 0;
+		return data[l][(size_t)cx + (size_t)cy * nx[l] + (size_t)cz * ((size_t)nx[l] * ny[l])];
+	}
+};
+
+void buildPyramid(const uint8_t* vox, int dx, int dy, int dz, int levels, Pyramid& P) {
+	P.store.resize(levels + 1); P.data.resize(levels + 1); P.nx.resize(levels + 1); P.ny.resize(levels + 1); P.nz.resize(levels + 1);
+	P.data[0] = vox; P.nx[0] = dx; P.ny[0] = dy; P.nz[0] = dz;
+	for (int l = 1; l <= levels; l++) {
+		int px = P.nx[l - 1], py = P.ny[l - 1], pz = P.nz[l - 1];
+		int cx = (px + 1) / 2, cy = (py + 1) / 2, cz = (pz + 1) / 2;
+		P.nx[l] = cx; P.ny[l] = cy; P.nz[l] = cz;
+		P.store[l].assign((size_t)cx * cy * cz, 0);
+		const uint8_t* src = P.data[l - 1];
+		uint8_t* dst = P.store[l].data();
+		auto slab = [&](int z0, int z1) {
+			for (int z = z0; z < z1; z++)
+				for (int y = 0; y < cy; y++)
+					for (int x = 0; x < cx; x++) {
+						uint8_t first = 0; bool have = false, mixed = false;
+						for (int k = 0; k < 8 && !mixed; k++) {
+							int sx = 2 * x + (k & 1), sy = 2 * y + ((k >> 1) & 1), sz = 2 * z + (k >> 2);
+							uint8_t v = (sx < px && sy < py && sz < pz) ? src[(size_t)sx + (size_t)sy * px + (size_t)sz * ((size_t)px * py)] : 0;
+							if (v == kMixed) mixed = true;
+							else if (!have) { first = v; have = true; }
+							else if (v != first) mixed = true;
+						}
+						dst[(size_t)x + (size_t)y * cx + (size_t)z * ((size_t)cx * cy)] = mixed ? kMixed : first;
+					}
+		};
+		unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+		int nthreads = (int)std::min<size_t>(hw, std::max<size_t>(1, ((size_t)cx * cy * cz) >> 16));
+		if (nthreads <= 1) slab(0, cz);
+		else {
+			std::vector<std::thread> th;
+			for (int t = 0; t < nthreads; t++) th.emplace_back(slab, (int)((int64_t)cz * t / nthreads), (int)((int64_t)cz * (t + 1) / nthreads));
+			for (auto& t : th) t.join();
+		}
+		P.data[l] = dst;
+	}
+}
+
+} // namespace
+
+extern "C" int rto_host_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ, RtoGpuNode** nodesOut, size_t* numNodes) {
+	if (!nodesOut || !numNodes) return rto_fail(RTO_ERR_INVALID, "rto_host_octree_build: null output");
+	*nodesOut = nullptr; *numNodes = 0;
+	// createOctreeFromVoxelGrid returns nullptr for an empty grid (OctreeVoxel.cpp:766): zero nodes, still RTO_OK
+	if (dimX == 0 || dimY == 0 || dimZ == 0) return RTO_OK;
+	if (!voxels || dimX < 0 || dimY < 0 || dimZ < 0) return rto_fail(RTO_ERR_INVALID, "rto_host_octree_build: bad grid");
+	for (size_t i = 0, n = (size_t)dimX * dimY * dimZ; i < n; i++)
+		if (voxels[i] == kMixed) return rto_fail(RTO_ERR_INVALID, "rto_host_octree_build: voxel value 255 is reserved");
+	int maxDim = std::max({ dimX, dimY, dimZ });
+	int root = 1, levels = 0;
+	while (root < maxDim) { root <<= 1; levels++; }
+	Pyramid P;
+	buildPyramid(voxels, dimX, dimY, dimZ, levels, P);
+
+	std::vector<RtoGpuNode> nodes;
+	struct Pending { int level; };
+	std::vector<int8_t> levelOf;              // level of node i (cell edge 2^level)
+	nodes.reserve(1 << 16); levelOf.reserve(1 << 16);
+	auto emit = [&](int x, int y, int z, int level) {
+		RtoGpuNode n;
+		n.x = x; n.y = y; n.z = z; n.size = 1 << level;
+		uint8_t s = P.at(level, x, y, z);
+		bool leaf = (level == 0) || (s != kMixed);
+		n.isLeaf = leaf; n.isUniform = leaf; n.isSolid = leaf && (s == 1);
+		for (int i = 0; i < 8; i++) n.child[i] = -1;
+		nodes.push_back(n); levelOf.push_back((int8_t)level);
+	};
+	emit(0, 0, 0, levels);
+	for (size_t i = 0; i < nodes.size(); i++) {   // the vector itself is the BFS queue
+		if (nodes[i].isLeaf) continue;
+		int level = levelOf[i] - 1, half = 1 << level;
+		int x0 = nodes[i].x, y0 = nodes[i].y, z0 = nodes[i].z;
+		for (int c = 0; c < 8; c++) {         // bit0 = x, bit1 = y, bit2 = z (OctreeVoxel.cpp:749-757)
+			nodes[i].child[c] = (int32_t)nodes.size();
+			emit(x0 + ((c & 1) ? half : 0), y0 + ((c & 2) ? half : 0), z0 + ((c & 4) ? half : 0), level);
+		}
+		if (nodes.size() > (size_t)0x7fffff00) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_host_octree_build: more than 2^31 nodes");
+	}
+	RtoGpuNode* out = (RtoGpuNode*)std::malloc(nodes.size() * sizeof(RtoGpuNode));
+	if (!out) return rto_fail(RTO_ERR_ALLOC, "rto_host_octree_build: out of memory");
+	std::memcpy(out, nodes.data(), nodes.size() * sizeof(RtoGpuNode));
+	*nodesOut = out; *numNodes = nodes.size();
+	return RTO_OK;
+}
+
+// =================================================================================================
+// Marching cubes in the reference's emission order
+// =================================================================================================
+namespace {
+
+struct McGrid {
+	const uint8_t* vox; int dx, dy, dz; float minX, minY, minZ, vs;
+	inline float scalar(int x, int y, int z) const {      // FILLED -> -1, EMPTY or outside -> +1 (OctreeVoxel.cpp:787-792)
+		if (x < 0 || y < 0 || z < 0 || x >= dx || y >= dy || z >= dz) return 1.0f;
+		return vox[(size_t)x + (size_t)y * dx + (size_t)z * ((size_t)dx * dy)] == 1 ? -1.0f : 1.0f;
+	}
+};
+
+inline V3 vertexInterp(V3 p1, V3 p2, float v1, float v2) {    // iso level 0 (OctreeVoxel.cpp:633-640)
+	if (std::fabs(0.0f - v1) < 0.00001f) return p1;
+	if (std::fabs(0.0f - v2) < 0.00001f) return p2;
+	if (std::fabs(v1 - v2) < 0.00001f) return p1;
+	float mu = (0.0f - v1) / (v2 - v1);
+	return p1 + mu * (p2 - p1);
+}
+
+inline void mcCell(const McGrid& g, int x, int y, int z, std::vector<RtoTriangle>& out) {
+	static const int off[8][3] = { {0,0,0},{1,0,0},{1,1,0},{0,1,0},{0,0,1},{1,0,1},{1,1,1},{0,1,1} };
+	float val[8]; int cube = 0;
+	for (int c = 0; c < 8; c++) { val[c] = g.scalar(x + off[c][0], y + off[c][1], z + off[c][2]); if (val[c] < 0) cube |= 1 << c; }
+	if (cube == 0 || cube == 255) return;
+	int flags = mc_edge_flags(cube);
+	V3 pos[8];
+	for (int c = 0; c < 8; c++)
+		pos[c] = mk3(g.minX + (x + off[c][0]) * g.vs, g.minY + (y + off[c][1]) * g.vs, g.minZ + (z + off[c][2]) * g.vs);
+	V3 vert[12];
+	for (int e = 0; e < 12; e++) if (flags & (1 << e)) {
+		int a = kMcEdgeCorner[e][0], b = kMcEdgeCorner[e][1];
+		vert[e] = vertexInterp(pos[a], pos[b], val[a], val[b]);
+	}
+	for (int i = 0; mc_tri_edge(cube, i) != -1; i += 3) {
+		RtoTriangle t;
+		V3 a = vert[mc_tri_edge(cube, i)], b = vert[mc_tri_edge(cube, i + 1)], c = vert[mc_tri_edge(cube, i + 2)];
+		t.v0[0] = a.x; t.v0[1] = a.y; t.v0[2] = a.z; t.v1[0] = b.x; t.v1[1] = b.y; t.v1[2] = b.z; t.v2[0] = c.x; t.v2[1] = c.y; t.v2[2] = c.z;
+		out.push_back(t);
+	}
+}
+
+} // namespace
+
+extern "C" int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const RtoGpuNode* nodes, size_t numNodes, RtoTriangle** trisOut, size_t* numTris) {
+	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_host_mc_mesh: null output");
+	*trisOut = nullptr; *numTris = 0;
+	if (numNodes == 0) return RTO_OK;
+	if (!voxels || !nodes || !gridMin) return rto_fail(RTO_ERR_INVALID, "rto_host_mc_mesh: null input");
+	McGrid g{ voxels, dimX, dimY, dimZ, gridMin[0], gridMin[1], gridMin[2], voxelSize };
+	std::vector<RtoTriangle> out;
+	// depth-first, children 0..7 in order: the recursion of MarchingCubesRenderer::render (Renderer.cpp:26-33)
+	std::vector<int32_t> stack; stack.push_back(0);
+	while (!stack.empty()) {
+		int32_t i = stack.back(); stack.pop_back();
+		if (i < 0 || (size_t)i >= numNodes) continue;
+		const RtoGpuNode& n = nodes[i];
+		if (!n.isLeaf) { for (int c = 7; c >= 0; c--) stack.push_back(n.child[c]); continue; }
+		// localMC(grid, x0, y0, z0, size): cells of the leaf region clipped to dim-1 (OctreeVoxel.cpp:795-797).
+		int x1 = std::min(n.x + n.size, dimX - 1), y1 = std::min(n.y + n.size, dimY - 1), z1 = std::min(n.z + n.size, dimZ - 1);
+		int lastX = n.x + n.size - 1, lastY = n.y + n.size - 1, lastZ = n.z + n.size - 1;
+		for (int z = n.z; z < z1; z++)
+			for (int y = n.y; y < y1; y++) {
+				if (z == lastZ || y == lastY || !n.isUniform) { for (int x = n.x; x < x1; x++) mcCell(g, x, y, z, out); }
+				else if (lastX < x1) mcCell(g, lastX, y, z, out);   // interior cells of a uniform leaf see one sign only
+			}
+	}
+	if (out.empty()) return RTO_OK;
+	RtoTriangle* buf = (RtoTriangle*)std::malloc(out.size() * sizeof(RtoTriangle));
+	if (!buf) return rto_fail(RTO_ERR_ALLOC, "rto_host_mc_mesh: out of memory");
+	std::memcpy(buf, out.data(), out.size() * sizeof(RtoTriangle));
+	*trisOut = buf; *numTris = out.size();
+	return RTO_OK;
+}
+
+// =================================================================================================
+// BVH with the reference's shape
+// =================================================================================================
+namespace {
+
+size_t subtreeNodes(size_t m) {            // nodes of the tree BVH::build makes for m triangles
+	if (m <= 2) return 1;
+	return 1 + subtreeNodes(m / 2) + subtreeNodes(m - m / 2);
+}
+
+struct Builder {
+	const RtoTriangle* tris; std::vector<V3> cen; std::vector<uint32_t> idx; std::vector<HostBvhNode>* nodes;
+
+	void build(size_t lo, size_t hi, size_t nodeIdx, int depth) {
+		HostBvhNode& nd = (*nodes)[nodeIdx];
+		const float M = std::numeric_limits<float>::max();
+		V3 mn = mk3(M, M, M), mx = mk3(-M, -M, -M);
+		for (size_t i = lo; i < hi; i++) {              // AABB::expand over triangle boxes (BVH.cpp:38-42); min/max are exact
+			const RtoTriangle& t = tris[idx[i]];
+			V3 tmn = mk3(M, M, M), tmx = mk3(-M, -M, -M);
+			const float* v[3] = { t.v0, t.v1, t.v2 };
+			for (int k = 0; k < 3; k++) { V3 p = mk3(v[k][0], v[k][1], v[k][2]); tmn = min3(tmn, p); tmx = max3(tmx, p); }
+			mn = min3(mn, tmn); mx = max3(mx, tmn); mn = min3(mn, tmx); mx = max3(mx, tmx);
+		}
+		nd.mn[0] = mn.x; nd.mn[1] = mn.y; nd.mn[2] = mn.z; nd.mx[0] = mx.x; nd.mx[1] = mx.y; nd.mx[2] = mx.z;
+		nd.left = nd.right = -1; nd.first = (uint32_t)lo; nd.count = (uint32_t)(hi - lo);
+		size_t m = hi - lo;
+		if (m <= 2) return;                             // leaf (BVH.cpp:46-49)
+		V3 ext = mx - mn;
+		int axis = 0;                                   // BVH.cpp:52-55
+		if (ext.y > ext.x) axis = 1;
+		if (comp(ext, 2) > comp(ext, axis)) axis = 2;
+		const V3* c = cen.data();
+		std::sort(idx.begin() + lo, idx.begin() + hi, [c, axis](uint32_t a, uint32_t b) { return comp(c[a], axis) < comp(c[b], axis); });   // BVH.cpp:58-60
+		size_t mid = m / 2;                             // BVH.cpp:63
+		size_t li = nodeIdx + 1, ri = li + subtreeNodes(mid);
+		nd.left = (int32_t)li; nd.right = (int32_t)ri; nd.count = 0;
+		if (depth < 3 && m > 20000) {
+			std::thread th([=] { build(lo, lo + mid, li, depth + 1); });
+			build(lo + mid, hi, ri, depth + 1);
+			th.join();
+		}
+		else { build(lo, lo + mid, li, depth + 1); build(lo + mid, hi, ri, depth + 1); }
+	}
+};
+
+} // namespace
+
+extern "C" int rto_host_bvh_build(const RtoTriangle* tris, size_t numTris, RtoHostBvh** out) {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_build: null output");
+	*out = nullptr;
+	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_build: null triangles");
+	if (numTris >= (size_t)1 << 30) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_host_bvh_build: more than 2^30 triangles");
+	RtoHostBvh* h = new (std::nothrow) RtoHostBvh();
+	if (!h) return rto_fail(RTO_ERR_ALLOC, "rto_host_bvh_build: out of memory");
+	h->tris = tris; h->numTris = numTris;
+	h->nodes.resize(subtreeNodes(numTris));
+	Builder b; b.tris = tris; b.nodes = &h->nodes;
+	b.cen.resize(numTris); b.idx.resize(numTris);
+	for (size_t i = 0; i < numTris; i++) {
+		const RtoTriangle& t = tris[i];
+		V3 s = mk3(t.v0[0], t.v0[1], t.v0[2]) + mk3(t.v1[0], t.v1[1], t.v1[2]) + mk3(t.v2[0], t.v2[1], t.v2[2]);
+		b.cen[i] = s / 3.0f;                            // centroid(), BVH.cpp:15-17
+		b.idx[i] = (uint32_t)i;
+	}
+	b.build(0, numTris, 0, 0);
+	h->order.swap(b.idx);
+	*out = h;
+	return RTO_OK;
+}
+
+extern "C" void rto_host_bvh_free(RtoHostBvh* bvh) { delete bvh; }
+extern "C" size_t rto_host_bvh_num_nodes(const RtoHostBvh* bvh) { return bvh ? bvh->nodes.size() : 0; }
+
+extern "C" int rto_host_bvh_export(const RtoHostBvh* bvh, float* boxes6, int32_t* meta4, size_t capacity) {
+	if (!bvh || !boxes6 || !meta4) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_export: null argument");
+	if (capacity < bvh->nodes.size()) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_export: capacity too small");
+	for (size_t i = 0; i < bvh->nodes.size(); i++) {    // nodes are stored in pre-order already
+		const HostBvhNode& n = bvh->nodes[i];
+		std::memcpy(boxes6 + 6 * i, n.mn, 12); std::memcpy(boxes6 + 6 * i + 3, n.mx, 12);
+		bool leaf = n.left < 0;
+		meta4[4 * i] = leaf; meta4[4 * i + 1] = leaf ? (int32_t)n.count : 0;
+		meta4[4 * i + 2] = (leaf && n.count > 0) ? (int32_t)bvh->order[n.first] : -1;
+		meta4[4 * i + 3] = (leaf && n.count > 1) ? (int32_t)bvh->order[n.first + 1] : -1;
+	}
+	return RTO_OK;
+}
+
+// =================================================================================================
+// Camera constants
+// =================================================================================================
+extern "C" int rto_host_camera_orbit(float theta, float phi, float radius, const float target[3], float fovDeg, float aspect,
+	int width, int height, RtoCamera* out, float* view16) {
+	if (!out || !target) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: null argument");
+	if (width <= 0 || height <= 0) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: bad image size");
+	V3 tgt = mk3(target[0], target[1], target[2]);
+	V3 eye = radius * mk3(cosf(theta) * sinf(phi), sinf(theta), cosf(theta) * cosf(phi)) + tgt;    // Camera.cpp:13-17
+	// glm::lookAtRH(eye, target, (0,1,0))
+	V3 f = normalize3(tgt - eye);
+	V3 s = normalize3(cross3(f, mk3(0.0f, 1.0f, 0.0f)));
+	V3 u = cross3(s, f);
+	float m[16] = { s.x, u.x, -f.x, 0.0f,  s.y, u.y, -f.y, 0.0f,  s.z, u.z, -f.z, 0.0f,  -dot3(s, eye), -dot3(u, eye), dot3(f, eye), 1.0f };
+	// glm::inverse(mat4): cofactor expansion, same grouping as glm/detail/func_matrix.inl compute_inverse<4,4>
+	auto M = [&](int c, int r) { return m[c * 4 + r]; };
+	float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3), c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3), c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+	float c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3), c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3), c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+	float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2), c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2), c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+	float c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3), c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3), c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+	float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2), c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2), c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+	float c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1), c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1), c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+	const float F0[4] = { c00, c00, c02, c03 }, F1[4] = { c04, c04, c06, c07 }, F2[4] = { c08, c08, c10, c11 };
+	const float F3[4] = { c12, c12, c14, c15 }, F4[4] = { c16, c16, c18, c19 }, F5[4] = { c20, c20, c22, c23 };
+	const float A0[4] = { M(1, 0), M(0, 0), M(0, 0), M(0, 0) }, A1[4] = { M(1, 1), M(0, 1), M(0, 1), M(0, 1) };
+	const float A2[4] = { M(1, 2), M(0, 2), M(0, 2), M(0, 2) }, A3[4] = { M(1, 3), M(0, 3), M(0, 3), M(0, 3) };
+	const float sgnA[4] = { 1.0f, -1.0f, 1.0f, -1.0f }, sgnB[4] = { -1.0f, 1.0f, -1.0f, 1.0f };
+	float inv[16];
+	for (int r = 0; r < 4; r++) {
+		inv[0 + r] = ((A1[r] * F0[r] - A2[r] * F1[r]) + A3[r] * F2[r]) * sgnA[r];
+		inv[4 + r] = ((A0[r] * F0[r] - A2[r] * F3[r]) + A3[r] * F4[r]) * sgnB[r];
+		inv[8 + r] = ((A0[r] * F1[r] - A1[r] * F3[r]) + A3[r] * F5[r]) * sgnA[r];
+		inv[12 + r] = ((A0[r] * F2[r] - A1[r] * F4[r]) + A2[r] * F5[r]) * sgnB[r];
+	}
+	float det = (M(0, 0) * inv[0] + M(0, 1) * inv[4]) + (M(0, 2) * inv[8] + M(0, 3) * inv[12]);
+	float ood = 1.0f / det;
+	for (int i = 0; i < 16; i++) out->invView[i] = inv[i] * ood;
+	out->camPos[0] = eye.x; out->camPos[1] = eye.y; out->camPos[2] = eye.z;
+	float fovRad = fovDeg * 0.01745329251994329576923690768489f;     // glm::radians
+	out->tanHalfFov = tanf(fovRad * 0.5f);
+	out->aspect = aspect; out->width = width; out->height = height;
+	if (view16) std::memcpy(view16, m, 64);
+	return RTO_OK;
+}
+
+// =================================================================================================
+// sceneCache.bin (CacheUtils.cpp:5-59)
+// =================================================================================================
+extern "C" int rto_host_grid_load(const char* path, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) {
+	if (!path || !dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_host_grid_load: null argument");
+	*voxelsOut = nullptr;
+	FILE* f = std::fopen(path, "rb");
+	if (!f) return rto_fail(RTO_ERR_IO, "rto_host_grid_load: cannot open file");
+	uint64_t n = 0;
+	bool ok = std::fread(dims, 4, 3, f) == 3 && std::fread(minAndVoxel, 4, 4, f) == 4 && std::fread(&n, 8, 1, f) == 1;
+	uint8_t* buf = nullptr;
+	if (ok) {
+		if (dims[0] < 0 || dims[1] < 0 || dims[2] < 0 || n != (uint64_t)dims[0] * dims[1] * dims[2]) ok = false;
+		else { buf = (uint8_t*)std::malloc(n ? n : 1); ok = buf && std::fread(buf, 1, n, f) == n; }
+	}
+	std::fclose(f);
+	if (!ok) { std::free(buf); return rto_fail(RTO_ERR_IO, "rto_host_grid_load: truncated or inconsistent file"); }
+	*voxelsOut = buf;
+	return RTO_OK;
+}
+
+extern "C" int rto_host_grid_save(const char* path, const int dims[3], const float minAndVoxel[4], const uint8_t* voxels) {
+	if (!path || !dims || !minAndVoxel || !voxels) return rto_fail(RTO_ERR_INVALID, "rto_host_grid_save: null argument");
+	FILE* f = std::fopen(path, "wb");
+	if (!f) return rto_fail(RTO_ERR_IO, "rto_host_grid_save: cannot open file");
+	uint64_t n = (uint64_t)dims[0] * dims[1] * dims[2];
+	bool ok = std::fwrite(dims, 4, 3, f) == 3 && std::fwrite(minAndVoxel, 4, 4, f) == 4 && std::fwrite(&n, 8, 1, f) == 1 && std::fwrite(voxels, 1, n, f) == n;
+	ok = (std::fclose(f) == 0) && ok;
+	return ok ? RTO_OK : rto_fail(RTO_ERR_IO, "rto_host_grid_save: write failed");
+}
+
+extern "C" void rto_host_free(void* p) { std::free(p); }

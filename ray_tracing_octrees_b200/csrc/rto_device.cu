@@ -1,0 +1,459 @@
+// rto_device.cu -- device scenes, kernel launches and the C ABI of librto.so (see include/rto_c.h).
+//
+// Built for sm_100a only with -fmad=false (exact parity with the CPU oracle needs unfused multiply/add).
+// There is no CPU fallback in this file: every entry point that traces rays requires a CUDA device.
+#include "rto_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+using namespace rto;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int rto_fail(int code, const char* fmt, ...) {
+	va_list ap; va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+extern "C" const char* rto_last_error(void) { return g_err; }
+extern "C" const char* rto_version(void) { return "rto-b200 0.1 (sm_100a)"; }
+
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return rto_fail(RTO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+static int require_device() {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		return rto_fail(RTO_ERR_NO_DEVICE, "no CUDA device available (%s); librto has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+	}
+	return RTO_OK;
+}
+
+extern "C" int rto_init(int device) {
+	int rc = require_device(); if (rc) return rc;
+	CUDA_TRY(cudaSetDevice(device));
+	cudaDeviceProp p;
+	CUDA_TRY(cudaGetDeviceProperties(&p, device));
+	if (p.major != 10) return rto_fail(RTO_ERR_NO_DEVICE, "device %d is sm_%d%d; librto is built for sm_100a only", device, p.major, p.minor);
+	return RTO_OK;
+}
+
+extern "C" int rto_device_info(int* smCount, int* ccMajor, int* ccMinor, size_t* l2Bytes, size_t* totalMem) {
+	int rc = require_device(); if (rc) return rc;
+	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+	cudaDeviceProp p; CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+	if (smCount) *smCount = p.multiProcessorCount;
+	if (ccMajor) *ccMajor = p.major;
+	if (ccMinor) *ccMinor = p.minor;
+	if (l2Bytes) *l2Bytes = (size_t)p.l2CacheSize;
+	if (totalMem) *totalMem = p.totalGlobalMem;
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene
+// ------------------------------------------------------------------------------------------------
+struct RtoScene {
+	int kind = RTO_MODE_BVH;          // RTO_MODE_BVH or RTO_MODE_OCTREE_GLSL (any octree)
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	bool timed = false;
+	uint64_t launches = 0;
+	size_t deviceBytes = 0, numPrims = 0, numNodes = 0;
+	BvhDev bvh{};
+	OctDev oct{};
+	std::vector<void*> owned;         // device allocations of the scene
+	// growable scratch (device outputs for RTO_MEM_HOST calls, cameras, ray lists)
+	void* scratch[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	size_t scratchBytes[6] = { 0, 0, 0, 0, 0, 0 };
+};
+
+static int scene_alloc(RtoScene* s, void** p, size_t bytes) {
+	*p = nullptr;
+	cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+	if (e != cudaSuccess) return rto_fail(RTO_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	s->owned.push_back(*p);
+	s->deviceBytes += bytes;
+	return RTO_OK;
+}
+
+static int scene_scratch(RtoScene* s, int slot, size_t bytes, void** p) {
+	if (s->scratchBytes[slot] < bytes) {
+		if (s->scratch[slot]) cudaFree(s->scratch[slot]);
+		s->scratch[slot] = nullptr; s->scratchBytes[slot] = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaMalloc(&s->scratch[slot], want);
+		if (e != cudaSuccess) return rto_fail(RTO_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+		s->scratchBytes[slot] = want;
+	}
+	*p = s->scratch[slot];
+	return RTO_OK;
+}
+
+static int scene_new(RtoScene** out) {
+	int rc = require_device(); if (rc) return rc;
+	RtoScene* s = new (std::nothrow) RtoScene();
+	if (!s) return rto_fail(RTO_ERR_ALLOC, "out of host memory");
+	cudaError_t e = cudaGetDevice(&s->device);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreate(&s->evStart);
+	if (e == cudaSuccess) e = cudaEventCreate(&s->evStop);
+	if (e != cudaSuccess) { delete s; return rto_fail(RTO_ERR_CUDA, "scene setup failed: %s", cudaGetErrorString(e)); }
+	*out = s;
+	return RTO_OK;
+}
+
+extern "C" void rto_scene_destroy(RtoScene* s) {
+	if (!s) return;
+	cudaSetDevice(s->device);
+	if (s->stream) cudaStreamSynchronize(s->stream);
+	for (void* p : s->owned) cudaFree(p);
+	for (void* p : s->scratch) if (p) cudaFree(p);
+	if (s->evStart) cudaEventDestroy(s->evStart);
+	if (s->evStop) cudaEventDestroy(s->evStop);
+	if (s->stream) cudaStreamDestroy(s->stream);
+	delete s;
+}
+
+extern "C" int rto_scene_info(const RtoScene* s, int* kind, size_t* numPrims, size_t* numNodes, size_t* deviceBytes, int* compactLayout) {
+	if (!s) return rto_fail(RTO_ERR_INVALID, "rto_scene_info: null scene");
+	if (kind) *kind = s->kind;
+	if (numPrims) *numPrims = s->numPrims;
+	if (numNodes) *numNodes = s->numNodes;
+	if (deviceBytes) *deviceBytes = s->deviceBytes;
+	if (compactLayout) *compactLayout = (s->kind == RTO_MODE_BVH) ? 0 : s->oct.compact;
+	return RTO_OK;
+}
+extern "C" void* rto_scene_stream(const RtoScene* s) { return s ? (void*)s->stream : nullptr; }
+extern "C" uint64_t rto_scene_launch_count(const RtoScene* s) { return s ? s->launches : 0; }
+extern "C" int rto_scene_sync(RtoScene* s) {
+	if (!s) return rto_fail(RTO_ERR_INVALID, "rto_scene_sync: null scene");
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	return RTO_OK;
+}
+extern "C" int rto_scene_last_kernel_ms(RtoScene* s, float* ms) {
+	if (!s || !ms) return rto_fail(RTO_ERR_INVALID, "rto_scene_last_kernel_ms: null argument");
+	if (!s->timed) return rto_fail(RTO_ERR_INVALID, "rto_scene_last_kernel_ms: nothing rendered yet");
+	CUDA_TRY(cudaEventSynchronize(s->evStop));
+	CUDA_TRY(cudaEventElapsedTime(ms, s->evStart, s->evStop));
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// octree upload: RayTracerBVH::setOctree's SSBO (RayTracerBVH.cpp:492-504) -> pointer-free device arrays
+// ------------------------------------------------------------------------------------------------
+// The compact layout needs the shape the reference builder always produces: every internal node has 8 children
+// with consecutive indices, child boxes are the 8 octants of the parent, leaf <=> uniform.
+static bool octree_is_compactable(const RtoGpuNode* n, size_t count) {
+	if (count == 0 || n[0].x != 0 || n[0].y != 0 || n[0].z != 0 || n[0].size <= 0 || (n[0].size & (n[0].size - 1))) return false;
+	if (count >= 0x3fffffffu) return false;
+	std::vector<uint8_t> seen(count, 0);
+	seen[0] = 1;
+	for (size_t i = 0; i < count; i++) {
+		const RtoGpuNode& p = n[i];
+		bool leafLike = (p.isLeaf == 1) || (p.isUniform == 1);
+		if (p.isLeaf != 0 && p.isLeaf != 1) return false;
+		if (p.isUniform != p.isLeaf) return false;
+		if (p.isSolid != 0 && p.isSolid != 1) return false;
+		if (leafLike) continue;
+		int first = p.child[0];
+		if (first <= 0 || ((first - 1) & 7) != 0 || (size_t)first + 7 >= count || p.size < 2) return false;
+		int half = p.size / 2;
+		for (int c = 0; c < 8; c++) {
+			if (p.child[c] != first + c) return false;
+			const RtoGpuNode& q = n[first + c];
+			if (q.size != half || q.x != p.x + ((c & 1) ? half : 0) || q.y != p.y + ((c & 2) ? half : 0) || q.z != p.z + ((c & 4) ? half : 0)) return false;
+			if (seen[first + c]) return false;
+			seen[first + c] = 1;
+		}
+	}
+	for (size_t i = 0; i < count; i++) if (!seen[i]) return false;
+	return true;
+}
+
+extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, RtoScene** out) {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: null output");
+	*out = nullptr;
+	if (!nodes || numNodes == 0 || !gridMin) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: empty octree (the reference's setOctree(nullptr) clears the scene; nothing to trace)");
+	if (numNodes > (size_t)0x7fffff00) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_scene_create_octree: too many nodes");
+	for (size_t i = 0; i < numNodes; i++)
+		for (int c = 0; c < 8; c++)
+			if (nodes[i].child[c] >= (int64_t)numNodes) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: node %zu child %d out of range", i, c);
+	RtoScene* s = nullptr;
+	int rc = scene_new(&s); if (rc) return rc;
+	s->kind = RTO_MODE_OCTREE_GLSL;
+	s->numNodes = numNodes;
+	size_t leaves = 0;
+	for (size_t i = 0; i < numNodes; i++) leaves += nodes[i].isLeaf ? 1 : 0;
+	s->numPrims = leaves;
+	OctDev& D = s->oct;
+	D.numNodes = (int)numNodes; D.rootSize = nodes[0].size;
+	D.gmin[0] = gridMin[0]; D.gmin[1] = gridMin[1]; D.gmin[2] = gridMin[2]; D.voxel = voxelSize;
+	D.compact = octree_is_compactable(nodes, numNodes) ? 1 : 0;
+	if (D.compact) {
+		// desc[] is offset by 7 words so that every sibling group (indices 1+8g .. 8+8g) is one aligned 32-byte sector
+		std::vector<uint32_t> desc(numNodes + 8, 0);
+		std::vector<int32_t> up((numNodes + 7) / 8 + 1, 0);
+		for (size_t i = 0; i < numNodes; i++) {
+			const RtoGpuNode& p = nodes[i];
+			if (p.isLeaf) desc[7 + i] = kOctLeaf | (p.isSolid ? kOctSolid : 0u);
+			else { desc[7 + i] = (uint32_t)p.child[0]; up[(p.child[0] - 1) >> 3] = (int32_t)i; }
+		}
+		void *dDesc = nullptr, *dUp = nullptr;
+		if ((rc = scene_alloc(s, &dDesc, desc.size() * 4)) || (rc = scene_alloc(s, &dUp, up.size() * 4))) { rto_scene_destroy(s); return rc; }
+		cudaError_t e = cudaMemcpyAsync(dDesc, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, s->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(dUp, up.data(), up.size() * 4, cudaMemcpyHostToDevice, s->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+		if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "octree upload failed: %s", cudaGetErrorString(e)); }
+		D.desc = (const uint32_t*)dDesc + 7; D.up = (const int32_t*)dUp;
+	}
+	else {
+		std::vector<int32_t> padded(numNodes * 16, -1);
+		for (size_t i = 0; i < numNodes; i++) std::memcpy(&padded[16 * i], &nodes[i], sizeof(RtoGpuNode));
+		void* dN = nullptr;
+		if ((rc = scene_alloc(s, &dN, padded.size() * 4))) { rto_scene_destroy(s); return rc; }
+		cudaError_t e = cudaMemcpyAsync(dN, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, s->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+		if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "octree upload failed: %s", cudaGetErrorString(e)); }
+		D.nodes16 = (const int4*)dN;
+	}
+	*out = s;
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BVH upload: reference-shaped host tree -> child-boxes-in-parent nodes + leaf-ordered triangles
+// ------------------------------------------------------------------------------------------------
+extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, RtoScene** out) {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null output");
+	*out = nullptr;
+	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null triangles");
+	int rc = require_device(); if (rc) return rc;
+	RtoHostBvh* ownedBvh = nullptr;
+	const RtoHostBvh* h = prebuilt;
+	if (!h) { rc = rto_host_bvh_build(tris, numTris, &ownedBvh); if (rc) return rc; h = ownedBvh; }
+	else if (h->numTris != numTris || h->tris != tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: prebuilt BVH belongs to another triangle array");
+
+	RtoScene* s = nullptr;
+	rc = scene_new(&s);
+	if (rc) { rto_host_bvh_free(ownedBvh); return rc; }
+	s->kind = RTO_MODE_BVH; s->numPrims = numTris; s->numNodes = h->nodes.size();
+
+	// inner nodes get consecutive ids in pre-order; a leaf is referenced as ~((firstPos << 1) | (count - 1))
+	std::vector<int32_t> innerId(h->nodes.size(), -1);
+	int32_t numInner = 0;
+	for (size_t i = 0; i < h->nodes.size(); i++) if (h->nodes[i].left >= 0) innerId[i] = numInner++;
+	auto refOf = [&](int32_t hostIdx) -> int32_t {
+		const HostBvhNode& n = h->nodes[hostIdx];
+		if (n.left >= 0) return innerId[hostIdx];
+		uint32_t cnt = n.count ? n.count : 1;      // (count 0 only for the empty tree, never referenced)
+		return ~(int32_t)((n.first << 1) | (cnt - 1));
+	};
+	std::vector<float> nodeBuf((size_t)std::max(numInner, 1) * 16, 0.0f);
+	for (size_t i = 0; i < h->nodes.size(); i++) {
+		const HostBvhNode& n = h->nodes[i];
+		if (n.left < 0) continue;
+		float* d = &nodeBuf[(size_t)innerId[i] * 16];
+		const HostBvhNode& L = h->nodes[n.left]; const HostBvhNode& R = h->nodes[n.right];
+		d[0] = L.mn[0]; d[1] = L.mn[1]; d[2] = L.mn[2]; d[3] = L.mx[0]; d[4] = L.mx[1]; d[5] = L.mx[2];
+		d[6] = R.mn[0]; d[7] = R.mn[1]; d[8] = R.mn[2]; d[9] = R.mx[0]; d[10] = R.mx[1]; d[11] = R.mx[2];
+		int32_t r0 = refOf(n.left), r1 = refOf(n.right);
+		std::memcpy(&d[12], &r0, 4); std::memcpy(&d[13], &r1, 4);
+	}
+	std::vector<float> triBuf(std::max<size_t>(numTris, 1) * 12, 0.0f);
+	for (size_t p = 0; p < numTris; p++) {
+		uint32_t id = h->order[p];
+		float* d = &triBuf[p * 12];
+		std::memcpy(d, &tris[id], 36);
+		int32_t iid = (int32_t)id;
+		std::memcpy(&d[9], &iid, 4);
+	}
+	BvhDev& D = s->bvh;
+	D.numTris = (int)numTris;
+	const HostBvhNode& root = h->nodes[0];
+	for (int k = 0; k < 3; k++) { D.rootLo[k] = root.mn[k]; D.rootHi[k] = root.mx[k]; }
+	D.rootRef = numTris ? refOf(0) : -1;
+	void *dN = nullptr, *dT = nullptr;
+	if ((rc = scene_alloc(s, &dN, nodeBuf.size() * 4)) || (rc = scene_alloc(s, &dT, triBuf.size() * 4))) { rto_scene_destroy(s); rto_host_bvh_free(ownedBvh); return rc; }
+	cudaError_t e = cudaMemcpyAsync(dN, nodeBuf.data(), nodeBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dT, triBuf.data(), triBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+	rto_host_bvh_free(ownedBvh);
+	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "BVH upload failed: %s", cudaGetErrorString(e)); }
+	D.nodes = (const float4*)dN; D.tris = (const float4*)dT;
+	*out = s;
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rendering
+// ------------------------------------------------------------------------------------------------
+static int check_mode(const RtoScene* s, int mode) {
+	if (s->kind == RTO_MODE_BVH) { if (mode != RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "scene is a BVH; mode must be RTO_MODE_BVH"); }
+	else if (mode != RTO_MODE_OCTREE_SKIP && mode != RTO_MODE_OCTREE_GLSL) return rto_fail(RTO_ERR_INVALID, "scene is an octree; mode must be RTO_MODE_OCTREE_SKIP or RTO_MODE_OCTREE_GLSL");
+	return RTO_OK;
+}
+
+static void launch_render(RtoScene* s, const RenderArgs& A, int width, int numCams, int mode) {
+	dim3 block(128), grid((width + 15) / 16, (A.y1 - A.y0 + 7) / 8, numCams);
+	if (s->kind == RTO_MODE_BVH) {
+		bool sh = (A.flags & RTO_FLAG_SHADOWS) != 0, prune = (A.flags & RTO_FLAG_NO_PRUNE) == 0;
+		if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, s->stream>>>(s->bvh, A);
+		else if (sh) k_render_bvh<true, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
+		else if (prune) k_render_bvh<false, true><<<grid, block, 0, s->stream>>>(s->bvh, A);
+		else k_render_bvh<false, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
+	}
+	else k_render_octree<<<grid, block, 0, s->stream>>>(s->oct, A, mode);
+	s->launches++;
+}
+
+extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams, int mode, uint32_t flags, float shadowBias,
+	int y0, int y1, const RtoFrame* frame) {
+	if (!s || !cams || !frame || numCams <= 0) return rto_fail(RTO_ERR_INVALID, "rto_render: null argument");
+	int rc = check_mode(s, mode); if (rc) return rc;
+	const int W = cams[0].width, H = cams[0].height;
+	if (W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 >= y1) return rto_fail(RTO_ERR_INVALID, "rto_render: bad image size or row range [%d,%d) of %dx%d", y0, y1, W, H);
+	for (int c = 1; c < numCams; c++) if (cams[c].width != W || cams[c].height != H) return rto_fail(RTO_ERR_INVALID, "rto_render_batch: all cameras must share one image size");
+	if (numCams > 65535) return rto_fail(RTO_ERR_INVALID, "rto_render_batch: at most 65535 cameras per call");
+	if (frame->memory != RTO_MEM_HOST && frame->memory != RTO_MEM_DEVICE) return rto_fail(RTO_ERR_INVALID, "rto_render: bad RtoFrame.memory");
+	CUDA_TRY(cudaSetDevice(s->device));
+	const size_t npix = (size_t)numCams * (size_t)(y1 - y0) * W;
+	RenderArgs A{};
+	A.cam0 = cams[0]; A.cams = nullptr; A.y0 = y0; A.y1 = y1; A.shadowBias = shadowBias; A.flags = flags;
+	if (numCams > 1) {
+		void* dC = nullptr;
+		if ((rc = scene_scratch(s, 3, sizeof(RtoCamera) * numCams, &dC))) return rc;
+		CUDA_TRY(cudaMemcpyAsync(dC, cams, sizeof(RtoCamera) * numCams, cudaMemcpyHostToDevice, s->stream));
+		A.cams = (const RtoCamera*)dC;
+	}
+	const bool host = frame->memory == RTO_MEM_HOST;
+	if (host) {
+		void* p = nullptr;
+		if (frame->rgba) { if ((rc = scene_scratch(s, 0, npix * 16, &p))) return rc; A.rgba = (float4*)p; }
+		if (frame->hitId) { if ((rc = scene_scratch(s, 1, npix * 4, &p))) return rc; A.hitId = (int*)p; }
+		if (frame->t) { if ((rc = scene_scratch(s, 2, npix * 4, &p))) return rc; A.t = (float*)p; }
+	}
+	else { A.rgba = (float4*)frame->rgba; A.hitId = frame->hitId; A.t = frame->t; }
+	CUDA_TRY(cudaEventRecord(s->evStart, s->stream));
+	launch_render(s, A, W, numCams, mode);
+	CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
+	s->timed = true;
+	CUDA_TRY(cudaGetLastError());
+	if (host) {
+		if (frame->rgba) CUDA_TRY(cudaMemcpyAsync(frame->rgba, A.rgba, npix * 16, cudaMemcpyDeviceToHost, s->stream));
+		if (frame->hitId) CUDA_TRY(cudaMemcpyAsync(frame->hitId, A.hitId, npix * 4, cudaMemcpyDeviceToHost, s->stream));
+		if (frame->t) CUDA_TRY(cudaMemcpyAsync(frame->t, A.t, npix * 4, cudaMemcpyDeviceToHost, s->stream));
+		CUDA_TRY(cudaStreamSynchronize(s->stream));
+	}
+	return RTO_OK;
+}
+
+extern "C" int rto_render(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, const RtoFrame* frame) {
+	return rto_render_batch(s, cam, 1, mode, flags, shadowBias, y0, y1, frame);
+}
+
+extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, uint64_t stats[5]) {
+	if (!s || !cam || !stats) return rto_fail(RTO_ERR_INVALID, "rto_render_stats: null argument");
+	int rc = check_mode(s, mode); if (rc) return rc;
+	if (cam->width <= 0 || y0 < 0 || y1 > cam->height || y0 >= y1) return rto_fail(RTO_ERR_INVALID, "rto_render_stats: bad row range");
+	CUDA_TRY(cudaSetDevice(s->device));
+	void* d = nullptr;
+	if ((rc = scene_scratch(s, 4, 5 * 8, &d))) return rc;
+	CUDA_TRY(cudaMemsetAsync(d, 0, 5 * 8, s->stream));
+	RenderArgs A{};
+	A.cam0 = *cam; A.y0 = y0; A.y1 = y1; A.shadowBias = shadowBias; A.flags = flags;
+	dim3 block(128), grid((cam->width + 15) / 16, (y1 - y0 + 7) / 8, 1);
+	if (s->kind == RTO_MODE_BVH) k_stats_bvh<<<grid, block, 0, s->stream>>>(s->bvh, A, (unsigned long long*)d);
+	else k_stats_octree<<<grid, block, 0, s->stream>>>(s->oct, A, mode, (unsigned long long*)d);
+	s->launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(stats, d, 5 * 8, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// explicit ray lists
+// ------------------------------------------------------------------------------------------------
+extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float* origins, const float* dirs, size_t numRays,
+	float tMin, float tMax, float* tOut, int32_t* idOut, int memory) {
+	if (!s || !origins || !dirs) return rto_fail(RTO_ERR_INVALID, "rto_trace_rays: null argument");
+	int rc = check_mode(s, mode); if (rc) return rc;
+	if (numRays == 0) return RTO_OK;
+	CUDA_TRY(cudaSetDevice(s->device));
+	const bool host = memory == RTO_MEM_HOST;
+	const float *dO = origins, *dD = dirs; float* dT = tOut; int32_t* dI = idOut;
+	if (host) {
+		void* p = nullptr;
+		if ((rc = scene_scratch(s, 0, numRays * 24, &p))) return rc;
+		dO = (const float*)p; dD = dO + 3 * numRays;
+		CUDA_TRY(cudaMemcpyAsync(p, origins, numRays * 12, cudaMemcpyHostToDevice, s->stream));
+		CUDA_TRY(cudaMemcpyAsync((float*)p + 3 * numRays, dirs, numRays * 12, cudaMemcpyHostToDevice, s->stream));
+		if (tOut) { if ((rc = scene_scratch(s, 1, numRays * 4, &p))) return rc; dT = (float*)p; }
+		if (idOut) { if ((rc = scene_scratch(s, 2, numRays * 4, &p))) return rc; dI = (int32_t*)p; }
+	}
+	unsigned blocks = (unsigned)((numRays + 127) / 128);
+	if (s->kind == RTO_MODE_BVH) k_trace_bvh<<<blocks, 128, 0, s->stream>>>(s->bvh, flags, dO, dD, numRays, dT, dI);
+	else k_trace_octree<<<blocks, 128, 0, s->stream>>>(s->oct, mode, dO, dD, numRays, tMin, tMax, dT, dI);
+	s->launches++;
+	CUDA_TRY(cudaGetLastError());
+	if (host) {
+		if (tOut) CUDA_TRY(cudaMemcpyAsync(tOut, dT, numRays * 4, cudaMemcpyDeviceToHost, s->stream));
+		if (idOut) CUDA_TRY(cudaMemcpyAsync(idOut, dI, numRays * 4, cudaMemcpyDeviceToHost, s->stream));
+		CUDA_TRY(cudaStreamSynchronize(s->stream));
+	}
+	return RTO_OK;
+}
+
+extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dirs, size_t numRays,
+	int64_t* offsets, int32_t* ids, size_t idsCapacity, size_t* totalOut) {
+	if (!s || !origins || !dirs || !offsets) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: null argument");
+	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: scene is not a BVH");
+	offsets[0] = 0;
+	if (totalOut) *totalOut = 0;
+	if (numRays == 0) return RTO_OK;
+	CUDA_TRY(cudaSetDevice(s->device));
+	int rc; void* p = nullptr;
+	if ((rc = scene_scratch(s, 0, numRays * 24, &p))) return rc;
+	float* dO = (float*)p; float* dD = dO + 3 * numRays;
+	CUDA_TRY(cudaMemcpyAsync(dO, origins, numRays * 12, cudaMemcpyHostToDevice, s->stream));
+	CUDA_TRY(cudaMemcpyAsync(dD, dirs, numRays * 12, cudaMemcpyHostToDevice, s->stream));
+	if ((rc = scene_scratch(s, 1, numRays * 4, &p))) return rc;
+	int* dCounts = (int*)p;
+	unsigned blocks = (unsigned)((numRays + 127) / 128);
+	k_bvh_query<<<blocks, 128, 0, s->stream>>>(s->bvh, dO, dD, numRays, nullptr, dCounts, nullptr);
+	s->launches++;
+	CUDA_TRY(cudaGetLastError());
+	std::vector<int> counts(numRays);
+	CUDA_TRY(cudaMemcpyAsync(counts.data(), dCounts, numRays * 4, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	int64_t total = 0;
+	for (size_t i = 0; i < numRays; i++) { offsets[i] = total; total += counts[i]; }
+	offsets[numRays] = total;
+	if (totalOut) *totalOut = (size_t)total;
+	if (!ids || total == 0) return RTO_OK;
+	if ((size_t)total > idsCapacity) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: ids capacity %zu < %lld candidates", idsCapacity, (long long)total);
+	if ((rc = scene_scratch(s, 2, (numRays + 1) * 8, &p))) return rc;
+	long long* dOff = (long long*)p;
+	CUDA_TRY(cudaMemcpyAsync(dOff, offsets, (numRays + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+	if ((rc = scene_scratch(s, 5, (size_t)total * 4, &p))) return rc;
+	int* dIds = (int*)p;
+	k_bvh_query<<<blocks, 128, 0, s->stream>>>(s->bvh, dO, dD, numRays, dOff, nullptr, dIds);
+	s->launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(ids, dIds, (size_t)total * 4, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	return RTO_OK;
+}

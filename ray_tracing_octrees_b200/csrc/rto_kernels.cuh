@@ -1,0 +1,674 @@
+// rto_kernels.cuh -- hand-written sm_100a ray-casting kernels (device code only).
+//
+// Three traversal semantics, each bit-compatible with the CPU oracle (see oracle/):
+//   BVH      BVH::query candidate set (BVH.cpp:76-113) + Moller-Trumbore closest hit / shadow any-hit
+//            (SURVEY.md 8c rule), ordered traversal with t-pruning; RTO_FLAG_NO_PRUNE replays the
+//            reference's full visit pattern.
+//   mode A   octreeRaySkip (VolumeRaycastRenderer.cpp:50-155): back-to-front Hamming order, first finite
+//            leaf result wins, (enterT, exitT) clamps handed from parent to child.
+//   mode B   GLSL intersectOctreeIterative (RayTracerBVH.cpp:239-327): LIFO order 7..0, first solid box hit
+//            wins, 512-step budget.
+// Exactness rules: this file is compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false; every
+// expression keeps the reference's operation order (rto_math.h); min/max are spelled as selects with the
+// reference's operand order so NaN/inf cases agree.
+#pragma once
+#include "rto_internal.h"
+#include <cfloat>
+#include <cuda_runtime.h>
+
+namespace rto {
+
+// ------------------------------------------------------------------------------------------------
+// Device scene descriptors (passed by value as kernel parameters)
+// ------------------------------------------------------------------------------------------------
+struct BvhDev {
+	const float4* nodes;     // inner nodes, 4 x float4 each: [lo0.xyz hi0.x][hi0.yz lo1.xy][lo1.z hi1.xyz][ref0 ref1 - -]
+	const float4* tris;      // 3 x float4 per triangle in leaf order: [v0.xyz v1.x][v1.yz v2.xy][v2.z id - -]
+	int   rootRef;           // >= 0: inner node index; < 0: ~leafRef, leafRef = (firstPos << 1) | (count - 1)
+	int   numTris;
+	float rootLo[3], rootHi[3];
+};
+
+struct OctDev {
+	const uint32_t* desc;    // compact layout: per node, bit31 = leaf, bit30 = solid, else index of first child (8 contiguous)
+	const int32_t*  up;      // compact layout: parent node of sibling group g = (node - 1) >> 3
+	const int4*     nodes16; // general layout: RtoGpuNode padded to 16 x int32
+	int   numNodes;
+	int   rootSize;
+	int   compact;
+	float gmin[3];
+	float voxel;
+};
+
+constexpr uint32_t kOctLeaf = 0x80000000u;
+constexpr uint32_t kOctSolid = 0x40000000u;
+constexpr int kMaxOctDepth = 32;
+constexpr int kBvhStack = 64;
+constexpr float kMissT = 1e30f;
+// pruning margin of the ordered BVH traversal: a subtree is skipped only if its box entry distance exceeds the
+// best hit by more than this relative slack (keeps co-planar / shared-edge candidates)
+constexpr float kPruneSlack = 1.00001f;
+
+struct Ray { V3 o, d; };
+
+// ------------------------------------------------------------------------------------------------
+// Pixel ray: GLSL generateRay (RayTracerBVH.cpp:338-355) with inverse(view), tan(fov/2) from the host
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Ray gen_ray(const RtoCamera& c, int px, int py) {
+	float nx = (float(px) + 0.5f) / float(c.width) * 2.0f - 1.0f;
+	float ny = 1.0f - (float(py) + 0.5f) / float(c.height) * 2.0f;
+	nx *= c.aspect;
+	nx *= c.tanHalfFov;
+	ny *= c.tanHalfFov;
+	// normalize(vec4(nx, ny, -1, 0)): dot4 = (x*x + y*y) + (z*z + w*w)
+	float len2 = (nx * nx + ny * ny) + ((-1.0f) * (-1.0f) + 0.0f * 0.0f);
+	float il = 1.0f / sqrtf(len2);
+	float vx = nx * il, vy = ny * il, vz = -1.0f * il, vw = 0.0f * il;
+	// mat4 * vec4 = (m0*v0 + m1*v1) + (m2*v2 + m3*v3), column-major
+	const float* m = c.invView;
+	float wx = (m[0] * vx + m[4] * vy) + (m[8] * vz + m[12] * vw);
+	float wy = (m[1] * vx + m[5] * vy) + (m[9] * vz + m[13] * vw);
+	float wz = (m[2] * vx + m[6] * vy) + (m[10] * vz + m[14] * vw);
+	Ray r;
+	r.o = mk3(c.camPos[0], c.camPos[1], c.camPos[2]);
+	r.d = normalize3(mk3(wx, wy, wz));
+	return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BVH
+// ------------------------------------------------------------------------------------------------
+struct RayBox {            // per-ray constants of BVH::query (BVH.cpp:107-113)
+	V3 o, inv; bool nx, ny, nz;
+};
+__device__ __forceinline__ RayBox make_raybox(V3 o, V3 d) {
+	RayBox r; r.o = o;
+	r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	r.nx = r.inv.x < 0; r.ny = r.inv.y < 0; r.nz = r.inv.z < 0;
+	return r;
+}
+
+// intersectAABB (BVH.cpp:76-87) with tmin = 0, tmax = FLT_MAX.  The per-axis early-outs of the reference are
+// equivalent to one final test because tmin only grows and tmax only shrinks (NaN candidates are never taken).
+__device__ __forceinline__ bool slab_ref(const RayBox& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float& tEntry) {
+	float tmin = 0.0f, tmax = FLT_MAX;
+	float t0 = ((r.nx ? hix : lox) - r.o.x) * r.inv.x;
+	float t1 = ((r.nx ? lox : hix) - r.o.x) * r.inv.x;
+	tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+	t0 = ((r.ny ? hiy : loy) - r.o.y) * r.inv.y;
+	t1 = ((r.ny ? loy : hiy) - r.o.y) * r.inv.y;
+	tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+	t0 = ((r.nz ? hiz : loz) - r.o.z) * r.inv.z;
+	t1 = ((r.nz ? loz : hiz) - r.o.z) * r.inv.z;
+	tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+	tEntry = tmin;
+	return !(tmax < tmin);
+}
+
+struct TriV { V3 v0, v1, v2; int id; };
+__device__ __forceinline__ TriV load_tri(const float4* __restrict__ tris, int pos) {
+	float4 a = __ldg(tris + 3 * (size_t)pos), b = __ldg(tris + 3 * (size_t)pos + 1), c = __ldg(tris + 3 * (size_t)pos + 2);
+	TriV t;
+	t.v0 = mk3(a.x, a.y, a.z); t.v1 = mk3(a.w, b.x, b.y); t.v2 = mk3(b.z, b.w, c.x); t.id = __float_as_int(c.y);
+	return t;
+}
+
+// Moller-Trumbore, SURVEY.md 8c rule (every comparison rejects NaN)
+__device__ __forceinline__ bool moller_trumbore(const TriV& tri, V3 o, V3 d, float& tOut) {
+	V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
+	V3 p = cross3(d, e2);
+	float det = dot3(e1, p);
+	if (!(fabsf(det) >= 1e-8f)) return false;
+	float inv = 1.0f / det;
+	V3 s = o - tri.v0;
+	float u = dot3(s, p) * inv;
+	if (!(u >= 0.0f && u <= 1.0f)) return false;
+	V3 q = cross3(s, e1);
+	float v = dot3(d, q) * inv;
+	if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+	float t = dot3(e2, q) * inv;
+	if (!(t > 1e-4f)) return false;
+	tOut = t;
+	return true;
+}
+
+// Closest hit.  Result = min over the reference's candidate set of (t, position in candidate order), i.e. the
+// oracle's "strict <, first candidate wins".  PRUNE: near-child-first order and subtrees entered only while their
+// box entry <= best * kPruneSlack.  !PRUNE: every box the reference's queryNode would test is tested.
+template <bool PRUNE>
+__device__ __forceinline__ void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos) {
+	bestT = kMissT; bestPos = -1;
+	if (S.numTris <= 0) return;
+	RayBox rb = make_raybox(o, d);
+	float te;
+	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return;
+	int   stackRef[kBvhStack];
+	float stackT[kBvhStack];
+	int sp = 0;
+	int cur = S.rootRef;
+	float tcut = kMissT * kPruneSlack;
+	while (true) {
+		if (cur >= 0) {
+			const float4* n = S.nodes + 4 * (size_t)cur;
+			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), r = __ldg(n + 3);
+			float e0, e1;
+			bool h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0);
+			bool h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1);
+			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
+			if (PRUNE) { h0 = h0 && (e0 <= tcut); h1 = h1 && (e1 <= tcut); }
+			if (h0 && h1) {
+				bool swap = PRUNE && (e1 < e0);
+				int nearRef = swap ? r1 : r0, farRef = swap ? r0 : r1;
+				float farT = swap ? e0 : e1;
+				if (sp < kBvhStack) { stackRef[sp] = farRef; stackT[sp] = farT; sp++; }
+				cur = nearRef;
+				continue;
+			}
+			if (h0) { cur = r0; continue; }
+			if (h1) { cur = r1; continue; }
+		}
+		else {
+			int ref = ~cur;
+			int pos = ref >> 1, cnt = (ref & 1) + 1;
+			for (int k = 0; k < cnt; k++) {
+				TriV tri = load_tri(S.tris, pos + k);
+				float t;
+				if (moller_trumbore(tri, o, d, t)) {
+					if (t < bestT || (t == bestT && pos + k < bestPos)) { bestT = t; bestPos = pos + k; tcut = t * kPruneSlack; }
+				}
+			}
+		}
+		// pop
+		bool got = false;
+		while (sp > 0) {
+			sp--;
+			if (!PRUNE || stackT[sp] <= tcut) { cur = stackRef[sp]; got = true; break; }
+		}
+		if (!got) break;
+	}
+}
+
+// Shadow / any-hit: true iff some candidate of the reference's query passes Moller-Trumbore.
+__device__ __forceinline__ bool bvh_any(const BvhDev& S, V3 o, V3 d) {
+	if (S.numTris <= 0) return false;
+	RayBox rb = make_raybox(o, d);
+	float te;
+	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return false;
+	int stackRef[kBvhStack];
+	int sp = 0;
+	int cur = S.rootRef;
+	while (true) {
+		if (cur >= 0) {
+			const float4* n = S.nodes + 4 * (size_t)cur;
+			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), r = __ldg(n + 3);
+			float e0, e1;
+			bool h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0);
+			bool h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1);
+			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
+			if (h0 && h1) {
+				bool swap = e1 < e0;
+				if (sp < kBvhStack) stackRef[sp++] = swap ? r0 : r1;
+				cur = swap ? r1 : r0;
+				continue;
+			}
+			if (h0) { cur = r0; continue; }
+			if (h1) { cur = r1; continue; }
+		}
+		else {
+			int ref = ~cur;
+			int pos = ref >> 1, cnt = (ref & 1) + 1;
+			for (int k = 0; k < cnt; k++) {
+				TriV tri = load_tri(S.tris, pos + k);
+				float t;
+				if (moller_trumbore(tri, o, d, t)) return true;
+			}
+		}
+		if (sp == 0) break;
+		cur = stackRef[--sp];
+	}
+	return false;
+}
+
+// Reference-order replay (left before right, nothing pruned): emits candidate positions in BVH::query order and
+// counts intersectAABB calls the reference would make (1 for the root + 2 per internal node entered).
+template <typename Emit>
+__device__ __forceinline__ void bvh_replay(const BvhDev& S, V3 o, V3 d, unsigned long long& boxTests, Emit emit) {
+	if (S.numTris < 0) return;
+	boxTests += 1;
+	RayBox rb = make_raybox(o, d);
+	float te;
+	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return;
+	if (S.numTris == 0) return;
+	int stackRef[kBvhStack];
+	int sp = 0;
+	int cur = S.rootRef;
+	while (true) {
+		if (cur >= 0) {
+			const float4* n = S.nodes + 4 * (size_t)cur;
+			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), r = __ldg(n + 3);
+			float e0, e1;
+			boxTests += 2;
+			bool h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0);
+			bool h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1);
+			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
+			if (h0 && h1) { if (sp < kBvhStack) stackRef[sp++] = r1; cur = r0; continue; }
+			if (h0) { cur = r0; continue; }
+			if (h1) { cur = r1; continue; }
+		}
+		else {
+			int ref = ~cur;
+			int pos = ref >> 1, cnt = (ref & 1) + 1;
+			for (int k = 0; k < cnt; k++) emit(pos + k);
+		}
+		if (sp == 0) break;
+		cur = stackRef[--sp];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Octree helpers
+// ------------------------------------------------------------------------------------------------
+// order of octants for octreeRaySkip: ascending popcount(octant ^ dirMask), ascending octant within a class
+// (VolumeRaycastRenderer.cpp:122-134).  nibble j of kSkipOrder[m] = j-th octant; nibble k of kSkipRank[m] = position of octant k.
+constexpr int popc3(int v) { return (v & 1) + ((v >> 1) & 1) + ((v >> 2) & 1); }
+constexpr uint32_t skip_order(int m) {
+	uint32_t r = 0; int j = 0;
+	for (int dist = 0; dist <= 3; dist++)
+		for (int o = 0; o < 8; o++)
+			if (popc3(o ^ m) == dist) { r |= (uint32_t)o << (4 * j); j++; }
+	return r;
+}
+constexpr uint32_t skip_rank(int m) {
+	uint32_t ord = skip_order(m), r = 0;
+	for (int j = 0; j < 8; j++) r |= (uint32_t)j << (4 * ((ord >> (4 * j)) & 7u));
+	return r;
+}
+__device__ __constant__ uint32_t kSkipOrder[8] = { skip_order(0), skip_order(1), skip_order(2), skip_order(3), skip_order(4), skip_order(5), skip_order(6), skip_order(7) };
+__device__ __constant__ uint32_t kSkipRank[8] = { skip_rank(0), skip_rank(1), skip_rank(2), skip_rank(3), skip_rank(4), skip_rank(5), skip_rank(6), skip_rank(7) };
+
+struct OctBox { V3 mn, mx; };
+// world box of a node: nodeMin = gridMin + vec3(x,y,z)*voxelSize; nodeMax = nodeMin + vec3(size)*voxelSize
+// (RayTracerBVH.cpp:262-263; identical operations in VolumeRaycastRenderer.cpp:70-77)
+__device__ __forceinline__ OctBox oct_box(const OctDev& S, int x, int y, int z, int size) {
+	OctBox b;
+	b.mn = mk3(S.gmin[0] + float(x) * S.voxel, S.gmin[1] + float(y) * S.voxel, S.gmin[2] + float(z) * S.voxel);
+	float w = float(size) * S.voxel;
+	b.mx = mk3(b.mn.x + w, b.mn.y + w, b.mn.z + w);
+	return b;
+}
+
+struct OctHit { float t; int id; V3 normal; unsigned visits; };
+
+// ---- mode B: GLSL intersectAABB (RayTracerBVH.cpp:226-236) -----------------------------------------------
+__device__ __forceinline__ bool glsl_box(const OctBox& b, V3 o, V3 inv, float& tNear, float& tFar) {
+	V3 t1 = (b.mn - o) * inv, t2 = (b.mx - o) * inv;
+	V3 tmn = min3(t1, t2), tmx = max3(t1, t2);
+	tNear = maxf(maxf(tmn.x, tmn.y), tmn.z);
+	tFar = minf(minf(tmx.x, tmx.y), tmx.z);
+	return (tNear <= tFar && tFar > 0.0f);
+}
+
+__device__ __forceinline__ V3 box_normal(const OctBox& b, V3 o, V3 d, float t) {     // RayTracerBVH.cpp:279-282
+	V3 center = 0.5f * (b.mn + b.mx);
+	V3 p = o + d * t;
+	return normalize3(p - center);
+}
+
+// compact layout: stackless walk; sibling order 7..0 == the pop order of the GLSL stack
+__device__ __forceinline__ OctHit octB_compact(const OctDev& S, V3 o, V3 d) {
+	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
+	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	const float closestT = kMissT;
+	int node = 0, x = 0, y = 0, z = 0, size = S.rootSize;
+	int steps = 0;
+	while (steps < 512) {
+		steps++;
+		OctBox b = oct_box(S, x, y, z, size);
+		float tNear, tFar;
+		if (glsl_box(b, o, inv, tNear, tFar) && !(tNear >= closestT)) {
+			uint32_t dsc = __ldg(S.desc + node);
+			if (dsc & kOctLeaf) {
+				if (dsc & kOctSolid) {
+					float tHit = maxf(0.0f, tNear);
+					if (tHit < closestT && tHit <= tFar) { h.t = tHit; h.id = node; h.normal = box_normal(b, o, d, tHit); break; }
+				}
+			}
+			else {       // children pushed 0..7, so 7 is visited first
+				size >>= 1; x += size; y += size; z += size;
+				node = (int)dsc + 7;
+				continue;
+			}
+		}
+		// next sibling (k-1) or climb
+		bool done = false;
+		while (true) {
+			if (node == 0) { done = true; break; }
+			int k = (node - 1) & 7;
+			if (k > 0) {
+				int nk = k - 1;
+				x = (x & ~size) | ((nk & 1) ? size : 0); y = (y & ~size) | ((nk & 2) ? size : 0); z = (z & ~size) | ((nk & 4) ? size : 0);
+				node -= 1;
+				break;
+			}
+			node = __ldg(S.up + ((node - 1) >> 3));
+			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
+		}
+		if (done) break;
+	}
+	h.visits = (unsigned)steps;
+	return h;
+}
+
+// general layout: the GLSL loop verbatim over 16-int nodes
+__device__ __forceinline__ OctHit octB_general(const OctDev& S, V3 o, V3 d) {
+	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
+	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	const float closestT = kMissT;
+	int stack[128]; int sp = 0; stack[sp++] = 0;
+	int steps = 0;
+	while (sp > 0 && steps < 512) {
+		int idx = stack[--sp];
+		if (idx < 0 || idx >= S.numNodes) continue;       // (the reference does not guard idx >= numNodes; such arrays are rejected at upload)
+		steps++;
+		const int4* n = S.nodes16 + 4 * (size_t)idx;
+		int4 a = __ldg(n), f = __ldg(n + 1);
+		OctBox b = oct_box(S, a.x, a.y, a.z, a.w);
+		float tNear, tFar;
+		if (!glsl_box(b, o, inv, tNear, tFar)) continue;
+		if (tNear >= closestT) continue;
+		if (f.z == 1 || f.x == 1) {                       // isUniform == 1, or isLeaf == 1 (RayTracerBVH.cpp:271,291)
+			if (f.y == 1) {
+				float tHit = maxf(0.0f, tNear);
+				if (tHit < closestT && tHit <= tFar) { h.t = tHit; h.id = idx; h.normal = box_normal(b, o, d, tHit); break; }
+			}
+			continue;
+		}
+		int4 c0 = __ldg(n + 2), c1 = __ldg(n + 3);
+		int ch[8] = { f.w, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z };
+#pragma unroll
+		for (int i = 0; i < 8; i++) if (ch[i] >= 0 && sp < 128) stack[sp++] = ch[i];
+	}
+	h.visits = (unsigned)steps;
+	return h;
+}
+
+// ---- mode A: octreeRaySkip (VolumeRaycastRenderer.cpp:50-155) ---------------------------------------------
+struct SkipRay { V3 o, inv; uint32_t order, rank; };
+__device__ __forceinline__ SkipRay make_skipray(V3 o, V3 d) {
+	SkipRay r; r.o = o;
+	r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	const float smallValue = 1e-10f;                                       // :84-87
+	if (fabsf(d.x) < smallValue) r.inv.x = d.x >= 0 ? 1e10f : -1e10f;
+	if (fabsf(d.y) < smallValue) r.inv.y = d.y >= 0 ? 1e10f : -1e10f;
+	if (fabsf(d.z) < smallValue) r.inv.z = d.z >= 0 ? 1e10f : -1e10f;
+	int dirMask = ((d.x > 0) ? 1 : 0) | ((d.y > 0) ? 2 : 0) | ((d.z > 0) ? 4 : 0);   // :114-116
+	r.order = kSkipOrder[dirMask]; r.rank = kSkipRank[dirMask];
+	return r;
+}
+__device__ __forceinline__ bool skip_box(const OctBox& b, const SkipRay& r, float tMin, float tMax, float& enterT, float& exitT) {
+	V3 t1 = (b.mn - r.o) * r.inv, t2 = (b.mx - r.o) * r.inv;
+	V3 tN = min3(t1, t2), tF = max3(t1, t2);
+	enterT = maxf(maxf(tN.x, tN.y), maxf(tN.z, tMin));                     // :96
+	exitT = minf(minf(tF.x, tF.y), minf(tF.z, tMax));                      // :97
+	return !(enterT > exitT);
+}
+
+__device__ __forceinline__ OctHit octA_compact(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
+	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
+	SkipRay r = make_skipray(o, d);
+	float minS[kMaxOctDepth], maxS[kMaxOctDepth];
+	int depth = 0;
+	float curMin = tMin, curMax = tMax;
+	int node = 0, x = 0, y = 0, z = 0, size = S.rootSize;
+	unsigned visits = 0;
+	while (true) {
+		visits++;
+		OctBox b = oct_box(S, x, y, z, size);
+		float enterT, exitT;
+		if (skip_box(b, r, curMin, curMax, enterT, exitT)) {
+			uint32_t dsc = __ldg(S.desc + node);
+			if (dsc & kOctLeaf) {
+				// a solid leaf returns enterT; the callers keep it only if it is < 1e30f (:143-149)
+				if ((dsc & kOctSolid) && enterT < 1e30f) { h.t = enterT; h.id = node; h.normal = box_normal(b, o, d, enterT); break; }
+			}
+			else {
+				minS[depth] = curMin; maxS[depth] = curMax; depth++;
+				curMin = enterT; curMax = exitT;
+				int k = (int)(r.order & 7u);
+				size >>= 1;
+				x += (k & 1) ? size : 0; y += (k & 2) ? size : 0; z += (k & 4) ? size : 0;
+				node = (int)dsc + k;
+				continue;
+			}
+		}
+		bool done = false;
+		while (true) {
+			if (node == 0) { done = true; break; }
+			int k = (node - 1) & 7;
+			int j = (int)((r.rank >> (4 * k)) & 7u);
+			if (j < 7) {
+				int nk = (int)((r.order >> (4 * (j + 1))) & 7u);
+				x = (x & ~size) | ((nk & 1) ? size : 0); y = (y & ~size) | ((nk & 2) ? size : 0); z = (z & ~size) | ((nk & 4) ? size : 0);
+				node = node - k + nk;
+				break;
+			}
+			node = __ldg(S.up + ((node - 1) >> 3));
+			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
+			depth--; curMin = minS[depth]; curMax = maxS[depth];
+		}
+		if (done) break;
+	}
+	h.visits = visits;
+	return h;
+}
+
+__device__ __forceinline__ OctHit octA_general(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
+	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
+	SkipRay r = make_skipray(o, d);
+	// explicit recursion frames: node being expanded, next order position, the (tMin, tMax) its children receive
+	int   nodeS[kMaxOctDepth]; int posS[kMaxOctDepth]; float minS[kMaxOctDepth], maxS[kMaxOctDepth];
+	int depth = 0;
+	unsigned visits = 0;
+	int cur = 0; float curMin = tMin, curMax = tMax;
+	while (true) {
+		bool descended = false;
+		if (cur >= 0 && cur < S.numNodes) {
+			visits++;
+			const int4* n = S.nodes16 + 4 * (size_t)cur;
+			int4 a = __ldg(n), f = __ldg(n + 1);
+			OctBox b = oct_box(S, a.x, a.y, a.z, a.w);
+			float enterT, exitT;
+			if (skip_box(b, r, curMin, curMax, enterT, exitT)) {
+				if (f.x != 0) {                              // node->isLeaf (:105)
+					if (f.y != 0 && enterT < 1e30f) { h.t = enterT; h.id = cur; h.normal = box_normal(b, o, d, enterT); break; }
+				}
+				else if (depth < kMaxOctDepth) {
+					nodeS[depth] = cur; posS[depth] = 0; minS[depth] = enterT; maxS[depth] = exitT; depth++;
+					descended = true;
+				}
+			}
+		}
+		(void)descended;
+		// take the next child of the innermost open frame
+		bool found = false;
+		while (depth > 0) {
+			int f = depth - 1;
+			if (posS[f] < 8) {
+				int k = (int)((r.order >> (4 * posS[f])) & 7u);
+				posS[f]++;
+				const int* ch = reinterpret_cast<const int*>(S.nodes16 + 4 * (size_t)nodeS[f]) + 7;
+				int c = __ldg(ch + k);
+				if (c < 0) continue;                         // null child: skipped without a call (:136-137)
+				cur = c; curMin = minS[f]; curMax = maxS[f];
+				found = true;
+				break;
+			}
+			depth--;
+		}
+		if (!found) break;
+	}
+	h.visits = visits;
+	return h;
+}
+
+__device__ __forceinline__ OctHit oct_trace(const OctDev& S, int mode, V3 o, V3 d, float tMin, float tMax) {
+	if (mode == RTO_MODE_OCTREE_SKIP) return S.compact ? octA_compact(S, o, d, tMin, tMax) : octA_general(S, o, d, tMin, tMax);
+	return S.compact ? octB_compact(S, o, d) : octB_general(S, o, d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pixel mapping: one warp = one 8x4 pixel tile, one 128-thread block = 16x8 pixels, blockIdx.z = camera
+// ------------------------------------------------------------------------------------------------
+struct RenderArgs {
+	RtoCamera cam0;               // used when cams == nullptr
+	const RtoCamera* cams;        // device array for batches
+	int y0, y1;
+	float4* rgba; int* hitId; float* t;
+	float shadowBias;
+	unsigned flags;
+};
+
+__device__ __forceinline__ bool pixel_of_thread(const RenderArgs& A, const RtoCamera& cam, int& px, int& py, size_t& pix) {
+	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	py = A.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+	if (px >= cam.width || py >= A.y1) return false;
+	pix = (size_t)blockIdx.z * (size_t)(A.y1 - A.y0) * cam.width + (size_t)(py - A.y0) * cam.width + px;
+	return true;
+}
+
+__device__ __forceinline__ void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, float t) {
+	if (A.rgba) A.rgba[pix] = make_float4(color.x, color.y, color.z, 1.0f);
+	if (A.hitId) A.hitId[pix] = id;
+	if (A.t) A.t[pix] = t;
+}
+
+template <bool SHADOWS, bool PRUNE>
+__global__ void __launch_bounds__(128) k_render_bvh(BvhDev S, RenderArgs A) {
+	RtoCamera cam = A.cam0;
+	if (A.cams) cam = A.cams[blockIdx.z];
+	int px, py; size_t pix;
+	if (!pixel_of_thread(A, cam, px, py, pix)) return;
+	Ray ray = gen_ray(cam, px, py);
+	float bestT; int bestPos;
+	bvh_closest<PRUNE>(S, ray.o, ray.d, bestT, bestPos);
+	V3 color = mk3(0.0f, 0.0f, 0.0f);
+	int id = -1;
+	if (bestPos >= 0) {
+		TriV tri = load_tri(S.tris, bestPos);
+		id = tri.id;
+		V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
+		V3 n = normalize3(cross3(e1, e2));
+		if (dot3(n, ray.d) > 0.0f) n = -n;
+		V3 hit = ray.o + ray.d * bestT;
+		bool shadowed = false;
+		if (SHADOWS) {
+			V3 so = hit + n * A.shadowBias;
+			V3 sd = normalize3(mk3(1.0f, 1.0f, 1.0f));
+			shadowed = bvh_any(S, so, sd);
+		}
+		color = shadowed ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
+	}
+	store_pixel(A, pix, color, id, bestT);
+}
+
+__global__ void __launch_bounds__(128) k_render_octree(OctDev S, RenderArgs A, int mode) {
+	RtoCamera cam = A.cam0;
+	if (A.cams) cam = A.cams[blockIdx.z];
+	int px, py; size_t pix;
+	if (!pixel_of_thread(A, cam, px, py, pix)) return;
+	Ray ray = gen_ray(cam, px, py);
+	OctHit h = oct_trace(S, mode, ray.o, ray.d, 0.0f, 1e30f);
+	V3 color = mk3(0.0f, 0.0f, 0.0f);
+	if (h.id >= 0) color = shade_lambert(h.normal);
+	store_pixel(A, pix, color, h.id, h.t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Explicit ray lists
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_trace_octree(OctDev S, int mode, const float* __restrict__ o3, const float* __restrict__ d3, size_t n,
+	float tMin, float tMax, float* tOut, int* idOut) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	V3 o = mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+	OctHit h = oct_trace(S, mode, o, d, tMin, tMax);
+	if (tOut) tOut[i] = h.t;
+	if (idOut) idOut[i] = h.id;
+}
+
+__global__ void __launch_bounds__(128) k_trace_bvh(BvhDev S, unsigned flags, const float* __restrict__ o3, const float* __restrict__ d3, size_t n,
+	float* tOut, int* idOut) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	V3 o = mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+	float bestT; int bestPos;
+	if (flags & RTO_FLAG_NO_PRUNE) bvh_closest<false>(S, o, d, bestT, bestPos); else bvh_closest<true>(S, o, d, bestT, bestPos);
+	if (tOut) tOut[i] = bestT;
+	if (idOut) idOut[i] = bestPos >= 0 ? __float_as_int(__ldg(S.tris + 3 * (size_t)bestPos + 2).y) : -1;
+}
+
+// BVH::query candidates: pass 1 counts per ray, pass 2 writes ids at the host-computed offsets
+__global__ void __launch_bounds__(128) k_bvh_query(BvhDev S, const float* __restrict__ o3, const float* __restrict__ d3, size_t n,
+	const long long* __restrict__ offsets, int* counts, int* ids) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	V3 o = mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+	unsigned long long boxes = 0;
+	int cnt = 0;
+	long long base = offsets ? offsets[i] : 0;
+	bvh_replay(S, o, d, boxes, [&](int pos) {
+		if (ids) ids[base + cnt] = __float_as_int(__ldg(S.tris + 3 * (size_t)pos + 2).y);
+		cnt++;
+	});
+	if (counts) counts[i] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Work counters of the reference algorithm (B, C, N)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_add(unsigned long long* dst, unsigned long long v) {
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
+}
+
+__global__ void __launch_bounds__(128) k_stats_bvh(BvhDev S, RenderArgs A, unsigned long long* stats) {
+	const RtoCamera& cam = A.cam0;
+	int px, py; size_t pix;
+	bool active = pixel_of_thread(A, cam, px, py, pix);
+	unsigned long long B = 0, C = 0, Bs = 0, Cs = 0, nS = 0;
+	if (active) {
+		Ray ray = gen_ray(cam, px, py);
+		bvh_replay(S, ray.o, ray.d, B, [&](int) { C++; });
+		if (A.flags & RTO_FLAG_SHADOWS) {
+			float bestT; int bestPos;
+			bvh_closest<false>(S, ray.o, ray.d, bestT, bestPos);
+			if (bestPos >= 0) {
+				TriV tri = load_tri(S.tris, bestPos);
+				V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
+				V3 n = normalize3(cross3(e1, e2));
+				if (dot3(n, ray.d) > 0.0f) n = -n;
+				V3 so = (ray.o + ray.d * bestT) + n * A.shadowBias;
+				V3 sd = normalize3(mk3(1.0f, 1.0f, 1.0f));
+				nS = 1;
+				bvh_replay(S, so, sd, Bs, [&](int) { Cs++; });
+			}
+		}
+	}
+	warp_add(stats + 0, B); warp_add(stats + 1, C); warp_add(stats + 2, Bs); warp_add(stats + 3, Cs); warp_add(stats + 4, nS);
+}
+
+__global__ void __launch_bounds__(128) k_stats_octree(OctDev S, RenderArgs A, int mode, unsigned long long* stats) {
+	const RtoCamera& cam = A.cam0;
+	int px, py; size_t pix;
+	bool active = pixel_of_thread(A, cam, px, py, pix);
+	unsigned long long N = 0;
+	if (active) {
+		Ray ray = gen_ray(cam, px, py);
+		OctHit h = oct_trace(S, mode, ray.o, ray.d, 0.0f, 1e30f);
+		N = h.visits;
+	}
+	warp_add(stats + 0, N);
+}
+
+} // namespace rto

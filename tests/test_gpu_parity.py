@@ -1,0 +1,305 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA kernels, reached through the C ABI, against the CPU
+oracle on the same inputs.  Bar: hit ids and leaf ids bit-exact; t and rgba bit-exact too (same IEEE operations in
+the same order, no FMA) -- the 1e-4 tolerance of the north star is never needed.  The only documented exception is
+the pruned BVH traversal at ill-conditioned grazing hits; tests allow <= 1e-4 of pixels there and
+require RTO_FLAG_NO_PRUNE to be exact."""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal, cam_from_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(rto):
+    import ctypes
+    rc = rto.lib().rto_init(0)
+    assert rc == 0, rto.lib().rto_last_error()
+    return rto
+
+
+def _cmp_frames(got, want, what, allow_frac=0.0):
+    n = len(want["id"])
+    bad = got["id"] != want["id"]
+    frac = bad.sum() / max(n, 1)
+    assert frac <= allow_frac, "%s: %d of %d ids differ" % (what, int(bad.sum()), n)
+    ok = ~bad
+    assert_bit_equal(got["t"][ok], want["t"][ok], what + " t")
+    assert_bit_equal(got["rgba"][ok], want["rgba"][ok], what + " rgba")
+    return int(bad.sum())
+
+
+# ---- golden vectors from the compiled reference -------------------------------------------------------------
+@pytest.mark.parametrize("name", ["a", "b", "inside"])
+def test_golden_sphere32(gpu, golden_sphere32, golden_meta, name):
+    rto = gpu
+    g = golden_sphere32
+    grid = rto.generate_test_volume(32)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    assert np.array_equal(nodes, g["flat"])
+    cam = cam_from_dict(rto.RtoCamera, golden_meta["sphere32_cams"][name])
+    oc = rto.Scene.octree(nodes, grid.min, grid.voxel_size)
+    assert oc.info()["compact"] == 1
+    for mode, key in ((rto.MODE_OCTREE_SKIP, 0), (rto.MODE_OCTREE_GLSL, 1)):
+        out = oc.render(cam, mode)
+        want = {k: g["oct%d_%s_%s" % (key, name, k)] for k in ("rgba", "id", "t")}
+        _cmp_frames(out, want, "octree mode %d" % key)
+        assert oc.stats(cam, mode)[0] == g["oct%d_%s_stats" % (key, name)][0]
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    sc = rto.Scene.bvh(tris)
+    bias = 1e-3 * grid.voxel_size
+    for flags in (0, 1):
+        want = {k: g["bvh%d_%s_%s" % (flags, name, k)] for k in ("rgba", "id", "t")}
+        _cmp_frames(sc.render(cam, rto.MODE_BVH, flags | rto.FLAG_NO_PRUNE, bias), want, "bvh exact flags %d" % flags)
+        _cmp_frames(sc.render(cam, rto.MODE_BVH, flags, bias), want, "bvh pruned flags %d" % flags, allow_frac=1e-4)
+        st = sc.stats(cam, rto.MODE_BVH, flags, bias)
+        ws = g["bvh%d_%s_stats" % (flags, name)]
+        assert st[0] == ws[0] and st[1] == ws[1]
+        if flags:
+            assert np.array_equal(st, ws)
+
+
+def test_golden_sphere32_query_and_edge_rays(gpu, golden_sphere32):
+    rto = gpu
+    g = golden_sphere32
+    grid = rto.generate_test_volume(32)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    sc = rto.Scene.bvh(tris)
+    off, ids = sc.query(g["query_o"], g["query_d"])
+    assert np.array_equal(off, g["query_off"]) and np.array_equal(ids, g["query_ids"])
+    oc = rto.Scene.octree(nodes, grid.min, grid.voxel_size)
+    t, ids = oc.trace_rays(g["edge_o"], g["edge_d"], rto.MODE_OCTREE_SKIP)
+    assert_bit_equal(t, g["edge_t"], "octreeRaySkip on axis-parallel rays")
+    assert np.array_equal(ids, g["edge_id"])
+
+
+@pytest.fixture(scope="module")
+def dt_scene(gpu, dt_grid_path):
+    rto = gpu
+    grid = rto.VoxelGrid.load(dt_grid_path)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    return dict(grid=grid, nodes=nodes, tris=tris, oct=rto.Scene.octree(nodes, grid.min, grid.voxel_size), bvh=rto.Scene.bvh(tris))
+
+
+@pytest.mark.parametrize("name", ["far", "near"])
+def test_golden_dt_rows(gpu, dt_scene, golden_dt, golden_meta, name):
+    rto = gpu
+    cam = cam_from_dict(rto.RtoCamera, golden_meta["dt_cams"][name])
+    bias = 1e-3 * dt_scene["grid"].voxel_size
+    for bi, (y0, y1) in enumerate(golden_dt["bands"]):
+        y0, y1 = int(y0), int(y1)
+        for mode, key in ((rto.MODE_OCTREE_SKIP, 0), (rto.MODE_OCTREE_GLSL, 1)):
+            want = {k: golden_dt["oct%d_%s_%d_%s" % (key, name, bi, k)] for k in ("rgba", "id", "t")}
+            _cmp_frames(dt_scene["oct"].render(cam, mode, y0=y0, y1=y1), want, "dt octree mode %d band %d" % (key, bi))
+            assert dt_scene["oct"].stats(cam, mode, y0=y0, y1=y1)[0] == golden_dt["oct%d_%s_%d_stats" % (key, name, bi)][0]
+        want = {k: golden_dt["bvh1_%s_%d_%s" % (name, bi, k)] for k in ("rgba", "id", "t")}
+        _cmp_frames(dt_scene["bvh"].render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS | rto.FLAG_NO_PRUNE, bias, y0, y1), want, "dt bvh exact band %d" % bi)
+        _cmp_frames(dt_scene["bvh"].render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias, y0, y1), want, "dt bvh pruned band %d" % bi, allow_frac=1e-4)
+        assert np.array_equal(dt_scene["bvh"].stats(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias, y0, y1), golden_dt["bvh1_%s_%d_stats" % (name, bi)])
+
+
+# ---- differential tests against the live oracle on seeded inputs --------------------------------------------
+@pytest.mark.parametrize("dims,fill,seed", [((20, 13, 7), 0.35, 1), ((16, 16, 16), 0.08, 2), ((1, 1, 1), 1.0, 3), ((33, 9, 17), 0.6, 4), ((8, 8, 8), 0.0, 5)])
+def test_random_grids_vs_oracle(gpu, checker, dims, fill, seed):
+    rto = gpu
+    rng = np.random.default_rng(seed)
+    data = (rng.random(dims[0] * dims[1] * dims[2]) < fill).astype(np.uint8)
+    grid = rto.VoxelGrid(dims, (-1.5, 0.25, 3.0), 0.37, data)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    oc_ref = checker.octree(grid.dims, grid.min, grid.voxel_size, grid.data)
+    oc_ref.build()
+    ext = max(dims) * grid.voxel_size
+    tgt = tuple(float(grid.min[i] + dims[i] * grid.voxel_size / 2) for i in range(3))
+    oc = rto.Scene.octree(nodes, grid.min, grid.voxel_size)
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    sc = rto.Scene.bvh(tris)
+    m_ref = oc_ref.mesh()
+    m_ref.build()
+    for (th, ph, r, w, h) in [(25, 130, 2.2 * ext, 160, 120), (-40, 10, 0.8 * ext, 120, 90), (5, 260, 0.2 * ext, 64, 64)]:
+        cam, _ = rto.Camera.from_degrees(th, ph, r, tgt).consts(45.0, float(np.float32(w) / np.float32(h)), w, h)
+        rcam, _ = checker.camera(th, ph, r, target=tgt, width=w, height=h)
+        assert bytes(cam) == bytes(rcam)
+        for mode, key in ((rto.MODE_OCTREE_SKIP, 0), (rto.MODE_OCTREE_GLSL, 1)):
+            want = oc_ref.render(rcam, key, stats=True)
+            _cmp_frames(oc.render(cam, mode), want, "octree mode %d" % key)
+            assert oc.stats(cam, mode)[0] == want["stats"][0]
+        for flags in (0, 1):
+            want = m_ref.render(rcam, flags, 1e-3 * grid.voxel_size, stats=True)
+            _cmp_frames(sc.render(cam, rto.MODE_BVH, flags | rto.FLAG_NO_PRUNE, 1e-3 * grid.voxel_size), want, "bvh exact")
+            _cmp_frames(sc.render(cam, rto.MODE_BVH, flags, 1e-3 * grid.voxel_size), want, "bvh pruned", allow_frac=1e-4)
+            if len(tris):
+                st = sc.stats(cam, rto.MODE_BVH, flags, 1e-3 * grid.voxel_size)
+                assert st[0] == want["stats"][0] and st[1] == want["stats"][1]
+
+
+def test_general_octree_layout_matches_compact(gpu, checker):
+    """Arrays that do not have the reference builder's shape (here: node order shuffled, a child removed) take the
+    64-byte general path; on the builder's own array both paths must agree with each other and the oracle."""
+    rto = gpu
+    grid = rto.generate_test_volume(16)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    # permute node storage order (keeps the tree, breaks sibling contiguity) -> general layout; ids are permuted too
+    rng = np.random.default_rng(5)
+    perm = np.concatenate([[0], 1 + rng.permutation(len(nodes) - 1)])          # new index -> old index
+    inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+    shuffled = nodes[perm].copy()
+    ch = shuffled[:, 7:15]
+    ch[ch >= 0] = inv[ch[ch >= 0]]
+    a = rto.Scene.octree(nodes, grid.min, grid.voxel_size)
+    b = rto.Scene.octree(shuffled, grid.min, grid.voxel_size)
+    assert a.info()["compact"] == 1 and b.info()["compact"] == 0
+    cam, _ = rto.Camera.from_degrees(20, 50, 1.4).consts(45.0, 1.5, 150, 100)
+    for mode in (rto.MODE_OCTREE_SKIP, rto.MODE_OCTREE_GLSL):
+        oa, ob = a.render(cam, mode), b.render(cam, mode)
+        assert_bit_equal(oa["t"], ob["t"], "t"); assert_bit_equal(oa["rgba"], ob["rgba"], "rgba")
+        hit = oa["id"] >= 0
+        assert np.array_equal(hit, ob["id"] >= 0)
+        assert np.array_equal(oa["id"][hit], perm[ob["id"][hit]])
+        assert a.stats(cam, mode)[0] == b.stats(cam, mode)[0]
+
+
+def test_bvh_query_matches_oracle(gpu, checker):
+    rto = gpu
+    rng = np.random.default_rng(9)
+    tris = rng.normal(0, 1, (500, 9)).astype(np.float32) * 0.2 + rng.normal(0, 1, (500, 1)).astype(np.float32)
+    bvh = rto.BVH(tris)
+    m = checker.mesh(tris)
+    m.build()
+    o = rng.normal(0, 3, (300, 3)).astype(np.float32)
+    d = rng.normal(0, 1, (300, 3)).astype(np.float32)
+    d[::7, 0] = 0.0                       # 1/0 = inf directions (BVH::query has no guard, BVH.cpp:110)
+    d[3::11, 1] = -0.0
+    off, ids = bvh.query_batch(o, d)
+    roff, rids = m.query(o, d)
+    assert np.array_equal(off, roff) and np.array_equal(ids, rids)
+    assert np.array_equal(bvh.query(o[0], d[0]), rids[roff[0]:roff[1]])
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3])
+def test_tiny_meshes(gpu, checker, n):
+    rto = gpu
+    rng = np.random.default_rng(n)
+    tris = (rng.normal(0, 1, (n, 9)) * 0.5).astype(np.float32)
+    sc = rto.Scene.bvh(tris)
+    m = checker.mesh(tris)
+    m.build()
+    cam, _ = rto.Camera.from_degrees(10, 20, 4.0).consts(45.0, 1.0, 64, 64)
+    rcam, _ = checker.camera(10, 20, 4.0, width=64, height=64, aspect=1.0)
+    want = m.render(rcam, 1, 1e-3)
+    _cmp_frames(sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS | rto.FLAG_NO_PRUNE, 1e-3), want, "tiny mesh")
+    _cmp_frames(sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3), want, "tiny mesh pruned")
+
+
+def test_degenerate_and_duplicate_triangles(gpu, checker):
+    rto = gpu
+    rng = np.random.default_rng(21)
+    base = rng.integers(-2, 3, (200, 3)).astype(np.float32)
+    tris = np.concatenate([base, base + [1, 0, 0], base + [0, 1, 0]], axis=1).astype(np.float32)
+    tris = np.concatenate([tris, tris[:50], np.zeros((5, 9), np.float32)], axis=0)      # duplicates + zero-area
+    sc = rto.Scene.bvh(tris)
+    m = checker.mesh(tris)
+    m.build()
+    cam, _ = rto.Camera.from_degrees(33, 47, 9.0).consts(45.0, 1.0, 128, 128)
+    rcam, _ = checker.camera(33, 47, 9.0, width=128, height=128, aspect=1.0)
+    want = m.render(rcam, 1, 1e-3)
+    _cmp_frames(sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS | rto.FLAG_NO_PRUNE, 1e-3), want, "duplicates exact")
+    _cmp_frames(sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3), want, "duplicates pruned")   # ties: first candidate wins
+
+
+def test_row_bands_and_batches_compose(gpu):
+    """A frame rendered in bands / as part of a camera batch equals the frame rendered at once (sharding invariant)."""
+    rto = gpu
+    grid = rto.generate_test_volume(32)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    sc = rto.Scene.bvh(tris)
+    cam, _ = rto.Camera.from_degrees(30, 40, 1.2).consts(45.0, 4 / 3, 200, 150)
+    full = sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-5)
+    parts = [sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-5, y0, y1) for (y0, y1) in [(0, 37), (37, 38), (38, 150)]]
+    for k in ("rgba", "id", "t"):
+        assert_bit_equal(np.concatenate([p[k] for p in parts]), full[k], "bands " + k)
+
+
+def test_error_paths(gpu):
+    rto = gpu
+    grid = rto.generate_test_volume(8)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    oc = rto.Scene.octree(nodes, grid.min, grid.voxel_size)
+    cam, _ = rto.Camera.from_degrees(30, 40, 1.2).consts(45.0, 1.0, 32, 32)
+    with pytest.raises(rto.RtoError):
+        oc.render(cam, rto.MODE_BVH)                      # wrong mode for the scene kind
+    with pytest.raises(rto.RtoError):
+        oc.render(cam, rto.MODE_OCTREE_GLSL, y0=10, y1=5)
+    with pytest.raises(rto.RtoError):
+        rto.Scene.octree(nodes[:0], grid.min, grid.voxel_size)
+    bad = nodes.copy(); bad[0, 7] = len(nodes) + 5
+    with pytest.raises(rto.RtoError):
+        rto.Scene.octree(bad, grid.min, grid.voxel_size)
+    rt = rto.RayTracerBVH()
+    assert rt.render_scene_compute(rto.Camera(0.5, 0.7, 1.2), 32, 32, 1.0, 45.0) is None     # no data: frame untouched
+
+
+# ---- full-size properties (BASELINE.json configs) ---------------------------------------------------------------
+def test_full_size_dt_1080p(gpu, dt_scene, checker, dt_grid_path):
+    """C2 at full size: the whole 1920x1080 frame, primary + shadow, vs the oracle on every 16th scanline band, plus
+    size-independent properties on the full frame."""
+    rto = gpu
+    cam, _ = rto.Camera.from_degrees(35, 40, 0.6 * 4250).consts(45.0, float(np.float32(1920) / np.float32(1080)), 1920, 1080)
+    bias = 1e-3 * dt_scene["grid"].voxel_size
+    full = dt_scene["bvh"].render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias)
+    exact = dt_scene["bvh"].render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS | rto.FLAG_NO_PRUNE, bias)
+    n = 1920 * 1080
+    mism = int((full["id"] != exact["id"]).sum())
+    assert mism <= 1e-4 * n, "pruned traversal differs from the exact candidate replay on %d pixels" % mism
+    hit = full["id"] >= 0
+    assert hit.sum() > 0.3 * n
+    assert ((full["t"][hit] > 1e-4) & (full["t"][hit] < 1e30)).all() and (full["t"][~hit] == np.float32(1e30)).all()
+    assert (full["rgba"][:, 3] == 1.0).all() and (full["rgba"][~hit, :3] == 0).all()
+    assert full["id"].max() < len(dt_scene["tris"])
+    # the hit point lies on the reported triangle's plane (independent check of id/t consistency)
+    # oracle on scanline bands
+    import gzip, tempfile, os
+    raw = gzip.open(dt_grid_path, "rb").read()
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "sceneCache.bin"); open(p, "wb").write(raw)
+        oc_ref = checker.octree(path=p)
+    oc_ref.build()
+    m_ref = oc_ref.mesh(); m_ref.build()
+    rcam, _ = checker.camera(35, 40, 0.6 * 4250, width=1920, height=1080)
+    assert bytes(rcam) == bytes(cam)
+    bad_total = 0
+    for y0 in range(8, 1080, 135):
+        want = m_ref.render(rcam, 1, bias, y0, y0 + 2)
+        sl = slice(y0 * 1920, (y0 + 2) * 1920)
+        got = {k: exact[k][sl] for k in ("rgba", "id", "t")}
+        _cmp_frames(got, want, "dt exact rows %d" % y0)
+        got = {k: full[k][sl] for k in ("rgba", "id", "t")}
+        bad_total += _cmp_frames(got, want, "dt pruned rows %d" % y0, allow_frac=1e-3)
+    assert bad_total <= 2
+
+
+def test_full_size_sphere128_and_octree_modes(gpu, checker):
+    """C1 (sphere 128^3 MC mesh, 1024x768) and both octree modes at full size against the oracle on bands."""
+    rto = gpu
+    grid = rto.generate_test_volume(128)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    sc = rto.Scene.bvh(tris)
+    oc = rto.Scene.octree(nodes, grid.min, grid.voxel_size)
+    cam, _ = rto.Camera.from_degrees(30, 40, 1.2).consts(45.0, float(np.float32(1024) / np.float32(768)), 1024, 768)
+    rcam, _ = checker.camera(30, 40, 1.2, width=1024, height=768)
+    oc_ref = checker.octree(grid.dims, grid.min, grid.voxel_size, grid.data); oc_ref.build()
+    m_ref = oc_ref.mesh(); m_ref.build()
+    bias = 1e-3 * grid.voxel_size
+    full = sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias)
+    fa, fb = oc.render(cam, rto.MODE_OCTREE_SKIP), oc.render(cam, rto.MODE_OCTREE_GLSL)
+    # mode A returns a solid leaf at least as far as ... no ordering guarantee between modes, but both hit the same pixels
+    assert np.array_equal(fa["id"] >= 0, fb["id"] >= 0)
+    for y0 in range(5, 768, 96):
+        sl = slice(y0 * 1024, (y0 + 3) * 1024)
+        _cmp_frames({k: full[k][sl] for k in full}, m_ref.render(rcam, 1, bias, y0, y0 + 3), "sphere bvh rows %d" % y0, allow_frac=1e-3)
+        _cmp_frames({k: fa[k][sl] for k in fa}, oc_ref.render(rcam, 0, y0, y0 + 3), "sphere mode A rows %d" % y0)
+        _cmp_frames({k: fb[k][sl] for k in fb}, oc_ref.render(rcam, 1, y0, y0 + 3), "sphere mode B rows %d" % y0)
