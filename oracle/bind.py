@@ -229,6 +229,18 @@ class Mesh:
 
 
 
+def load_scene_cache(path):
+    """Parse a (optionally gzip-compressed) sceneCache.bin (CacheUtils.cpp:5-59) with numpy ->
+    (dims, gmin, voxel, data).  Avoids the reference loader's std::cout chatter in bench output."""
+    import gzip
+    raw = gzip.open(path, "rb").read() if path.endswith(".gz") else open(path, "rb").read()
+    dims = tuple(int(x) for x in np.frombuffer(raw, np.int32, 3, 0))
+    mv = np.frombuffer(raw, np.float32, 4, 12)
+    n = int(np.frombuffer(raw, np.uint64, 1, 28)[0])
+    assert n == dims[0] * dims[1] * dims[2]
+    return dims, mv[:3].copy(), float(mv[3]), np.frombuffer(raw, np.uint8, n, 36).copy()
+
+
 def sphere_grid(dim):
     """generateTestVolume closed form (main.cpp:337-372) + grid setup of main.cpp:1050-1070."""
     c = np.float32(0.5) * np.float32(dim - 1)

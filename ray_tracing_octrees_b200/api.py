@@ -191,7 +191,7 @@ class Scene:
     def render(self, cam, mode, flags=0, shadow_bias=0.0, y0=0, y1=None, want=("rgba", "id", "t")):
         """Host-memory render of rows [y0, y1): returns dict(rgba (n,4) f32, id (n,) i32, t (n,) f32)."""
         y1 = cam.height if y1 is None else y1
-        n = (y1 - y0) * cam.width
+        n = max(0, y1 - y0) * max(0, cam.width)          # invalid ranges are reported by the library (RTO_ERR_INVALID)
         out = dict(rgba=np.empty((n, 4), np.float32) if "rgba" in want else None,
                    id=np.empty(n, np.int32) if "id" in want else None,
                    t=np.empty(n, np.float32) if "t" in want else None)

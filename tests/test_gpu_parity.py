@@ -261,11 +261,8 @@ def test_full_size_dt_1080p(gpu, dt_scene, checker, dt_grid_path):
     assert full["id"].max() < len(dt_scene["tris"])
     # the hit point lies on the reported triangle's plane (independent check of id/t consistency)
     # oracle on scanline bands
-    import gzip, tempfile, os
-    raw = gzip.open(dt_grid_path, "rb").read()
-    with tempfile.TemporaryDirectory() as td:
-        p = os.path.join(td, "sceneCache.bin"); open(p, "wb").write(raw)
-        oc_ref = checker.octree(path=p)
+    from oracle import bind
+    oc_ref = checker.octree(*bind.load_scene_cache(dt_grid_path))
     oc_ref.build()
     m_ref = oc_ref.mesh(); m_ref.build()
     rcam, _ = checker.camera(35, 40, 0.6 * 4250, width=1920, height=1080)
