@@ -296,6 +296,119 @@ extern "C" int rto_host_bvh_export(const RtoHostBvh* bvh, float* boxes6, int32_t
 }
 
 // =================================================================================================
+// Device node arrays
+// =================================================================================================
+static inline int32_t leafRefOf(const HostBvhNode& n) {
+	uint32_t cnt = n.count ? n.count : 1;          // count 0 only for the empty tree, which is never referenced
+	return ~(int32_t)((n.first << 1) | (cnt - 1));
+}
+
+void rto_build_reference_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef) {
+	std::vector<int32_t> innerId(h.nodes.size(), -1);
+	int32_t numInner = 0;
+	for (size_t i = 0; i < h.nodes.size(); i++) if (h.nodes[i].left >= 0) innerId[i] = numInner++;
+	auto refOf = [&](int32_t i) { return h.nodes[i].left >= 0 ? innerId[i] : leafRefOf(h.nodes[i]); };
+	nodeBuf.assign((size_t)std::max(numInner, 1) * 16, 0.0f);
+	for (size_t i = 0; i < h.nodes.size(); i++) {
+		const HostBvhNode& n = h.nodes[i];
+		if (n.left < 0) continue;
+		float* d = &nodeBuf[(size_t)innerId[i] * 16];
+		const HostBvhNode& L = h.nodes[n.left]; const HostBvhNode& R = h.nodes[n.right];
+		std::memcpy(d, L.mn, 12); std::memcpy(d + 3, L.mx, 12); std::memcpy(d + 6, R.mn, 12); std::memcpy(d + 9, R.mx, 12);
+		int32_t r0 = refOf(n.left), r1 = refOf(n.right);
+		std::memcpy(&d[12], &r0, 4); std::memcpy(&d[13], &r1, 4);
+	}
+	rootRef = h.numTris ? refOf(0) : -1;
+}
+
+namespace {
+struct SahPrim { float mn[3], mx[3], c[3]; int32_t ref; };
+struct SahBuilder {
+	std::vector<SahPrim> prims; std::vector<float>* out;
+	static inline float halfArea(const float* mn, const float* mx) {
+		float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+		return dx * dy + dy * dz + dz * dx;
+	}
+	// returns the ref of the subtree over prims[lo, hi) and its exact bounds
+	int32_t build(size_t lo, size_t hi, float* bmn, float* bmx) {
+		const float M = std::numeric_limits<float>::max();
+		float cmn[3] = { M, M, M }, cmx[3] = { -M, -M, -M };
+		for (int k = 0; k < 3; k++) { bmn[k] = M; bmx[k] = -M; }
+		for (size_t i = lo; i < hi; i++)
+			for (int k = 0; k < 3; k++) {
+				bmn[k] = std::min(bmn[k], prims[i].mn[k]); bmx[k] = std::max(bmx[k], prims[i].mx[k]);
+				cmn[k] = std::min(cmn[k], prims[i].c[k]); cmx[k] = std::max(cmx[k], prims[i].c[k]);
+			}
+		if (hi - lo == 1) return prims[lo].ref;
+		constexpr int NB = 32;
+		int bestAxis = -1, bestSplit = 0; float bestCost = M;
+		for (int ax = 0; ax < 3; ax++) {
+			float ext = cmx[ax] - cmn[ax];
+			if (!(ext > 0.0f)) continue;
+			float scale = NB / ext;
+			int cnt[NB] = { 0 }; float bn[NB][3], bx[NB][3];
+			for (int b = 0; b < NB; b++) for (int k = 0; k < 3; k++) { bn[b][k] = M; bx[b][k] = -M; }
+			for (size_t i = lo; i < hi; i++) {
+				int b = std::min(NB - 1, std::max(0, (int)((prims[i].c[ax] - cmn[ax]) * scale)));
+				cnt[b]++;
+				for (int k = 0; k < 3; k++) { bn[b][k] = std::min(bn[b][k], prims[i].mn[k]); bx[b][k] = std::max(bx[b][k], prims[i].mx[k]); }
+			}
+			float rightArea[NB]; int rightCnt[NB];
+			float an[3] = { M, M, M }, axx[3] = { -M, -M, -M }; int c = 0;
+			for (int b = NB - 1; b > 0; b--) {
+				for (int k = 0; k < 3; k++) { an[k] = std::min(an[k], bn[b][k]); axx[k] = std::max(axx[k], bx[b][k]); }
+				c += cnt[b]; rightCnt[b] = c; rightArea[b] = c ? halfArea(an, axx) : 0.0f;
+			}
+			for (int k = 0; k < 3; k++) { an[k] = M; axx[k] = -M; }
+			c = 0;
+			for (int b = 0; b < NB - 1; b++) {
+				for (int k = 0; k < 3; k++) { an[k] = std::min(an[k], bn[b][k]); axx[k] = std::max(axx[k], bx[b][k]); }
+				c += cnt[b];
+				if (c == 0 || rightCnt[b + 1] == 0) continue;
+				float cost = halfArea(an, axx) * c + rightArea[b + 1] * rightCnt[b + 1];
+				if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestSplit = b + 1; }
+			}
+		}
+		size_t mid;
+		if (bestAxis < 0) mid = lo + (hi - lo) / 2;        // all centroids coincide: split the list in half
+		else {
+			float scale = NB / (cmx[bestAxis] - cmn[bestAxis]), base = cmn[bestAxis];
+			auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const SahPrim& p) {
+				return std::min(NB - 1, std::max(0, (int)((p.c[bestAxis] - base) * scale))) < bestSplit; });
+			mid = (size_t)(it - prims.begin());
+			if (mid == lo || mid == hi) mid = lo + (hi - lo) / 2;
+		}
+		size_t idx = out->size() / 16;
+		out->resize(out->size() + 16, 0.0f);
+		float lmn[3], lmx[3], rmn[3], rmx[3];
+		int32_t r0 = build(lo, mid, lmn, lmx);
+		int32_t r1 = build(mid, hi, rmn, rmx);
+		float* d = &(*out)[idx * 16];
+		std::memcpy(d, lmn, 12); std::memcpy(d + 3, lmx, 12); std::memcpy(d + 6, rmn, 12); std::memcpy(d + 9, rmx, 12);
+		std::memcpy(&d[12], &r0, 4); std::memcpy(&d[13], &r1, 4);
+		return (int32_t)idx;
+	}
+};
+} // namespace
+
+void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef) {
+	SahBuilder b; b.out = &nodeBuf;
+	nodeBuf.clear();
+	for (const HostBvhNode& n : h.nodes) {
+		if (n.left >= 0 || n.count == 0) continue;
+		SahPrim p;
+		for (int k = 0; k < 3; k++) { p.mn[k] = n.mn[k]; p.mx[k] = n.mx[k]; p.c[k] = 0.5f * n.mn[k] + 0.5f * n.mx[k]; }
+		p.ref = leafRefOf(n);
+		b.prims.push_back(p);
+	}
+	if (b.prims.empty()) { nodeBuf.assign(16, 0.0f); rootRef = -1; return; }
+	nodeBuf.reserve(b.prims.size() * 16);
+	float mn[3], mx[3];
+	rootRef = b.build(0, b.prims.size(), mn, mx);
+	if (nodeBuf.empty()) nodeBuf.assign(16, 0.0f);
+}
+
+// =================================================================================================
 // Camera constants
 // =================================================================================================
 extern "C" int rto_host_camera_orbit(float theta, float phi, float radius, const float target[3], float fovDeg, float aspect,

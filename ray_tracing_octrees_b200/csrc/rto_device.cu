@@ -72,12 +72,14 @@ struct RtoScene {
 	bool timed = false;
 	uint64_t launches = 0;
 	size_t deviceBytes = 0, numPrims = 0, numNodes = 0;
-	BvhDev bvh{};
+	BvhDev bvh{};                     // reference topology (BVH::query replay, stats, RTO_FLAG_NO_PRUNE)
+	BvhDev bvhFast{};                 // SAH topology over the same leaves (production closest-hit / shadow rays)
 	OctDev oct{};
 	std::vector<void*> owned;         // device allocations of the scene
 	// growable scratch (device outputs for RTO_MEM_HOST calls, cameras, ray lists)
-	void* scratch[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-	size_t scratchBytes[6] = { 0, 0, 0, 0, 0, 0 };
+	void* scratch[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	size_t scratchBytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	int smCount = 0;
 };
 
 static int scene_alloc(RtoScene* s, void** p, size_t bytes) {
@@ -110,6 +112,7 @@ static int scene_new(RtoScene** out) {
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreate(&s->evStart);
 	if (e == cudaSuccess) e = cudaEventCreate(&s->evStop);
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->smCount, cudaDevAttrMultiProcessorCount, s->device);
 	if (e != cudaSuccess) { delete s; return rto_fail(RTO_ERR_CUDA, "scene setup failed: %s", cudaGetErrorString(e)); }
 	*out = s;
 	return RTO_OK;
@@ -251,27 +254,13 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 	if (rc) { rto_host_bvh_free(ownedBvh); return rc; }
 	s->kind = RTO_MODE_BVH; s->numPrims = numTris; s->numNodes = h->nodes.size();
 
-	// inner nodes get consecutive ids in pre-order; a leaf is referenced as ~((firstPos << 1) | (count - 1))
-	std::vector<int32_t> innerId(h->nodes.size(), -1);
-	int32_t numInner = 0;
-	for (size_t i = 0; i < h->nodes.size(); i++) if (h->nodes[i].left >= 0) innerId[i] = numInner++;
-	auto refOf = [&](int32_t hostIdx) -> int32_t {
-		const HostBvhNode& n = h->nodes[hostIdx];
-		if (n.left >= 0) return innerId[hostIdx];
-		uint32_t cnt = n.count ? n.count : 1;      // (count 0 only for the empty tree, never referenced)
-		return ~(int32_t)((n.first << 1) | (cnt - 1));
-	};
-	std::vector<float> nodeBuf((size_t)std::max(numInner, 1) * 16, 0.0f);
-	for (size_t i = 0; i < h->nodes.size(); i++) {
-		const HostBvhNode& n = h->nodes[i];
-		if (n.left < 0) continue;
-		float* d = &nodeBuf[(size_t)innerId[i] * 16];
-		const HostBvhNode& L = h->nodes[n.left]; const HostBvhNode& R = h->nodes[n.right];
-		d[0] = L.mn[0]; d[1] = L.mn[1]; d[2] = L.mn[2]; d[3] = L.mx[0]; d[4] = L.mx[1]; d[5] = L.mx[2];
-		d[6] = R.mn[0]; d[7] = R.mn[1]; d[8] = R.mn[2]; d[9] = R.mx[0]; d[10] = R.mx[1]; d[11] = R.mx[2];
-		int32_t r0 = refOf(n.left), r1 = refOf(n.right);
-		std::memcpy(&d[12], &r0, 4); std::memcpy(&d[13], &r1, 4);
-	}
+	// two node arrays over the same reference leaves (rto_internal.h): the reference's own topology for replaying
+	// BVH::query, and a binned-SAH topology for the production closest-hit / shadow traversal
+	std::vector<float> nodeBuf, fastBuf;
+	int32_t refRoot = -1, fastRoot = -1;
+	rto_build_reference_topology(*h, nodeBuf, refRoot);
+	static const bool refTopology = getenv("RTO_BVH_REFERENCE_TOPOLOGY") != nullptr;     // tuning aid: trace through the reference's tree
+	if (!refTopology) rto_build_fast_topology(*h, fastBuf, fastRoot);
 	std::vector<float> triBuf(std::max<size_t>(numTris, 1) * 12, 0.0f);
 	for (size_t p = 0; p < numTris; p++) {
 		uint32_t id = h->order[p];
@@ -284,15 +273,19 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 	D.numTris = (int)numTris;
 	const HostBvhNode& root = h->nodes[0];
 	for (int k = 0; k < 3; k++) { D.rootLo[k] = root.mn[k]; D.rootHi[k] = root.mx[k]; }
-	D.rootRef = numTris ? refOf(0) : -1;
-	void *dN = nullptr, *dT = nullptr;
-	if ((rc = scene_alloc(s, &dN, nodeBuf.size() * 4)) || (rc = scene_alloc(s, &dT, triBuf.size() * 4))) { rto_scene_destroy(s); rto_host_bvh_free(ownedBvh); return rc; }
+	D.rootRef = refRoot;
+	void *dN = nullptr, *dT = nullptr, *dF = nullptr;
+	if ((rc = scene_alloc(s, &dN, nodeBuf.size() * 4)) || (rc = scene_alloc(s, &dT, triBuf.size() * 4)) ||
+		(!fastBuf.empty() && (rc = scene_alloc(s, &dF, fastBuf.size() * 4)))) { rto_scene_destroy(s); rto_host_bvh_free(ownedBvh); return rc; }
 	cudaError_t e = cudaMemcpyAsync(dN, nodeBuf.data(), nodeBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(dT, triBuf.data(), triBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
+	if (e == cudaSuccess && dF) e = cudaMemcpyAsync(dF, fastBuf.data(), fastBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
 	rto_host_bvh_free(ownedBvh);
 	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "BVH upload failed: %s", cudaGetErrorString(e)); }
 	D.nodes = (const float4*)dN; D.tris = (const float4*)dT;
+	s->bvhFast = D;
+	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = fastRoot; }
 	*out = s;
 	return RTO_OK;
 }
@@ -306,17 +299,22 @@ static int check_mode(const RtoScene* s, int mode) {
 	return RTO_OK;
 }
 
-static void launch_render(RtoScene* s, const RenderArgs& A, int width, int numCams, int mode) {
+// BVH scenes: per-thread while-loop kernel; default flags trace the SAH topology with t-pruning, RTO_FLAG_NO_PRUNE
+// visits every box the reference's queryNode visits, on the reference's own topology (verification path).
+// Octree scenes: thread-per-pixel kernel.  (Two other schedulings of the BVH loop were built, measured and removed in
+// round 1 -- a persistent per-lane refill kernel and a warp-phased while-while kernel; see profiles/README.md.)
+static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCams, int mode) {
 	dim3 block(128), grid((width + 15) / 16, (A.y1 - A.y0 + 7) / 8, numCams);
 	if (s->kind == RTO_MODE_BVH) {
 		bool sh = (A.flags & RTO_FLAG_SHADOWS) != 0, prune = (A.flags & RTO_FLAG_NO_PRUNE) == 0;
-		if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, s->stream>>>(s->bvh, A);
+		if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, s->stream>>>(s->bvhFast, A);
+		else if (prune) k_render_bvh<false, true><<<grid, block, 0, s->stream>>>(s->bvhFast, A);
 		else if (sh) k_render_bvh<true, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
-		else if (prune) k_render_bvh<false, true><<<grid, block, 0, s->stream>>>(s->bvh, A);
 		else k_render_bvh<false, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
 	}
 	else k_render_octree<<<grid, block, 0, s->stream>>>(s->oct, A, mode);
 	s->launches++;
+	return RTO_OK;
 }
 
 extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams, int mode, uint32_t flags, float shadowBias,
@@ -346,8 +344,9 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 		if (frame->t) { if ((rc = scene_scratch(s, 2, npix * 4, &p))) return rc; A.t = (float*)p; }
 	}
 	else { A.rgba = (float4*)frame->rgba; A.hitId = frame->hitId; A.t = frame->t; }
+	if ((unsigned long long)npix >= 0xffffffffull) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render: more than 2^32 pixels in one call");
 	CUDA_TRY(cudaEventRecord(s->evStart, s->stream));
-	launch_render(s, A, W, numCams, mode);
+	if ((rc = launch_render(s, A, W, numCams, mode))) return rc;
 	CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
 	s->timed = true;
 	CUDA_TRY(cudaGetLastError());
@@ -405,7 +404,7 @@ extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float
 		if (idOut) { if ((rc = scene_scratch(s, 2, numRays * 4, &p))) return rc; dI = (int32_t*)p; }
 	}
 	unsigned blocks = (unsigned)((numRays + 127) / 128);
-	if (s->kind == RTO_MODE_BVH) k_trace_bvh<<<blocks, 128, 0, s->stream>>>(s->bvh, flags, dO, dD, numRays, dT, dI);
+	if (s->kind == RTO_MODE_BVH) k_trace_bvh<<<blocks, 128, 0, s->stream>>>((flags & RTO_FLAG_NO_PRUNE) ? s->bvh : s->bvhFast, flags, dO, dD, numRays, dT, dI);
 	else k_trace_octree<<<blocks, 128, 0, s->stream>>>(s->oct, mode, dO, dD, numRays, tMin, tMax, dT, dI);
 	s->launches++;
 	CUDA_TRY(cudaGetLastError());

@@ -21,3 +21,15 @@ struct RtoHostBvh {
 	std::vector<HostBvhNode> nodes;            // pre-order: left subtree directly after its parent
 	std::vector<uint32_t>    order;            // triangle ids in leaf (depth-first, left-to-right) order
 };
+
+// ---- device node arrays built from the host BVH (host_builders.cpp) ------------------------------------------
+// Node layout (16 floats): child0 lo xyz, hi xyz; child1 lo xyz, hi xyz; ref0, ref1 (int bits); 2 pad.
+// A ref >= 0 is an inner node index, < 0 is ~((firstPos << 1) | (count - 1)) for a reference leaf whose triangles sit at
+// positions firstPos.. in leaf order.
+//   reference topology: the reference's own tree (pre-order) -- needed to replay BVH::query's visit order and box counts;
+//   fast topology     : a binned-SAH tree over the SAME reference leaves with exact union boxes.  The candidate set of
+//                       BVH::query depends only on which leaf boxes pass the slab test (a leaf box that passes makes every
+//                       enclosing exact box pass, by monotonic rounding), so any tree over the same leaves yields the same
+//                       candidates; only the visit order changes, and the closest-hit rule is order independent.
+void rto_build_reference_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef);
+void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef);

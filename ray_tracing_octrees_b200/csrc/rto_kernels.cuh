@@ -105,6 +105,22 @@ __device__ __forceinline__ bool slab_ref(const RayBox& r, float lox, float loy, 
 	return !(tmax < tmin);
 }
 
+// Fast form of the same test: when all reciprocal direction components are finite and non-zero no NaN can arise, and
+// min/max (FMNMX) of the two plane distances equals the sign-selected form above bit for bit.
+__device__ __forceinline__ bool slab_fast(V3 o, V3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float& tEntry) {
+	float ax = (lox - o.x) * inv.x, bx = (hix - o.x) * inv.x;
+	float ay = (loy - o.y) * inv.y, by = (hiy - o.y) * inv.y;
+	float az = (loz - o.z) * inv.z, bz = (hiz - o.z) * inv.z;
+	float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+	float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), FLT_MAX));
+	tEntry = tmin;
+	return !(tmax < tmin);
+}
+__device__ __forceinline__ bool ray_needs_exact_box(const RayBox& rb) {
+	float ax = fabsf(rb.inv.x), ay = fabsf(rb.inv.y), az = fabsf(rb.inv.z);
+	return !(ax > 0.0f && ax <= FLT_MAX && ay > 0.0f && ay <= FLT_MAX && az > 0.0f && az <= FLT_MAX);
+}
+
 struct TriV { V3 v0, v1, v2; int id; };
 __device__ __forceinline__ TriV load_tri(const float4* __restrict__ tris, int pos) {
 	float4 a = __ldg(tris + 3 * (size_t)pos), b = __ldg(tris + 3 * (size_t)pos + 1), c = __ldg(tris + 3 * (size_t)pos + 2);
@@ -147,13 +163,16 @@ __device__ __forceinline__ void bvh_closest(const BvhDev& S, V3 o, V3 d, float& 
 	int sp = 0;
 	int cur = S.rootRef;
 	float tcut = kMissT * kPruneSlack;
+	const bool exactBox = ray_needs_exact_box(rb);
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), r = __ldg(n + 3);
+			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2);
+			float2 r = __ldg(reinterpret_cast<const float2*>(n + 3));
 			float e0, e1;
-			bool h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0);
-			bool h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1);
+			bool h0, h1;
+			if (!exactBox) { h0 = slab_fast(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_fast(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
+			else { h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
 			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
 			if (PRUNE) { h0 = h0 && (e0 <= tcut); h1 = h1 && (e1 <= tcut); }
 			if (h0 && h1) {
@@ -197,13 +216,16 @@ __device__ __forceinline__ bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 	int stackRef[kBvhStack];
 	int sp = 0;
 	int cur = S.rootRef;
+	const bool exactBox = ray_needs_exact_box(rb);
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), r = __ldg(n + 3);
+			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2);
+			float2 r = __ldg(reinterpret_cast<const float2*>(n + 3));
 			float e0, e1;
-			bool h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0);
-			bool h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1);
+			bool h0, h1;
+			if (!exactBox) { h0 = slab_fast(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_fast(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
+			else { h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
 			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
 			if (h0 && h1) {
 				bool swap = e1 < e0;
@@ -471,7 +493,6 @@ __device__ __forceinline__ OctHit octA_general(const OctDev& S, V3 o, V3 d, floa
 	unsigned visits = 0;
 	int cur = 0; float curMin = tMin, curMax = tMax;
 	while (true) {
-		bool descended = false;
 		if (cur >= 0 && cur < S.numNodes) {
 			visits++;
 			const int4* n = S.nodes16 + 4 * (size_t)cur;
@@ -484,11 +505,9 @@ __device__ __forceinline__ OctHit octA_general(const OctDev& S, V3 o, V3 d, floa
 				}
 				else if (depth < kMaxOctDepth) {
 					nodeS[depth] = cur; posS[depth] = 0; minS[depth] = enterT; maxS[depth] = exitT; depth++;
-					descended = true;
 				}
 			}
 		}
-		(void)descended;
 		// take the next child of the innermost open frame
 		bool found = false;
 		while (depth > 0) {
