@@ -243,15 +243,19 @@ def run_ours(args, rank, world, local_rank):
     # ---- optional: NCCL framebuffer gather to rank 0 (the one collective of the path), timed separately --------
     gather = None
     if world > 1:
-        bufs = [torch.empty_like(hid) for _ in range(world)] if rank == 0 else None
+        from ray_tracing_octrees_b200 import sharding
+        sharding.gather_planes(hid, dst=0)                      # warm up the communicator
         torch.cuda.synchronize(); dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.gather(hid, bufs, dst=0)
+        for plane in (rgba, hid, tt):
+            sharding.gather_planes(plane, dst=0)
         g1.record(); torch.cuda.synchronize()
         gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather = {"plane": "hitId", "bytes_per_rank": hid.numel() * 4, "ms": float(gms.item())}
+        nbytes = rgba.numel() * 4 + hid.numel() * 4 + tt.numel() * 4
+        gather = {"what": "all three planes of one step (F frames) from every rank to rank 0 over NCCL", "bytes_per_rank": nbytes,
+                  "ms": float(gms.item()), "GBps_into_rank0": nbytes * (world - 1) / (float(gms.item()) * 1e-3) / 1e9}
 
     if rank != 0:
         if world > 1:

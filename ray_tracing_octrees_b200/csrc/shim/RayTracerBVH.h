@@ -1,0 +1,118 @@
+// RayTracerBVH.h (shim) -- the reference's ray caster class (453-skeleton/RayTracerBVH.h:15-80) without OpenGL.
+// setOctree / ensureComputeInitialized / renderSceneCompute keep their signatures; the frame lands in a host Framebuffer
+// (frame()) instead of a GL texture.  render(..., Framebuffer&) and setMesh() are the north-star extensions.
+#pragma once
+#include "BVH.h"
+#include "Camera.h"
+#include "OctreeVoxel.h"
+#include <cstdio>
+#include <queue>
+#include <unordered_map>
+
+struct Ray { rto_shim::vec3 origin, direction; };                          // RayTracerBVH.h:15-18
+struct GPUNodes { int x, y, z, size; int isLeaf, isSolid; int isUniform; int child[8]; };   // RayTracerBVH.h:21-26
+static_assert(sizeof(GPUNodes) == sizeof(RtoGpuNode), "GPUNodes must be 15 x int32");
+
+struct Framebuffer {                       // host copy of one frame: row 0 = top scanline
+	int width = 0, height = 0;
+	std::vector<float> rgba;               // 4 floats per pixel (RGBA32F like the reference's output texture)
+	std::vector<int32_t> hitId;            // octree: node index == leaf id of setOctree's BFS numbering; mesh: triangle index; -1 miss
+	std::vector<float> t;                  // hit distance, 1e30f on miss
+};
+
+class RayTracerBVH {
+public:
+	RayTracerBVH() = default;
+	~RayTracerBVH() { rto_scene_destroy(m_scene); }
+	RayTracerBVH(const RayTracerBVH&) = delete;
+	RayTracerBVH& operator=(const RayTracerBVH&) = delete;
+
+	// RayTracerBVH.cpp:430-505: BFS flatten (root = 0, discovery order) and upload.  setOctree(nullptr, ...) clears.
+	void setOctree(OctreeNode* root, const VoxelGrid& grid) {
+		m_flatNodes.clear();
+		rto_scene_destroy(m_scene); m_scene = nullptr; m_mode = RTO_MODE_OCTREE_GLSL;
+		if (!root) return;
+		std::queue<OctreeNode*> q; std::unordered_map<OctreeNode*, int> index;
+		q.push(root); index[root] = 0;
+		m_flatNodes.push_back(GPUNodes{ 0, 0, 0, 0, 0, 0, 0, { -1, -1, -1, -1, -1, -1, -1, -1 } });
+		while (!q.empty()) {
+			OctreeNode* nd = q.front(); q.pop();
+			int idx = index[nd];
+			GPUNodes g{ nd->x, nd->y, nd->z, nd->size, nd->isLeaf ? 1 : 0, nd->isSolid ? 1 : 0, nd->isUniform ? 1 : 0, { -1, -1, -1, -1, -1, -1, -1, -1 } };
+			if (!nd->isLeaf)
+				for (int i = 0; i < 8; i++) if (OctreeNode* c = nd->children[i]) {
+					auto it = index.find(c);
+					if (it == index.end()) { it = index.emplace(c, (int)m_flatNodes.size()).first; m_flatNodes.push_back(GPUNodes{ 0, 0, 0, 0, 0, 0, 0, { -1, -1, -1, -1, -1, -1, -1, -1 } }); }
+					g.child[i] = it->second; q.push(c);
+				}
+			m_flatNodes[idx] = g;
+		}
+		float gmin[3] = { grid.minX, grid.minY, grid.minZ };
+		if (rto_scene_create_octree(reinterpret_cast<const RtoGpuNode*>(m_flatNodes.data()), m_flatNodes.size(), gmin, grid.voxelSize, &m_scene) != RTO_OK)
+			std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error());
+	}
+	// extension: ray cast a triangle soup through the reference-shaped BVH
+	void setMesh(const BVH& bvh, float sceneScale) { rto_scene_destroy(m_scene); m_scene = nullptr; m_external = bvh.scene(); m_mode = RTO_MODE_BVH; m_shadowBias = 1e-3f * sceneScale; }
+
+	void ensureComputeInitialized() { if (!m_inited && rto_init(0) == RTO_OK) m_inited = true; else if (!m_inited) std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); }
+	void setFrustumCullingEnabled(bool) {}                                 // culling changes hit results; parity path is unculled
+	void setTraversalMode(int mode) { m_mode = mode; }                      // RTO_MODE_OCTREE_GLSL (reference shader) or RTO_MODE_OCTREE_SKIP
+	void setShadows(bool on) { m_flags = on ? RTO_FLAG_SHADOWS : 0u; }
+
+	// RayTracerBVH.cpp:614-704.  Like the reference, errors are printed and the frame is left untouched.
+	void renderSceneCompute(const Camera& camera, int width, int height, float aspect, float fovDeg) { render(camera, width, height, aspect, fovDeg, m_frame); }
+	void renderSceneComputeWithCulling(const Camera& camera, int width, int height, float aspect, float fovDeg, bool) { renderSceneCompute(camera, width, height, aspect, fovDeg); }
+	bool render(const Camera& camera, int width, int height, float aspect, float fovDeg, Framebuffer& fb) {
+		RtoScene* sc = m_scene ? m_scene : m_external;
+		if (!m_inited) { std::fprintf(stderr, "[RayTracerBVH] Compute pipeline not initialized or failed.\n"); return false; }
+		if (!sc) return false;                                             // no data: skip (RayTracerBVH.cpp:624-627)
+		RtoCamera cam;
+		if (camera.consts(fovDeg, aspect, width, height, cam, nullptr) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
+		fb.width = width; fb.height = height;
+		fb.rgba.resize((size_t)width * height * 4); fb.hitId.resize((size_t)width * height); fb.t.resize((size_t)width * height);
+		RtoFrame fr{ fb.rgba.data(), fb.hitId.data(), fb.t.data(), RTO_MEM_HOST };
+		if (rto_render(sc, &cam, m_mode, m_flags, m_shadowBias, 0, height, &fr) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
+		return true;
+	}
+	const Framebuffer& frame() const { return m_frame; }
+	const std::vector<GPUNodes>& flatNodes() const { return m_flatNodes; }
+
+private:
+	std::vector<GPUNodes> m_flatNodes;
+	RtoScene* m_scene = nullptr;
+	RtoScene* m_external = nullptr;       // owned by a BVH (setMesh)
+	int m_mode = RTO_MODE_OCTREE_GLSL;
+	unsigned m_flags = 0;
+	float m_shadowBias = 0.0f;
+	bool m_inited = false;
+	Framebuffer m_frame;
+};
+
+inline std::vector<MCTriangle> rto_shim_marching_cubes(const OctreeNode* root, const VoxelGrid& grid) {
+	std::vector<MCTriangle> out;
+	if (!root) return out;
+	// flatten for librto (any order works for the mesh as long as child links are consistent: use BFS like setOctree)
+	std::vector<RtoGpuNode> flat; std::vector<const OctreeNode*> order; std::unordered_map<const OctreeNode*, int> index;
+	order.push_back(root); index[root] = 0;
+	for (size_t i = 0; i < order.size(); i++) {
+		const OctreeNode* nd = order[i];
+		RtoGpuNode g{ nd->x, nd->y, nd->z, nd->size, nd->isLeaf ? 1 : 0, nd->isSolid ? 1 : 0, nd->isUniform ? 1 : 0, { -1, -1, -1, -1, -1, -1, -1, -1 } };
+		if (!nd->isLeaf) for (int c = 0; c < 8; c++) if (nd->children[c]) { index[nd->children[c]] = (int)order.size(); g.child[c] = (int)order.size(); order.push_back(nd->children[c]); }
+		flat.push_back(g);
+	}
+	RtoTriangle* tris = nullptr; size_t n = 0;
+	float gmin[3] = { grid.minX, grid.minY, grid.minZ };
+	if (rto_host_mc_mesh(reinterpret_cast<const uint8_t*>(grid.data.data()), grid.dimX, grid.dimY, grid.dimZ, gmin, grid.voxelSize, flat.data(), flat.size(), &tris, &n) != RTO_OK) return out;
+	out.resize(n);
+	for (size_t i = 0; i < n; i++) {
+		const float* v = tris[i].v0;
+		for (int k = 0; k < 3; k++) out[i].v[k] = rto_shim::vec3(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+		// flat normal as localMC computes it: normalize(cross(e1, e2)) in glm operation order
+		float e1[3] = { v[3] - v[0], v[4] - v[1], v[5] - v[2] }, e2[3] = { v[6] - v[0], v[7] - v[1], v[8] - v[2] };
+		float cx = e1[1] * e2[2] - e2[1] * e1[2], cy = e1[2] * e2[0] - e2[2] * e1[0], cz = e1[0] * e2[1] - e2[0] * e1[1];
+		float il = 1.0f / __builtin_sqrtf((cx * cx + cy * cy) + cz * cz);
+		for (int k = 0; k < 3; k++) out[i].normal[k] = rto_shim::vec3(cx * il, cy * il, cz * il);
+	}
+	rto_host_free(tris);
+	return out;
+}
