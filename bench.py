@@ -196,10 +196,12 @@ def run_ours(args, rank, world, local_rank):
     launches = scene.launch_count - launches0
     clocks = sampler.stop()
     # rays actually traced: primaries + one shadow ray per primary hit (counted on the device, outside the timed region)
+    rays_per_step = []
     for k in range(args.steps):
         step_device(args.warmup + k)
         torch.cuda.synchronize()
-        rays += F * W * H + int((hid >= 0).sum().item())
+        rays_per_step.append(F * W * H + int((hid >= 0).sum().item()))
+    rays = sum(rays_per_step)
 
     # ---- kernel duration for the roofline (CUDA events on the launching stream around each launch) ------------
     if not kern_ms:
@@ -222,12 +224,12 @@ def run_ours(args, rank, world, local_rank):
         step_host(k)
     sync_all()
     te = time.perf_counter()
-    e2e_rays = 0
     for k in range(e2e_steps):
-        step_host(args.warmup + k)
-        e2e_rays += F * W * H + int((h_id >= 0).sum().item())
+        step_host(args.warmup + k)                      # synchronous: returns when the planes are in host memory
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - te
+    e2e_rays = sum(rays_per_step[:e2e_steps])            # same frames as the device-timed steps
+    assert int((h_id >= 0).sum().item()) + F * W * H == rays_per_step[e2e_steps - 1], "host planes differ from device planes"
     if world > 1:
         dist.barrier()
 
@@ -326,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "frames sharded over %d GPU(s), scene replicated" % world, "scene_build_s": build_s},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": F * ctypes.sizeof(rto.RtoCamera), "d2h_bytes_per_step": F * W * H * 24,
-                    "steps": e2e_steps, "api": "rto_render_batch(RTO_MEM_HOST) into pinned host planes"},
+                    "steps": e2e_steps, "api": "rto_render_batch(RTO_MEM_HOST) into pinned host planes; per-frame D2H overlaps the next frame's kernel"},
             "gpu_launches": int(launches_all),
             "roofline": roofline, "cpu_baseline": cpu}
     if gather:

@@ -68,7 +68,8 @@ struct RtoScene {
 	int kind = RTO_MODE_BVH;          // RTO_MODE_BVH or RTO_MODE_OCTREE_GLSL (any octree)
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	cudaStream_t copyStream = nullptr;            // device->host plane copies of RTO_MEM_HOST batches overlap the next frame's kernel
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evFrame = nullptr;
 	bool timed = false;
 	uint64_t launches = 0;
 	size_t deviceBytes = 0, numPrims = 0, numNodes = 0;
@@ -110,6 +111,8 @@ static int scene_new(RtoScene** out) {
 	if (!s) return rto_fail(RTO_ERR_ALLOC, "out of host memory");
 	cudaError_t e = cudaGetDevice(&s->device);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->evFrame, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreate(&s->evStart);
 	if (e == cudaSuccess) e = cudaEventCreate(&s->evStop);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->smCount, cudaDevAttrMultiProcessorCount, s->device);
@@ -126,6 +129,8 @@ extern "C" void rto_scene_destroy(RtoScene* s) {
 	for (void* p : s->scratch) if (p) cudaFree(p);
 	if (s->evStart) cudaEventDestroy(s->evStart);
 	if (s->evStop) cudaEventDestroy(s->evStop);
+	if (s->evFrame) cudaEventDestroy(s->evFrame);
+	if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }
@@ -346,6 +351,27 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 	else { A.rgba = (float4*)frame->rgba; A.hitId = frame->hitId; A.t = frame->t; }
 	if ((unsigned long long)npix >= 0xffffffffull) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render: more than 2^32 pixels in one call");
 	CUDA_TRY(cudaEventRecord(s->evStart, s->stream));
+	if (host && numCams > 1) {
+		// one launch per frame; the planes of frame i travel to the host on the copy stream while frame i+1 is traced
+		const size_t fpix = (size_t)(y1 - y0) * W;
+		for (int c = 0; c < numCams; c++) {
+			RenderArgs Ac = A;
+			Ac.cam0 = cams[c]; Ac.cams = nullptr;
+			Ac.rgba = A.rgba ? A.rgba + c * fpix : nullptr; Ac.hitId = A.hitId ? A.hitId + c * fpix : nullptr; Ac.t = A.t ? A.t + c * fpix : nullptr;
+			if ((rc = launch_render(s, Ac, W, 1, mode))) return rc;
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaEventRecord(s->evFrame, s->stream));
+			CUDA_TRY(cudaStreamWaitEvent(s->copyStream, s->evFrame, 0));
+			if (frame->rgba) CUDA_TRY(cudaMemcpyAsync(frame->rgba + 4 * c * fpix, Ac.rgba, fpix * 16, cudaMemcpyDeviceToHost, s->copyStream));
+			if (frame->hitId) CUDA_TRY(cudaMemcpyAsync(frame->hitId + c * fpix, Ac.hitId, fpix * 4, cudaMemcpyDeviceToHost, s->copyStream));
+			if (frame->t) CUDA_TRY(cudaMemcpyAsync(frame->t + c * fpix, Ac.t, fpix * 4, cudaMemcpyDeviceToHost, s->copyStream));
+		}
+		CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
+		s->timed = true;
+		CUDA_TRY(cudaStreamSynchronize(s->copyStream));
+		CUDA_TRY(cudaStreamSynchronize(s->stream));
+		return RTO_OK;
+	}
 	if ((rc = launch_render(s, A, W, numCams, mode))) return rc;
 	CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
 	s->timed = true;
