@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librto.so")
-SOURCES = ["rto_device.cu", "host_builders.cpp"]
+SOURCES = ["rto_device.cu", "host_builders.cpp", "host_layouts.cpp"]
 DEPS = SOURCES + ["rto_kernels.cuh", "rto_internal.h", "rto_math.h", "mc_tables.h", "../../include/rto_c.h"]
 
 

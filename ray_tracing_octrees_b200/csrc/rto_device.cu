@@ -162,81 +162,36 @@ extern "C" int rto_scene_last_kernel_ms(RtoScene* s, float* ms) {
 // ------------------------------------------------------------------------------------------------
 // octree upload: RayTracerBVH::setOctree's SSBO (RayTracerBVH.cpp:492-504) -> pointer-free device arrays
 // ------------------------------------------------------------------------------------------------
-// The compact layout needs the shape the reference builder always produces: every internal node has 8 children
-// with consecutive indices, child boxes are the 8 octants of the parent, leaf <=> uniform.
-static bool octree_is_compactable(const RtoGpuNode* n, size_t count) {
-	if (count == 0 || n[0].x != 0 || n[0].y != 0 || n[0].z != 0 || n[0].size <= 0 || (n[0].size & (n[0].size - 1))) return false;
-	if (count >= 0x3fffffffu) return false;
-	std::vector<uint8_t> seen(count, 0);
-	seen[0] = 1;
-	for (size_t i = 0; i < count; i++) {
-		const RtoGpuNode& p = n[i];
-		bool leafLike = (p.isLeaf == 1) || (p.isUniform == 1);
-		if (p.isLeaf != 0 && p.isLeaf != 1) return false;
-		if (p.isUniform != p.isLeaf) return false;
-		if (p.isSolid != 0 && p.isSolid != 1) return false;
-		if (leafLike) continue;
-		int first = p.child[0];
-		if (first <= 0 || ((first - 1) & 7) != 0 || (size_t)first + 7 >= count || p.size < 2) return false;
-		int half = p.size / 2;
-		for (int c = 0; c < 8; c++) {
-			if (p.child[c] != first + c) return false;
-			const RtoGpuNode& q = n[first + c];
-			if (q.size != half || q.x != p.x + ((c & 1) ? half : 0) || q.y != p.y + ((c & 2) ? half : 0) || q.z != p.z + ((c & 4) ? half : 0)) return false;
-			if (seen[first + c]) return false;
-			seen[first + c] = 1;
-		}
-	}
-	for (size_t i = 0; i < count; i++) if (!seen[i]) return false;
-	return true;
-}
-
 extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, RtoScene** out) {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: null output");
 	*out = nullptr;
 	if (!nodes || numNodes == 0 || !gridMin) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: empty octree (the reference's setOctree(nullptr) clears the scene; nothing to trace)");
-	if (numNodes > (size_t)0x7fffff00) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_scene_create_octree: too many nodes");
-	for (size_t i = 0; i < numNodes; i++)
-		for (int c = 0; c < 8; c++)
-			if (nodes[i].child[c] >= (int64_t)numNodes) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: node %zu child %d out of range", i, c);
+	OctLayout L;
+	int rc = rto_build_octree_layout(nodes, numNodes, L); if (rc) return rc;
 	RtoScene* s = nullptr;
-	int rc = scene_new(&s); if (rc) return rc;
+	rc = scene_new(&s); if (rc) return rc;
 	s->kind = RTO_MODE_OCTREE_GLSL;
-	s->numNodes = numNodes;
-	size_t leaves = 0;
-	for (size_t i = 0; i < numNodes; i++) leaves += nodes[i].isLeaf ? 1 : 0;
-	s->numPrims = leaves;
+	s->numNodes = numNodes; s->numPrims = L.numLeaves;
 	OctDev& D = s->oct;
 	D.numNodes = (int)numNodes; D.rootSize = nodes[0].size;
 	D.gmin[0] = gridMin[0]; D.gmin[1] = gridMin[1]; D.gmin[2] = gridMin[2]; D.voxel = voxelSize;
-	D.compact = octree_is_compactable(nodes, numNodes) ? 1 : 0;
-	if (D.compact) {
-		// desc[] is offset by 7 words so that every sibling group (indices 1+8g .. 8+8g) is one aligned 32-byte sector
-		std::vector<uint32_t> desc(numNodes + 8, 0);
-		std::vector<int32_t> up((numNodes + 7) / 8 + 1, 0);
-		for (size_t i = 0; i < numNodes; i++) {
-			const RtoGpuNode& p = nodes[i];
-			if (p.isLeaf) desc[7 + i] = kOctLeaf | (p.isSolid ? kOctSolid : 0u);
-			else { desc[7 + i] = (uint32_t)p.child[0]; up[(p.child[0] - 1) >> 3] = (int32_t)i; }
-		}
-		void *dDesc = nullptr, *dUp = nullptr;
-		if ((rc = scene_alloc(s, &dDesc, desc.size() * 4)) || (rc = scene_alloc(s, &dUp, up.size() * 4))) { rto_scene_destroy(s); return rc; }
-		cudaError_t e = cudaMemcpyAsync(dDesc, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, s->stream);
-		if (e == cudaSuccess) e = cudaMemcpyAsync(dUp, up.data(), up.size() * 4, cudaMemcpyHostToDevice, s->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-		if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "octree upload failed: %s", cudaGetErrorString(e)); }
-		D.desc = (const uint32_t*)dDesc + 7; D.up = (const int32_t*)dUp;
+	D.compact = L.compact ? 1 : 0;
+	auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+		int r = scene_alloc(s, dst, bytes); if (r) return r;
+		cudaError_t e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s->stream);
+		return e == cudaSuccess ? RTO_OK : rto_fail(RTO_ERR_CUDA, "octree upload failed: %s", cudaGetErrorString(e));
+	};
+	void *dDesc = nullptr, *dUp = nullptr, *dInner = nullptr, *dN = nullptr;
+	if (L.compact) {
+		if ((rc = up(L.desc.data(), L.desc.size() * 4, &dDesc)) || (rc = up(L.up.data(), L.up.size() * 4, &dUp)) || (rc = up(L.inner.data(), L.inner.size() * 4, &dInner))) { rto_scene_destroy(s); return rc; }
+		D.desc = (const uint32_t*)dDesc + 7; D.up = (const int32_t*)dUp; D.inner = (const int4*)dInner;
 	}
 	else {
-		std::vector<int32_t> padded(numNodes * 16, -1);
-		for (size_t i = 0; i < numNodes; i++) std::memcpy(&padded[16 * i], &nodes[i], sizeof(RtoGpuNode));
-		void* dN = nullptr;
-		if ((rc = scene_alloc(s, &dN, padded.size() * 4))) { rto_scene_destroy(s); return rc; }
-		cudaError_t e = cudaMemcpyAsync(dN, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, s->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-		if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "octree upload failed: %s", cudaGetErrorString(e)); }
+		if ((rc = up(L.padded.data(), L.padded.size() * 4, &dN))) { rto_scene_destroy(s); return rc; }
 		D.nodes16 = (const int4*)dN;
 	}
+	cudaError_t e = cudaStreamSynchronize(s->stream);
+	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "octree upload failed: %s", cudaGetErrorString(e)); }
 	*out = s;
 	return RTO_OK;
 }
@@ -259,38 +214,24 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 	if (rc) { rto_host_bvh_free(ownedBvh); return rc; }
 	s->kind = RTO_MODE_BVH; s->numPrims = numTris; s->numNodes = h->nodes.size();
 
-	// two node arrays over the same reference leaves (rto_internal.h): the reference's own topology for replaying
-	// BVH::query, and a binned-SAH topology for the production closest-hit / shadow traversal
-	std::vector<float> nodeBuf, fastBuf;
-	int32_t refRoot = -1, fastRoot = -1;
-	rto_build_reference_topology(*h, nodeBuf, refRoot);
-	static const bool refTopology = getenv("RTO_BVH_REFERENCE_TOPOLOGY") != nullptr;     // tuning aid: trace through the reference's tree
-	if (!refTopology) rto_build_fast_topology(*h, fastBuf, fastRoot);
-	std::vector<float> triBuf(std::max<size_t>(numTris, 1) * 12, 0.0f);
-	for (size_t p = 0; p < numTris; p++) {
-		uint32_t id = h->order[p];
-		float* d = &triBuf[p * 12];
-		std::memcpy(d, &tris[id], 36);
-		int32_t iid = (int32_t)id;
-		std::memcpy(&d[9], &iid, 4);
-	}
+	BvhLayout L;
+	rto_build_bvh_layout(*h, L);
+	rto_host_bvh_free(ownedBvh);
 	BvhDev& D = s->bvh;
 	D.numTris = (int)numTris;
-	const HostBvhNode& root = h->nodes[0];
-	for (int k = 0; k < 3; k++) { D.rootLo[k] = root.mn[k]; D.rootHi[k] = root.mx[k]; }
-	D.rootRef = refRoot;
+	for (int k = 0; k < 3; k++) { D.rootLo[k] = L.rootLo[k]; D.rootHi[k] = L.rootHi[k]; }
+	D.rootRef = L.refRoot;
 	void *dN = nullptr, *dT = nullptr, *dF = nullptr;
-	if ((rc = scene_alloc(s, &dN, nodeBuf.size() * 4)) || (rc = scene_alloc(s, &dT, triBuf.size() * 4)) ||
-		(!fastBuf.empty() && (rc = scene_alloc(s, &dF, fastBuf.size() * 4)))) { rto_scene_destroy(s); rto_host_bvh_free(ownedBvh); return rc; }
-	cudaError_t e = cudaMemcpyAsync(dN, nodeBuf.data(), nodeBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(dT, triBuf.data(), triBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
-	if (e == cudaSuccess && dF) e = cudaMemcpyAsync(dF, fastBuf.data(), fastBuf.size() * 4, cudaMemcpyHostToDevice, s->stream);
+	if ((rc = scene_alloc(s, &dN, L.refNodes.size() * 4)) || (rc = scene_alloc(s, &dT, L.tris.size() * 4)) ||
+		(!L.fastNodes.empty() && (rc = scene_alloc(s, &dF, L.fastNodes.size() * 4)))) { rto_scene_destroy(s); return rc; }
+	cudaError_t e = cudaMemcpyAsync(dN, L.refNodes.data(), L.refNodes.size() * 4, cudaMemcpyHostToDevice, s->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dT, L.tris.data(), L.tris.size() * 4, cudaMemcpyHostToDevice, s->stream);
+	if (e == cudaSuccess && dF) e = cudaMemcpyAsync(dF, L.fastNodes.data(), L.fastNodes.size() * 4, cudaMemcpyHostToDevice, s->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-	rto_host_bvh_free(ownedBvh);
 	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "BVH upload failed: %s", cudaGetErrorString(e)); }
 	D.nodes = (const float4*)dN; D.tris = (const float4*)dT;
 	s->bvhFast = D;
-	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = fastRoot; }
+	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = L.fastRoot; }
 	*out = s;
 	return RTO_OK;
 }

@@ -33,3 +33,22 @@ struct RtoHostBvh {
 //                       candidates; only the visit order changes, and the closest-hit rule is order independent.
 void rto_build_reference_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef);
 void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef);
+
+// ---- device layouts, built on the host (host_layouts.cpp) and uploaded verbatim by rto_device.cu --------------
+struct OctLayout {
+	bool compact = false;
+	size_t numLeaves = 0;
+	std::vector<uint32_t> desc;     // compact: 7 pad words + one word per node (bit31 leaf, bit30 solid, else first child)
+	std::vector<int32_t>  up;       // compact: parent node of sibling group (node - 1) >> 3
+	std::vector<int32_t>  inner;    // compact: 4 ints per internal node (first child, rank of first internal child, parent rank,
+	                                //          leafMask | solidMask << 8 | own octant << 16), ranked in BFS order
+	std::vector<int32_t>  padded;   // general: RtoGpuNode padded to 16 ints
+};
+int rto_build_octree_layout(const RtoGpuNode* nodes, size_t numNodes, OctLayout& out);
+
+struct BvhLayout {
+	std::vector<float> refNodes, fastNodes, tris;     // 16 floats per inner node; 12 floats per triangle (leaf order, id in [9])
+	int32_t refRoot = -1, fastRoot = -1;
+	float rootLo[3] = { 0, 0, 0 }, rootHi[3] = { 0, 0, 0 };
+};
+void rto_build_bvh_layout(const RtoHostBvh& h, BvhLayout& out);

@@ -14,9 +14,48 @@
 #pragma once
 #include "rto_internal.h"
 #include <cfloat>
+#include <cstring>
 #include <cuda_runtime.h>
 
+// Traversal code is written once and is callable from device code (the product) and from host code (tests/emu, which runs
+// the very same functions on the CPU so that logic errors are found without a GPU).  librto.so never calls them on the host.
+#define RTO_DEV __host__ __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
+#define RTO_LDG(p) __ldg(p)
+#else
+#define RTO_LDG(p) (*(p))
+#endif
+
 namespace rto {
+
+RTO_DEV int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+	return f2i(f);
+#else
+	int i; std::memcpy(&i, &f, 4); return i;
+#endif
+}
+RTO_DEV int clz32(unsigned v) {
+#if defined(__CUDA_ARCH__)
+	return __clz((int)v);
+#else
+	return v ? __builtin_clz(v) : 32;
+#endif
+}
+RTO_DEV int popc32(unsigned v) {
+#if defined(__CUDA_ARCH__)
+	return popc32(v);
+#else
+	return __builtin_popcount(v);
+#endif
+}
+RTO_DEV int ffs32(unsigned v) {
+#if defined(__CUDA_ARCH__)
+	return __ffs((int)v);
+#else
+	return __builtin_ffs((int)v);
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------
 // Device scene descriptors (passed by value as kernel parameters)
@@ -33,6 +72,8 @@ struct OctDev {
 	const uint32_t* desc;    // compact layout: per node, bit31 = leaf, bit30 = solid, else index of first child (8 contiguous)
 	const int32_t*  up;      // compact layout: parent node of sibling group g = (node - 1) >> 3
 	const int4*     nodes16; // general layout: RtoGpuNode padded to 16 x int32
+	const int4*     inner;   // compact layout, one 16-byte record per INTERNAL node in BFS order (rank): x = index of first child,
+	                         // y = rank of the first internal child, z = rank of the parent, w = leafMask | solidMask<<8 | childIdx<<16
 	int   numNodes;
 	int   rootSize;
 	int   compact;
@@ -54,7 +95,7 @@ struct Ray { V3 o, d; };
 // ------------------------------------------------------------------------------------------------
 // Pixel ray: GLSL generateRay (RayTracerBVH.cpp:338-355) with inverse(view), tan(fov/2) from the host
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Ray gen_ray(const RtoCamera& c, int px, int py) {
+RTO_DEV Ray gen_ray(const RtoCamera& c, int px, int py) {
 	float nx = (float(px) + 0.5f) / float(c.width) * 2.0f - 1.0f;
 	float ny = 1.0f - (float(py) + 0.5f) / float(c.height) * 2.0f;
 	nx *= c.aspect;
@@ -81,7 +122,7 @@ __device__ __forceinline__ Ray gen_ray(const RtoCamera& c, int px, int py) {
 struct RayBox {            // per-ray constants of BVH::query (BVH.cpp:107-113)
 	V3 o, inv; bool nx, ny, nz;
 };
-__device__ __forceinline__ RayBox make_raybox(V3 o, V3 d) {
+RTO_DEV RayBox make_raybox(V3 o, V3 d) {
 	RayBox r; r.o = o;
 	r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 	r.nx = r.inv.x < 0; r.ny = r.inv.y < 0; r.nz = r.inv.z < 0;
@@ -90,7 +131,7 @@ __device__ __forceinline__ RayBox make_raybox(V3 o, V3 d) {
 
 // intersectAABB (BVH.cpp:76-87) with tmin = 0, tmax = FLT_MAX.  The per-axis early-outs of the reference are
 // equivalent to one final test because tmin only grows and tmax only shrinks (NaN candidates are never taken).
-__device__ __forceinline__ bool slab_ref(const RayBox& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float& tEntry) {
+RTO_DEV bool slab_ref(const RayBox& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float& tEntry) {
 	float tmin = 0.0f, tmax = FLT_MAX;
 	float t0 = ((r.nx ? hix : lox) - r.o.x) * r.inv.x;
 	float t1 = ((r.nx ? lox : hix) - r.o.x) * r.inv.x;
@@ -107,7 +148,7 @@ __device__ __forceinline__ bool slab_ref(const RayBox& r, float lox, float loy, 
 
 // Fast form of the same test: when all reciprocal direction components are finite and non-zero no NaN can arise, and
 // min/max (FMNMX) of the two plane distances equals the sign-selected form above bit for bit.
-__device__ __forceinline__ bool slab_fast(V3 o, V3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float& tEntry) {
+RTO_DEV bool slab_fast(V3 o, V3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float& tEntry) {
 	float ax = (lox - o.x) * inv.x, bx = (hix - o.x) * inv.x;
 	float ay = (loy - o.y) * inv.y, by = (hiy - o.y) * inv.y;
 	float az = (loz - o.z) * inv.z, bz = (hiz - o.z) * inv.z;
@@ -116,21 +157,21 @@ __device__ __forceinline__ bool slab_fast(V3 o, V3 inv, float lox, float loy, fl
 	tEntry = tmin;
 	return !(tmax < tmin);
 }
-__device__ __forceinline__ bool ray_needs_exact_box(const RayBox& rb) {
+RTO_DEV bool ray_needs_exact_box(const RayBox& rb) {
 	float ax = fabsf(rb.inv.x), ay = fabsf(rb.inv.y), az = fabsf(rb.inv.z);
 	return !(ax > 0.0f && ax <= FLT_MAX && ay > 0.0f && ay <= FLT_MAX && az > 0.0f && az <= FLT_MAX);
 }
 
 struct TriV { V3 v0, v1, v2; int id; };
-__device__ __forceinline__ TriV load_tri(const float4* __restrict__ tris, int pos) {
-	float4 a = __ldg(tris + 3 * (size_t)pos), b = __ldg(tris + 3 * (size_t)pos + 1), c = __ldg(tris + 3 * (size_t)pos + 2);
+RTO_DEV TriV load_tri(const float4* __restrict__ tris, int pos) {
+	float4 a = RTO_LDG(tris + 3 * (size_t)pos), b = RTO_LDG(tris + 3 * (size_t)pos + 1), c = RTO_LDG(tris + 3 * (size_t)pos + 2);
 	TriV t;
-	t.v0 = mk3(a.x, a.y, a.z); t.v1 = mk3(a.w, b.x, b.y); t.v2 = mk3(b.z, b.w, c.x); t.id = __float_as_int(c.y);
+	t.v0 = mk3(a.x, a.y, a.z); t.v1 = mk3(a.w, b.x, b.y); t.v2 = mk3(b.z, b.w, c.x); t.id = f2i(c.y);
 	return t;
 }
 
 // Moller-Trumbore, SURVEY.md 8c rule (every comparison rejects NaN)
-__device__ __forceinline__ bool moller_trumbore(const TriV& tri, V3 o, V3 d, float& tOut) {
+RTO_DEV bool moller_trumbore(const TriV& tri, V3 o, V3 d, float& tOut) {
 	V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
 	V3 p = cross3(d, e2);
 	float det = dot3(e1, p);
@@ -152,7 +193,7 @@ __device__ __forceinline__ bool moller_trumbore(const TriV& tri, V3 o, V3 d, flo
 // oracle's "strict <, first candidate wins".  PRUNE: near-child-first order and subtrees entered only while their
 // box entry <= best * kPruneSlack.  !PRUNE: every box the reference's queryNode would test is tested.
 template <bool PRUNE>
-__device__ __forceinline__ void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos) {
+RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos) {
 	bestT = kMissT; bestPos = -1;
 	if (S.numTris <= 0) return;
 	RayBox rb = make_raybox(o, d);
@@ -167,13 +208,13 @@ __device__ __forceinline__ void bvh_closest(const BvhDev& S, V3 o, V3 d, float& 
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2);
-			float2 r = __ldg(reinterpret_cast<const float2*>(n + 3));
+			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
+			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
 			float e0, e1;
 			bool h0, h1;
 			if (!exactBox) { h0 = slab_fast(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_fast(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
 			else { h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
-			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
+			int r0 = f2i(r.x), r1 = f2i(r.y);
 			if (PRUNE) { h0 = h0 && (e0 <= tcut); h1 = h1 && (e1 <= tcut); }
 			if (h0 && h1) {
 				bool swap = PRUNE && (e1 < e0);
@@ -208,7 +249,7 @@ __device__ __forceinline__ void bvh_closest(const BvhDev& S, V3 o, V3 d, float& 
 }
 
 // Shadow / any-hit: true iff some candidate of the reference's query passes Moller-Trumbore.
-__device__ __forceinline__ bool bvh_any(const BvhDev& S, V3 o, V3 d) {
+RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 	if (S.numTris <= 0) return false;
 	RayBox rb = make_raybox(o, d);
 	float te;
@@ -220,13 +261,13 @@ __device__ __forceinline__ bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2);
-			float2 r = __ldg(reinterpret_cast<const float2*>(n + 3));
+			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
+			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
 			float e0, e1;
 			bool h0, h1;
 			if (!exactBox) { h0 = slab_fast(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_fast(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
 			else { h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
-			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
+			int r0 = f2i(r.x), r1 = f2i(r.y);
 			if (h0 && h1) {
 				bool swap = e1 < e0;
 				if (sp < kBvhStack) stackRef[sp++] = swap ? r0 : r1;
@@ -254,7 +295,7 @@ __device__ __forceinline__ bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 // Reference-order replay (left before right, nothing pruned): emits candidate positions in BVH::query order and
 // counts intersectAABB calls the reference would make (1 for the root + 2 per internal node entered).
 template <typename Emit>
-__device__ __forceinline__ void bvh_replay(const BvhDev& S, V3 o, V3 d, unsigned long long& boxTests, Emit emit) {
+RTO_DEV void bvh_replay(const BvhDev& S, V3 o, V3 d, unsigned long long& boxTests, Emit emit) {
 	if (S.numTris < 0) return;
 	boxTests += 1;
 	RayBox rb = make_raybox(o, d);
@@ -267,12 +308,12 @@ __device__ __forceinline__ void bvh_replay(const BvhDev& S, V3 o, V3 d, unsigned
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = __ldg(n), b = __ldg(n + 1), c = __ldg(n + 2), r = __ldg(n + 3);
+			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2), r = RTO_LDG(n + 3);
 			float e0, e1;
 			boxTests += 2;
 			bool h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0);
 			bool h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1);
-			int r0 = __float_as_int(r.x), r1 = __float_as_int(r.y);
+			int r0 = f2i(r.x), r1 = f2i(r.y);
 			if (h0 && h1) { if (sp < kBvhStack) stackRef[sp++] = r1; cur = r0; continue; }
 			if (h0) { cur = r0; continue; }
 			if (h1) { cur = r1; continue; }
@@ -292,26 +333,29 @@ __device__ __forceinline__ void bvh_replay(const BvhDev& S, V3 o, V3 d, unsigned
 // ------------------------------------------------------------------------------------------------
 // order of octants for octreeRaySkip: ascending popcount(octant ^ dirMask), ascending octant within a class
 // (VolumeRaycastRenderer.cpp:122-134).  nibble j of kSkipOrder[m] = j-th octant; nibble k of kSkipRank[m] = position of octant k.
-constexpr int popc3(int v) { return (v & 1) + ((v >> 1) & 1) + ((v >> 2) & 1); }
-constexpr uint32_t skip_order(int m) {
+__host__ __device__ constexpr int popc3(int v) { return (v & 1) + ((v >> 1) & 1) + ((v >> 2) & 1); }
+__host__ __device__ constexpr uint32_t skip_order(int m) {
 	uint32_t r = 0; int j = 0;
 	for (int dist = 0; dist <= 3; dist++)
 		for (int o = 0; o < 8; o++)
 			if (popc3(o ^ m) == dist) { r |= (uint32_t)o << (4 * j); j++; }
 	return r;
 }
-constexpr uint32_t skip_rank(int m) {
+__host__ __device__ constexpr uint32_t skip_rank(int m) {
 	uint32_t ord = skip_order(m), r = 0;
 	for (int j = 0; j < 8; j++) r |= (uint32_t)j << (4 * ((ord >> (4 * j)) & 7u));
 	return r;
 }
-__device__ __constant__ uint32_t kSkipOrder[8] = { skip_order(0), skip_order(1), skip_order(2), skip_order(3), skip_order(4), skip_order(5), skip_order(6), skip_order(7) };
-__device__ __constant__ uint32_t kSkipRank[8] = { skip_rank(0), skip_rank(1), skip_rank(2), skip_rank(3), skip_rank(4), skip_rank(5), skip_rank(6), skip_rank(7) };
+RTO_DEV void skip_tables(int dirMask, uint32_t& order, uint32_t& rank) {
+	constexpr uint32_t ord[8] = { skip_order(0), skip_order(1), skip_order(2), skip_order(3), skip_order(4), skip_order(5), skip_order(6), skip_order(7) };
+	constexpr uint32_t rnk[8] = { skip_rank(0), skip_rank(1), skip_rank(2), skip_rank(3), skip_rank(4), skip_rank(5), skip_rank(6), skip_rank(7) };
+	order = ord[dirMask]; rank = rnk[dirMask];
+}
 
 struct OctBox { V3 mn, mx; };
 // world box of a node: nodeMin = gridMin + vec3(x,y,z)*voxelSize; nodeMax = nodeMin + vec3(size)*voxelSize
 // (RayTracerBVH.cpp:262-263; identical operations in VolumeRaycastRenderer.cpp:70-77)
-__device__ __forceinline__ OctBox oct_box(const OctDev& S, int x, int y, int z, int size) {
+RTO_DEV OctBox oct_box(const OctDev& S, int x, int y, int z, int size) {
 	OctBox b;
 	b.mn = mk3(S.gmin[0] + float(x) * S.voxel, S.gmin[1] + float(y) * S.voxel, S.gmin[2] + float(z) * S.voxel);
 	float w = float(size) * S.voxel;
@@ -322,7 +366,7 @@ __device__ __forceinline__ OctBox oct_box(const OctDev& S, int x, int y, int z, 
 struct OctHit { float t; int id; V3 normal; unsigned visits; };
 
 // ---- mode B: GLSL intersectAABB (RayTracerBVH.cpp:226-236) -----------------------------------------------
-__device__ __forceinline__ bool glsl_box(const OctBox& b, V3 o, V3 inv, float& tNear, float& tFar) {
+RTO_DEV bool glsl_box(const OctBox& b, V3 o, V3 inv, float& tNear, float& tFar) {
 	V3 t1 = (b.mn - o) * inv, t2 = (b.mx - o) * inv;
 	V3 tmn = min3(t1, t2), tmx = max3(t1, t2);
 	tNear = maxf(maxf(tmn.x, tmn.y), tmn.z);
@@ -330,14 +374,14 @@ __device__ __forceinline__ bool glsl_box(const OctBox& b, V3 o, V3 inv, float& t
 	return (tNear <= tFar && tFar > 0.0f);
 }
 
-__device__ __forceinline__ V3 box_normal(const OctBox& b, V3 o, V3 d, float t) {     // RayTracerBVH.cpp:279-282
+RTO_DEV V3 box_normal(const OctBox& b, V3 o, V3 d, float t) {     // RayTracerBVH.cpp:279-282
 	V3 center = 0.5f * (b.mn + b.mx);
 	V3 p = o + d * t;
 	return normalize3(p - center);
 }
 
 // compact layout: stackless walk; sibling order 7..0 == the pop order of the GLSL stack
-__device__ __forceinline__ OctHit octB_compact(const OctDev& S, V3 o, V3 d) {
+RTO_DEV OctHit octB_compact(const OctDev& S, V3 o, V3 d) {
 	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
 	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 	const float closestT = kMissT;
@@ -348,7 +392,7 @@ __device__ __forceinline__ OctHit octB_compact(const OctDev& S, V3 o, V3 d) {
 		OctBox b = oct_box(S, x, y, z, size);
 		float tNear, tFar;
 		if (glsl_box(b, o, inv, tNear, tFar) && !(tNear >= closestT)) {
-			uint32_t dsc = __ldg(S.desc + node);
+			uint32_t dsc = RTO_LDG(S.desc + node);
 			if (dsc & kOctLeaf) {
 				if (dsc & kOctSolid) {
 					float tHit = maxf(0.0f, tNear);
@@ -372,7 +416,7 @@ __device__ __forceinline__ OctHit octB_compact(const OctDev& S, V3 o, V3 d) {
 				node -= 1;
 				break;
 			}
-			node = __ldg(S.up + ((node - 1) >> 3));
+			node = RTO_LDG(S.up + ((node - 1) >> 3));
 			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
 		}
 		if (done) break;
@@ -382,7 +426,7 @@ __device__ __forceinline__ OctHit octB_compact(const OctDev& S, V3 o, V3 d) {
 }
 
 // general layout: the GLSL loop verbatim over 16-int nodes
-__device__ __forceinline__ OctHit octB_general(const OctDev& S, V3 o, V3 d) {
+RTO_DEV OctHit octB_general(const OctDev& S, V3 o, V3 d) {
 	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
 	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 	const float closestT = kMissT;
@@ -393,7 +437,7 @@ __device__ __forceinline__ OctHit octB_general(const OctDev& S, V3 o, V3 d) {
 		if (idx < 0 || idx >= S.numNodes) continue;       // (the reference does not guard idx >= numNodes; such arrays are rejected at upload)
 		steps++;
 		const int4* n = S.nodes16 + 4 * (size_t)idx;
-		int4 a = __ldg(n), f = __ldg(n + 1);
+		int4 a = RTO_LDG(n), f = RTO_LDG(n + 1);
 		OctBox b = oct_box(S, a.x, a.y, a.z, a.w);
 		float tNear, tFar;
 		if (!glsl_box(b, o, inv, tNear, tFar)) continue;
@@ -405,7 +449,7 @@ __device__ __forceinline__ OctHit octB_general(const OctDev& S, V3 o, V3 d) {
 			}
 			continue;
 		}
-		int4 c0 = __ldg(n + 2), c1 = __ldg(n + 3);
+		int4 c0 = RTO_LDG(n + 2), c1 = RTO_LDG(n + 3);
 		int ch[8] = { f.w, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z };
 #pragma unroll
 		for (int i = 0; i < 8; i++) if (ch[i] >= 0 && sp < 128) stack[sp++] = ch[i];
@@ -416,7 +460,7 @@ __device__ __forceinline__ OctHit octB_general(const OctDev& S, V3 o, V3 d) {
 
 // ---- mode A: octreeRaySkip (VolumeRaycastRenderer.cpp:50-155) ---------------------------------------------
 struct SkipRay { V3 o, inv; uint32_t order, rank; };
-__device__ __forceinline__ SkipRay make_skipray(V3 o, V3 d) {
+RTO_DEV SkipRay make_skipray(V3 o, V3 d) {
 	SkipRay r; r.o = o;
 	r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 	const float smallValue = 1e-10f;                                       // :84-87
@@ -424,10 +468,10 @@ __device__ __forceinline__ SkipRay make_skipray(V3 o, V3 d) {
 	if (fabsf(d.y) < smallValue) r.inv.y = d.y >= 0 ? 1e10f : -1e10f;
 	if (fabsf(d.z) < smallValue) r.inv.z = d.z >= 0 ? 1e10f : -1e10f;
 	int dirMask = ((d.x > 0) ? 1 : 0) | ((d.y > 0) ? 2 : 0) | ((d.z > 0) ? 4 : 0);   // :114-116
-	r.order = kSkipOrder[dirMask]; r.rank = kSkipRank[dirMask];
+	skip_tables(dirMask, r.order, r.rank);
 	return r;
 }
-__device__ __forceinline__ bool skip_box(const OctBox& b, const SkipRay& r, float tMin, float tMax, float& enterT, float& exitT) {
+RTO_DEV bool skip_box(const OctBox& b, const SkipRay& r, float tMin, float tMax, float& enterT, float& exitT) {
 	V3 t1 = (b.mn - r.o) * r.inv, t2 = (b.mx - r.o) * r.inv;
 	V3 tN = min3(t1, t2), tF = max3(t1, t2);
 	enterT = maxf(maxf(tN.x, tN.y), maxf(tN.z, tMin));                     // :96
@@ -435,7 +479,7 @@ __device__ __forceinline__ bool skip_box(const OctBox& b, const SkipRay& r, floa
 	return !(enterT > exitT);
 }
 
-__device__ __forceinline__ OctHit octA_compact(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
+RTO_DEV OctHit octA_compact(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
 	SkipRay r = make_skipray(o, d);
 	float minS[kMaxOctDepth], maxS[kMaxOctDepth];
@@ -448,7 +492,7 @@ __device__ __forceinline__ OctHit octA_compact(const OctDev& S, V3 o, V3 d, floa
 		OctBox b = oct_box(S, x, y, z, size);
 		float enterT, exitT;
 		if (skip_box(b, r, curMin, curMax, enterT, exitT)) {
-			uint32_t dsc = __ldg(S.desc + node);
+			uint32_t dsc = RTO_LDG(S.desc + node);
 			if (dsc & kOctLeaf) {
 				// a solid leaf returns enterT; the callers keep it only if it is < 1e30f (:143-149)
 				if ((dsc & kOctSolid) && enterT < 1e30f) { h.t = enterT; h.id = node; h.normal = box_normal(b, o, d, enterT); break; }
@@ -474,7 +518,7 @@ __device__ __forceinline__ OctHit octA_compact(const OctDev& S, V3 o, V3 d, floa
 				node = node - k + nk;
 				break;
 			}
-			node = __ldg(S.up + ((node - 1) >> 3));
+			node = RTO_LDG(S.up + ((node - 1) >> 3));
 			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
 			depth--; curMin = minS[depth]; curMax = maxS[depth];
 		}
@@ -484,7 +528,7 @@ __device__ __forceinline__ OctHit octA_compact(const OctDev& S, V3 o, V3 d, floa
 	return h;
 }
 
-__device__ __forceinline__ OctHit octA_general(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
+RTO_DEV OctHit octA_general(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
 	SkipRay r = make_skipray(o, d);
 	// explicit recursion frames: node being expanded, next order position, the (tMin, tMax) its children receive
@@ -496,7 +540,7 @@ __device__ __forceinline__ OctHit octA_general(const OctDev& S, V3 o, V3 d, floa
 		if (cur >= 0 && cur < S.numNodes) {
 			visits++;
 			const int4* n = S.nodes16 + 4 * (size_t)cur;
-			int4 a = __ldg(n), f = __ldg(n + 1);
+			int4 a = RTO_LDG(n), f = RTO_LDG(n + 1);
 			OctBox b = oct_box(S, a.x, a.y, a.z, a.w);
 			float enterT, exitT;
 			if (skip_box(b, r, curMin, curMax, enterT, exitT)) {
@@ -516,7 +560,7 @@ __device__ __forceinline__ OctHit octA_general(const OctDev& S, V3 o, V3 d, floa
 				int k = (int)((r.order >> (4 * posS[f])) & 7u);
 				posS[f]++;
 				const int* ch = reinterpret_cast<const int*>(S.nodes16 + 4 * (size_t)nodeS[f]) + 7;
-				int c = __ldg(ch + k);
+				int c = RTO_LDG(ch + k);
 				if (c < 0) continue;                         // null child: skipped without a call (:136-137)
 				cur = c; curMin = minS[f]; curMax = maxS[f];
 				found = true;
@@ -530,9 +574,217 @@ __device__ __forceinline__ OctHit octA_general(const OctDev& S, V3 o, V3 d, floa
 	return h;
 }
 
-__device__ __forceinline__ OctHit oct_trace(const OctDev& S, int mode, V3 o, V3 d, float tMin, float tMax) {
-	if (mode == RTO_MODE_OCTREE_SKIP) return S.compact ? octA_compact(S, o, d, tMin, tMax) : octA_general(S, o, d, tMin, tMax);
-	return S.compact ? octB_compact(S, o, d) : octB_general(S, o, d);
+
+// ------------------------------------------------------------------------------------------------
+// Octree fast paths (compact layout): all 8 children of an internal node are classified at once.
+//
+// The reference tests every child box separately; its arithmetic per child is (plane - o) * inv on planes computed as
+// gridMin + float(coord) * voxel (+ float(size) * voxel).  Here the 12 plane distances of the 8 children (2 per axis for each
+// half) are computed once per internal node with exactly those operations and combined per child with min/max, which yields
+// the same tNear/tFar values as the per-child code as long as no NaN occurs -- guaranteed when 1/d is finite and non-zero.
+// (FMNMX and the reference's select forms can differ only in the sign of a zero, which no comparison sees; the one place a
+// zero could surface -- mode A returning enterT == 0 -- re-runs the ray through the exact per-node path.)  One 16-byte record
+// per internal node carries first-child index, child leaf/solid masks and the links needed for a stackless walk; the masks
+// of children still to visit live in registers, 8 bits per level.  Rays with an infinite/zero reciprocal component, trees
+// deeper than 16 levels and the visit counters of rto_render_stats use the per-node paths above.
+// ------------------------------------------------------------------------------------------------
+struct ChildPlanes { float n0[3], f0[3], n1[3], f1[3]; };     // per axis: near/far distances of the low and the high half
+
+RTO_DEV ChildPlanes oct_child_planes(const OctDev& S, V3 o, V3 inv, int x, int y, int z, int h) {
+	ChildPlanes P;
+	const float w = float(h) * S.voxel;
+	const int c[3] = { x, y, z };
+	const float oo[3] = { o.x, o.y, o.z }, ii[3] = { inv.x, inv.y, inv.z };
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		float lo0 = S.gmin[a] + float(c[a]) * S.voxel, lo1 = S.gmin[a] + float(c[a] + h) * S.voxel;
+		float t1 = (lo0 - oo[a]) * ii[a], t2 = ((lo0 + w) - oo[a]) * ii[a];
+		float u1 = (lo1 - oo[a]) * ii[a], u2 = ((lo1 + w) - oo[a]) * ii[a];
+		P.n0[a] = fminf(t1, t2); P.f0[a] = fmaxf(t1, t2);
+		P.n1[a] = fminf(u1, u2); P.f1[a] = fmaxf(u1, u2);
+	}
+	return P;
+}
+
+RTO_DEV bool inv_is_regular(V3 inv) {
+	float ax = fabsf(inv.x), ay = fabsf(inv.y), az = fabsf(inv.z);
+	return ax > 0.0f && ax <= FLT_MAX && ay > 0.0f && ay <= FLT_MAX && az > 0.0f && az <= FLT_MAX;
+}
+
+RTO_DEV void oct_child_coords(int k, int h, int& x, int& y, int& z) {
+	x += (k & 1) ? h : 0; y += (k & 2) ? h : 0; z += (k & 4) ? h : 0;
+}
+
+RTO_DEV OctHit octB_fast(const OctDev& S, V3 o, V3 d) {
+	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	if (!inv_is_regular(inv) || S.rootSize > 65536) return octB_compact(S, o, d);
+	OctHit hit; hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
+	int x = 0, y = 0, z = 0, size = S.rootSize;
+	int steps = 1;                                             // the root is popped first
+	{
+		OctBox b = oct_box(S, 0, 0, 0, size);
+		float tNear, tFar;
+		hit.visits = 1;
+		if (!glsl_box(b, o, inv, tNear, tFar) || tNear >= kMissT) return hit;
+		uint32_t dsc = RTO_LDG(S.desc);
+		if (dsc & kOctLeaf) {
+			if (dsc & kOctSolid) { float tHit = maxf(0.0f, tNear); if (tHit < kMissT && tHit <= tFar) { hit.t = tHit; hit.id = 0; hit.normal = box_normal(b, o, d, tHit); } }
+			return hit;
+		}
+	}
+	unsigned long long mlo = 0ull, mhi = 0ull;                 // remaining-children masks, 8 bits per level
+	int level = 0, rank = 0, pos = 8;
+	int4 e = RTO_LDG(S.inner);
+	bool entering = true;
+	unsigned M = 0;
+	while (true) {
+		const int h = size >> 1;
+		const unsigned leafMask = (unsigned)e.w & 0xffu, solidMask = ((unsigned)e.w >> 8) & 0xffu;
+		if (entering) {
+			ChildPlanes P = oct_child_planes(S, o, inv, x, y, z, h);
+			unsigned hits = 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), (k & 4) ? P.n1[2] : P.n0[2]);
+				float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), (k & 4) ? P.f1[2] : P.f0[2]);
+				bool hk = (tn <= tf) && (tf > 0.0f) && !(tn >= kMissT);
+				hits |= hk ? (1u << k) : 0u;
+			}
+			M = hits & ~(leafMask & ~solidMask);               // children that can do more than burn a step: solid leaves and internal nodes
+			pos = 8;
+		}
+		unsigned below = M & ((1u << pos) - 1u);
+		if (below == 0u) {                                     // the remaining `pos` children are popped, tested and dropped
+			steps += pos;
+			if (steps >= 512 || level == 0) break;
+			pos = ((unsigned)e.w >> 16) & 7u;
+			rank = e.z;
+			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
+			level--;
+			M = (unsigned)(((level < 8) ? (mlo >> (8 * level)) : (mhi >> (8 * (level - 8)))) & 0xffull);
+			e = RTO_LDG(S.inner + rank);
+			entering = false;
+			continue;
+		}
+		const int j = 31 - clz32(below);
+		steps += pos - 1 - j;
+		if (steps >= 512) break;
+		steps++;
+		pos = j;
+		int cx = x, cy = y, cz = z;
+		oct_child_coords(j, h, cx, cy, cz);
+		if ((leafMask >> j) & 1u) {                            // solid leaf whose box the ray hits: the reference's exact per-node values
+			OctBox b = oct_box(S, cx, cy, cz, h);
+			float tNear, tFar;
+			if (glsl_box(b, o, inv, tNear, tFar) && !(tNear >= kMissT)) {
+				float tHit = maxf(0.0f, tNear);
+				if (tHit < kMissT && tHit <= tFar) { hit.t = tHit; hit.id = e.x + j; hit.normal = box_normal(b, o, d, tHit); break; }
+			}
+			entering = false;
+			continue;
+		}
+		if (level < 8) mlo = (mlo & ~(0xffull << (8 * level))) | ((unsigned long long)M << (8 * level));
+		else mhi = (mhi & ~(0xffull << (8 * (level - 8)))) | ((unsigned long long)M << (8 * (level - 8)));
+		level++;
+		rank = e.y + popc32(~leafMask & ((1u << j) - 1u) & 0xffu);
+		x = cx; y = cy; z = cz; size = h;
+		e = RTO_LDG(S.inner + rank);
+		entering = true;
+	}
+	hit.visits = (unsigned)(steps > 512 ? 512 : steps);
+	return hit;
+}
+
+RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
+	SkipRay r = make_skipray(o, d);
+	if (!inv_is_regular(r.inv) || S.rootSize > 65536) return octA_compact(S, o, d, tMin, tMax);
+	OctHit hit; hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
+	int x = 0, y = 0, z = 0, size = S.rootSize;
+	float curMin, curMax;                                      // (enterT, exitT) of the current internal node = clamps of its children
+	{
+		OctBox b = oct_box(S, 0, 0, 0, size);
+		if (!skip_box(b, r, tMin, tMax, curMin, curMax)) return hit;
+		uint32_t dsc = RTO_LDG(S.desc);
+		if (dsc & kOctLeaf) {
+			if ((dsc & kOctSolid) && curMin < 1e30f) { hit.t = curMin; hit.id = 0; hit.normal = box_normal(b, o, d, curMin); }
+			return hit;
+		}
+	}
+	float minS[16], maxS[16];
+	unsigned long long mlo = 0ull, mhi = 0ull;                 // remaining-children masks in VISIT-ORDER space, 8 bits per level
+	int level = 0, rank = 0, posO = -1;
+	int4 e = RTO_LDG(S.inner);
+	bool entering = true;
+	unsigned Mo = 0;
+	for (int guard = 0; guard < (1 << 24); guard++) {          // (a finite walk visits < 2 * nodes steps; the bound only keeps a corrupted array from hanging the GPU)
+		const int h = size >> 1;
+		const unsigned leafMask = (unsigned)e.w & 0xffu, solidMask = ((unsigned)e.w >> 8) & 0xffu;
+		if (entering) {
+			ChildPlanes P = oct_child_planes(S, r.o, r.inv, x, y, z, h);
+			const unsigned skipMask = leafMask & ~solidMask;   // empty leaves return 1e30f whatever their box test says
+			Mo = 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), fmaxf((k & 4) ? P.n1[2] : P.n0[2], curMin));
+				float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), fminf((k & 4) ? P.f1[2] : P.f0[2], curMax));
+				bool hk = !(tn > tf) && !((skipMask >> k) & 1u);
+				Mo |= hk ? (1u << ((r.rank >> (4 * k)) & 7u)) : 0u;
+			}
+			posO = -1;
+		}
+		unsigned rem = (posO < 0) ? Mo : (Mo & ~((2u << posO) - 1u));   // order positions after the last consumed one
+		if (rem == 0u) {
+			if (level == 0) break;
+			posO = (int)((r.rank >> (4 * (((unsigned)e.w >> 16) & 7u))) & 7u);
+			rank = e.z;
+			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
+			level--;
+			Mo = (unsigned)(((level < 8) ? (mlo >> (8 * level)) : (mhi >> (8 * (level - 8)))) & 0xffull);
+			curMin = minS[level]; curMax = maxS[level];
+			e = RTO_LDG(S.inner + rank);
+			entering = false;
+			continue;
+		}
+		const int jO = ffs32(rem) - 1;
+		const int k = (int)((r.order >> (4 * jO)) & 7u);
+		posO = jO;
+		int cx = x, cy = y, cz = z;
+		oct_child_coords(k, h, cx, cy, cz);
+		OctBox b = oct_box(S, cx, cy, cz, h);
+		float enterT, exitT;
+		bool ok = skip_box(b, r, curMin, curMax, enterT, exitT);
+		if ((leafMask >> k) & 1u) {                            // solid leaf
+			if (ok && enterT < 1e30f) {
+				if (enterT == 0.0f) return octA_compact(S, o, d, tMin, tMax);     // zero of either sign: take the reference's select forms
+				hit.t = enterT; hit.id = e.x + k; hit.normal = box_normal(b, o, d, enterT);
+				break;
+			}
+			entering = false;
+			continue;
+		}
+		if (!ok) { entering = false; continue; }               // (cannot happen: same values as the batch test)
+		if (level < 8) mlo = (mlo & ~(0xffull << (8 * level))) | ((unsigned long long)Mo << (8 * level));
+		else mhi = (mhi & ~(0xffull << (8 * (level - 8)))) | ((unsigned long long)Mo << (8 * (level - 8)));
+		minS[level] = curMin; maxS[level] = curMax;
+		level++;
+		curMin = enterT; curMax = exitT;
+		rank = e.y + popc32(~leafMask & ((1u << k) - 1u) & 0xffu);
+		x = cx; y = cy; z = cz; size = h;
+		e = RTO_LDG(S.inner + rank);
+		entering = true;
+	}
+	return hit;
+}
+
+// COUNT: the caller needs OctHit::visits (rto_render_stats) -> per-node paths, which count what the reference visits.
+template <bool COUNT>
+RTO_DEV OctHit oct_trace(const OctDev& S, int mode, V3 o, V3 d, float tMin, float tMax) {
+	if (mode == RTO_MODE_OCTREE_SKIP) {
+		if (!S.compact) return octA_general(S, o, d, tMin, tMax);
+		return COUNT ? octA_compact(S, o, d, tMin, tMax) : octA_fast(S, o, d, tMin, tMax);
+	}
+	if (!S.compact) return octB_general(S, o, d);
+	return COUNT ? octB_compact(S, o, d) : octB_fast(S, o, d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,7 +808,7 @@ __device__ __forceinline__ bool pixel_of_thread(const RenderArgs& A, const RtoCa
 	return true;
 }
 
-__device__ __forceinline__ void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, float t) {
+RTO_DEV void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, float t) {
 	if (A.rgba) A.rgba[pix] = make_float4(color.x, color.y, color.z, 1.0f);
 	if (A.hitId) A.hitId[pix] = id;
 	if (A.t) A.t[pix] = t;
@@ -597,7 +849,7 @@ __global__ void __launch_bounds__(128) k_render_octree(OctDev S, RenderArgs A, i
 	int px, py; size_t pix;
 	if (!pixel_of_thread(A, cam, px, py, pix)) return;
 	Ray ray = gen_ray(cam, px, py);
-	OctHit h = oct_trace(S, mode, ray.o, ray.d, 0.0f, 1e30f);
+	OctHit h = oct_trace<false>(S, mode, ray.o, ray.d, 0.0f, 1e30f);
 	V3 color = mk3(0.0f, 0.0f, 0.0f);
 	if (h.id >= 0) color = shade_lambert(h.normal);
 	store_pixel(A, pix, color, h.id, h.t);
@@ -611,7 +863,7 @@ __global__ void __launch_bounds__(128) k_trace_octree(OctDev S, int mode, const 
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	V3 o = mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
-	OctHit h = oct_trace(S, mode, o, d, tMin, tMax);
+	OctHit h = oct_trace<false>(S, mode, o, d, tMin, tMax);
 	if (tOut) tOut[i] = h.t;
 	if (idOut) idOut[i] = h.id;
 }
@@ -624,7 +876,7 @@ __global__ void __launch_bounds__(128) k_trace_bvh(BvhDev S, unsigned flags, con
 	float bestT; int bestPos;
 	if (flags & RTO_FLAG_NO_PRUNE) bvh_closest<false>(S, o, d, bestT, bestPos); else bvh_closest<true>(S, o, d, bestT, bestPos);
 	if (tOut) tOut[i] = bestT;
-	if (idOut) idOut[i] = bestPos >= 0 ? __float_as_int(__ldg(S.tris + 3 * (size_t)bestPos + 2).y) : -1;
+	if (idOut) idOut[i] = bestPos >= 0 ? f2i(RTO_LDG(S.tris + 3 * (size_t)bestPos + 2).y) : -1;
 }
 
 // BVH::query candidates: pass 1 counts per ray, pass 2 writes ids at the host-computed offsets
@@ -637,7 +889,7 @@ __global__ void __launch_bounds__(128) k_bvh_query(BvhDev S, const float* __rest
 	int cnt = 0;
 	long long base = offsets ? offsets[i] : 0;
 	bvh_replay(S, o, d, boxes, [&](int pos) {
-		if (ids) ids[base + cnt] = __float_as_int(__ldg(S.tris + 3 * (size_t)pos + 2).y);
+		if (ids) ids[base + cnt] = f2i(RTO_LDG(S.tris + 3 * (size_t)pos + 2).y);
 		cnt++;
 	});
 	if (counts) counts[i] = cnt;
@@ -684,7 +936,7 @@ __global__ void __launch_bounds__(128) k_stats_octree(OctDev S, RenderArgs A, in
 	unsigned long long N = 0;
 	if (active) {
 		Ray ray = gen_ray(cam, px, py);
-		OctHit h = oct_trace(S, mode, ray.o, ray.d, 0.0f, 1e30f);
+		OctHit h = oct_trace<true>(S, mode, ray.o, ray.d, 0.0f, 1e30f);
 		N = h.visits;
 	}
 	warp_add(stats + 0, N);

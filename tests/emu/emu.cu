@@ -1,0 +1,104 @@
+// tests/emu/emu.cu -- TEST INFRASTRUCTURE: runs the product's traversal functions (rto_kernels.cuh, RTO_DEV = host + device)
+// on the CPU over the product's own device layouts (host_layouts.cpp), pixel by pixel.  Purpose: find logic errors
+// (wrong links, endless walks, mismatches against the oracle) in this GPU-less container before spending GPU minutes.
+// This is NOT a fallback: it is not part of librto.so and nothing in the package loads it.
+#include "../../ray_tracing_octrees_b200/csrc/rto_kernels.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+using namespace rto;
+
+int rto_fail(int code, const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); return code; }
+
+struct EmuOct { OctLayout L; OctDev D; };
+struct EmuBvh { BvhLayout L; BvhDev ref, fast; std::vector<RtoTriangle> tris; };
+
+extern "C" {
+
+void* emu_octree_create(const RtoGpuNode* nodes, size_t n, const float* gmin, float voxel) {
+	EmuOct* e = new EmuOct();
+	if (rto_build_octree_layout(nodes, n, e->L) != RTO_OK) { delete e; return nullptr; }
+	OctDev& D = e->D;
+	D.numNodes = (int)n; D.rootSize = nodes[0].size; D.compact = e->L.compact;
+	D.gmin[0] = gmin[0]; D.gmin[1] = gmin[1]; D.gmin[2] = gmin[2]; D.voxel = voxel;
+	D.desc = e->L.compact ? e->L.desc.data() + 7 : nullptr; D.up = e->L.up.data();
+	D.inner = (const int4*)e->L.inner.data(); D.nodes16 = (const int4*)e->L.padded.data();
+	return e;
+}
+void emu_octree_free(void* h) { delete (EmuOct*)h; }
+
+// count = 1: per-node paths with visit counters (what rto_render_stats runs); count = 0: production (fast) paths
+void emu_render_octree(void* h, const RtoCamera* cam, int mode, int count, int y0, int y1, float* rgba, int32_t* ids, float* t, uint64_t* visits, uint32_t* perPixelVisits) {
+	EmuOct* e = (EmuOct*)h;
+	uint64_t v = 0;
+	for (int py = y0; py < y1; py++)
+		for (int px = 0; px < cam->width; px++) {
+			size_t pix = (size_t)(py - y0) * cam->width + px;
+			Ray ray = gen_ray(*cam, px, py);
+			OctHit hit = count ? oct_trace<true>(e->D, mode, ray.o, ray.d, 0.0f, 1e30f) : oct_trace<false>(e->D, mode, ray.o, ray.d, 0.0f, 1e30f);
+			v += hit.visits;
+			if (perPixelVisits) perPixelVisits[pix] = hit.visits;
+			V3 color = mk3(0.0f, 0.0f, 0.0f);
+			if (hit.id >= 0) color = shade_lambert(hit.normal);
+			if (rgba) { rgba[4 * pix] = color.x; rgba[4 * pix + 1] = color.y; rgba[4 * pix + 2] = color.z; rgba[4 * pix + 3] = 1.0f; }
+			if (ids) ids[pix] = hit.id;
+			if (t) t[pix] = hit.t;
+		}
+	if (visits) *visits = v;
+}
+void emu_trace_octree(void* h, int mode, int count, const float* o3, const float* d3, size_t n, float tMin, float tMax, float* t, int32_t* ids) {
+	EmuOct* e = (EmuOct*)h;
+	for (size_t i = 0; i < n; i++) {
+		V3 o = mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+		OctHit hit = count ? oct_trace<true>(e->D, mode, o, d, tMin, tMax) : oct_trace<false>(e->D, mode, o, d, tMin, tMax);
+		t[i] = hit.t; ids[i] = hit.id;
+	}
+}
+
+void* emu_bvh_create(const RtoTriangle* tris, size_t n) {
+	EmuBvh* e = new EmuBvh();
+	e->tris.assign(tris, tris + n);
+	RtoHostBvh* hb = nullptr;
+	if (rto_host_bvh_build(e->tris.data(), n, &hb) != RTO_OK) { delete e; return nullptr; }
+	rto_build_bvh_layout(*hb, e->L);
+	rto_host_bvh_free(hb);
+	BvhDev D;
+	D.numTris = (int)n; D.rootRef = e->L.refRoot;
+	for (int k = 0; k < 3; k++) { D.rootLo[k] = e->L.rootLo[k]; D.rootHi[k] = e->L.rootHi[k]; }
+	D.nodes = (const float4*)e->L.refNodes.data(); D.tris = (const float4*)e->L.tris.data();
+	e->ref = D; e->fast = D;
+	if (!e->L.fastNodes.empty()) { e->fast.nodes = (const float4*)e->L.fastNodes.data(); e->fast.rootRef = e->L.fastRoot; }
+	return e;
+}
+void emu_bvh_free(void* h) { delete (EmuBvh*)h; }
+
+void emu_render_bvh(void* h, const RtoCamera* cam, unsigned flags, float bias, int y0, int y1, float* rgba, int32_t* ids, float* t) {
+	EmuBvh* e = (EmuBvh*)h;
+	const bool prune = !(flags & RTO_FLAG_NO_PRUNE);
+	const BvhDev& S = prune ? e->fast : e->ref;
+	for (int py = y0; py < y1; py++)
+		for (int px = 0; px < cam->width; px++) {
+			size_t pix = (size_t)(py - y0) * cam->width + px;
+			Ray ray = gen_ray(*cam, px, py);
+			float bestT; int bestPos;
+			if (prune) bvh_closest<true>(S, ray.o, ray.d, bestT, bestPos); else bvh_closest<false>(S, ray.o, ray.d, bestT, bestPos);
+			V3 color = mk3(0.0f, 0.0f, 0.0f); int id = -1;
+			if (bestPos >= 0) {
+				TriV tri = load_tri(S.tris, bestPos);
+				id = tri.id;
+				V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
+				V3 n = normalize3(cross3(e1, e2));
+				if (dot3(n, ray.d) > 0.0f) n = -n;
+				V3 hp = ray.o + ray.d * bestT;
+				bool shadowed = false;
+				if (flags & RTO_FLAG_SHADOWS) shadowed = bvh_any(S, hp + n * bias, normalize3(mk3(1.0f, 1.0f, 1.0f)));
+				color = shadowed ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
+			}
+			if (rgba) { rgba[4 * pix] = color.x; rgba[4 * pix + 1] = color.y; rgba[4 * pix + 2] = color.z; rgba[4 * pix + 3] = 1.0f; }
+			if (ids) ids[pix] = id;
+			if (t) t[pix] = bestT;
+		}
+}
+
+} // extern "C"
