@@ -30,7 +30,7 @@ namespace rto {
 
 RTO_DEV int f2i(float f) {
 #if defined(__CUDA_ARCH__)
-	return f2i(f);
+	return __float_as_int(f);
 #else
 	int i; std::memcpy(&i, &f, 4); return i;
 #endif
@@ -44,7 +44,7 @@ RTO_DEV int clz32(unsigned v) {
 }
 RTO_DEV int popc32(unsigned v) {
 #if defined(__CUDA_ARCH__)
-	return popc32(v);
+	return __popc(v);
 #else
 	return __builtin_popcount(v);
 #endif
