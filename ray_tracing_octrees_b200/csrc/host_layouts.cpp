@@ -92,7 +92,8 @@ void rto_build_bvh_layout(const RtoHostBvh& h, BvhLayout& L) {
 	for (size_t p = 0; p < h.numTris; p++) {
 		uint32_t id = h.order[p];
 		float* d = &L.tris[p * 12];
-		std::memcpy(d, &h.tris[id], 36);
+		const RtoTriangle& T = h.tris[id];
+		for (int k = 0; k < 3; k++) { d[k] = T.v0[k]; d[3 + k] = T.v1[k] - T.v0[k]; d[6 + k] = T.v2[k] - T.v0[k]; }     // v0, e1, e2 (rto_kernels.cuh TriV)
 		int32_t iid = (int32_t)id;
 		std::memcpy(&d[9], &iid, 4);
 	}

@@ -47,7 +47,7 @@ struct OctLayout {
 int rto_build_octree_layout(const RtoGpuNode* nodes, size_t numNodes, OctLayout& out);
 
 struct BvhLayout {
-	std::vector<float> refNodes, fastNodes, tris;     // 16 floats per inner node; 12 floats per triangle (leaf order, id in [9])
+	std::vector<float> refNodes, fastNodes, tris;     // 16 floats per inner node; 12 floats per triangle in leaf order: v0, v1 - v0, v2 - v0, id in [9]
 	int32_t refRoot = -1, fastRoot = -1;
 	float rootLo[3] = { 0, 0, 0 }, rootHi[3] = { 0, 0, 0 };
 };

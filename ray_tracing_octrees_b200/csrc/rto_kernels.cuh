@@ -62,7 +62,7 @@ RTO_DEV int ffs32(unsigned v) {
 // ------------------------------------------------------------------------------------------------
 struct BvhDev {
 	const float4* nodes;     // inner nodes, 4 x float4 each: [lo0.xyz hi0.x][hi0.yz lo1.xy][lo1.z hi1.xyz][ref0 ref1 - -]
-	const float4* tris;      // 3 x float4 per triangle in leaf order: [v0.xyz v1.x][v1.yz v2.xy][v2.z id - -]
+	const float4* tris;      // 3 x float4 per triangle in leaf order: [v0.xyz e1.x][e1.yz e2.xy][e2.z id - -], e1 = v1 - v0, e2 = v2 - v0
 	int   rootRef;           // >= 0: inner node index; < 0: ~leafRef, leafRef = (firstPos << 1) | (count - 1)
 	int   numTris;
 	float rootLo[3], rootHi[3];
@@ -91,6 +91,7 @@ constexpr float kMissT = 1e30f;
 constexpr float kPruneSlack = 1.00001f;
 
 struct Ray { V3 o, d; };
+struct alignas(8) StackEnt { int ref; float t; };     // postponed far child of the ordered BVH traversal and its box entry distance
 
 // ------------------------------------------------------------------------------------------------
 // Pixel ray: GLSL generateRay (RayTracerBVH.cpp:338-355) with inverse(view), tan(fov/2) from the host
@@ -146,33 +147,27 @@ RTO_DEV bool slab_ref(const RayBox& r, float lox, float loy, float loz, float hi
 	return !(tmax < tmin);
 }
 
-// Fast form of the same test: when all reciprocal direction components are finite and non-zero no NaN can arise, and
-// min/max (FMNMX) of the two plane distances equals the sign-selected form above bit for bit.
-RTO_DEV bool slab_fast(V3 o, V3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float& tEntry) {
-	float ax = (lox - o.x) * inv.x, bx = (hix - o.x) * inv.x;
-	float ay = (loy - o.y) * inv.y, by = (hiy - o.y) * inv.y;
-	float az = (loz - o.z) * inv.z, bz = (hiz - o.z) * inv.z;
-	float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-	float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), FLT_MAX));
-	tEntry = tmin;
-	return !(tmax < tmin);
-}
+// Rays with a zero or infinite reciprocal component keep the select form above (NaN cases); all others may use the
+// octant-specialised form below.
 RTO_DEV bool ray_needs_exact_box(const RayBox& rb) {
 	float ax = fabsf(rb.inv.x), ay = fabsf(rb.inv.y), az = fabsf(rb.inv.z);
 	return !(ax > 0.0f && ax <= FLT_MAX && ay > 0.0f && ay <= FLT_MAX && az > 0.0f && az <= FLT_MAX);
 }
 
-struct TriV { V3 v0, v1, v2; int id; };
+// The device record holds v0 and the two edges e1 = v1 - v0, e2 = v2 - v0 the rule starts from (one IEEE subtraction each,
+// done once on the host: same bits as computing them per test), so a test costs 6 subtractions less.
+struct TriV { V3 v0, e1, e2; int id; };
 RTO_DEV TriV load_tri(const float4* __restrict__ tris, int pos) {
-	float4 a = RTO_LDG(tris + 3 * (size_t)pos), b = RTO_LDG(tris + 3 * (size_t)pos + 1), c = RTO_LDG(tris + 3 * (size_t)pos + 2);
+	float4 a = RTO_LDG(tris + 3 * (size_t)pos), b = RTO_LDG(tris + 3 * (size_t)pos + 1);
+	float2 c = RTO_LDG(reinterpret_cast<const float2*>(tris + 3 * (size_t)pos + 2));
 	TriV t;
-	t.v0 = mk3(a.x, a.y, a.z); t.v1 = mk3(a.w, b.x, b.y); t.v2 = mk3(b.z, b.w, c.x); t.id = f2i(c.y);
+	t.v0 = mk3(a.x, a.y, a.z); t.e1 = mk3(a.w, b.x, b.y); t.e2 = mk3(b.z, b.w, c.x); t.id = f2i(c.y);
 	return t;
 }
 
 // Moller-Trumbore, SURVEY.md 8c rule (every comparison rejects NaN)
 RTO_DEV bool moller_trumbore(const TriV& tri, V3 o, V3 d, float& tOut) {
-	V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
+	const V3 e1 = tri.e1, e2 = tri.e2;
 	V3 p = cross3(d, e2);
 	float det = dot3(e1, p);
 	if (!(fabsf(det) >= 1e-8f)) return false;
@@ -189,22 +184,51 @@ RTO_DEV bool moller_trumbore(const TriV& tri, V3 o, V3 d, float& tOut) {
 	return true;
 }
 
+// Octant-specialised form: with the signs of 1/d known at compile time (OCT bit a set <=> 1/d negative on axis a) the near and
+// far plane of every axis are known, so the selects of BVH.cpp:78-86 disappear and the running max/min collapse into 3-input
+// min/max (FMNMX3 on sm_100).  Same six subtractions and products as slab_ref, hence the same tmin/tmax when no NaN arises
+// (1/d finite and non-zero).  A warp of primary rays almost always shares one octant, and every shadow ray does.
+template <int OCT>
+RTO_DEV bool slab_oct(V3 o, V3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float tcap, float& tEntry) {
+	float t0x = (((OCT & 1) ? hix : lox) - o.x) * inv.x, t1x = (((OCT & 1) ? lox : hix) - o.x) * inv.x;
+	float t0y = (((OCT & 2) ? hiy : loy) - o.y) * inv.y, t1y = (((OCT & 2) ? loy : hiy) - o.y) * inv.y;
+	float t0z = (((OCT & 4) ? hiz : loz) - o.z) * inv.z, t1z = (((OCT & 4) ? loz : hiz) - o.z) * inv.z;
+	float tmin = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), 0.0f);
+	// tcap = FLT_MAX gives intersectAABB's tmax; tcap = the pruning distance (< FLT_MAX) folds "entry <= tcap" into the same
+	// comparison: tmin <= min(tmax, FLT_MAX) && tmin <= tcap  <=>  tmin <= min(tmax, tcap)
+	float tmax = fminf(fminf(fminf(t1x, t1y), t1z), tcap);
+	tEntry = tmin;
+	return !(tmax < tmin);
+}
+constexpr int kOctGeneric = 8;
+RTO_DEV int ray_octant(const RayBox& rb) {
+	if (ray_needs_exact_box(rb)) return kOctGeneric;
+	return (rb.nx ? 1 : 0) | (rb.ny ? 2 : 0) | (rb.nz ? 4 : 0);
+}
+
+// both child boxes of an inner node (layout in BvhDev)
+// h0/h1: the child's box passes intersectAABB and is entered no later than tcap (tcap = FLT_MAX: no pruning)
+template <int OCT>
+RTO_DEV void node_boxes(const RayBox& rb, float4 a, float4 b, float4 c, float tcap, bool& h0, bool& h1, float& e0, float& e1) {
+	if (OCT < kOctGeneric) {
+		h0 = slab_oct<OCT>(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, tcap, e0);
+		h1 = slab_oct<OCT>(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, tcap, e1);
+	}
+	else {
+		h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0) && (e0 <= tcap);
+		h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1) && (e1 <= tcap);
+	}
+}
+
 // Closest hit.  Result = min over the reference's candidate set of (t, position in candidate order), i.e. the
 // oracle's "strict <, first candidate wins".  PRUNE: near-child-first order and subtrees entered only while their
 // box entry <= best * kPruneSlack.  !PRUNE: every box the reference's queryNode would test is tested.
-template <bool PRUNE>
-RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos) {
-	bestT = kMissT; bestPos = -1;
-	if (S.numTris <= 0) return;
-	RayBox rb = make_raybox(o, d);
-	float te;
-	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return;
-	int   stackRef[kBvhStack];
-	float stackT[kBvhStack];
+template <bool PRUNE, int OCT>
+RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, float& bestT, int& bestPos) {
+	StackEnt stack[kBvhStack];                 // one 8-byte local store / load per push / pop
 	int sp = 0;
 	int cur = S.rootRef;
 	float tcut = kMissT * kPruneSlack;
-	const bool exactBox = ray_needs_exact_box(rb);
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
@@ -212,15 +236,13 @@ RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos
 			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
 			float e0, e1;
 			bool h0, h1;
-			if (!exactBox) { h0 = slab_fast(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_fast(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
-			else { h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
+			node_boxes<OCT>(rb, a, b, c, PRUNE ? tcut : FLT_MAX, h0, h1, e0, e1);
 			int r0 = f2i(r.x), r1 = f2i(r.y);
-			if (PRUNE) { h0 = h0 && (e0 <= tcut); h1 = h1 && (e1 <= tcut); }
 			if (h0 && h1) {
 				bool swap = PRUNE && (e1 < e0);
 				int nearRef = swap ? r1 : r0, farRef = swap ? r0 : r1;
 				float farT = swap ? e0 : e1;
-				if (sp < kBvhStack) { stackRef[sp] = farRef; stackT[sp] = farT; sp++; }
+				if (sp < kBvhStack) { StackEnt e; e.ref = farRef; e.t = farT; stack[sp++] = e; }
 				cur = nearRef;
 				continue;
 			}
@@ -241,23 +263,40 @@ RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos
 		// pop
 		bool got = false;
 		while (sp > 0) {
-			sp--;
-			if (!PRUNE || stackT[sp] <= tcut) { cur = stackRef[sp]; got = true; break; }
+			StackEnt e = stack[--sp];
+			if (!PRUNE || e.t <= tcut) { cur = e.ref; got = true; break; }
 		}
 		if (!got) break;
 	}
 }
 
-// Shadow / any-hit: true iff some candidate of the reference's query passes Moller-Trumbore.
-RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
-	if (S.numTris <= 0) return false;
+template <bool PRUNE>
+RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos) {
+	bestT = kMissT; bestPos = -1;
+	if (S.numTris <= 0) return;
 	RayBox rb = make_raybox(o, d);
 	float te;
-	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return false;
+	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return;
+	if (!PRUNE) { bvh_closest_loop<false, kOctGeneric>(S, rb, o, d, bestT, bestPos); return; }      // verification path: one generic loop
+	switch (ray_octant(rb)) {
+	case 0: bvh_closest_loop<PRUNE, 0>(S, rb, o, d, bestT, bestPos); break;
+	case 1: bvh_closest_loop<PRUNE, 1>(S, rb, o, d, bestT, bestPos); break;
+	case 2: bvh_closest_loop<PRUNE, 2>(S, rb, o, d, bestT, bestPos); break;
+	case 3: bvh_closest_loop<PRUNE, 3>(S, rb, o, d, bestT, bestPos); break;
+	case 4: bvh_closest_loop<PRUNE, 4>(S, rb, o, d, bestT, bestPos); break;
+	case 5: bvh_closest_loop<PRUNE, 5>(S, rb, o, d, bestT, bestPos); break;
+	case 6: bvh_closest_loop<PRUNE, 6>(S, rb, o, d, bestT, bestPos); break;
+	case 7: bvh_closest_loop<PRUNE, 7>(S, rb, o, d, bestT, bestPos); break;
+	default: bvh_closest_loop<PRUNE, kOctGeneric>(S, rb, o, d, bestT, bestPos); break;
+	}
+}
+
+// Shadow / any-hit: true iff some candidate of the reference's query passes Moller-Trumbore.
+template <int OCT>
+RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 	int stackRef[kBvhStack];
 	int sp = 0;
 	int cur = S.rootRef;
-	const bool exactBox = ray_needs_exact_box(rb);
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
@@ -265,8 +304,7 @@ RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
 			float e0, e1;
 			bool h0, h1;
-			if (!exactBox) { h0 = slab_fast(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_fast(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
-			else { h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0); h1 = slab_ref(rb, b.z, b.w, c.x, c.y, c.z, c.w, e1); }
+			node_boxes<OCT>(rb, a, b, c, FLT_MAX, h0, h1, e0, e1);
 			int r0 = f2i(r.x), r1 = f2i(r.y);
 			if (h0 && h1) {
 				bool swap = e1 < e0;
@@ -290,6 +328,24 @@ RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 		cur = stackRef[--sp];
 	}
 	return false;
+}
+
+RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
+	if (S.numTris <= 0) return false;
+	RayBox rb = make_raybox(o, d);
+	float te;
+	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return false;
+	switch (ray_octant(rb)) {
+	case 0: return bvh_any_loop<0>(S, rb, o, d);
+	case 1: return bvh_any_loop<1>(S, rb, o, d);
+	case 2: return bvh_any_loop<2>(S, rb, o, d);
+	case 3: return bvh_any_loop<3>(S, rb, o, d);
+	case 4: return bvh_any_loop<4>(S, rb, o, d);
+	case 5: return bvh_any_loop<5>(S, rb, o, d);
+	case 6: return bvh_any_loop<6>(S, rb, o, d);
+	case 7: return bvh_any_loop<7>(S, rb, o, d);
+	default: return bvh_any_loop<kOctGeneric>(S, rb, o, d);
+	}
 }
 
 // Reference-order replay (left before right, nothing pruned): emits candidate positions in BVH::query order and
@@ -828,8 +884,7 @@ __global__ void __launch_bounds__(128) k_render_bvh(BvhDev S, RenderArgs A) {
 	if (bestPos >= 0) {
 		TriV tri = load_tri(S.tris, bestPos);
 		id = tri.id;
-		V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
-		V3 n = normalize3(cross3(e1, e2));
+		V3 n = normalize3(cross3(tri.e1, tri.e2));
 		if (dot3(n, ray.d) > 0.0f) n = -n;
 		V3 hit = ray.o + ray.d * bestT;
 		bool shadowed = false;
@@ -916,8 +971,7 @@ __global__ void __launch_bounds__(128) k_stats_bvh(BvhDev S, RenderArgs A, unsig
 			bvh_closest<false>(S, ray.o, ray.d, bestT, bestPos);
 			if (bestPos >= 0) {
 				TriV tri = load_tri(S.tris, bestPos);
-				V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
-				V3 n = normalize3(cross3(e1, e2));
+				V3 n = normalize3(cross3(tri.e1, tri.e2));
 				if (dot3(n, ray.d) > 0.0f) n = -n;
 				V3 so = (ray.o + ray.d * bestT) + n * A.shadowBias;
 				V3 sd = normalize3(mk3(1.0f, 1.0f, 1.0f));

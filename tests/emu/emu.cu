@@ -87,7 +87,7 @@ void emu_render_bvh(void* h, const RtoCamera* cam, unsigned flags, float bias, i
 			if (bestPos >= 0) {
 				TriV tri = load_tri(S.tris, bestPos);
 				id = tri.id;
-				V3 e1 = tri.v1 - tri.v0, e2 = tri.v2 - tri.v0;
+				V3 e1 = tri.e1, e2 = tri.e2;
 				V3 n = normalize3(cross3(e1, e2));
 				if (dot3(n, ray.d) > 0.0f) n = -n;
 				V3 hp = ray.o + ray.d * bestT;
