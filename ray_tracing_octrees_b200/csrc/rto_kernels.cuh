@@ -86,6 +86,7 @@ constexpr uint32_t kOctSolid = 0x40000000u;
 constexpr int kMaxOctDepth = 32;
 constexpr int kBvhStack = 64;
 constexpr float kMissT = 1e30f;
+constexpr float kBelowMissT = 9.99999940e29f;    // the largest float below 1e30f (tests/test_abi.py checks the bit pattern)
 // pruning margin of the ordered BVH traversal: a subtree is skipped only if its box entry distance exceeds the
 // best hit by more than this relative slack (keeps co-planar / shared-edge candidates)
 constexpr float kPruneSlack = 1.00001f;
@@ -535,6 +536,20 @@ RTO_DEV bool skip_box(const OctBox& b, const SkipRay& r, float tMin, float tMax,
 	return !(enterT > exitT);
 }
 
+// The same test with the octant of 1/d known (OCT < 8, voxel > 0, no NaN anywhere): the near/far plane of each axis is picked
+// without a comparison and the clamps use FMNMX; values equal skip_box's except possibly the sign of a zero, which no
+// comparison sees (a zero that would be RETURNED re-runs the ray through the per-node path, see octA_fast_loop).
+template <int OCT>
+RTO_DEV bool skip_box_oct(const OctBox& b, const SkipRay& r, float tMin, float tMax, float& enterT, float& exitT) {
+	if (OCT >= 8) return skip_box(b, r, tMin, tMax, enterT, exitT);
+	V3 t1 = (b.mn - r.o) * r.inv, t2 = (b.mx - r.o) * r.inv;
+	V3 tN = mk3((OCT & 1) ? t2.x : t1.x, (OCT & 2) ? t2.y : t1.y, (OCT & 4) ? t2.z : t1.z);
+	V3 tF = mk3((OCT & 1) ? t1.x : t2.x, (OCT & 2) ? t1.y : t2.y, (OCT & 4) ? t1.z : t2.z);
+	enterT = fmaxf(fmaxf(tN.x, tN.y), fmaxf(tN.z, tMin));
+	exitT = fminf(fminf(tF.x, tF.y), fminf(tF.z, tMax));
+	return !(enterT > exitT);
+}
+
 RTO_DEV OctHit octA_compact(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 	OctHit h; h.t = kMissT; h.id = -1; h.normal = mk3(0.0f, 0.0f, 0.0f); h.visits = 0;
 	SkipRay r = make_skipray(o, d);
@@ -646,6 +661,9 @@ RTO_DEV OctHit octA_general(const OctDev& S, V3 o, V3 d, float tMin, float tMax)
 // ------------------------------------------------------------------------------------------------
 struct ChildPlanes { float n0[3], f0[3], n1[3], f1[3]; };     // per axis: near/far distances of the low and the high half
 
+// OCT < 8: bit a set <=> 1/d negative on axis a (and voxel > 0), so the smaller of the two plane distances is known without a
+// min/max: the products are monotonic in the plane position.  OCT == 8: generic min/max.
+template <int OCT>
 RTO_DEV ChildPlanes oct_child_planes(const OctDev& S, V3 o, V3 inv, int x, int y, int z, int h) {
 	ChildPlanes P;
 	const float w = float(h) * S.voxel;
@@ -656,8 +674,15 @@ RTO_DEV ChildPlanes oct_child_planes(const OctDev& S, V3 o, V3 inv, int x, int y
 		float lo0 = S.gmin[a] + float(c[a]) * S.voxel, lo1 = S.gmin[a] + float(c[a] + h) * S.voxel;
 		float t1 = (lo0 - oo[a]) * ii[a], t2 = ((lo0 + w) - oo[a]) * ii[a];
 		float u1 = (lo1 - oo[a]) * ii[a], u2 = ((lo1 + w) - oo[a]) * ii[a];
-		P.n0[a] = fminf(t1, t2); P.f0[a] = fmaxf(t1, t2);
-		P.n1[a] = fminf(u1, u2); P.f1[a] = fmaxf(u1, u2);
+		if (OCT < 8) {
+			const bool neg = (OCT >> a) & 1;
+			P.n0[a] = neg ? t2 : t1; P.f0[a] = neg ? t1 : t2;
+			P.n1[a] = neg ? u2 : u1; P.f1[a] = neg ? u1 : u2;
+		}
+		else {
+			P.n0[a] = fminf(t1, t2); P.f0[a] = fmaxf(t1, t2);
+			P.n1[a] = fminf(u1, u2); P.f1[a] = fmaxf(u1, u2);
+		}
 	}
 	return P;
 }
@@ -671,9 +696,8 @@ RTO_DEV void oct_child_coords(int k, int h, int& x, int& y, int& z) {
 	x += (k & 1) ? h : 0; y += (k & 2) ? h : 0; z += (k & 4) ? h : 0;
 }
 
-RTO_DEV OctHit octB_fast(const OctDev& S, V3 o, V3 d) {
-	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-	if (!inv_is_regular(inv) || S.rootSize > 65536) return octB_compact(S, o, d);
+template <int OCT>
+RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 	OctHit hit; hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
 	int x = 0, y = 0, z = 0, size = S.rootSize;
 	int steps = 1;                                             // the root is popped first
@@ -697,13 +721,16 @@ RTO_DEV OctHit octB_fast(const OctDev& S, V3 o, V3 d) {
 		const int h = size >> 1;
 		const unsigned leafMask = (unsigned)e.w & 0xffu, solidMask = ((unsigned)e.w >> 8) & 0xffu;
 		if (entering) {
-			ChildPlanes P = oct_child_planes(S, o, inv, x, y, z, h);
+			ChildPlanes P = oct_child_planes<OCT>(S, o, inv, x, y, z, h);
+			// "tNear < closestT" (closestT stays 1e30 until the hit that ends the walk) is folded into the far distance of one axis:
+			// tn <= tf && tf > 0 && tn < 1e30  <=>  tn <= min(tf, kBelowMissT) && min(tf, kBelowMissT) > 0
+			P.f0[2] = fminf(P.f0[2], kBelowMissT); P.f1[2] = fminf(P.f1[2], kBelowMissT);
 			unsigned hits = 0;
 #pragma unroll
 			for (int k = 0; k < 8; k++) {
 				float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), (k & 4) ? P.n1[2] : P.n0[2]);
 				float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), (k & 4) ? P.f1[2] : P.f0[2]);
-				bool hk = (tn <= tf) && (tf > 0.0f) && !(tn >= kMissT);
+				bool hk = (tn <= tf) && (tf > 0.0f);
 				hits |= hk ? (1u << k) : 0u;
 			}
 			M = hits & ~(leafMask & ~solidMask);               // children that can do more than burn a step: solid leaves and internal nodes
@@ -751,9 +778,29 @@ RTO_DEV OctHit octB_fast(const OctDev& S, V3 o, V3 d) {
 	return hit;
 }
 
-RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
-	SkipRay r = make_skipray(o, d);
-	if (!inv_is_regular(r.inv) || S.rootSize > 65536) return octA_compact(S, o, d, tMin, tMax);
+// dispatch on the octant of 1/d (one instantiation per sign pattern; a warp of primary rays almost always shares one)
+#define RTO_OCT_DISPATCH(CALL) \
+	switch (oct) { \
+	case 0: return CALL(0); case 1: return CALL(1); case 2: return CALL(2); case 3: return CALL(3); \
+	case 4: return CALL(4); case 5: return CALL(5); case 6: return CALL(6); case 7: return CALL(7); \
+	default: return CALL(8); }
+
+RTO_DEV int inv_octant(V3 inv, float voxel) {
+	if (!(voxel > 0.0f)) return 8;
+	return ((inv.x < 0) ? 1 : 0) | ((inv.y < 0) ? 2 : 0) | ((inv.z < 0) ? 4 : 0);
+}
+
+RTO_DEV OctHit octB_fast(const OctDev& S, V3 o, V3 d) {
+	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	if (!inv_is_regular(inv) || S.rootSize > 65536) return octB_compact(S, o, d);
+	const int oct = inv_octant(inv, S.voxel);
+#define RTO_CALL_B(K) octB_fast_loop<K>(S, o, d, inv)
+	RTO_OCT_DISPATCH(RTO_CALL_B)
+#undef RTO_CALL_B
+}
+
+template <int OCT>
+RTO_DEV OctHit octA_fast_loop(const OctDev& S, V3 o, V3 d, float tMin, float tMax, const SkipRay& r) {
 	OctHit hit; hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
 	int x = 0, y = 0, z = 0, size = S.rootSize;
 	float curMin, curMax;                                      // (enterT, exitT) of the current internal node = clamps of its children
@@ -766,6 +813,10 @@ RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 			return hit;
 		}
 	}
+	// visit order of the octants: a compile-time table when the octant of 1/d is (then dirMask == ~OCT & 7: octA_fast sends rays
+	// with an exactly-zero direction component, where the two differ, to OCT == 8)
+	const uint32_t order = (OCT < 8) ? skip_order((~OCT) & 7) : r.order;
+	const uint32_t rnk = (OCT < 8) ? skip_rank((~OCT) & 7) : r.rank;
 	float minS[16], maxS[16];
 	unsigned long long mlo = 0ull, mhi = 0ull;                 // remaining-children masks in VISIT-ORDER space, 8 bits per level
 	int level = 0, rank = 0, posO = -1;
@@ -776,22 +827,28 @@ RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 		const int h = size >> 1;
 		const unsigned leafMask = (unsigned)e.w & 0xffu, solidMask = ((unsigned)e.w >> 8) & 0xffu;
 		if (entering) {
-			ChildPlanes P = oct_child_planes(S, r.o, r.inv, x, y, z, h);
+			ChildPlanes P = oct_child_planes<OCT>(S, r.o, r.inv, x, y, z, h);
 			const unsigned skipMask = leafMask & ~solidMask;   // empty leaves return 1e30f whatever their box test says
-			Mo = 0;
+			// the parent's clamps (tMin, tMax of the recursive call) enter every child's max/min once: fold them into one axis
+			P.n0[2] = fmaxf(P.n0[2], curMin); P.n1[2] = fmaxf(P.n1[2], curMin);
+			P.f0[2] = fminf(P.f0[2], curMax); P.f1[2] = fminf(P.f1[2], curMax);
+			Mo = 0;                                            // bit j = j-th child in VISIT order (octant `order` nibble j) passes its box test
+			unsigned skipO = 0;
 #pragma unroll
-			for (int k = 0; k < 8; k++) {
-				float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), fmaxf((k & 4) ? P.n1[2] : P.n0[2], curMin));
-				float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), fminf((k & 4) ? P.f1[2] : P.f0[2], curMax));
-				bool hk = !(tn > tf) && !((skipMask >> k) & 1u);
-				Mo |= hk ? (1u << ((r.rank >> (4 * k)) & 7u)) : 0u;
+			for (int j = 0; j < 8; j++) {
+				const int k = (int)((order >> (4 * j)) & 7u);  // a compile-time constant when the octant is (OCT < 8)
+				float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), (k & 4) ? P.n1[2] : P.n0[2]);
+				float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), (k & 4) ? P.f1[2] : P.f0[2]);
+				Mo |= !(tn > tf) ? (1u << j) : 0u;
+				skipO |= ((skipMask >> k) & 1u) << j;
 			}
+			Mo &= ~skipO;
 			posO = -1;
 		}
 		unsigned rem = (posO < 0) ? Mo : (Mo & ~((2u << posO) - 1u));   // order positions after the last consumed one
 		if (rem == 0u) {
 			if (level == 0) break;
-			posO = (int)((r.rank >> (4 * (((unsigned)e.w >> 16) & 7u))) & 7u);
+			posO = (int)((rnk >> (4 * (((unsigned)e.w >> 16) & 7u))) & 7u);
 			rank = e.z;
 			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
 			level--;
@@ -802,13 +859,13 @@ RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 			continue;
 		}
 		const int jO = ffs32(rem) - 1;
-		const int k = (int)((r.order >> (4 * jO)) & 7u);
+		const int k = (int)((order >> (4 * jO)) & 7u);
 		posO = jO;
 		int cx = x, cy = y, cz = z;
 		oct_child_coords(k, h, cx, cy, cz);
 		OctBox b = oct_box(S, cx, cy, cz, h);
 		float enterT, exitT;
-		bool ok = skip_box(b, r, curMin, curMax, enterT, exitT);
+		bool ok = skip_box_oct<OCT>(b, r, curMin, curMax, enterT, exitT);
 		if ((leafMask >> k) & 1u) {                            // solid leaf
 			if (ok && enterT < 1e30f) {
 				if (enterT == 0.0f) return octA_compact(S, o, d, tMin, tMax);     // zero of either sign: take the reference's select forms
@@ -830,6 +887,16 @@ RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 		entering = true;
 	}
 	return hit;
+}
+
+RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
+	SkipRay r = make_skipray(o, d);
+	if (!inv_is_regular(r.inv) || S.rootSize > 65536 || !(tMin == tMin) || !(tMax == tMax)) return octA_compact(S, o, d, tMin, tMax);
+	int oct = inv_octant(r.inv, S.voxel);
+	if (d.x == 0.0f || d.y == 0.0f || d.z == 0.0f) oct = 8;    // dirMask (d > 0) and the sign of the clamped reciprocal disagree
+#define RTO_CALL_A(K) octA_fast_loop<K>(S, o, d, tMin, tMax, r)
+	RTO_OCT_DISPATCH(RTO_CALL_A)
+#undef RTO_CALL_A
 }
 
 // COUNT: the caller needs OctHit::visits (rto_render_stats) -> per-node paths, which count what the reference visits.
