@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librto.so")
+# RTO_LIB_VARIANT=<name> loads librto_<name>.so, an experimental build made by `python -m ray_tracing_octrees_b200.build --variant
+# <name> -D...` for A/B kernel timing (tools/profile_case.py); the product is always librto.so
+LIB_PATH = os.path.join(HERE, "librto_%s.so" % os.environ["RTO_LIB_VARIANT"] if os.environ.get("RTO_LIB_VARIANT") else "librto.so")
 
 RTO_OK = 0
 MODE_BVH, MODE_OCTREE_SKIP, MODE_OCTREE_GLSL = 0, 1, 2

@@ -16,12 +16,12 @@ SOURCES = ["rto_device.cu", "host_builders.cpp", "host_layouts.cpp"]
 DEPS = SOURCES + ["rto_kernels.cuh", "rto_internal.h", "rto_math.h", "mc_tables.h", "../../include/rto_c.h"]
 
 
-def nvcc_cmd(extra=()):
+def nvcc_cmd(extra=(), out=None):
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     return ["nvcc", "-ccbin", ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
             "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
             "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2", "-shared",
-            *extra, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
+            *extra, "-o", out or OUT, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
 
 
 def needs_build():
@@ -44,5 +44,19 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_variant(name, defines):
+    """Experimental build librto_<name>.so with extra -D flags (A/B kernel timing; never loaded unless RTO_LIB_VARIANT=<name>)."""
+    out = os.path.join(HERE, "librto_%s.so" % name)
+    r = subprocess.run(nvcc_cmd(list(defines), out), capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building " + out)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -252,8 +252,9 @@ static int check_mode(const RtoScene* s, int mode) {
 
 // BVH scenes: per-thread while-loop kernel; default flags trace the SAH topology with t-pruning, RTO_FLAG_NO_PRUNE
 // visits every box the reference's queryNode visits, on the reference's own topology (verification path).
-// Octree scenes: thread-per-pixel kernel.  (Two other schedulings of the BVH loop were built, measured and removed in
-// round 1 -- a persistent per-lane refill kernel and a warp-phased while-while kernel; see profiles/README.md.)
+// Octree scenes: thread-per-pixel kernel.  (Other schedulings were built, measured and removed in round 1 -- for the BVH loop a
+// persistent per-lane refill kernel, a warp-phased while-while kernel and a per-step warp vote; for the octree walks a persistent
+// kernel refilling idle lanes from a pixel counter; see profiles/README.md.)
 static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCams, int mode) {
 	dim3 block(128), grid((width + 15) / 16, (A.y1 - A.y0 + 7) / 8, numCams);
 	if (s->kind == RTO_MODE_BVH) {
