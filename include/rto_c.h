@@ -141,6 +141,27 @@ RTO_API int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, co
 RTO_API int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt /* may be NULL */,
 	RtoScene** out);
 
+/* ---- scene construction on the GPU (the steps in front of the ray path) ----------------------------
+ * Same results as the host builders above, bit for bit (the tests compare both), at memory-bandwidth speed. */
+
+/* createOctreeFromVoxelGrid + setOctree numbering on the device: same array as rto_host_octree_build (malloc'ed; rto_host_free). */
+RTO_API int rto_device_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	RtoGpuNode** nodesOut, size_t* numNodes);
+
+/* Voxel grid -> device octree scene without a host-side tree: upload the grid, build and linearise on the GPU
+ * (replaces createOctreeFromVoxelGrid + RayTracerBVH::setOctree, main.cpp:1077, 1127-1131). */
+RTO_API int rto_scene_create_octree_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, RtoScene** out);
+
+/* MarchingCubesRenderer::render(root, grid, 0,0,0, root->size) on the device: same triangle soup, same order as
+ * rto_host_mc_mesh (malloc'ed; rto_host_free).  Builds the octree it needs for the emission order itself. */
+RTO_API int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, RtoTriangle** trisOut, size_t* numTris);
+
+/* Diagnostic: the compact device layout of an octree scene (desc: numNodes + 8 words, up: (numNodes + 7) / 8 + 1 words,
+ * inner: 4 words per internal node); any pointer may be NULL.  Lets tests compare the two construction routes. */
+RTO_API int rto_scene_octree_layout_read(RtoScene* scene, uint32_t* desc, int32_t* up, int32_t* inner4, size_t* numInner);
+
 RTO_API void rto_scene_destroy(RtoScene* scene);
 RTO_API int rto_scene_info(const RtoScene* scene, int* kind /* RtoMode of a BVH or octree scene */,
 	size_t* numPrims, size_t* numNodes, size_t* deviceBytes, int* compactLayout);

@@ -83,6 +83,23 @@ def create_octree_from_voxel_grid(grid):
     return _take(ptr, n.value, np.int32, (n.value, 15))
 
 
+def create_octree_on_device(grid):
+    """Same array as create_octree_from_voxel_grid, built on the GPU (rto_device_octree_build)."""
+    ptr = C.c_void_p()
+    n = C.c_size_t()
+    check(lib().rto_device_octree_build(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], C.byref(ptr), C.byref(n)))
+    return _take(ptr, n.value, np.int32, (n.value, 15))
+
+
+def marching_cubes_mesh_on_device(grid):
+    """Same triangle soup as marching_cubes_mesh, extracted on the GPU (rto_device_mc_mesh)."""
+    ptr = C.c_void_p()
+    n = C.c_size_t()
+    check(lib().rto_device_mc_mesh(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min), grid.voxel_size,
+                                   C.byref(ptr), C.byref(n)))
+    return _take(ptr, n.value, np.float32, (n.value, 9))
+
+
 def marching_cubes_mesh(grid, nodes):
     """-> (m, 9) float32 triangle soup (v0, v1, v2) in the reference's emission order."""
     nodes = np.ascontiguousarray(nodes, np.int32)
@@ -158,6 +175,25 @@ class Scene:
         h = C.c_void_p()
         check(lib().rto_scene_create_octree(_p(nodes), len(nodes), _p(gm), float(voxel_size), C.byref(h)))
         return Scene(h)
+
+    @staticmethod
+    def octree_from_grid(grid):
+        """Voxel grid -> octree scene, built and linearised on the GPU (rto_scene_create_octree_from_grid)."""
+        h = C.c_void_p()
+        check(lib().rto_scene_create_octree_from_grid(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min),
+                                                      float(grid.voxel_size), C.byref(h)))
+        return Scene(h)
+
+    def octree_layout(self):
+        """Diagnostic: (desc, up, inner) arrays of a compact octree scene as numpy arrays."""
+        n = self.info()["nodes"]
+        desc = np.zeros(n + 8, np.uint32)
+        up = np.zeros((n + 7) // 8 + 1, np.int32)
+        ninner = max((n - 1) // 8, 1)
+        inner = np.zeros((ninner, 4), np.int32)
+        k = C.c_size_t()
+        check(lib().rto_scene_octree_layout_read(self.h, _p(desc), _p(up), _p(inner), C.byref(k)))
+        return desc, up, inner
 
     @staticmethod
     def bvh(tris, prebuilt=None):

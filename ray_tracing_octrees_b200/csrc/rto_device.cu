@@ -2,6 +2,7 @@
 //
 // Built for sm_100a only with -fmad=false (exact parity with the CPU oracle needs unfused multiply/add).
 // There is no CPU fallback in this file: every entry point that traces rays requires a CUDA device.
+#include "rto_scene.cuh"
 #include "rto_kernels.cuh"
 
 #include <cstdarg>
@@ -28,9 +29,8 @@ int rto_fail(int code, const char* fmt, ...) {
 extern "C" const char* rto_last_error(void) { return g_err; }
 extern "C" const char* rto_version(void) { return "rto-b200 0.1 (sm_100a)"; }
 
-#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return rto_fail(RTO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
-
-static int require_device() {
+static int require_device() { return rto_require_device(); }
+int rto_require_device() {
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
 	if (e != cudaSuccess || n <= 0) {
@@ -67,28 +67,9 @@ extern "C" int rto_device_info(int* smCount, int* ccMajor, int* ccMinor, size_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// scene
+// scene (struct in rto_scene.cuh)
 // ------------------------------------------------------------------------------------------------
-struct RtoScene {
-	int kind = RTO_MODE_BVH;          // RTO_MODE_BVH or RTO_MODE_OCTREE_GLSL (any octree)
-	int device = 0;
-	cudaStream_t stream = nullptr;
-	cudaStream_t copyStream = nullptr;            // device->host plane copies of RTO_MEM_HOST batches overlap the next frame's kernel
-	cudaEvent_t evStart = nullptr, evStop = nullptr, evFrame = nullptr;
-	bool timed = false;
-	uint64_t launches = 0;
-	size_t deviceBytes = 0, numPrims = 0, numNodes = 0;
-	BvhDev bvh{};                     // reference topology (BVH::query replay, stats, RTO_FLAG_NO_PRUNE)
-	BvhDev bvhFast{};                 // SAH topology over the same leaves (production closest-hit / shadow rays)
-	OctDev oct{};
-	std::vector<void*> owned;         // device allocations of the scene
-	// growable scratch (device outputs for RTO_MEM_HOST calls, cameras, ray lists)
-	void* scratch[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-	size_t scratchBytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-	int smCount = 0;
-};
-
-static int scene_alloc(RtoScene* s, void** p, size_t bytes) {
+int rto_scene_alloc(RtoScene* s, void** p, size_t bytes) {
 	*p = nullptr;
 	cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
 	if (e != cudaSuccess) return rto_fail(RTO_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -96,8 +77,13 @@ static int scene_alloc(RtoScene* s, void** p, size_t bytes) {
 	s->deviceBytes += bytes;
 	return RTO_OK;
 }
+int rto_scene_adopt(RtoScene* s, void* p, size_t bytes) {
+	s->owned.push_back(p);
+	s->deviceBytes += bytes;
+	return RTO_OK;
+}
 
-static int scene_scratch(RtoScene* s, int slot, size_t bytes, void** p) {
+int rto_scene_scratch(RtoScene* s, int slot, size_t bytes, void** p) {
 	if (s->scratchBytes[slot] < bytes) {
 		if (s->scratch[slot]) cudaFree(s->scratch[slot]);
 		s->scratch[slot] = nullptr; s->scratchBytes[slot] = 0;
@@ -110,7 +96,7 @@ static int scene_scratch(RtoScene* s, int slot, size_t bytes, void** p) {
 	return RTO_OK;
 }
 
-static int scene_new(RtoScene** out) {
+int rto_scene_new(RtoScene** out) {
 	int rc = require_device(); if (rc) return rc;
 	RtoScene* s = new (std::nothrow) RtoScene();
 	if (!s) return rto_fail(RTO_ERR_ALLOC, "out of host memory");
@@ -125,6 +111,9 @@ static int scene_new(RtoScene** out) {
 	*out = s;
 	return RTO_OK;
 }
+static int scene_alloc(RtoScene* s, void** p, size_t bytes) { return rto_scene_alloc(s, p, bytes); }
+static int scene_scratch(RtoScene* s, int slot, size_t bytes, void** p) { return rto_scene_scratch(s, slot, bytes, p); }
+static int scene_new(RtoScene** out) { return rto_scene_new(out); }
 
 extern "C" void rto_scene_destroy(RtoScene* s) {
 	if (!s) return;

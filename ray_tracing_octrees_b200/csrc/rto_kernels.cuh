@@ -12,7 +12,7 @@
 // expression keeps the reference's operation order (rto_math.h); min/max are spelled as selects with the
 // reference's operand order so NaN/inf cases agree.
 #pragma once
-#include "rto_internal.h"
+#include "rto_devtypes.h"
 #include <cfloat>
 #include <cstring>
 #include <cuda_runtime.h>
@@ -56,40 +56,6 @@ RTO_DEV int ffs32(unsigned v) {
 	return __builtin_ffs((int)v);
 #endif
 }
-
-// ------------------------------------------------------------------------------------------------
-// Device scene descriptors (passed by value as kernel parameters)
-// ------------------------------------------------------------------------------------------------
-struct BvhDev {
-	const float4* nodes;     // inner nodes, 4 x float4 each: [lo0.xyz hi0.x][hi0.yz lo1.xy][lo1.z hi1.xyz][ref0 ref1 - -]
-	const float4* tris;      // 3 x float4 per triangle in leaf order: [v0.xyz e1.x][e1.yz e2.xy][e2.z id - -], e1 = v1 - v0, e2 = v2 - v0
-	int   rootRef;           // >= 0: inner node index; < 0: ~leafRef, leafRef = (firstPos << 1) | (count - 1)
-	int   numTris;
-	float rootLo[3], rootHi[3];
-};
-
-struct OctDev {
-	const uint32_t* desc;    // compact layout: per node, bit31 = leaf, bit30 = solid, else index of first child (8 contiguous)
-	const int32_t*  up;      // compact layout: parent node of sibling group g = (node - 1) >> 3
-	const int4*     nodes16; // general layout: RtoGpuNode padded to 16 x int32
-	const int4*     inner;   // compact layout, one 16-byte record per INTERNAL node in BFS order (rank): x = index of first child,
-	                         // y = rank of the first internal child, z = rank of the parent, w = leafMask | solidMask<<8 | childIdx<<16
-	int   numNodes;
-	int   rootSize;
-	int   compact;
-	float gmin[3];
-	float voxel;
-};
-
-constexpr uint32_t kOctLeaf = 0x80000000u;
-constexpr uint32_t kOctSolid = 0x40000000u;
-constexpr int kMaxOctDepth = 32;
-constexpr int kBvhStack = 64;
-constexpr float kMissT = 1e30f;
-constexpr float kBelowMissT = 9.99999940e29f;    // the largest float below 1e30f (tests/test_abi.py checks the bit pattern)
-// pruning margin of the ordered BVH traversal: a subtree is skipped only if its box entry distance exceeds the
-// best hit by more than this relative slack (keeps co-planar / shared-edge candidates)
-constexpr float kPruneSlack = 1.00001f;
 
 struct Ray { V3 o, d; };
 struct alignas(8) StackEnt { int ref; float t; };     // postponed far child of the ordered BVH traversal and its box entry distance

@@ -1,0 +1,34 @@
+// rto_scene.cuh -- the device scene object and its allocation helpers, shared by the translation units that enqueue GPU work
+// (rto_device.cu: uploads, rendering; rto_build.cu: scene construction on the GPU).  Not part of the ABI.
+#pragma once
+#include "rto_devtypes.h"
+#include <vector>
+
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return rto_fail(RTO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+// RTO_OK, or RTO_ERR_NO_DEVICE with a message: there is no CPU fallback for anything that traces or builds on the device
+int rto_require_device();
+
+struct RtoScene {
+	int kind = RTO_MODE_BVH;          // RTO_MODE_BVH or RTO_MODE_OCTREE_GLSL (any octree)
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaStream_t copyStream = nullptr;            // device->host plane copies of RTO_MEM_HOST batches overlap the next frame's kernel
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evFrame = nullptr;
+	bool timed = false;
+	uint64_t launches = 0;
+	size_t deviceBytes = 0, numPrims = 0, numNodes = 0;
+	rto::BvhDev bvh{};                // reference topology (BVH::query replay, stats, RTO_FLAG_NO_PRUNE)
+	rto::BvhDev bvhFast{};            // SAH topology over the same leaves (production closest-hit / shadow rays)
+	rto::OctDev oct{};
+	std::vector<void*> owned;         // device allocations of the scene
+	// growable scratch (device outputs for RTO_MEM_HOST calls, cameras, ray lists)
+	void* scratch[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	size_t scratchBytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	int smCount = 0;
+};
+
+int rto_scene_new(RtoScene** out);                             // stream, events, device id
+int rto_scene_alloc(RtoScene* s, void** p, size_t bytes);      // device memory owned by the scene
+int rto_scene_adopt(RtoScene* s, void* p, size_t bytes);       // take ownership of an existing cudaMalloc'ed block
+int rto_scene_scratch(RtoScene* s, int slot, size_t bytes, void** p);

@@ -1,0 +1,88 @@
+"""GPU scene construction (rto_build.cu) against the host builders, which tests/test_oracle_pinning.py and
+tests/test_host_builders.py pin to the reference: same octree array, same triangle soup, same device layout, bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _grids(rto, dt_grid_path):
+    rng = np.random.default_rng(7)
+    out = {}
+    out["sphere32"] = rto.generate_test_volume(32)
+    out["sphere48_offgrid"] = rto.VoxelGrid((48, 48, 48), (-3.25, 0.5, 7.0), 0.37, rto.generate_test_volume(48).data)
+    d = (20, 33, 7)
+    out["ragged_noise"] = rto.VoxelGrid(d, (-1.0, -2.0, -3.0), 0.5, (rng.random(d[0] * d[1] * d[2]) < 0.3).astype(np.uint8))
+    d = (17, 17, 17)
+    out["odd_dense"] = rto.VoxelGrid(d, (0, 0, 0), 1.0, (rng.random(d[0] * d[1] * d[2]) < 0.9).astype(np.uint8))
+    out["all_empty"] = rto.VoxelGrid((8, 8, 8), (0, 0, 0), 1.0, np.zeros(512, np.uint8))
+    out["all_filled"] = rto.VoxelGrid((8, 8, 8), (0, 0, 0), 1.0, np.ones(512, np.uint8))
+    out["all_filled_ragged"] = rto.VoxelGrid((5, 8, 3), (0, 0, 0), 1.0, np.ones(120, np.uint8))
+    out["single_voxel"] = rto.VoxelGrid((1, 1, 1), (0, 0, 0), 1.0, np.ones(1, np.uint8))
+    out["thin_slab"] = rto.VoxelGrid((16, 1, 16), (0, 0, 0), 2.0, (rng.random(256) < 0.5).astype(np.uint8))
+    out["city128"] = rto.city_block_grid(128, 99, 8)
+    out["dt"] = rto.VoxelGrid.load(dt_grid_path)
+    return out
+
+
+@pytest.fixture(scope="module")
+def grids(rto, dt_grid_path):
+    assert rto.lib().rto_init(0) == 0, rto.lib().rto_last_error().decode()
+    return _grids(rto, dt_grid_path)
+
+
+NAMES = ["sphere32", "sphere48_offgrid", "ragged_noise", "odd_dense", "all_empty", "all_filled", "all_filled_ragged", "single_voxel",
+         "thin_slab", "city128", "dt"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_device_octree_equals_host_octree(rto, grids, name):
+    g = grids[name]
+    host = rto.create_octree_from_voxel_grid(g)
+    dev = rto.create_octree_on_device(g)
+    assert dev.shape == host.shape, "%s: %s vs %s nodes" % (name, dev.shape, host.shape)
+    assert np.array_equal(dev, host), "%s: GPUNodes arrays differ" % name
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_device_mesh_equals_host_mesh(rto, grids, name):
+    g = grids[name]
+    host = rto.marching_cubes_mesh(g, rto.create_octree_from_voxel_grid(g))
+    dev = rto.marching_cubes_mesh_on_device(g)
+    assert dev.shape == host.shape, "%s: %d vs %d triangles" % (name, len(dev), len(host))
+    assert_bit_equal(dev, host, name + " triangles")
+
+
+@pytest.mark.parametrize("name", ["sphere32", "ragged_noise", "odd_dense", "all_filled", "single_voxel", "city128", "dt"])
+def test_scene_from_grid_has_the_same_device_layout(rto, grids, name):
+    g = grids[name]
+    a = rto.Scene.octree(rto.create_octree_from_voxel_grid(g), g.min, g.voxel_size)
+    b = rto.Scene.octree_from_grid(g)
+    ia, ib = a.info(), b.info()
+    assert ia["nodes"] == ib["nodes"] and ia["prims"] == ib["prims"] and ib["compact"] == 1 and ia["compact"] == 1
+    for x, y, what in zip(a.octree_layout(), b.octree_layout(), ("desc", "up", "inner")):
+        assert np.array_equal(x, y), "%s: %s differs" % (name, what)
+
+
+def test_scene_from_grid_renders_like_the_oracle(rto, checker, grids):
+    g = grids["sphere32"]
+    sc = rto.Scene.octree_from_grid(g)
+    cam, _ = rto.Camera.from_degrees(30, 40, 1.2).consts(45.0, float(np.float32(96) / np.float32(64)), 96, 64)
+    rcam, _ = checker.camera(30, 40, 1.2, width=96, height=64)
+    oc = checker.octree(g.dims, g.min, g.voxel_size, g.data)
+    oc.build()
+    for mode, key in ((rto.MODE_OCTREE_SKIP, 0), (rto.MODE_OCTREE_GLSL, 1)):
+        got, want = sc.render(cam, mode), oc.render(rcam, key)
+        assert np.array_equal(got["id"], want["id"])
+        assert_bit_equal(got["t"], want["t"], "t")
+        assert_bit_equal(got["rgba"], want["rgba"].reshape(-1, 4), "rgba")
+
+
+def test_reserved_voxel_value_is_rejected(rto, grids):
+    g = rto.VoxelGrid((4, 4, 4), (0, 0, 0), 1.0, np.full(64, 255, np.uint8))
+    with pytest.raises(rto.RtoError):
+        rto.create_octree_on_device(g)
+    with pytest.raises(rto.RtoError):
+        rto.create_octree_from_voxel_grid(g)
