@@ -80,6 +80,8 @@ def lib():
                               "there is no fallback implementation." % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("RTO_LIB_VARIANT") and not hasattr(L, name):
+                continue                    # experimental builds of older sources may lack newer entry points
             fn = getattr(L, name)           # AttributeError here == header/library mismatch
             fn.restype, fn.argtypes = res, args
         _lib = L

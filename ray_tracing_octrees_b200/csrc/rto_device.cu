@@ -253,7 +253,8 @@ static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCam
 		else if (sh) k_render_bvh<true, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
 		else k_render_bvh<false, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
 	}
-	else k_render_octree<<<grid, block, 0, s->stream>>>(s->oct, A, mode);
+	else if (mode == RTO_MODE_OCTREE_SKIP) k_render_octree<RTO_MODE_OCTREE_SKIP><<<grid, block, 0, s->stream>>>(s->oct, A);
+	else k_render_octree<RTO_MODE_OCTREE_GLSL><<<grid, block, 0, s->stream>>>(s->oct, A);
 	s->launches++;
 	return RTO_OK;
 }

@@ -691,82 +691,88 @@ RTO_DEV unsigned walk_pop_mask(const OctWalk& w) {
 }
 
 // ---- mode B ------------------------------------------------------------------------------------------------------
-// returns true when the walk is over before it starts (root missed or root is a leaf); hit is final then
-RTO_DEV bool octB_init(const OctDev& S, V3 o, V3 d, V3 inv, OctWalk& w, OctHit& hit) {
-	hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 1;
-	w.x = 0; w.y = 0; w.z = 0; w.size = S.rootSize;
-	w.steps = 1;                                               // the root is popped first
-	OctBox b = oct_box(S, 0, 0, 0, w.size);
-	float tNear, tFar;
-	if (!glsl_box(b, o, inv, tNear, tFar) || tNear >= kMissT) return true;
-	uint32_t dsc = RTO_LDG(S.desc);
-	if (dsc & kOctLeaf) {
-		if (dsc & kOctSolid) { float tHit = maxf(0.0f, tNear); if (tHit < kMissT && tHit <= tFar) { hit.t = tHit; hit.id = 0; hit.normal = box_normal(b, o, d, tHit); } }
-		return true;
-	}
-	w.mlo = 0ull; w.mhi = 0ull; w.level = 0; w.rank = 0; w.pos = 8; w.M = 0;
-	w.e = RTO_LDG(S.inner);
-	w.entering = true;
-	return false;
-}
-
-// one iteration; true = finished (hit is final)
+// One loop, state in plain locals: the init/step form used for mode A below (which needs a warp vote between steps) costs this
+// lighter walk 10-25 % (measured: 512^3 city 4.16 -> 5.27 ms, sphere 0.76 -> 0.92 ms per 8 frames), so it keeps the plain loop.
 template <int OCT>
-RTO_DEV bool octB_step(const OctDev& S, V3 o, V3 d, V3 inv, OctWalk& w, OctHit& hit) {
-	const int h = w.size >> 1;
-	const unsigned leafMask = (unsigned)w.e.w & 0xffu, solidMask = ((unsigned)w.e.w >> 8) & 0xffu;
-	if (w.entering) {
-		ChildPlanes P = oct_child_planes<OCT>(S, o, inv, w.x, w.y, w.z, h);
-		// "tNear < closestT" (closestT stays 1e30 until the hit that ends the walk) is folded into the far distance of one axis:
-		// tn <= tf && tf > 0 && tn < 1e30  <=>  tn <= min(tf, kBelowMissT) && min(tf, kBelowMissT) > 0
-		P.f0[2] = fminf(P.f0[2], kBelowMissT); P.f1[2] = fminf(P.f1[2], kBelowMissT);
-		unsigned hits = 0;
-#pragma unroll
-		for (int k = 0; k < 8; k++) {
-			float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), (k & 4) ? P.n1[2] : P.n0[2]);
-			float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), (k & 4) ? P.f1[2] : P.f0[2]);
-			bool hk = (tn <= tf) && (tf > 0.0f);
-			hits |= hk ? (1u << k) : 0u;
-		}
-		w.M = hits & ~(leafMask & ~solidMask);                 // children that can do more than burn a step: solid leaves and internal nodes
-		w.pos = 8;
-		w.entering = false;
-	}
-	unsigned below = w.M & ((1u << w.pos) - 1u);
-	if (below == 0u) {                                         // the remaining `pos` children are popped, tested and dropped
-		w.steps += w.pos;
-		if (w.steps >= 512 || w.level == 0) return true;
-		w.pos = ((unsigned)w.e.w >> 16) & 7u;
-		w.rank = w.e.z;
-		w.x &= ~w.size; w.y &= ~w.size; w.z &= ~w.size; w.size <<= 1;
-		w.level--;
-		w.M = walk_pop_mask(w);
-		w.e = RTO_LDG(S.inner + w.rank);
-		return false;
-	}
-	const int j = 31 - clz32(below);
-	w.steps += w.pos - 1 - j;
-	if (w.steps >= 512) return true;
-	w.steps++;
-	w.pos = j;
-	int cx = w.x, cy = w.y, cz = w.z;
-	oct_child_coords(j, h, cx, cy, cz);
-	if ((leafMask >> j) & 1u) {                                // solid leaf whose box the ray hits: the reference's exact per-node values
-		OctBox b = oct_box(S, cx, cy, cz, h);
+RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
+	OctHit hit; hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
+	int x = 0, y = 0, z = 0, size = S.rootSize;
+	int steps = 1;                                             // the root is popped first
+	{
+		OctBox b = oct_box(S, 0, 0, 0, size);
 		float tNear, tFar;
-		if (glsl_box(b, o, inv, tNear, tFar) && !(tNear >= kMissT)) {
-			float tHit = maxf(0.0f, tNear);
-			if (tHit < kMissT && tHit <= tFar) { hit.t = tHit; hit.id = w.e.x + j; hit.normal = box_normal(b, o, d, tHit); return true; }
+		hit.visits = 1;
+		if (!glsl_box(b, o, inv, tNear, tFar) || tNear >= kMissT) return hit;
+		uint32_t dsc = RTO_LDG(S.desc);
+		if (dsc & kOctLeaf) {
+			if (dsc & kOctSolid) { float tHit = maxf(0.0f, tNear); if (tHit < kMissT && tHit <= tFar) { hit.t = tHit; hit.id = 0; hit.normal = box_normal(b, o, d, tHit); } }
+			return hit;
 		}
-		return false;
 	}
-	walk_push_mask(w);
-	w.level++;
-	w.rank = w.e.y + popc32(~leafMask & ((1u << j) - 1u) & 0xffu);
-	w.x = cx; w.y = cy; w.z = cz; w.size = h;
-	w.e = RTO_LDG(S.inner + w.rank);
-	w.entering = true;
-	return false;
+	unsigned long long mlo = 0ull, mhi = 0ull;                 // remaining-children masks, 8 bits per level
+	int level = 0, rank = 0, pos = 8;
+	int4 e = RTO_LDG(S.inner);
+	bool entering = true;
+	unsigned M = 0;
+	while (true) {
+		const int h = size >> 1;
+		const unsigned leafMask = (unsigned)e.w & 0xffu, solidMask = ((unsigned)e.w >> 8) & 0xffu;
+		if (entering) {
+			ChildPlanes P = oct_child_planes<OCT>(S, o, inv, x, y, z, h);
+			// "tNear < closestT" (closestT stays 1e30 until the hit that ends the walk) is folded into the far distance of one axis:
+			// tn <= tf && tf > 0 && tn < 1e30  <=>  tn <= min(tf, kBelowMissT) && min(tf, kBelowMissT) > 0
+			P.f0[2] = fminf(P.f0[2], kBelowMissT); P.f1[2] = fminf(P.f1[2], kBelowMissT);
+			unsigned hits = 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), (k & 4) ? P.n1[2] : P.n0[2]);
+				float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), (k & 4) ? P.f1[2] : P.f0[2]);
+				bool hk = (tn <= tf) && (tf > 0.0f);
+				hits |= hk ? (1u << k) : 0u;
+			}
+			M = hits & ~(leafMask & ~solidMask);               // children that can do more than burn a step: solid leaves and internal nodes
+			pos = 8;
+		}
+		unsigned below = M & ((1u << pos) - 1u);
+		if (below == 0u) {                                     // the remaining `pos` children are popped, tested and dropped
+			steps += pos;
+			if (steps >= 512 || level == 0) break;
+			pos = ((unsigned)e.w >> 16) & 7u;
+			rank = e.z;
+			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
+			level--;
+			M = (unsigned)(((level < 8) ? (mlo >> (8 * level)) : (mhi >> (8 * (level - 8)))) & 0xffull);
+			e = RTO_LDG(S.inner + rank);
+			entering = false;
+			continue;
+		}
+		const int j = 31 - clz32(below);
+		steps += pos - 1 - j;
+		if (steps >= 512) break;
+		steps++;
+		pos = j;
+		int cx = x, cy = y, cz = z;
+		oct_child_coords(j, h, cx, cy, cz);
+		if ((leafMask >> j) & 1u) {                            // solid leaf whose box the ray hits: the reference's exact per-node values
+			OctBox b = oct_box(S, cx, cy, cz, h);
+			float tNear, tFar;
+			if (glsl_box(b, o, inv, tNear, tFar) && !(tNear >= kMissT)) {
+				float tHit = maxf(0.0f, tNear);
+				if (tHit < kMissT && tHit <= tFar) { hit.t = tHit; hit.id = e.x + j; hit.normal = box_normal(b, o, d, tHit); break; }
+			}
+			entering = false;
+			continue;
+		}
+		if (level < 8) mlo = (mlo & ~(0xffull << (8 * level))) | ((unsigned long long)M << (8 * level));
+		else mhi = (mhi & ~(0xffull << (8 * (level - 8)))) | ((unsigned long long)M << (8 * (level - 8)));
+		level++;
+		rank = e.y + popc32(~leafMask & ((1u << j) - 1u) & 0xffu);
+		x = cx; y = cy; z = cz; size = h;
+		e = RTO_LDG(S.inner + rank);
+		entering = true;
+	}
+	hit.visits = (unsigned)(steps > 512 ? 512 : steps);
+	return hit;
 }
 
 // dispatch on the octant of 1/d (one instantiation per sign pattern; a warp of primary rays almost always shares one)
@@ -780,16 +786,12 @@ RTO_DEV int inv_octant(V3 inv, float voxel) {
 	if (!(voxel > 0.0f)) return 8;
 	return ((inv.x < 0) ? 1 : 0) | ((inv.y < 0) ? 2 : 0) | ((inv.z < 0) ? 4 : 0);
 }
-RTO_DEV bool octB_is_fast(const OctDev& S, V3 inv) { return inv_is_regular(inv) && S.rootSize <= 65536; }
-
 RTO_DEV OctHit octB_fast(const OctDev& S, V3 o, V3 d) {
 	V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-	if (!octB_is_fast(S, inv)) return octB_compact(S, o, d);
-	OctWalk w; OctHit hit;
-	if (octB_init(S, o, d, inv, w, hit)) return hit;
+	if (!inv_is_regular(inv) || S.rootSize > 65536) return octB_compact(S, o, d);
 	const int oct = inv_octant(inv, S.voxel);
-	// (no per-step vote here, unlike octA_fast: measured 7 % slower in this mode, whose lanes stay together well enough on their own)
-#define RTO_CALL_B(K) while (!octB_step<K>(S, o, d, inv, w, hit)) {}
+	OctHit hit;
+#define RTO_CALL_B(K) hit = octB_fast_loop<K>(S, o, d, inv)
 	RTO_OCT_DISPATCH(oct, RTO_CALL_B)
 #undef RTO_CALL_B
 	return hit;
@@ -891,13 +893,14 @@ RTO_DEV int octA_octant(const OctDev& S, const SkipRay& r, V3 d) {
 RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 	SkipRay r = make_skipray(o, d);
 	if (!octA_is_fast(S, r, tMin, tMax)) return octA_compact(S, o, d, tMin, tMax);
+	const int oct = octA_octant(S, r, d);
 	OctWalk w; OctClamps cs; OctHit hit;
 	if (octA_init(S, o, d, tMin, tMax, r, w, hit)) return hit;
-	const int oct = octA_octant(S, r, d);
 #if defined(__CUDA_ARCH__)
 	// The lanes of the warp that walk with this octant instantiation vote once per step.  Without it the lanes drift apart after
 	// the first divergent branch inside a step and never re-join: ncu showed 7 (512^3 city) to 15 (DT grid) of 32 lanes active in
-	// EVERY instruction of the loop; with it the kernel is 1.5x (DT) to 2.4x (city) faster (profiles/README.md).
+	// EVERY instruction of the loop; with it the kernel is 1.5x (DT) to 2.4x (city) faster (profiles/README.md).  (The same vote
+	// around a single hand-inlined loop instead of init/step measured 3 % slower.)
 	const unsigned arm = __match_any_sync(__activemask(), oct);
 	bool fin = false;
 #define RTO_CALL_A(K) for (;;) { if (!fin) fin = octA_step<K>(S, o, d, tMin, tMax, r, w, cs, hit); if (__ballot_sync(arm, !fin) == 0u) break; }
@@ -975,7 +978,14 @@ __global__ void __launch_bounds__(128) k_render_bvh(BvhDev S, RenderArgs A) {
 	store_pixel(A, pix, color, id, bestT);
 }
 
-__global__ void __launch_bounds__(128, 6) k_render_octree(OctDev S, RenderArgs A, int mode) {
+// One instantiation per traversal mode so that each gets its own register budget: the mode-A walk wants ~80 registers (it
+// spills at 64), the lighter mode-B walk runs better with 8 resident blocks per SM (64 registers).
+#ifndef RTO_OCT_B_MIN_BLOCKS
+#define RTO_OCT_B_MIN_BLOCKS 8
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(128, MODE == RTO_MODE_OCTREE_SKIP ? 6 : RTO_OCT_B_MIN_BLOCKS) k_render_octree(OctDev S, RenderArgs A) {
+	const int mode = MODE;
 	RtoCamera cam = A.cam0;
 	if (A.cams) cam = A.cams[blockIdx.z];
 	int px, py; size_t pix;

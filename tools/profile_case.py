@@ -16,6 +16,7 @@ def main():
     ap.add_argument("case")
     ap.add_argument("--reps", type=int, default=6)
     ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--phi-step", type=float, default=360.0 / 64, help="orbit step between frames in degrees (tools/bench_configs.py uses 45)")
     a = ap.parse_args()
     assert rto.lib().rto_init(0) == 0
     W, H, F = 1920, 1080, a.frames
@@ -38,7 +39,7 @@ def main():
     else:
         sc = rto.Scene.octree(nodes, g.min, g.voxel_size)
         mode = rto.MODE_OCTREE_SKIP if a.case.endswith("A") else rto.MODE_OCTREE_GLSL
-    cams = [rto.Camera.from_degrees(theta, 40.0 + 360.0 * k / 64, radius).consts(45.0, float(np.float32(W) / np.float32(H)), W, H)[0] for k in range(F)]
+    cams = [rto.Camera.from_degrees(theta, 40.0 + a.phi_step * k, radius).consts(45.0, float(np.float32(W) / np.float32(H)), W, H)[0] for k in range(F)]
     rgba = torch.empty((F, H, W, 4), dtype=torch.float32, device="cuda")
     hid = torch.empty((F, H, W), dtype=torch.int32, device="cuda")
     tt = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
