@@ -158,6 +158,19 @@ RTO_API int rto_scene_create_octree_from_grid(const uint8_t* voxels, int dimX, i
 RTO_API int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
 	const float gridMin[3], float voxelSize, RtoTriangle** trisOut, size_t* numTris);
 
+/* BVH scene built on the device: the fast, NOT reference-shaped route (linear BVH: Morton sort, leaves of two neighbours, radix
+ * tree, exact union boxes).  BVH::build's tree depends on std::sort's order on equal centroids (BVH.cpp:58-60) and cannot be
+ * rebuilt in parallel; rto_scene_create_bvh stays the route whose hit ids equal the reference's exactly.  Here hit ids (indices
+ * into `tris`) can differ only at near-ties (equal t on a shared edge, a ray grazing a leaf-box edge).  rto_bvh_query and
+ * rto_render_stats need the reference tree and return RTO_ERR_UNSUPPORTED on such a scene. */
+RTO_API int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTris, RtoScene** out);
+
+/* Voxel grid -> octree -> Marching-Cubes mesh -> linear BVH, all on the GPU, nothing but the grid crosses the bus
+ * (replaces createOctreeFromVoxelGrid + MarchingCubesRenderer::render + BVH::BVH for the mesh path).  Hit ids index the
+ * triangle soup rto_host_mc_mesh / rto_device_mc_mesh return for the same grid. */
+RTO_API int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, RtoScene** out);
+
 /* Diagnostic: the compact device layout of an octree scene (desc: numNodes + 8 words, up: (numNodes + 7) / 8 + 1 words,
  * inner: 4 words per internal node); any pointer may be NULL.  Lets tests compare the two construction routes. */
 RTO_API int rto_scene_octree_layout_read(RtoScene* scene, uint32_t* desc, int32_t* up, int32_t* inner4, size_t* numInner);

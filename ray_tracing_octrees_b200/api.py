@@ -202,6 +202,22 @@ class Scene:
         check(lib().rto_scene_create_bvh(_p(tris), len(tris), prebuilt.h if prebuilt is not None else None, C.byref(h)))
         return Scene(h, keep=(tris,))
 
+    @staticmethod
+    def bvh_device(tris):
+        """Triangles -> linear BVH built on the GPU (rto_scene_create_bvh_device): the fast, not reference-shaped route."""
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        h = C.c_void_p()
+        check(lib().rto_scene_create_bvh_device(_p(tris), len(tris), C.byref(h)))
+        return Scene(h)
+
+    @staticmethod
+    def bvh_from_grid(grid):
+        """Voxel grid -> octree -> MC mesh -> linear BVH, all on the GPU (rto_scene_create_bvh_from_grid)."""
+        h = C.c_void_p()
+        check(lib().rto_scene_create_bvh_from_grid(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min),
+                                                   float(grid.voxel_size), C.byref(h)))
+        return Scene(h)
+
     def info(self):
         kind, compact = C.c_int(), C.c_int()
         prims, nodes, nbytes = C.c_size_t(), C.c_size_t(), C.c_size_t()

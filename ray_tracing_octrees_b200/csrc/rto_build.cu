@@ -13,6 +13,7 @@
 #include "mc_tables.h"
 
 #include <cub/cub.cuh>
+#include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -570,5 +571,250 @@ extern "C" int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 	cudaStreamDestroy(st);
 	if (rc) return rc;
 	*trisOut = host; *numTris = M.numTris;
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BVH build on the device: the fast, NON-reference-shaped mode.
+//
+// BVH::build (BVH.cpp:33-71) sorts with std::sort, whose order on equal centroids is a property of one libstdc++ version on one
+// input sequence; no parallel algorithm can reproduce that tree, and rto_host_bvh_build stays the route whose leaves (hence
+// candidate sets, hence hit ids) equal the reference's exactly.  This route builds a linear BVH instead (Morton sort, leaves of
+// two Morton-neighbours, Karras' radix tree, bottom-up exact union boxes) in milliseconds where the host route takes seconds to
+// a minute.  The traversal kernels and the closest-hit rule (min t, then position) are the same; hit ids can differ from the
+// reference only where two triangles are hit at the same t to the last bit (shared edges) or a ray grazes the edge of a leaf
+// box -- the "documented near-tie" class of the north star; tests/test_gpu_builders.py measures the rate against the oracle.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ int float_as_ordered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ordered_as_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_lbvh_bounds(const RtoTriangle* __restrict__ tris, size_t n, int* bounds /* lo xyz, hi xyz as ordered ints */) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+	float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+	for (; i < n; i += stride) {
+		const float* v = reinterpret_cast<const float*>(tris + i);
+#pragma unroll
+		for (int k = 0; k < 9; k++) { float f = v[k]; lo[k % 3] = fminf(lo[k % 3], f); hi[k % 3] = fmaxf(hi[k % 3], f); }
+	}
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+		if ((threadIdx.x & 31) == 0) { atomicMin(bounds + a, float_as_ordered(lo[a])); atomicMax(bounds + 3 + a, float_as_ordered(hi[a])); }
+	}
+}
+
+__global__ void k_lbvh_codes(const RtoTriangle* __restrict__ tris, size_t n, const int* __restrict__ bounds, uint64_t* __restrict__ codes, uint32_t* __restrict__ ids) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* v = reinterpret_cast<const float*>(tris + i);
+	uint32_t q[3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const float lo = ordered_as_float(bounds[a]), hi = ordered_as_float(bounds[3 + a]);
+		const float c = (v[a] + v[3 + a] + v[6 + a]) * (1.0f / 3.0f);
+		const float ext = hi - lo;
+		float u = ext > 0.0f ? (c - lo) / ext : 0.0f;
+		u = fminf(fmaxf(u, 0.0f), 1.0f);
+		q[a] = (uint32_t)fminf(u * 2097152.0f, 2097151.0f);
+	}
+	codes[i] = morton3(q[0], q[1], q[2]);
+	ids[i] = (uint32_t)i;
+}
+
+// triangle records in sorted order (v0, e1, e2, id: rto_kernels.cuh TriV) and the exact box of every leaf (two neighbours)
+__global__ void k_lbvh_leaves(const RtoTriangle* __restrict__ tris, const uint32_t* __restrict__ order, size_t n, float4* __restrict__ rec, float* __restrict__ leafBox /* 6 per leaf */) {
+	const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t numLeaves = (n + 1) / 2;
+	if (leaf >= numLeaves) return;
+	float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+	for (size_t p = 2 * leaf; p < 2 * leaf + 2 && p < n; p++) {
+		const uint32_t id = order[p];
+		const float* v = reinterpret_cast<const float*>(tris + id);
+		float f[9];
+#pragma unroll
+		for (int k = 0; k < 9; k++) { f[k] = v[k]; lo[k % 3] = fminf(lo[k % 3], f[k]); hi[k % 3] = fmaxf(hi[k % 3], f[k]); }
+		rec[3 * p] = make_float4(f[0], f[1], f[2], f[3] - f[0]);
+		rec[3 * p + 1] = make_float4(f[4] - f[1], f[5] - f[2], f[6] - f[0], f[7] - f[1]);
+		rec[3 * p + 2] = make_float4(f[8] - f[2], __int_as_float((int)id), 0.0f, 0.0f);
+	}
+#pragma unroll
+	for (int a = 0; a < 3; a++) { leafBox[6 * leaf + a] = lo[a]; leafBox[6 * leaf + 3 + a] = hi[a]; }
+}
+
+// common-prefix length of the keys of leaves i and j (key = Morton code of the leaf's first triangle, ties broken by index)
+__device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ codes, int numLeaves, int i, int j) {
+	if (j < 0 || j >= numLeaves) return -1;
+	const uint64_t a = codes[2 * (size_t)i], b = codes[2 * (size_t)j];
+	if (a == b) return 64 + __clz(i ^ j);
+	return __clzll((long long)(a ^ b));
+}
+
+// Karras 2012: internal node i of the binary radix tree over the sorted leaves; child refs into the node, parent links for the fit pass
+__global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int numLeaves, size_t numTris, float4* __restrict__ nodes, int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= numLeaves - 1) return;
+	const int d = (lbvh_delta(codes, numLeaves, i, i + 1) - lbvh_delta(codes, numLeaves, i, i - 1)) >= 0 ? 1 : -1;
+	const int dmin = lbvh_delta(codes, numLeaves, i, i - d);
+	int lmax = 2;
+	while (lbvh_delta(codes, numLeaves, i, i + lmax * d) > dmin) lmax <<= 1;
+	int l = 0;
+	for (int t = lmax >> 1; t >= 1; t >>= 1) if (lbvh_delta(codes, numLeaves, i, i + (l + t) * d) > dmin) l += t;
+	const int j = i + l * d;
+	const int dnode = lbvh_delta(codes, numLeaves, i, j);
+	int s = 0;
+	for (int t = (l + 1) >> 1; ; t = (t + 1) >> 1) {
+		if (lbvh_delta(codes, numLeaves, i, i + (s + t) * d) > dnode) s += t;
+		if (t == 1) break;
+	}
+	const int gamma = i + s * d + min(d, 0);
+	const int first = min(i, j), last = max(i, j);
+	auto leafRef = [&](int leaf) {
+		const size_t p = 2 * (size_t)leaf;
+		const int cnt = (p + 1 < numTris) ? 2 : 1;
+		return ~(int)((p << 1) | (size_t)(cnt - 1));
+	};
+	int r0, r1;
+	if (gamma == first) { r0 = leafRef(gamma); parentOfLeaf[gamma] = 2 * i; } else { r0 = gamma; parentOfInner[gamma] = 2 * i; }
+	if (gamma + 1 == last) { r1 = leafRef(gamma + 1); parentOfLeaf[gamma + 1] = 2 * i + 1; } else { r1 = gamma + 1; parentOfInner[gamma + 1] = 2 * i + 1; }
+	nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(r0), __int_as_float(r1), 0.0f, 0.0f);
+	if (i == 0) parentOfInner[0] = -1;
+}
+
+__device__ __forceinline__ void lbvh_store_child_box(float* node16, int slot, const float lo[3], const float hi[3]) {
+	float* d = node16 + 6 * slot;
+	d[0] = lo[0]; d[1] = lo[1]; d[2] = lo[2]; d[3] = hi[0]; d[4] = hi[1]; d[5] = hi[2];
+}
+
+// bottom-up: every leaf writes its box into its parent's slot; the second child to arrive at a node unites the two and climbs
+__global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, float* nodes /* 16 floats per inner node */, const int* __restrict__ parentOfInner,
+	const int* __restrict__ parentOfLeaf, int* arrived, float* rootBox) {
+	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+	if (leaf >= numLeaves) return;
+	float lo[3], hi[3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) { lo[a] = leafBox[6 * (size_t)leaf + a]; hi[a] = leafBox[6 * (size_t)leaf + 3 + a]; }
+	int link = parentOfLeaf[leaf];
+	for (;;) {
+		const int node = link >> 1, slot = link & 1;
+		float* n16 = nodes + 16 * (size_t)node;
+		lbvh_store_child_box(n16, slot, lo, hi);
+		__threadfence();
+		if (atomicAdd(arrived + node, 1) == 0) return;          // the sibling subtree is not finished yet: its thread will continue
+		volatile float* other = n16 + 6 * (slot ^ 1);
+#pragma unroll
+		for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], other[a]); hi[a] = fmaxf(hi[a], other[3 + a]); }
+		link = parentOfInner[node];
+		if (link < 0) {
+#pragma unroll
+			for (int a = 0; a < 3; a++) { rootBox[a] = lo[a]; rootBox[3 + a] = hi[a]; }
+			return;
+		}
+	}
+}
+
+// tris: device array of numTris RtoTriangle (reference emission order, index == hit id).  Fills s->bvh / s->bvhFast.
+int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
+	cudaStream_t st = s->stream;
+	BvhDev D{};
+	D.numTris = (int)numTris; D.rootRef = -1;
+	s->numPrims = numTris;
+	if (numTris == 0) { s->bvh = D; s->bvhFast = D; s->numNodes = 0; return RTO_OK; }
+	if (numTris >= (size_t)1 << 30) return rto_fail(RTO_ERR_UNSUPPORTED, "BVH build on the device: more than 2^30 triangles");
+	DevPool tmp;
+	const int numLeaves = (int)((numTris + 1) / 2), numInner = numLeaves - 1;
+	int* dBounds = nullptr;
+	BUILD_TRY(tmp.alloc(&dBounds, 6));
+	{
+		int init[6]; const float big = FLT_MAX;
+		int hiInit, loInit; std::memcpy(&loInit, &big, 4); float nb = -FLT_MAX; std::memcpy(&hiInit, &nb, 4);
+		hiInit = hiInit ^ 0x7fffffff;         // ordered form of -FLT_MAX
+		for (int a = 0; a < 3; a++) { init[a] = loInit; init[3 + a] = hiInit; }
+		BUILD_TRY(cudaMemcpyAsync(dBounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+		BUILD_TRY(cudaStreamSynchronize(st));
+	}
+	k_lbvh_bounds<<<1184, 256, 0, st>>>(dTris, numTris, dBounds);
+	uint64_t *codes = nullptr, *codesSorted = nullptr; uint32_t *ids = nullptr, *order = nullptr;
+	BUILD_TRY(tmp.alloc(&codes, numTris)); BUILD_TRY(tmp.alloc(&codesSorted, numTris)); BUILD_TRY(tmp.alloc(&ids, numTris)); BUILD_TRY(tmp.alloc(&order, numTris));
+	const unsigned blocksT = (unsigned)((numTris + 255) / 256), blocksL = (unsigned)((numLeaves + 255) / 256);
+	k_lbvh_codes<<<blocksT, 256, 0, st>>>(dTris, numTris, dBounds, codes, ids);
+	size_t sortBytes = 0;
+	BUILD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, codes, codesSorted, ids, order, (int)numTris, 0, 63, st));
+	uint8_t* sortTmp = nullptr;
+	BUILD_TRY(tmp.alloc(&sortTmp, sortBytes));
+	BUILD_TRY(cub::DeviceRadixSort::SortPairs(sortTmp, sortBytes, codes, codesSorted, ids, order, (int)numTris, 0, 63, st));
+	tmp.free_now(codes); tmp.free_now(ids); tmp.free_now(sortTmp);
+	// scene-owned outputs
+	void *dRec = nullptr, *dNodes = nullptr;
+	int rc;
+	if ((rc = rto_scene_alloc(s, &dRec, numTris * 48))) return rc;
+	if ((rc = rto_scene_alloc(s, &dNodes, (size_t)(numInner > 0 ? numInner : 1) * 64))) return rc;
+	float* leafBox = nullptr; float* dRoot = nullptr;
+	BUILD_TRY(tmp.alloc(&leafBox, 6 * (size_t)numLeaves)); BUILD_TRY(tmp.alloc(&dRoot, 6));
+	k_lbvh_leaves<<<blocksL, 256, 0, st>>>(dTris, order, numTris, (float4*)dRec, leafBox);
+	float root[6];
+	if (numInner == 0) {
+		BUILD_TRY(cudaMemcpyAsync(root, leafBox, sizeof(root), cudaMemcpyDeviceToHost, st));
+		BUILD_TRY(cudaStreamSynchronize(st));
+		D.rootRef = ~(int)(numTris - 1);          // leafRef = (0 << 1) | (count - 1)
+	}
+	else {
+		int *pInner = nullptr, *pLeaf = nullptr, *arrived = nullptr;
+		BUILD_TRY(tmp.alloc(&pInner, numInner)); BUILD_TRY(tmp.alloc(&pLeaf, numLeaves)); BUILD_TRY(tmp.alloc(&arrived, numInner));
+		BUILD_TRY(cudaMemsetAsync(arrived, 0, sizeof(int) * (size_t)numInner, st));
+		k_lbvh_tree<<<(unsigned)((numInner + 255) / 256), 256, 0, st>>>(codesSorted, numLeaves, numTris, (float4*)dNodes, pInner, pLeaf);
+		k_lbvh_fit<<<blocksL, 256, 0, st>>>(numLeaves, leafBox, (float*)dNodes, pInner, pLeaf, arrived, dRoot);
+		BUILD_TRY(cudaGetLastError());
+		BUILD_TRY(cudaMemcpyAsync(root, dRoot, sizeof(root), cudaMemcpyDeviceToHost, st));
+		BUILD_TRY(cudaStreamSynchronize(st));
+		D.rootRef = 0;
+	}
+	for (int a = 0; a < 3; a++) { D.rootLo[a] = root[a]; D.rootHi[a] = root[3 + a]; }
+	D.nodes = (const float4*)dNodes; D.tris = (const float4*)dRec;
+	s->bvh = D; s->bvhFast = D;
+	s->numNodes = (size_t)numLeaves + (size_t)numInner;
+	s->deviceBuiltBvh = true;
+	return RTO_OK;
+}
+
+} // namespace
+
+extern "C" int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTris, RtoScene** out) {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_device: null output");
+	*out = nullptr;
+	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_device: null triangles");
+	RtoScene* s = nullptr;
+	int rc = rto_scene_new(&s); if (rc) return rc;
+	s->kind = RTO_MODE_BVH;
+	DevPool pool;
+	RtoTriangle* d = nullptr;
+	cudaError_t e = pool.alloc(&d, numTris);
+	if (e == cudaSuccess && numTris) e = cudaMemcpyAsync(d, tris, numTris * sizeof(RtoTriangle), cudaMemcpyHostToDevice, s->stream);
+	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "rto_scene_create_bvh_device: %s", cudaGetErrorString(e)); }
+	rc = lbvh_build(s, d, numTris);
+	if (rc) { rto_scene_destroy(s); return rc; }
+	*out = s;
+	return RTO_OK;
+}
+
+extern "C" int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	RtoScene** out) {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid: null output");
+	*out = nullptr;
+	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid: empty grid");
+	RtoScene* s = nullptr;
+	int rc = rto_scene_new(&s); if (rc) return rc;
+	s->kind = RTO_MODE_BVH;
+	{
+		OctBuild B; McBuild M;
+		rc = oct_pyramid(B, voxels, false, dimX, dimY, dimZ, s->stream);
+		if (!rc) rc = oct_emit(B, true, false, s->stream);
+		if (!rc) rc = mc_extract(B, gridMin, voxelSize, M, s->stream);
+		if (!rc) rc = lbvh_build(s, M.tris, M.numTris);
+		if (!rc) { cudaError_t e = cudaStreamSynchronize(s->stream); if (e != cudaSuccess) rc = rto_fail(RTO_ERR_CUDA, "scene build on the device failed: %s", cudaGetErrorString(e)); }
+	}
+	if (rc) { rto_scene_destroy(s); return rc; }
+	*out = s;
 	return RTO_OK;
 }

@@ -329,6 +329,7 @@ extern "C" int rto_render(RtoScene* s, const RtoCamera* cam, int mode, uint32_t 
 extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, uint64_t stats[5]) {
 	if (!s || !cam || !stats) return rto_fail(RTO_ERR_INVALID, "rto_render_stats: null argument");
 	int rc = check_mode(s, mode); if (rc) return rc;
+	if (s->deviceBuiltBvh) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render_stats: the scene's BVH was built on the device; the reference's work counters need the reference-shaped tree (rto_scene_create_bvh)");
 	if (cam->width <= 0 || y0 < 0 || y1 > cam->height || y0 >= y1) return rto_fail(RTO_ERR_INVALID, "rto_render_stats: bad row range");
 	CUDA_TRY(cudaSetDevice(s->device));
 	void* d = nullptr;
@@ -383,6 +384,7 @@ extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dir
 	int64_t* offsets, int32_t* ids, size_t idsCapacity, size_t* totalOut) {
 	if (!s || !origins || !dirs || !offsets) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: null argument");
 	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: scene is not a BVH");
+	if (s->deviceBuiltBvh) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_bvh_query: the scene's BVH was built on the device; BVH::query's candidate order needs the reference-shaped tree (rto_scene_create_bvh)");
 	offsets[0] = 0;
 	if (totalOut) *totalOut = 0;
 	if (numRays == 0) return RTO_OK;

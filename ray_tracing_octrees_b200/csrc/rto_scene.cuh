@@ -26,6 +26,7 @@ struct RtoScene {
 	void* scratch[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	size_t scratchBytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	int smCount = 0;
+	bool deviceBuiltBvh = false;      // linear BVH built on the device: the reference-shaped tree (BVH::query replay, work counters) does not exist
 };
 
 int rto_scene_new(RtoScene** out);                             // stream, events, device id

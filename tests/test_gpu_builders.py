@@ -86,3 +86,68 @@ def test_reserved_voxel_value_is_rejected(rto, grids):
         rto.create_octree_on_device(g)
     with pytest.raises(rto.RtoError):
         rto.create_octree_from_voxel_grid(g)
+
+
+# ---- linear BVH built on the device: the fast route, not reference-shaped ----------------------------------------------
+def _near_tie_report(dev, host):
+    ids_differ = dev["id"] != host["id"]
+    same = ~ids_differ
+    # the same triangle gives the same t and colour to the last bit whatever tree found it
+    assert np.array_equal(dev["t"][same].view(np.uint32), host["t"][same].view(np.uint32))
+    assert np.array_equal(dev["rgba"][same].view(np.uint32), host["rgba"][same].view(np.uint32))
+    rel = np.abs(dev["t"][ids_differ].astype(np.float64) - host["t"][ids_differ]) / np.maximum(host["t"][ids_differ], 1e-30)
+    return int(ids_differ.sum()), (float(rel.max()) if rel.size else 0.0)
+
+
+@pytest.mark.parametrize("name,theta,phi,radius,size", [("sphere32", 30, 40, 1.2, (256, 192)), ("ragged_noise", 20, 70, 30.0, (128, 128)),
+                                                       ("city128", 35, 40, 115.0, (320, 240)), ("dt", 35, 40, 0.6 * 4250, (960, 540))])
+def test_device_bvh_hits_equal_reference_tree_hits_except_near_ties(rto, grids, name, theta, phi, radius, size):
+    g = grids[name]
+    tris = rto.marching_cubes_mesh(g, rto.create_octree_from_voxel_grid(g))
+    host = rto.Scene.bvh(tris)
+    dev = rto.Scene.bvh_device(tris)
+    grid_dev = rto.Scene.bvh_from_grid(g)
+    assert dev.info()["prims"] == len(tris) == grid_dev.info()["prims"]
+    w, h = size
+    cam, _ = rto.Camera.from_degrees(theta, phi, radius).consts(45.0, float(np.float32(w) / np.float32(h)), w, h)
+    bias = 1e-3 * g.voxel_size
+    for flags in (0, rto.FLAG_SHADOWS, rto.FLAG_NO_PRUNE):
+        a = host.render(cam, rto.MODE_BVH, flags, bias)
+        b = dev.render(cam, rto.MODE_BVH, flags, bias)
+        c = grid_dev.render(cam, rto.MODE_BVH, flags, bias)
+        # triangles -> device BVH and grid -> device BVH are the same build on the same triangle soup
+        assert np.array_equal(b["id"], c["id"]) and np.array_equal(b["t"].view(np.uint32), c["t"].view(np.uint32))
+        if flags & rto.FLAG_SHADOWS:
+            # a shadow ray starts at the hit point: only pixels whose primary hit agrees are comparable bit for bit
+            same = a["id"] == b["id"]
+            frac = 1.0 - same.mean()
+            lit_differs = (a["rgba"][same] != b["rgba"][same]).any(axis=1).mean()
+            assert frac <= 1e-4 and lit_differs <= 1e-4, (name, frac, lit_differs)
+            continue
+        n_diff, max_rel = _near_tie_report(b, a)
+        assert n_diff <= 1e-4 * w * h, "%s: %d of %d hit ids differ from the reference-shaped tree" % (name, n_diff, w * h)
+        assert max_rel <= 1e-4, "%s: differing ids are not near-ties (relative t gap %g)" % (name, max_rel)
+
+
+def test_device_bvh_edge_cases(rto, grids):
+    cam, _ = rto.Camera.from_degrees(30, 40, 6.0).consts(45.0, 1.0, 64, 64)
+    # no triangles, one triangle, two, three (one and a half leaves)
+    base = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0], [0, 0, 1, 1, 0, 1, 0, 1, 1], [0, 0, -1, 1, 0, -1, 0, 1, -1]], np.float32)
+    for n in (0, 1, 2, 3):
+        tris = base[:n]
+        dev = rto.Scene.bvh_device(tris)
+        b = dev.render(cam, rto.MODE_BVH, 0, 0.0)
+        if n == 0:
+            assert (b["id"] == -1).all()
+            continue
+        a = rto.Scene.bvh(tris).render(cam, rto.MODE_BVH, 0, 0.0)
+        assert np.array_equal(a["id"], b["id"]) and np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    # all-empty grid: no surface, an empty scene that renders misses
+    e = rto.Scene.bvh_from_grid(grids["all_empty"])
+    assert e.info()["prims"] == 0
+    assert (e.render(cam, rto.MODE_BVH, 0, 0.0)["id"] == -1).all()
+    # the reference-tree-only entry points say so instead of answering from the wrong tree
+    dev = rto.Scene.bvh_device(base)
+    with pytest.raises(rto.RtoError) as err:
+        dev.stats(cam, rto.MODE_BVH, 0, 0.0)
+    assert err.value.code == 6
