@@ -50,6 +50,35 @@ def main():
         tmd, tris_d = t(lambda: rto.marching_cubes_mesh_on_device(g), 2)
         r["triangles"] = int(len(tris_h)); r["mc_host_s"] = tm; r["mc_device_s_incl_readback"] = tmd
         r["mc_equal"] = bool(tris_h.shape == tris_d.shape and np.array_equal(tris_h.view(np.uint32), tris_d.view(np.uint32)))
+        # mesh scene: host route (reference-shaped BVH + SAH topology, exact ids) vs device route (linear BVH)
+        import torch
+        W, H = 1920, 1080
+        ext = float(max(g.dims) * g.voxel_size)
+        cams = [rto.Camera.from_degrees(35, 40.0 + 45.0 * k, 0.6 * ext if name == "dt" else 0.9 * ext).consts(45.0, float(np.float32(W) / np.float32(H)), W, H)[0] for k in range(4)]
+        bias = 1e-3 * g.voxel_size
+        t0 = time.perf_counter(); hb = rto.HostBVH(tris_h); r["bvh_host_build_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); sh = rto.Scene.bvh(None, prebuilt=hb); r["bvh_host_layout_upload_s"] = time.perf_counter() - t0
+        td2, sd = t(lambda: rto.Scene.bvh_device(tris_h), 2); r["bvh_device_from_host_tris_s"] = td2
+        tg, sg = t(lambda: rto.Scene.bvh_from_grid(g), 2); r["mesh_scene_from_grid_on_device_s"] = tg
+        r["mesh_scene_host_route_total_s"] = r["octree_host_s"] + r["mc_host_s"] + r["bvh_host_build_s"] + r["bvh_host_layout_upload_s"]
+        F = len(cams)
+        rgba = torch.empty((F, H, W, 4), dtype=torch.float32, device="cuda"); hid = torch.empty((F, H, W), dtype=torch.int32, device="cuda"); tt = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
+        ids = {}
+        for label, sc in (("host", sh), ("device", sg)):
+            ms = []
+            for _ in range(4):
+                sc.render_device(cams, rto.MODE_BVH, rto.FLAG_SHADOWS, bias, 0, H, rgba.data_ptr(), hid.data_ptr(), tt.data_ptr()); ms.append(sc.last_kernel_ms())
+            ids[label] = hid.clone(); ids[label + "_t"] = tt.clone()
+            hits = int((hid >= 0).sum().item())
+            r["render_%s_tree_ms" % label] = float(np.median(ms[1:])); r["render_%s_tree_Mrays_s" % label] = (F * W * H + hits) / float(np.median(ms[1:])) / 1e3
+        diff = ids["host"] != ids["device"]
+        r["pixels"] = F * W * H; r["hit_ids_differing"] = int(diff.sum().item())
+        if r["hit_ids_differing"]:
+            ta, tb = ids["host_t"][diff].double(), ids["device_t"][diff].double()
+            r["max_rel_t_gap_where_ids_differ"] = float(((ta - tb).abs() / ta.clamp_min(1e-30)).max().item())
+            r["differing_with_device_tree_closer"] = int((tb < ta).sum().item()); r["differing_with_host_tree_closer"] = int((ta < tb).sum().item())
+            r["differing_with_equal_t"] = int((ta == tb).sum().item())
+        del sh, sd, sg, hb
         rep[name] = r
         print(name, json.dumps(r), flush=True)
     if a.out:
