@@ -78,6 +78,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """All host threads this process may use.  (torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently run the
+    CPU reference on one thread; the count is therefore taken from the affinity mask and passed to the oracle explicitly.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def orbit_cameras(rto, first_frame, count):
     cams = []
     aspect = float(np.float32(W) / np.float32(H))
@@ -99,7 +108,7 @@ def run_reference(args, rank, world):
     oc.build()
     mesh = oc.mesh()
     mesh.build()
-    cores = chk.num_threads()
+    cores = host_cores()
     bias = 1e-3 * oc.voxel
     cam, _ = chk.camera(THETA_DEG, PHI0_DEG, RADIUS, width=W, height=H)
     # per-step sample: one whole 1080p orbit frame (a fraction of a second on a many-core host)
@@ -107,7 +116,7 @@ def run_reference(args, rank, world):
 
     def step(k):
         c, _ = chk.camera(THETA_DEG, PHI0_DEG + PHI_STEP_DEG * (k % 64), RADIUS, width=W, height=H)
-        out = mesh.render(c, 1, bias, y0, y0 + rows)
+        out = mesh.render(c, 1, bias, y0, y0 + rows, threads=cores)
         return rows * W + int((out["id"] >= 0).sum()), out["sec"]
     for k in range(args.warmup):
         step(k)
@@ -303,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
         oc.build()
         mesh = oc.mesh()
         mesh.build()
-        cores = chk.num_threads()
+        cores = host_cores()
         crays, csec, cframes = 0, 0.0, 0
         while csec < 2.0 and cframes < 64:        # whole 1080p orbit frames until ~2 s of wall time on all host cores
             ccam, _ = chk.camera(THETA_DEG, PHI0_DEG + PHI_STEP_DEG * cframes, RADIUS, width=W, height=H)

@@ -42,9 +42,9 @@ int rto_require_device() {
 
 extern "C" int rto_init(int device) {
 	{	// constants whose exact bit patterns the traversal code relies on
-		float a = kMissT, b = kBelowMissT; uint32_t ua, ub;
-		std::memcpy(&ua, &a, 4); std::memcpy(&ub, &b, 4);
-		if (ua != 0x7149f2cau || ub != 0x7149f2c9u) return rto_fail(RTO_ERR_UNSUPPORTED, "librto was built with a compiler that rounds 1e30f differently");
+		float a = kMissT, b = kBelowMissT, c = kMinPositive; uint32_t ua, ub, uc;
+		std::memcpy(&ua, &a, 4); std::memcpy(&ub, &b, 4); std::memcpy(&uc, &c, 4);
+		if (ua != 0x7149f2cau || ub != 0x7149f2c9u || uc != 1u) return rto_fail(RTO_ERR_UNSUPPORTED, "librto was built with a compiler that rounds 1e30f differently");
 	}
 	int rc = require_device(); if (rc) return rc;
 	CUDA_TRY(cudaSetDevice(device));

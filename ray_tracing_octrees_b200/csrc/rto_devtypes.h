@@ -36,6 +36,7 @@ constexpr int kMaxOctDepth = 32;
 constexpr int kBvhStack = 64;
 constexpr float kMissT = 1e30f;
 constexpr float kBelowMissT = 9.99999940e29f;    // the largest float below 1e30f (rto_init checks the bit pattern)
+constexpr float kMinPositive = 1.40129846e-45f;  // the smallest positive (denormal) float, bit pattern 0x00000001 (rto_init checks)
 // pruning margin of the ordered BVH traversal: a subtree is skipped only if its box entry distance exceeds the
 // best hit by more than this relative slack (keeps co-planar / shared-edge candidates)
 constexpr float kPruneSlack = 1.00001f;

@@ -60,6 +60,24 @@ RTO_DEV int ffs32(unsigned v) {
 struct Ray { V3 o, d; };
 struct alignas(8) StackEnt { int ref; float t; };     // postponed far child of the ordered BVH traversal and its box entry distance
 
+// 3-input min / max: one FMNMX3 on sm_100 (the compiler fuses nested fmaxf only sometimes; when it sees common sub-expressions
+// across the 8 children of an octree node it prefers 24 two-input operations to 16 three-input ones, and the ALU pipe that
+// executes them is what bounds the octree kernels).  NaN-free inputs only: callers guarantee it.
+RTO_DEV float fmax3f(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+	float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+#else
+	return fmaxf(fmaxf(a, b), c);
+#endif
+}
+RTO_DEV float fmin3f(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+	float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+#else
+	return fminf(fminf(a, b), c);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // Pixel ray: GLSL generateRay (RayTracerBVH.cpp:338-355) with inverse(view), tan(fov/2) from the host
 // ------------------------------------------------------------------------------------------------
@@ -672,23 +690,14 @@ struct OctWalk {
 	int x, y, z, size;              // current internal node
 	int level, rank, pos;           // depth below the root, rank of the node's 16-byte record, position among its children
 	int4 e;                         // the record
-	unsigned M;                     // children still to visit (mode B: octant space, mode A: visit-order space)
-	unsigned long long mlo, mhi;    // M of the ancestors, 8 bits per level
+	unsigned M;                     // children still to visit, in visit-order space
 	bool entering;                  // the node was just entered: classify its 8 children first
 	int steps;                      // mode B: nodes popped so far (512-step budget)
 	float curMin, curMax;           // mode A: (enterT, exitT) of the current node = clamps of its children
 };
 // mode A: clamps of the ancestors (kept apart from OctWalk so that the scalars above stay in registers while this dynamically
 // indexed array lives in local memory)
-struct OctClamps { float mn[16], mx[16]; };
-
-RTO_DEV void walk_push_mask(OctWalk& w) {
-	if (w.level < 8) w.mlo = (w.mlo & ~(0xffull << (8 * w.level))) | ((unsigned long long)w.M << (8 * w.level));
-	else w.mhi = (w.mhi & ~(0xffull << (8 * (w.level - 8)))) | ((unsigned long long)w.M << (8 * (w.level - 8)));
-}
-RTO_DEV unsigned walk_pop_mask(const OctWalk& w) {
-	return (unsigned)(((w.level < 8) ? (w.mlo >> (8 * w.level)) : (w.mhi >> (8 * (w.level - 8)))) & 0xffull);
-}
+struct OctClamps { float mn[16], mx[16]; unsigned char mask[16]; };     // + M of the ancestors
 
 // ---- mode B ------------------------------------------------------------------------------------------------------
 // One loop, state in plain locals: the init/step form used for mode A below (which needs a warp vote between steps) costs this
@@ -709,7 +718,8 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 			return hit;
 		}
 	}
-	unsigned long long mlo = 0ull, mhi = 0ull;                 // remaining-children masks, 8 bits per level
+	unsigned char maskS[16];                                   // remaining-children masks of the ancestors (local memory: the LSU pipe idles,
+	                                                           // the ALU pipe that would shift them in and out of registers is the bound)
 	int level = 0, rank = 0, pos = 8;
 	int4 e = RTO_LDG(S.inner);
 	bool entering = true;
@@ -722,13 +732,15 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 			// "tNear < closestT" (closestT stays 1e30 until the hit that ends the walk) is folded into the far distance of one axis:
 			// tn <= tf && tf > 0 && tn < 1e30  <=>  tn <= min(tf, kBelowMissT) && min(tf, kBelowMissT) > 0
 			P.f0[2] = fminf(P.f0[2], kBelowMissT); P.f1[2] = fminf(P.f1[2], kBelowMissT);
+			// and "tFar > 0" into the near distance of the same axis: tf > 0 <=> tf >= the smallest positive float (no flush-to-zero
+			// in this build), so tn <= tf && tf > 0  <=>  max(tn, kMinPositive) <= tf
+			P.n0[2] = fmaxf(P.n0[2], kMinPositive); P.n1[2] = fmaxf(P.n1[2], kMinPositive);
 			unsigned hits = 0;
 #pragma unroll
 			for (int k = 0; k < 8; k++) {
-				float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), (k & 4) ? P.n1[2] : P.n0[2]);
-				float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), (k & 4) ? P.f1[2] : P.f0[2]);
-				bool hk = (tn <= tf) && (tf > 0.0f);
-				hits |= hk ? (1u << k) : 0u;
+				float tn = fmax3f((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1], (k & 4) ? P.n1[2] : P.n0[2]);
+				float tf = fmin3f((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1], (k & 4) ? P.f1[2] : P.f0[2]);
+				hits |= (tn <= tf) ? (1u << k) : 0u;
 			}
 			M = hits & ~(leafMask & ~solidMask);               // children that can do more than burn a step: solid leaves and internal nodes
 			pos = 8;
@@ -741,7 +753,7 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 			rank = e.z;
 			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
 			level--;
-			M = (unsigned)(((level < 8) ? (mlo >> (8 * level)) : (mhi >> (8 * (level - 8)))) & 0xffull);
+			M = maskS[level];
 			e = RTO_LDG(S.inner + rank);
 			entering = false;
 			continue;
@@ -763,8 +775,7 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 			entering = false;
 			continue;
 		}
-		if (level < 8) mlo = (mlo & ~(0xffull << (8 * level))) | ((unsigned long long)M << (8 * level));
-		else mhi = (mhi & ~(0xffull << (8 * (level - 8)))) | ((unsigned long long)M << (8 * (level - 8)));
+		maskS[level] = (unsigned char)M;
 		level++;
 		rank = e.y + popc32(~leafMask & ((1u << j) - 1u) & 0xffu);
 		x = cx; y = cy; z = cz; size = h;
@@ -808,7 +819,7 @@ RTO_DEV bool octA_init(const OctDev& S, V3 o, V3 d, float tMin, float tMax, cons
 		if ((dsc & kOctSolid) && w.curMin < 1e30f) { hit.t = w.curMin; hit.id = 0; hit.normal = box_normal(b, o, d, w.curMin); }
 		return true;
 	}
-	w.mlo = 0ull; w.mhi = 0ull; w.level = 0; w.rank = 0; w.pos = -1; w.M = 0; w.steps = 0;
+	w.level = 0; w.rank = 0; w.pos = -1; w.M = 0; w.steps = 0;
 	w.e = RTO_LDG(S.inner);
 	w.entering = true;
 	return false;
@@ -832,8 +843,8 @@ RTO_DEV bool octA_step(const OctDev& S, V3 o, V3 d, float tMin, float tMax, cons
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
 			const int k = (int)((order >> (4 * j)) & 7u);      // a compile-time constant when the octant is (OCT < 8)
-			float tn = fmaxf(fmaxf((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1]), (k & 4) ? P.n1[2] : P.n0[2]);
-			float tf = fminf(fminf((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1]), (k & 4) ? P.f1[2] : P.f0[2]);
+			float tn = fmax3f((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1], (k & 4) ? P.n1[2] : P.n0[2]);
+			float tf = fmin3f((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1], (k & 4) ? P.f1[2] : P.f0[2]);
 			Mo |= !(tn > tf) ? (1u << j) : 0u;
 			skipO |= ((skipMask >> k) & 1u) << j;
 		}
@@ -848,7 +859,7 @@ RTO_DEV bool octA_step(const OctDev& S, V3 o, V3 d, float tMin, float tMax, cons
 		w.rank = w.e.z;
 		w.x &= ~w.size; w.y &= ~w.size; w.z &= ~w.size; w.size <<= 1;
 		w.level--;
-		w.M = walk_pop_mask(w);
+		w.M = cs.mask[w.level];
 		w.curMin = cs.mn[w.level]; w.curMax = cs.mx[w.level];
 		w.e = RTO_LDG(S.inner + w.rank);
 		return false;
@@ -870,7 +881,7 @@ RTO_DEV bool octA_step(const OctDev& S, V3 o, V3 d, float tMin, float tMax, cons
 		return false;
 	}
 	if (!ok) return false;                                     // (cannot happen: same values as the batch test)
-	walk_push_mask(w);
+	cs.mask[w.level] = (unsigned char)w.M;
 	cs.mn[w.level] = w.curMin; cs.mx[w.level] = w.curMax;
 	w.level++;
 	w.curMin = enterT; w.curMax = exitT;
