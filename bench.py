@@ -314,7 +314,7 @@ def run_ours(args, rank, world, local_rank):
         mesh.build()
         cores = host_cores()
         crays, csec, cframes = 0, 0.0, 0
-        while csec < 2.0 and cframes < 64:        # whole 1080p orbit frames until ~2 s of wall time on all host cores
+        while csec < 10.0 and cframes < 64:       # whole 1080p orbit frames until ~10 s of wall time on all host cores (or the whole orbit)
             ccam, _ = chk.camera(THETA_DEG, PHI0_DEG + PHI_STEP_DEG * cframes, RADIUS, width=W, height=H)
             out = mesh.render(ccam, 1, bias, 0, H, threads=cores)
             crays += W * H + int((out["id"] >= 0).sum())
