@@ -125,6 +125,14 @@ RTO_API int rto_host_camera_orbit(float theta, float phi, float radius, const fl
 RTO_API int rto_host_grid_load(const char* path, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut);
 RTO_API int rto_host_grid_save(const char* path, const int dims[3], const float minAndVoxel[4], const uint8_t* voxels);
 
+/* loadCSVDataIntoVoxelGrid (BuildingLoader.cpp:153-290), the producer of sceneCache.bin: parses the DT vertex / face CSV files
+ * (header line skipped; vertex lines "mesh,vertex,easting,northing,elevation,lat,lon,elevMin", face lines "mesh,v1,v2,v3"),
+ * pads the bounds by one voxel, caps the grid at 1000 cells per axis by enlarging the voxel, and fills every voxel whose centre
+ * projects into a face within the face's bounding box.  Same grid as the reference, bit for bit.  Empty / unreadable input gives
+ * dims 0 and no voxels (the reference returns an empty VoxelGrid).  voxels: malloc'ed, x-fastest; rto_host_free. */
+RTO_API int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize,
+	int dims[3], float minAndVoxel[4], uint8_t** voxelsOut);
+
 RTO_API void rto_host_free(void* p);
 
 /* ---- device scenes ----------------------------------------------------------------------------------- */
@@ -157,6 +165,10 @@ RTO_API int rto_scene_create_octree_from_grid(const uint8_t* voxels, int dimX, i
  * rto_host_mc_mesh (malloc'ed; rto_host_free).  Builds the octree it needs for the emission order itself. */
 RTO_API int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
 	const float gridMin[3], float voxelSize, RtoTriangle** trisOut, size_t* numTris);
+
+/* rto_host_csv_voxelize with the fill on the GPU (one warp per face); same grid, bit for bit. */
+RTO_API int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize,
+	int dims[3], float minAndVoxel[4], uint8_t** voxelsOut);
 
 /* BVH scene built on the device: the fast, NOT reference-shaped route (linear BVH: Morton sort, leaves of two neighbours, radix
  * tree, exact union boxes).  BVH::build's tree depends on std::sort's order on equal centroids (BVH.cpp:58-60) and cannot be

@@ -46,6 +46,7 @@ class Backend:
         sig = {
             "grid_create": (vp, [i32, i32, i32, f32, f32, f32, f32, vp]),
             "grid_load": (vp, [C.c_char_p]),
+            "grid_from_csv": (vp, [C.c_char_p, C.c_char_p, f32]),
             "grid_info": (None, [vp, vp, vp]),
             "grid_data": (None, [vp, vp]),
             "octree_build": (i32, [vp]),
@@ -71,8 +72,8 @@ class Backend:
             setattr(self, name, fn)
 
     # -- convenience constructors -----------------------------------------------------------------
-    def octree(self, dims=None, gmin=None, voxel=None, data=None, path=None):
-        return Octree(self, dims, gmin, voxel, data, path)
+    def octree(self, dims=None, gmin=None, voxel=None, data=None, path=None, csv=None):
+        return Octree(self, dims, gmin, voxel, data, path, csv)
 
     def mesh(self, tris):
         return Mesh(self, tris=tris)
@@ -117,9 +118,11 @@ def best():
     return ref() if ref_available() else port()
 
 class Octree:
-    def __init__(self, L, dims=None, gmin=None, voxel=None, data=None, path=None):
+    def __init__(self, L, dims=None, gmin=None, voxel=None, data=None, path=None, csv=None):
         self.L = L
-        if path is not None:
+        if csv is not None:                      # (verts.csv, faces.csv, voxelSize): loadCSVDataIntoVoxelGrid, BuildingLoader.cpp:153-290
+            self.h = L.grid_from_csv(os.fsencode(csv[0]), os.fsencode(csv[1]), float(csv[2]))
+        elif path is not None:
             self.h = L.grid_load(path.encode())
             if not self.h:
                 raise IOError(path)

@@ -19,7 +19,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <limits>
+#include <sstream>
+#include <string>
 #include <queue>
 #include <unordered_map>
 #include <vector>
@@ -393,6 +396,82 @@ void* orc_grid_create(int dx, int dy, int dz, float minX, float minY, float minZ
 	o->g.data.assign(data, data + (size_t)dx * dy * dz);
 	return o;
 }
+// ---- CSV voxeliser: restatement of loadCSVDataIntoVoxelGrid, BuildingLoader.cpp:153-290 (+ the loaders :35-129 and
+// isPointInTriangle :131-150).  Vertex line: mesh, vertex, easting, northing, elevation, latitude, longitude, elevMin; face line: mesh, v1, v2, v3.
+static void csvSplit(const std::string& line, std::vector<std::string>& tok) {          // :51-56 + trim :28-33
+	tok.clear();
+	std::istringstream ss(line); std::string t;
+	while (std::getline(ss, t, ',')) {
+		size_t a = t.find_first_not_of(" \t\n\r"), b = t.find_last_not_of(" \t\n\r");
+		tok.push_back(a == std::string::npos ? "" : t.substr(a, b - a + 1));
+	}
+}
+static bool pointInTri(V3 p, V3 a, V3 b, V3 c) {                                        // :131-150
+	V3 v0 = c - a, v1 = b - a, v2 = p - a;
+	float d00 = dot(v0, v0), d01 = dot(v0, v1), d02 = dot(v0, v2), d11 = dot(v1, v1), d12 = dot(v1, v2);
+	float inv = d00 * d11 - d01 * d01;
+	if (std::fabs(inv) < 1e-7f) return false;
+	inv = 1.0f / inv;
+	float u = (d11 * d02 - d01 * d12) * inv, v = (d00 * d12 - d01 * d02) * inv;
+	return (u >= 0) && (v >= 0) && (u + v <= 1);
+}
+void* orc_grid_from_csv(const char* vertsPath, const char* facesPath, float voxelSize) {
+	Octree* o = new Octree();
+	struct VRow { int mesh, num; double e, n, h; };
+	struct FRow { int mesh, a, b, c; };
+	std::vector<VRow> vr; std::vector<FRow> fr; std::vector<std::string> tok; std::string line;
+	{ std::ifstream f(vertsPath); if (f) { std::getline(f, line);                    // :44 header
+		while (std::getline(f, line)) { if (line.empty()) continue; csvSplit(line, tok); if (tok.size() < 8) continue;
+			try { VRow v; v.mesh = std::stoi(tok[0]); v.num = std::stoi(tok[1]); v.e = std::stod(tok[2]); v.n = std::stod(tok[3]); v.h = std::stod(tok[4]);
+				std::stod(tok[5]); std::stod(tok[6]); std::stod(tok[7]); vr.push_back(v); } catch (const std::exception&) {} } } }
+	{ std::ifstream f(facesPath); if (f) { std::getline(f, line);
+		while (std::getline(f, line)) { if (line.empty()) continue; csvSplit(line, tok); if (tok.size() < 4) continue;
+			try { FRow q; q.mesh = std::stoi(tok[0]); q.a = std::stoi(tok[1]); q.b = std::stoi(tok[2]); q.c = std::stoi(tok[3]); fr.push_back(q); } catch (const std::exception&) {} } } }
+	if (vr.empty() || fr.empty()) return o;                                             // :158 (empty grid)
+	std::unordered_map<int, std::unordered_map<int, VRow>> vmap;                        // :161-164
+	for (const VRow& v : vr) vmap[v.mesh][v.num] = v;
+	const double M = std::numeric_limits<double>::max();
+	double mn[3] = { M, M, M }, mx[3] = { -M, -M, -M };
+	for (const VRow& v : vr) if (std::isfinite(v.e) && std::isfinite(v.n) && std::isfinite(v.h)) {      // :174-183
+		mn[0] = std::min(mn[0], v.e); mn[1] = std::min(mn[1], v.n); mn[2] = std::min(mn[2], v.h);
+		mx[0] = std::max(mx[0], v.e); mx[1] = std::max(mx[1], v.n); mx[2] = std::max(mx[2], v.h);
+	}
+	const double pad = voxelSize;                                                       // :185-191
+	for (int a = 0; a < 3; a++) { mn[a] -= pad; mx[a] += pad; }
+	size_t d[3];
+	for (int a = 0; a < 3; a++) d[a] = (size_t)std::ceil((mx[a] - mn[a]) / voxelSize);     // :194-196
+	const size_t MAXD = 1000;                                                           // :199-208
+	if (d[0] > MAXD || d[1] > MAXD || d[2] > MAXD) {
+		float scale = std::max({ d[0] / MAXD, d[1] / MAXD, d[2] / MAXD });
+		voxelSize *= scale;
+		for (int a = 0; a < 3; a++) d[a] = (size_t)std::ceil((mx[a] - mn[a]) / voxelSize);
+	}
+	Grid& g = o->g;
+	g.dx = (int)d[0]; g.dy = (int)d[1]; g.dz = (int)d[2]; g.minX = (float)mn[0]; g.minY = (float)mn[1]; g.minZ = (float)mn[2]; g.voxel = voxelSize;
+	g.data.assign(d[0] * d[1] * d[2], 0);
+	for (const FRow& q : fr) {                                                          // :230-287
+		auto m = vmap.find(q.mesh); if (m == vmap.end()) continue;
+		auto ia = m->second.find(q.a), ib = m->second.find(q.b), ic = m->second.find(q.c);
+		if (ia == m->second.end() || ib == m->second.end() || ic == m->second.end()) continue;
+		V3 v1 = { (float)ia->second.e, (float)ia->second.n, (float)ia->second.h }, v2 = { (float)ib->second.e, (float)ib->second.n, (float)ib->second.h },
+			v3 = { (float)ic->second.e, (float)ic->second.n, (float)ic->second.h };
+		float tmn[3] = { std::min({ v1.x, v2.x, v3.x }), std::min({ v1.y, v2.y, v3.y }), std::min({ v1.z, v2.z, v3.z }) };
+		float tmx[3] = { std::max({ v1.x, v2.x, v3.x }), std::max({ v1.y, v2.y, v3.y }), std::max({ v1.z, v2.z, v3.z }) };
+		const float gm[3] = { g.minX, g.minY, g.minZ }; const int dd[3] = { g.dx, g.dy, g.dz };
+		int s[3], e[3];
+		for (int a = 0; a < 3; a++) { s[a] = std::max(0, (int)((tmn[a] - gm[a]) / voxelSize)); e[a] = std::min(dd[a] - 1, (int)((tmx[a] - gm[a]) / voxelSize) + 1); }
+		if (e[0] < s[0] || e[1] < s[1] || e[2] < s[2]) continue;
+		for (int z = s[2]; z <= e[2]; z++) for (int y = s[1]; y <= e[1]; y++) for (int x = s[0]; x <= e[0]; x++) {
+			V3 c = { g.minX + (x + 0.5f) * voxelSize, g.minY + (y + 0.5f) * voxelSize, g.minZ + (z + 0.5f) * voxelSize };
+			if (pointInTri(c, v1, v2, v3)) {
+				size_t idx = (size_t)x + (size_t)y * g.dx + (size_t)z * g.dx * g.dy;
+				if (idx < g.data.size()) g.data[idx] = 1;
+			}
+		}
+	}
+	return o;
+}
+
 void* orc_grid_load(const char* path) {     // sceneCache.bin format, CacheUtils.cpp:33-59
 	FILE* f = std::fopen(path, "rb");
 	if (!f) return nullptr;

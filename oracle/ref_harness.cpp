@@ -12,6 +12,7 @@
 //   BVH::BVH / BVH::query                       453-skeleton/BVH.cpp:19-113
 //   Camera::getView / getPos                    453-skeleton/Camera.cpp:11-29
 //   loadVoxelGrid                               453-skeleton/CacheUtils.cpp:33-59
+//   loadCSVDataIntoVoxelGrid (CSV voxeliser)    453-skeleton/BuildingLoader.cpp:153-290
 //   glm 0.9.9.7 arithmetic                      thirdparty/glm-0.9.9.7
 //
 // What is an EXTENSION RULE written here with glm types (the reference
@@ -94,6 +95,16 @@ void* ref_grid_create(int dx, int dy, int dz, float minX, float minY, float minZ
 	h->grid.voxelSize = voxelSize;
 	h->grid.data.resize((size_t)dx * dy * dz);
 	std::memcpy(h->grid.data.data(), data, h->grid.data.size());
+	return h;
+}
+
+// real loadCSVDataIntoVoxelGrid (BuildingLoader.cpp:153-290); its std::cout chatter is silenced for the duration of the call
+void* ref_grid_from_csv(const char* verts, const char* faces, float voxelSize) {
+	RefOctree* h = new RefOctree();
+	std::streambuf* keepOut = std::cout.rdbuf(nullptr);
+	std::streambuf* keepErr = std::cerr.rdbuf(nullptr);
+	h->grid = loadCSVDataIntoVoxelGrid(verts, faces, voxelSize);
+	std::cout.rdbuf(keepOut); std::cerr.rdbuf(keepErr);
 	return h;
 }
 

@@ -49,6 +49,8 @@ SIGNATURES = {
     "rto_host_camera_orbit": (_i, [_f, _f, _f, _vp, _f, _f, _i, _i, C.POINTER(RtoCamera), _vp]),
     "rto_host_grid_load": (_i, [C.c_char_p, _vp, _vp, _pp]),
     "rto_host_grid_save": (_i, [C.c_char_p, _vp, _vp, _vp]),
+    "rto_host_csv_voxelize": (_i, [C.c_char_p, C.c_char_p, _f, _vp, _vp, _pp]),
+    "rto_device_csv_voxelize": (_i, [C.c_char_p, C.c_char_p, _f, _vp, _vp, _pp]),
     "rto_host_free": (None, [_vp]),
     "rto_scene_create_octree": (_i, [_vp, _sz, _vp, _f, _pp]),
     "rto_scene_create_bvh": (_i, [_vp, _sz, _vp, _pp]),

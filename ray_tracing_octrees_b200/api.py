@@ -75,6 +75,20 @@ class VoxelGrid:
         check(lib().rto_host_grid_save(path.encode(), _p(dims), _p(mv), _p(self.data)))
 
 
+def load_csv_data_into_voxel_grid(verts_csv, faces_csv, voxel_size=5.0, device=False):
+    """loadCSVDataIntoVoxelGrid (BuildingLoader.cpp:153-290): DT vertex/face CSV files -> VoxelGrid (None when the input is empty,
+    where the reference returns an empty grid).  device=True rasterises the faces on the GPU (same grid)."""
+    dims = np.zeros(3, np.int32)
+    mv = np.zeros(4, np.float32)
+    ptr = C.c_void_p()
+    fn = lib().rto_device_csv_voxelize if device else lib().rto_host_csv_voxelize
+    check(fn(os.fsencode(verts_csv), os.fsencode(faces_csv), float(voxel_size), _p(dims), _p(mv), C.byref(ptr)))
+    n = int(dims[0]) * int(dims[1]) * int(dims[2])
+    if n == 0:
+        return None
+    return VoxelGrid(dims, mv[:3], mv[3], _take(ptr, n, np.uint8, (n,)))
+
+
 def create_octree_from_voxel_grid(grid):
     """-> (n, 15) int32 array of GPUNodes in the reference's BFS numbering (row index == node / leaf id)."""
     ptr = C.c_void_p()

@@ -15,13 +15,19 @@
 // Compiled with -ffp-contract=off; arithmetic follows rto_math.h (glm operation order).
 #include "rto_internal.h"
 #include "mc_tables.h"
+#include "rto_voxelize.h"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <cmath>
+#include <fstream>
+#include <sstream>
+#include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 using namespace rto;
@@ -485,3 +491,134 @@ extern "C" int rto_host_grid_save(const char* path, const int dims[3], const flo
 }
 
 extern "C" void rto_host_free(void* p) { std::free(p); }
+
+// =================================================================================================
+// CSV voxeliser: loadCSVDataIntoVoxelGrid (BuildingLoader.cpp:153-290) -- the producer of sceneCache.bin
+// =================================================================================================
+namespace {
+
+// fields of one CSV line, split on ',' and stripped of blanks (BuildingLoader.cpp:28-33, 51-56)
+void csvFields(const std::string& line, std::vector<std::string>& out) {
+	out.clear();
+	std::istringstream ss(line);
+	std::string tok;
+	while (std::getline(ss, tok, ',')) {
+		size_t b = tok.find_first_not_of(" \t\n\r"), e = tok.find_last_not_of(" \t\n\r");
+		out.push_back(b == std::string::npos ? std::string() : tok.substr(b, e - b + 1));
+	}
+}
+
+struct CsvVert { double e, n, h; };
+
+} // namespace
+
+int rto_csv_load(const char* vertsCsv, const char* facesCsv, float voxelSize, CsvScene& out) {
+	out = CsvScene();
+	out.voxelSize = voxelSize;
+	if (!vertsCsv || !facesCsv) return rto_fail(RTO_ERR_INVALID, "csv voxeliser: null path");
+	if (!(voxelSize > 0.0f)) return rto_fail(RTO_ERR_INVALID, "csv voxeliser: voxel size must be positive");
+	std::unordered_map<long long, CsvVert> verts;          // (mesh, vertex number) -> last definition wins (BuildingLoader.cpp:161-164)
+	const double DMAX = std::numeric_limits<double>::max();
+	double lo[3] = { DMAX, DMAX, DMAX }, hi[3] = { -DMAX, -DMAX, -DMAX };
+	size_t numVerts = 0;
+	std::vector<std::string> f;
+	std::string line;
+	{
+		std::ifstream in(vertsCsv);
+		if (!in) return RTO_OK;                             // unreadable file: empty grid, like the reference (BuildingLoader.cpp:38-41)
+		std::getline(in, line);                             // header
+		while (std::getline(in, line)) {
+			if (line.empty()) continue;
+			csvFields(line, f);
+			if (f.size() < 8) continue;
+			try {
+				int mesh = std::stoi(f[0]), num = std::stoi(f[1]);
+				CsvVert v; v.e = std::stod(f[2]); v.n = std::stod(f[3]); v.h = std::stod(f[4]);
+				(void)std::stod(f[5]); (void)std::stod(f[6]); (void)std::stod(f[7]);      // latitude, longitude, elevMin must parse too
+				verts[((long long)mesh << 32) | (unsigned int)num] = v;
+				numVerts++;
+				if (std::isfinite(v.e) && std::isfinite(v.n) && std::isfinite(v.h)) {     // bounds over every vertex read (:174-183)
+					lo[0] = std::min(lo[0], v.e); lo[1] = std::min(lo[1], v.n); lo[2] = std::min(lo[2], v.h);
+					hi[0] = std::max(hi[0], v.e); hi[1] = std::max(hi[1], v.n); hi[2] = std::max(hi[2], v.h);
+				}
+			}
+			catch (const std::exception&) { continue; }
+		}
+	}
+	struct Face { int mesh, a, b, c; };
+	std::vector<Face> faces;
+	{
+		std::ifstream in(facesCsv);
+		if (!in) return RTO_OK;
+		std::getline(in, line);
+		while (std::getline(in, line)) {
+			if (line.empty()) continue;
+			csvFields(line, f);
+			if (f.size() < 4) continue;
+			try { Face fc; fc.mesh = std::stoi(f[0]); fc.a = std::stoi(f[1]); fc.b = std::stoi(f[2]); fc.c = std::stoi(f[3]); faces.push_back(fc); }
+			catch (const std::exception&) { continue; }
+		}
+	}
+	if (numVerts == 0 || faces.empty()) return RTO_OK;      // :158
+	if (!(lo[0] <= hi[0])) return rto_fail(RTO_ERR_INVALID, "csv voxeliser: no vertex with finite coordinates");
+	// padding of one voxel, dimensions, cap at 1000 cells per axis by enlarging the voxel (:185-208)
+	double vs = voxelSize;
+	for (int a = 0; a < 3; a++) { lo[a] -= vs; hi[a] += vs; }
+	size_t dim[3];
+	for (int a = 0; a < 3; a++) dim[a] = (size_t)std::ceil((hi[a] - lo[a]) / voxelSize);
+	const size_t MAX_DIM = 1000;
+	if (dim[0] > MAX_DIM || dim[1] > MAX_DIM || dim[2] > MAX_DIM) {
+		float scale = (float)std::max({ dim[0] / MAX_DIM, dim[1] / MAX_DIM, dim[2] / MAX_DIM });
+		voxelSize *= scale;
+		for (int a = 0; a < 3; a++) dim[a] = (size_t)std::ceil((hi[a] - lo[a]) / voxelSize);
+	}
+	for (int a = 0; a < 3; a++) { out.dims[a] = (int)dim[a]; out.gridMin[a] = (float)lo[a]; }
+	out.voxelSize = voxelSize;
+	out.tris.reserve(faces.size());
+	for (const Face& fc : faces) {                          // faces with a missing vertex are skipped (:232-241)
+		auto a = verts.find(((long long)fc.mesh << 32) | (unsigned int)fc.a);
+		auto b = verts.find(((long long)fc.mesh << 32) | (unsigned int)fc.b);
+		auto c = verts.find(((long long)fc.mesh << 32) | (unsigned int)fc.c);
+		if (a == verts.end() || b == verts.end() || c == verts.end()) continue;
+		RtoTriangle t;
+		t.v0[0] = (float)a->second.e; t.v0[1] = (float)a->second.n; t.v0[2] = (float)a->second.h;
+		t.v1[0] = (float)b->second.e; t.v1[1] = (float)b->second.n; t.v1[2] = (float)b->second.h;
+		t.v2[0] = (float)c->second.e; t.v2[1] = (float)c->second.n; t.v2[2] = (float)c->second.h;
+		out.tris.push_back(t);
+	}
+	return RTO_OK;
+}
+
+extern "C" int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) {
+	if (!dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_host_csv_voxelize: null output");
+	*voxelsOut = nullptr; dims[0] = dims[1] = dims[2] = 0;
+	CsvScene S;
+	int rc = rto_csv_load(vertsCsv, facesCsv, voxelSize, S); if (rc) return rc;
+	for (int a = 0; a < 3; a++) { dims[a] = S.dims[a]; minAndVoxel[a] = S.gridMin[a]; }
+	minAndVoxel[3] = S.voxelSize;
+	const size_t n = (size_t)S.dims[0] * S.dims[1] * S.dims[2];
+	if (n == 0) return RTO_OK;
+	uint8_t* vox = (uint8_t*)std::calloc(n, 1);
+	if (!vox) return rto_fail(RTO_ERR_ALLOC, "rto_host_csv_voxelize: out of memory");
+	auto work = [&](size_t f0, size_t f1) {
+		for (size_t i = f0; i < f1; i++) {
+			const RtoTriangle& t = S.tris[i];
+			VoxRange r = vox_face_range(t, S.gridMin, S.voxelSize, S.dims);
+			if (r.empty) continue;
+			V3 a = mk3(t.v0[0], t.v0[1], t.v0[2]), b = mk3(t.v1[0], t.v1[1], t.v1[2]), c = mk3(t.v2[0], t.v2[1], t.v2[2]);
+			for (int z = r.z0; z <= r.z1; z++) for (int y = r.y0; y <= r.y1; y++) for (int x = r.x0; x <= r.x1; x++)
+				if (vox_point_in_triangle(vox_center(S.gridMin, S.voxelSize, x, y, z), a, b, c))
+					vox[(size_t)x + (size_t)y * S.dims[0] + (size_t)z * ((size_t)S.dims[0] * S.dims[1])] = 1;      // every writer stores the same value
+		}
+	};
+	unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	size_t nt = std::min<size_t>(hw, std::max<size_t>(1, S.tris.size() / 256));
+	if (nt <= 1) work(0, S.tris.size());
+	else {
+		std::vector<std::thread> th;
+		for (size_t k = 0; k < nt; k++) th.emplace_back(work, S.tris.size() * k / nt, S.tris.size() * (k + 1) / nt);
+		for (auto& t : th) t.join();
+	}
+	*voxelsOut = vox;
+	return RTO_OK;
+}

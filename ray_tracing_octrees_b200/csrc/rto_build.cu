@@ -11,6 +11,7 @@
 // Memory traffic, not arithmetic, bounds all of it (bytes in, bytes out, a few passes); see DESIGN.md section 5.
 #include "rto_scene.cuh"
 #include "mc_tables.h"
+#include "rto_voxelize.h"
 
 #include <cub/cub.cuh>
 #include <cfloat>
@@ -820,5 +821,65 @@ extern "C" int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, i
 	}
 	if (rc) { rto_scene_destroy(s); return rc; }
 	*out = s;
+	return RTO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CSV voxeliser, fill on the device: the files are parsed on the host (rto_csv_load), one warp rasterises one
+// face into the grid with the reference's arithmetic (rto_voxelize.h).  Every writer stores FILLED, so the order does not matter
+// (the reference's OpenMP loop relies on the same fact, BuildingLoader.cpp:229, 279).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct VoxGridDev { int dims[3]; float gmin[3]; float voxel; };
+
+__global__ void k_voxelize(const RtoTriangle* __restrict__ tris, size_t numFaces, VoxGridDev G, uint8_t* __restrict__ vox) {
+	const size_t face = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (face >= numFaces) return;
+	const RtoTriangle t = tris[face];
+	const VoxRange r = vox_face_range(t, G.gmin, G.voxel, G.dims);
+	if (r.empty) return;
+	const V3 a = mk3(t.v0[0], t.v0[1], t.v0[2]), b = mk3(t.v1[0], t.v1[1], t.v1[2]), c = mk3(t.v2[0], t.v2[1], t.v2[2]);
+	const long long nx = r.x1 - r.x0 + 1, ny = r.y1 - r.y0 + 1, nz = r.z1 - r.z0 + 1, n = nx * ny * nz;
+	for (long long i = lane; i < n; i += 32) {
+		const int x = r.x0 + (int)(i % nx), y = r.y0 + (int)((i / nx) % ny), z = r.z0 + (int)(i / (nx * ny));
+		if (vox_point_in_triangle(vox_center(G.gmin, G.voxel, x, y, z), a, b, c))
+			vox[(size_t)x + (size_t)y * G.dims[0] + (size_t)z * ((size_t)G.dims[0] * G.dims[1])] = 1;
+	}
+}
+} // namespace
+
+extern "C" int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) {
+	if (!dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_device_csv_voxelize: null output");
+	*voxelsOut = nullptr; dims[0] = dims[1] = dims[2] = 0;
+	int rc = rto_require_device(); if (rc) return rc;
+	CsvScene S;
+	rc = rto_csv_load(vertsCsv, facesCsv, voxelSize, S); if (rc) return rc;
+	for (int a = 0; a < 3; a++) { dims[a] = S.dims[a]; minAndVoxel[a] = S.gridMin[a]; }
+	minAndVoxel[3] = S.voxelSize;
+	const size_t n = (size_t)S.dims[0] * S.dims[1] * S.dims[2];
+	if (n == 0) return RTO_OK;
+	uint8_t* host = (uint8_t*)std::malloc(n);
+	if (!host) return rto_fail(RTO_ERR_ALLOC, "rto_device_csv_voxelize: out of host memory");
+	DevPool pool;
+	cudaStream_t st = nullptr;
+	uint8_t* dVox = nullptr; RtoTriangle* dTris = nullptr;
+	cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = pool.alloc(&dVox, n);
+	if (e == cudaSuccess) e = pool.alloc(&dTris, S.tris.size());
+	if (e == cudaSuccess) e = cudaMemsetAsync(dVox, 0, n, st);
+	if (e == cudaSuccess && !S.tris.empty()) e = cudaMemcpyAsync(dTris, S.tris.data(), S.tris.size() * sizeof(RtoTriangle), cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess && !S.tris.empty()) {
+		VoxGridDev G; for (int a = 0; a < 3; a++) { G.dims[a] = S.dims[a]; G.gmin[a] = S.gridMin[a]; } G.voxel = S.voxelSize;
+		const size_t threads = S.tris.size() * 32;
+		k_voxelize<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dTris, S.tris.size(), G, dVox);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(host, dVox, n, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (st) cudaStreamDestroy(st);
+	if (e != cudaSuccess) { std::free(host); return rto_fail(RTO_ERR_CUDA, "rto_device_csv_voxelize: %s", cudaGetErrorString(e)); }
+	*voxelsOut = host;
 	return RTO_OK;
 }

@@ -52,3 +52,15 @@ struct BvhLayout {
 	float rootLo[3] = { 0, 0, 0 }, rootHi[3] = { 0, 0, 0 };
 };
 void rto_build_bvh_layout(const RtoHostBvh& h, BvhLayout& out);
+
+// ---- CSV voxeliser (BuildingLoader.cpp:35-290), host part shared by the host and the device fill (host_builders.cpp) ----------
+struct CsvScene {
+	std::vector<RtoTriangle> tris;      // one per face whose three vertices exist, in file order (vertices cast double -> float)
+	int   dims[3] = { 0, 0, 0 };
+	float gridMin[3] = { 0, 0, 0 };
+	float voxelSize = 0;
+};
+// Parses both files and derives the grid geometry exactly like loadCSVDataIntoVoxelGrid.  dims == 0 when either file is empty
+// or unreadable (the reference returns an empty VoxelGrid then).
+int rto_csv_load(const char* vertsCsv, const char* facesCsv, float voxelSize, CsvScene& out);
+// cell range of one face and the centre-in-triangle predicate, identical on host and device (rto_voxelize.h)

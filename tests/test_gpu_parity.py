@@ -300,3 +300,30 @@ def test_full_size_sphere128_and_octree_modes(gpu, checker):
         _cmp_frames({k: full[k][sl] for k in full}, m_ref.render(rcam, 1, bias, y0, y0 + 3), "sphere bvh rows %d" % y0, allow_frac=1e-3)
         _cmp_frames({k: fa[k][sl] for k in fa}, oc_ref.render(rcam, 0, y0, y0 + 3), "sphere mode A rows %d" % y0)
         _cmp_frames({k: fb[k][sl] for k in fb}, oc_ref.render(rcam, 1, y0, y0 + 3), "sphere mode B rows %d" % y0)
+
+
+def test_city_block_octree_and_mesh_vs_oracle(gpu, checker):
+    """C3-shaped input (synthetic city blocks; 192^3 here so that the oracle's top-down octree build stays in seconds), both
+    octree modes and the mesh path against the oracle on scanline bands, from an oblique and from an axis-aligned camera
+    (the latter puts the sign changes of 1/d -- the octant boundaries the kernels specialise on -- in the middle of the image)."""
+    rto = gpu
+    grid = rto.city_block_grid(192, 4242, 12)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    oc = rto.Scene.octree_from_grid(grid)
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    sc = rto.Scene.bvh(tris)
+    oc_ref = checker.octree(grid.dims, grid.min, grid.voxel_size, grid.data); oc_ref.build()
+    m_ref = oc_ref.mesh(); m_ref.build()
+    W, H = 640, 360
+    bias = 1e-3 * grid.voxel_size
+    for theta, phi in ((35, 40), (20, 90), (60, 180), (1, 0)):
+        cam, _ = rto.Camera.from_degrees(theta, phi, 0.9 * 192).consts(45.0, float(np.float32(W) / np.float32(H)), W, H)
+        rcam, _ = checker.camera(theta, phi, 0.9 * 192, width=W, height=H)
+        assert bytes(rcam) == bytes(cam)
+        fa, fb = oc.render(cam, rto.MODE_OCTREE_SKIP), oc.render(cam, rto.MODE_OCTREE_GLSL)
+        fm = sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias)
+        for y0 in range(2, H, 45):
+            sl = slice(y0 * W, (y0 + 2) * W)
+            _cmp_frames({k: fa[k][sl] for k in fa}, oc_ref.render(rcam, 0, y0, y0 + 2), "city mode A rows %d cam %d/%d" % (y0, theta, phi))
+            _cmp_frames({k: fb[k][sl] for k in fb}, oc_ref.render(rcam, 1, y0, y0 + 2), "city mode B rows %d cam %d/%d" % (y0, theta, phi))
+            _cmp_frames({k: fm[k][sl] for k in fm}, m_ref.render(rcam, 1, bias, y0, y0 + 2), "city mesh rows %d cam %d/%d" % (y0, theta, phi), allow_frac=1e-3)
