@@ -335,8 +335,10 @@ struct SahBuilder {
 		float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
 		return dx * dy + dy * dz + dz * dx;
 	}
-	// returns the ref of the subtree over prims[lo, hi) and its exact bounds
-	int32_t build(size_t lo, size_t hi, float* bmn, float* bmx) {
+	// Returns the ref of the subtree over prims[lo, hi) and its exact bounds.  A subtree over m leaves has m - 1 inner nodes, so the
+	// pre-order position of every node is known in advance (root at `idx`, left subtree at idx + 1, right at idx + (mid - lo)) and
+	// the top of the tree can be built by several threads into one preallocated array.
+	int32_t build(size_t lo, size_t hi, size_t idx, int depth, float* bmn, float* bmx) {
 		const float M = std::numeric_limits<float>::max();
 		float cmn[3] = { M, M, M }, cmx[3] = { -M, -M, -M };
 		for (int k = 0; k < 3; k++) { bmn[k] = M; bmx[k] = -M; }
@@ -384,11 +386,17 @@ struct SahBuilder {
 			mid = (size_t)(it - prims.begin());
 			if (mid == lo || mid == hi) mid = lo + (hi - lo) / 2;
 		}
-		size_t idx = out->size() / 16;
-		out->resize(out->size() + 16, 0.0f);
 		float lmn[3], lmx[3], rmn[3], rmx[3];
-		int32_t r0 = build(lo, mid, lmn, lmx);
-		int32_t r1 = build(mid, hi, rmn, rmx);
+		int32_t r0, r1;
+		if (depth < 4 && hi - lo > 65536) {
+			std::thread th([&] { r0 = build(lo, mid, idx + 1, depth + 1, lmn, lmx); });
+			r1 = build(mid, hi, idx + (mid - lo), depth + 1, rmn, rmx);
+			th.join();
+		}
+		else {
+			r0 = build(lo, mid, idx + 1, depth + 1, lmn, lmx);
+			r1 = build(mid, hi, idx + (mid - lo), depth + 1, rmn, rmx);
+		}
 		float* d = &(*out)[idx * 16];
 		std::memcpy(d, lmn, 12); std::memcpy(d + 3, lmx, 12); std::memcpy(d + 6, rmn, 12); std::memcpy(d + 9, rmx, 12);
 		std::memcpy(&d[12], &r0, 4); std::memcpy(&d[13], &r1, 4);
@@ -408,10 +416,9 @@ void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, i
 		b.prims.push_back(p);
 	}
 	if (b.prims.empty()) { nodeBuf.assign(16, 0.0f); rootRef = -1; return; }
-	nodeBuf.reserve(b.prims.size() * 16);
+	nodeBuf.assign(std::max<size_t>(b.prims.size() - 1, 1) * 16, 0.0f);
 	float mn[3], mx[3];
-	rootRef = b.build(0, b.prims.size(), mn, mx);
-	if (nodeBuf.empty()) nodeBuf.assign(16, 0.0f);
+	rootRef = b.build(0, b.prims.size(), 0, 0, mn, mx);
 }
 
 // =================================================================================================
