@@ -408,12 +408,21 @@ struct SahBuilder {
 void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef) {
 	SahBuilder b; b.out = &nodeBuf;
 	nodeBuf.clear();
-	for (const HostBvhNode& n : h.nodes) {
-		if (n.left >= 0 || n.count == 0) continue;
-		SahPrim p;
-		for (int k = 0; k < 3; k++) { p.mn[k] = n.mn[k]; p.mx[k] = n.mx[k]; p.c[k] = 0.5f * n.mn[k] + 0.5f * n.mx[k]; }
-		p.ref = leafRefOf(n);
-		b.prims.push_back(p);
+	// one primitive per triangle, in reference leaf order (position p == tie-break rank of the closest-hit rule); its box is the
+	// triangle's own box grown by 2^-16 of the scene's extent on every side, far more than the rounding of the Moller-Trumbore
+	// test can move a hit and far less than a triangle
+	float ext = 0.0f;
+	if (!h.nodes.empty()) for (int k = 0; k < 3; k++) ext = std::max(ext, std::max(std::fabs(h.nodes[0].mn[k]), std::fabs(h.nodes[0].mx[k])));
+	const float grow = ext * (1.0f / 65536.0f);
+	b.prims.resize(h.numTris);
+	for (size_t p = 0; p < h.numTris; p++) {
+		const RtoTriangle& t = h.tris[h.order[p]];
+		SahPrim& q = b.prims[p];
+		for (int k = 0; k < 3; k++) {
+			float mn = std::min(t.v0[k], std::min(t.v1[k], t.v2[k])), mx = std::max(t.v0[k], std::max(t.v1[k], t.v2[k]));
+			q.mn[k] = mn - grow; q.mx[k] = mx + grow; q.c[k] = 0.5f * mn + 0.5f * mx;
+		}
+		q.ref = ~(int32_t)((uint32_t)p << 1);
 	}
 	if (b.prims.empty()) { nodeBuf.assign(16, 0.0f); rootRef = -1; return; }
 	nodeBuf.assign(std::max<size_t>(b.prims.size() - 1, 1) * 16, 0.0f);

@@ -88,10 +88,14 @@ void rto_build_bvh_layout(const RtoHostBvh& h, BvhLayout& L) {
 	rto_build_reference_topology(h, L.refNodes, L.refRoot);
 	static const bool refTopology = getenv("RTO_BVH_REFERENCE_TOPOLOGY") != nullptr;     // tuning aid: trace through the reference's tree
 	if (!refTopology) rto_build_fast_topology(h, L.fastNodes, L.fastRoot);
-	L.tris.assign(std::max<size_t>(h.numTris, 1) * 12, 0.0f);
+	L.tris.assign(std::max<size_t>(h.numTris, 1) * 16, 0.0f);
+	for (const HostBvhNode& n : h.nodes) {              // every triangle carries the exact box of its reference leaf (floats 10..15)
+		if (n.left >= 0) continue;
+		for (uint32_t p = n.first; p < n.first + n.count; p++) { std::memcpy(&L.tris[(size_t)p * 16 + 10], n.mn, 12); std::memcpy(&L.tris[(size_t)p * 16 + 13], n.mx, 12); }
+	}
 	for (size_t p = 0; p < h.numTris; p++) {
 		uint32_t id = h.order[p];
-		float* d = &L.tris[p * 12];
+		float* d = &L.tris[p * 16];
 		const RtoTriangle& T = h.tris[id];
 		for (int k = 0; k < 3; k++) { d[k] = T.v0[k]; d[3 + k] = T.v1[k] - T.v0[k]; d[6 + k] = T.v2[k] - T.v0[k]; }     // v0, e1, e2 (rto_kernels.cuh TriV)
 		int32_t iid = (int32_t)id;

@@ -629,55 +629,56 @@ __global__ void k_lbvh_codes(const RtoTriangle* __restrict__ tris, size_t n, con
 }
 
 // triangle records in sorted order (v0, e1, e2, id: rto_kernels.cuh TriV) and the exact box of every leaf (two neighbours)
-__global__ void k_lbvh_leaves(const RtoTriangle* __restrict__ tris, const uint32_t* __restrict__ order, size_t n, float4* __restrict__ rec, float* __restrict__ leafBox /* 6 per leaf */) {
+__global__ void k_lbvh_leaves(const RtoTriangle* __restrict__ tris, const uint32_t* __restrict__ order, size_t n, int perLeaf, float4* __restrict__ rec, float* __restrict__ leafBox /* 6 per leaf */) {
 	const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const size_t numLeaves = (n + 1) / 2;
+	const size_t numLeaves = (n + perLeaf - 1) / perLeaf;
 	if (leaf >= numLeaves) return;
 	float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-	for (size_t p = 2 * leaf; p < 2 * leaf + 2 && p < n; p++) {
+	for (size_t p = perLeaf * leaf; p < perLeaf * leaf + perLeaf && p < n; p++) {
 		const uint32_t id = order[p];
 		const float* v = reinterpret_cast<const float*>(tris + id);
 		float f[9];
 #pragma unroll
 		for (int k = 0; k < 9; k++) { f[k] = v[k]; lo[k % 3] = fminf(lo[k % 3], f[k]); hi[k % 3] = fmaxf(hi[k % 3], f[k]); }
-		rec[3 * p] = make_float4(f[0], f[1], f[2], f[3] - f[0]);
-		rec[3 * p + 1] = make_float4(f[4] - f[1], f[5] - f[2], f[6] - f[0], f[7] - f[1]);
-		rec[3 * p + 2] = make_float4(f[8] - f[2], __int_as_float((int)id), 0.0f, 0.0f);
+		rec[4 * p] = make_float4(f[0], f[1], f[2], f[3] - f[0]);
+		rec[4 * p + 1] = make_float4(f[4] - f[1], f[5] - f[2], f[6] - f[0], f[7] - f[1]);
+		rec[4 * p + 2] = make_float4(f[8] - f[2], __int_as_float((int)id), 0.0f, 0.0f);      // (reference-leaf box unused: BvhDev::leafBox == 0)
+		rec[4 * p + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
 #pragma unroll
 	for (int a = 0; a < 3; a++) { leafBox[6 * leaf + a] = lo[a]; leafBox[6 * leaf + 3 + a] = hi[a]; }
 }
 
 // common-prefix length of the keys of leaves i and j (key = Morton code of the leaf's first triangle, ties broken by index)
-__device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ codes, int numLeaves, int i, int j) {
+__device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ codes, int perLeaf, int numLeaves, int i, int j) {
 	if (j < 0 || j >= numLeaves) return -1;
-	const uint64_t a = codes[2 * (size_t)i], b = codes[2 * (size_t)j];
+	const uint64_t a = codes[perLeaf * (size_t)i], b = codes[perLeaf * (size_t)j];
 	if (a == b) return 64 + __clz(i ^ j);
 	return __clzll((long long)(a ^ b));
 }
 
 // Karras 2012: internal node i of the binary radix tree over the sorted leaves; child refs into the node, parent links for the fit pass
-__global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int numLeaves, size_t numTris, float4* __restrict__ nodes, int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf) {
+__global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int perLeaf, int numLeaves, size_t numTris, float4* __restrict__ nodes, int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= numLeaves - 1) return;
-	const int d = (lbvh_delta(codes, numLeaves, i, i + 1) - lbvh_delta(codes, numLeaves, i, i - 1)) >= 0 ? 1 : -1;
-	const int dmin = lbvh_delta(codes, numLeaves, i, i - d);
+	const int d = (lbvh_delta(codes, perLeaf, numLeaves, i, i + 1) - lbvh_delta(codes, perLeaf, numLeaves, i, i - 1)) >= 0 ? 1 : -1;
+	const int dmin = lbvh_delta(codes, perLeaf, numLeaves, i, i - d);
 	int lmax = 2;
-	while (lbvh_delta(codes, numLeaves, i, i + lmax * d) > dmin) lmax <<= 1;
+	while (lbvh_delta(codes, perLeaf, numLeaves, i, i + lmax * d) > dmin) lmax <<= 1;
 	int l = 0;
-	for (int t = lmax >> 1; t >= 1; t >>= 1) if (lbvh_delta(codes, numLeaves, i, i + (l + t) * d) > dmin) l += t;
+	for (int t = lmax >> 1; t >= 1; t >>= 1) if (lbvh_delta(codes, perLeaf, numLeaves, i, i + (l + t) * d) > dmin) l += t;
 	const int j = i + l * d;
-	const int dnode = lbvh_delta(codes, numLeaves, i, j);
+	const int dnode = lbvh_delta(codes, perLeaf, numLeaves, i, j);
 	int s = 0;
 	for (int t = (l + 1) >> 1; ; t = (t + 1) >> 1) {
-		if (lbvh_delta(codes, numLeaves, i, i + (s + t) * d) > dnode) s += t;
+		if (lbvh_delta(codes, perLeaf, numLeaves, i, i + (s + t) * d) > dnode) s += t;
 		if (t == 1) break;
 	}
 	const int gamma = i + s * d + min(d, 0);
 	const int first = min(i, j), last = max(i, j);
 	auto leafRef = [&](int leaf) {
-		const size_t p = 2 * (size_t)leaf;
-		const int cnt = (p + 1 < numTris) ? 2 : 1;
+		const size_t p = perLeaf * (size_t)leaf;
+		const int cnt = (perLeaf == 2 && p + 1 < numTris) ? 2 : 1;
 		return ~(int)((p << 1) | (size_t)(cnt - 1));
 	};
 	int r0, r1;
@@ -723,12 +724,15 @@ __global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, flo
 int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	cudaStream_t st = s->stream;
 	BvhDev D{};
-	D.numTris = (int)numTris; D.rootRef = -1;
+	D.numTris = (int)numTris; D.rootRef = -1; D.leafBox = 0;
 	s->numPrims = numTris;
 	if (numTris == 0) { s->bvh = D; s->bvhFast = D; s->numNodes = 0; return RTO_OK; }
 	if (numTris >= (size_t)1 << 30) return rto_fail(RTO_ERR_UNSUPPORTED, "BVH build on the device: more than 2^30 triangles");
 	DevPool tmp;
-	const int numLeaves = (int)((numTris + 1) / 2), numInner = numLeaves - 1;
+	// triangles per leaf: 1 (measured 1.2-1.7x faster to traverse than leaves of two Morton neighbours: tight leaf boxes save
+	// Moller-Trumbore tests, the block that runs with the fewest lanes) or 2 (RTO_LBVH_LEAF=2, tuning aid)
+	static const int perLeaf = [] { const char* e = getenv("RTO_LBVH_LEAF"); return (e && e[0] == '2') ? 2 : 1; }();
+	const int numLeaves = (int)((numTris + perLeaf - 1) / perLeaf), numInner = numLeaves - 1;
 	int* dBounds = nullptr;
 	BUILD_TRY(tmp.alloc(&dBounds, 6));
 	{
@@ -753,11 +757,11 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	// scene-owned outputs
 	void *dRec = nullptr, *dNodes = nullptr;
 	int rc;
-	if ((rc = rto_scene_alloc(s, &dRec, numTris * 48))) return rc;
+	if ((rc = rto_scene_alloc(s, &dRec, numTris * 64))) return rc;
 	if ((rc = rto_scene_alloc(s, &dNodes, (size_t)(numInner > 0 ? numInner : 1) * 64))) return rc;
 	float* leafBox = nullptr; float* dRoot = nullptr;
 	BUILD_TRY(tmp.alloc(&leafBox, 6 * (size_t)numLeaves)); BUILD_TRY(tmp.alloc(&dRoot, 6));
-	k_lbvh_leaves<<<blocksL, 256, 0, st>>>(dTris, order, numTris, (float4*)dRec, leafBox);
+	k_lbvh_leaves<<<blocksL, 256, 0, st>>>(dTris, order, numTris, perLeaf, (float4*)dRec, leafBox);
 	float root[6];
 	if (numInner == 0) {
 		BUILD_TRY(cudaMemcpyAsync(root, leafBox, sizeof(root), cudaMemcpyDeviceToHost, st));
@@ -768,7 +772,7 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 		int *pInner = nullptr, *pLeaf = nullptr, *arrived = nullptr;
 		BUILD_TRY(tmp.alloc(&pInner, numInner)); BUILD_TRY(tmp.alloc(&pLeaf, numLeaves)); BUILD_TRY(tmp.alloc(&arrived, numInner));
 		BUILD_TRY(cudaMemsetAsync(arrived, 0, sizeof(int) * (size_t)numInner, st));
-		k_lbvh_tree<<<(unsigned)((numInner + 255) / 256), 256, 0, st>>>(codesSorted, numLeaves, numTris, (float4*)dNodes, pInner, pLeaf);
+		k_lbvh_tree<<<(unsigned)((numInner + 255) / 256), 256, 0, st>>>(codesSorted, perLeaf, numLeaves, numTris, (float4*)dNodes, pInner, pLeaf);
 		k_lbvh_fit<<<blocksL, 256, 0, st>>>(numLeaves, leafBox, (float*)dNodes, pInner, pLeaf, arrived, dRoot);
 		BUILD_TRY(cudaGetLastError());
 		BUILD_TRY(cudaMemcpyAsync(root, dRoot, sizeof(root), cudaMemcpyDeviceToHost, st));

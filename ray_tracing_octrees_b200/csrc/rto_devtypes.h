@@ -11,9 +11,13 @@ namespace rto {
 // ------------------------------------------------------------------------------------------------
 struct BvhDev {
 	const float4* nodes;     // inner nodes, 4 x float4 each: [lo0.xyz hi0.x][hi0.yz lo1.xy][lo1.z hi1.xyz][ref0 ref1 - -]
-	const float4* tris;      // 3 x float4 per triangle in leaf order: [v0.xyz e1.x][e1.yz e2.xy][e2.z id - -], e1 = v1 - v0, e2 = v2 - v0
+	const float4* tris;      // 4 x float4 (64 B) per triangle in leaf order: [v0.xyz e1.x][e1.yz e2.xy][e2.z id lo.xy][lo.z hi.xyz], e1 = v1 - v0,
+	                         // e2 = v2 - v0, lo/hi = the exact box of the REFERENCE leaf the triangle belongs to
 	int   rootRef;           // >= 0: inner node index; < 0: ~leafRef, leafRef = (firstPos << 1) | (count - 1)
 	int   numTris;
+	int   leafBox;           // 1: the tree's leaves are single triangles under (inflated) boxes of their own, and a triangle is a candidate
+	                         // only if the box of its reference leaf (in its record) passes intersectAABB: tested at the leaf.
+	                         // 0: the tree's leaves are the reference's leaves and their boxes were tested in the parent node.
 	float rootLo[3], rootHi[3];
 };
 

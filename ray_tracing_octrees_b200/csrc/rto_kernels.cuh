@@ -143,8 +143,8 @@ RTO_DEV bool ray_needs_exact_box(const RayBox& rb) {
 // done once on the host: same bits as computing them per test), so a test costs 6 subtractions less.
 struct TriV { V3 v0, e1, e2; int id; };
 RTO_DEV TriV load_tri(const float4* __restrict__ tris, int pos) {
-	float4 a = RTO_LDG(tris + 3 * (size_t)pos), b = RTO_LDG(tris + 3 * (size_t)pos + 1);
-	float2 c = RTO_LDG(reinterpret_cast<const float2*>(tris + 3 * (size_t)pos + 2));
+	float4 a = RTO_LDG(tris + 4 * (size_t)pos), b = RTO_LDG(tris + 4 * (size_t)pos + 1);
+	float2 c = RTO_LDG(reinterpret_cast<const float2*>(tris + 4 * (size_t)pos + 2));
 	TriV t;
 	t.v0 = mk3(a.x, a.y, a.z); t.e1 = mk3(a.w, b.x, b.y); t.e2 = mk3(b.z, b.w, c.x); t.id = f2i(c.y);
 	return t;
@@ -205,6 +205,18 @@ RTO_DEV void node_boxes(const RayBox& rb, float4 a, float4 b, float4 c, float tc
 	}
 }
 
+// the box of the reference leaf a triangle belongs to (triangle record, BvhDev): the test BVH::queryNode makes before it emits the
+// leaf's triangles, for trees whose own leaves are finer than the reference's (BvhDev::leafBox)
+template <int OCT>
+RTO_DEV bool ref_leaf_box_passes(const BvhDev& S, const RayBox& rb, int pos, float tcap) {
+	const float4* rec = S.tris + 4 * (size_t)pos;
+	float2 c = RTO_LDG(reinterpret_cast<const float2*>(rec + 2) + 1);
+	float4 d = RTO_LDG(rec + 3);
+	float e;
+	if (OCT < kOctGeneric) return slab_oct<OCT>(rb.o, rb.inv, c.x, c.y, d.x, d.y, d.z, d.w, tcap, e);
+	return slab_ref(rb, c.x, c.y, d.x, d.y, d.z, d.w, e) && (e <= tcap);
+}
+
 // Closest hit.  Result = min over the reference's candidate set of (t, position in candidate order), i.e. the
 // oracle's "strict <, first candidate wins".  PRUNE: near-child-first order and subtrees entered only while their
 // box entry <= best * kPruneSlack.  !PRUNE: every box the reference's queryNode would test is tested.
@@ -240,6 +252,7 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 				int ref = ~cur;
 				int pos = ref >> 1, cnt = (ref & 1) + 1;
 				for (int k = 0; k < cnt; k++) {
+					if (S.leafBox && !ref_leaf_box_passes<OCT>(S, rb, pos + k, PRUNE ? tcut : FLT_MAX)) continue;
 					TriV tri = load_tri(S.tris, pos + k);
 					float t;
 					if (moller_trumbore(tri, o, d, t)) {
@@ -308,6 +321,7 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 			int ref = ~cur;
 			int pos = ref >> 1, cnt = (ref & 1) + 1;
 			for (int k = 0; k < cnt; k++) {
+				if (S.leafBox && !ref_leaf_box_passes<OCT>(S, rb, pos + k, FLT_MAX)) continue;
 				TriV tri = load_tri(S.tris, pos + k);
 				float t;
 				if (moller_trumbore(tri, o, d, t)) return true;
@@ -1033,7 +1047,7 @@ __global__ void __launch_bounds__(128) k_trace_bvh(BvhDev S, unsigned flags, con
 	float bestT; int bestPos;
 	if (flags & RTO_FLAG_NO_PRUNE) bvh_closest<false>(S, o, d, bestT, bestPos); else bvh_closest<true>(S, o, d, bestT, bestPos);
 	if (tOut) tOut[i] = bestT;
-	if (idOut) idOut[i] = bestPos >= 0 ? f2i(RTO_LDG(S.tris + 3 * (size_t)bestPos + 2).y) : -1;
+	if (idOut) idOut[i] = bestPos >= 0 ? f2i(RTO_LDG(S.tris + 4 * (size_t)bestPos + 2).y) : -1;
 }
 
 // BVH::query candidates: pass 1 counts per ray, pass 2 writes ids at the host-computed offsets
@@ -1046,7 +1060,7 @@ __global__ void __launch_bounds__(128) k_bvh_query(BvhDev S, const float* __rest
 	int cnt = 0;
 	long long base = offsets ? offsets[i] : 0;
 	bvh_replay(S, o, d, boxes, [&](int pos) {
-		if (ids) ids[base + cnt] = f2i(RTO_LDG(S.tris + 3 * (size_t)pos + 2).y);
+		if (ids) ids[base + cnt] = f2i(RTO_LDG(S.tris + 4 * (size_t)pos + 2).y);
 		cnt++;
 	});
 	if (counts) counts[i] = cnt;

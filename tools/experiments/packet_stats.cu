@@ -32,7 +32,7 @@ static void trace_ray(const BvhDev& S, V3 o, V3 d, std::vector<int>& inner, std:
 		} else {
 			leaves.push_back(cur);
 			int ref = ~cur; int pos = ref >> 1, cnt = (ref & 1) + 1;
-			for (int k = 0; k < cnt; k++) { TriV tri = load_tri(S.tris, pos + k); float t; if (moller_trumbore(tri, o, d, t)) if (t < bestT || (t == bestT && pos + k < bestPos)) { bestT = t; bestPos = pos + k; tcut = t * kPruneSlack; } }
+			for (int k = 0; k < cnt; k++) { TriV tri = load_tri(S.tris, pos + k); float t; if ((!S.leafBox || ref_leaf_box_passes<kOctGeneric>(S, rb, pos + k, tcut)) && moller_trumbore(tri, o, d, t)) if (t < bestT || (t == bestT && pos + k < bestPos)) { bestT = t; bestPos = pos + k; tcut = t * kPruneSlack; } }
 		}
 		if (pop) { bool got = false; while (sp > 0) { StackEnt e = stack[--sp]; if (e.t <= tcut) { cur = e.ref; got = true; break; } } if (!got) break; }
 	}
@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
 	RtoTriangle* tris; size_t nt; rto_host_mc_mesh(vox.data(), dims[0], dims[1], dims[2], mv, mv[3], nodes, nn, &tris, &nt);
 	RtoHostBvh* hb; rto_host_bvh_build(tris, nt, &hb);
 	BvhLayout L; rto_build_bvh_layout(*hb, L);
-	BvhDev S; S.numTris = (int)nt; S.rootRef = L.fastRoot; S.nodes = (const float4*)L.fastNodes.data(); S.tris = (const float4*)L.tris.data();
+	BvhDev S; S.numTris = (int)nt; S.rootRef = L.fastRoot; S.leafBox = 1; S.nodes = (const float4*)L.fastNodes.data(); S.tris = (const float4*)L.tris.data();
 	for (int k = 0; k < 3; k++) { S.rootLo[k] = L.rootLo[k]; S.rootHi[k] = L.rootHi[k]; }
 	printf("tris %zu\n", nt);
 	const int W = 1920, H = 1080;
