@@ -252,11 +252,14 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 				int ref = ~cur;
 				int pos = ref >> 1, cnt = (ref & 1) + 1;
 				for (int k = 0; k < cnt; k++) {
-					if (S.leafBox && !ref_leaf_box_passes<OCT>(S, rb, pos + k, PRUNE ? tcut : FLT_MAX)) continue;
 					TriV tri = load_tri(S.tris, pos + k);
 					float t;
 					if (moller_trumbore(tri, o, d, t)) {
-						if (t < bestT || (t == bestT && pos + k < bestPos)) { bestT = t; bestPos = pos + k; tcut = t * kPruneSlack; }
+						// (the reference-leaf box is checked only for a hit that would be taken: two out of three tests miss anyway, and
+						// the box, which contains the triangle, almost never fails)
+						if ((t < bestT || (t == bestT && pos + k < bestPos)) && (!S.leafBox || ref_leaf_box_passes<OCT>(S, rb, pos + k, FLT_MAX))) {
+							bestT = t; bestPos = pos + k; tcut = t * kPruneSlack;
+						}
 					}
 				}
 			}
@@ -321,10 +324,9 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 			int ref = ~cur;
 			int pos = ref >> 1, cnt = (ref & 1) + 1;
 			for (int k = 0; k < cnt; k++) {
-				if (S.leafBox && !ref_leaf_box_passes<OCT>(S, rb, pos + k, FLT_MAX)) continue;
 				TriV tri = load_tri(S.tris, pos + k);
 				float t;
-				if (moller_trumbore(tri, o, d, t)) return true;
+				if (moller_trumbore(tri, o, d, t) && (!S.leafBox || ref_leaf_box_passes<OCT>(S, rb, pos + k, FLT_MAX))) return true;
 			}
 		}
 		if (sp == 0) break;
