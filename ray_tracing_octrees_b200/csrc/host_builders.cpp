@@ -18,6 +18,7 @@
 #include "rto_voxelize.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -331,6 +332,8 @@ namespace {
 struct SahPrim { float mn[3], mx[3], c[3]; int32_t ref; };
 struct SahBuilder {
 	std::vector<SahPrim> prims; std::vector<float>* out;
+	std::atomic<int> maxDepth{ 0 };
+	bool medianOnly = false;        // balanced fallback: split every range in half along its widest centroid axis
 	static inline float halfArea(const float* mn, const float* mx) {
 		float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
 		return dx * dy + dy * dz + dz * dx;
@@ -348,9 +351,10 @@ struct SahBuilder {
 				cmn[k] = std::min(cmn[k], prims[i].c[k]); cmx[k] = std::max(cmx[k], prims[i].c[k]);
 			}
 		if (hi - lo == 1) return prims[lo].ref;
+		{ int seen = maxDepth.load(std::memory_order_relaxed); while (depth + 1 > seen && !maxDepth.compare_exchange_weak(seen, depth + 1)) {} }
 		constexpr int NB = 32;
 		int bestAxis = -1, bestSplit = 0; float bestCost = M;
-		for (int ax = 0; ax < 3; ax++) {
+		for (int ax = 0; ax < 3 && !medianOnly; ax++) {
 			float ext = cmx[ax] - cmn[ax];
 			if (!(ext > 0.0f)) continue;
 			float scale = NB / ext;
@@ -378,7 +382,14 @@ struct SahBuilder {
 			}
 		}
 		size_t mid;
-		if (bestAxis < 0) mid = lo + (hi - lo) / 2;        // all centroids coincide: split the list in half
+		if (medianOnly) {
+			int ax = 0;
+			if (cmx[1] - cmn[1] > cmx[ax] - cmn[ax]) ax = 1;
+			if (cmx[2] - cmn[2] > cmx[ax] - cmn[ax]) ax = 2;
+			mid = lo + (hi - lo) / 2;
+			std::nth_element(prims.begin() + lo, prims.begin() + mid, prims.begin() + hi, [ax](const SahPrim& a, const SahPrim& b) { return a.c[ax] < b.c[ax]; });
+		}
+		else if (bestAxis < 0) mid = lo + (hi - lo) / 2;   // all centroids coincide: split the list in half
 		else {
 			float scale = NB / (cmx[bestAxis] - cmn[bestAxis]), base = cmn[bestAxis];
 			auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const SahPrim& p) {
@@ -428,6 +439,15 @@ void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, i
 	nodeBuf.assign(std::max<size_t>(b.prims.size() - 1, 1) * 16, 0.0f);
 	float mn[3], mx[3];
 	rootRef = b.build(0, b.prims.size(), 0, 0, mn, mx);
+	// the kernels keep at most kBvhStack (96) postponed subtrees: a SAH tree deeper than 92 levels (pathological inputs) is replaced
+	// by a balanced median-split tree over the same primitives, whose depth is ceil(log2 n) <= 31
+	int depthLimit = 92;
+	if (const char* e = getenv("RTO_BVH_MAX_DEPTH")) { int v = atoi(e); if (v >= 4 && v < 92) depthLimit = v; }      // (tests force the fallback with it)
+	if (b.maxDepth.load() > depthLimit) {
+		b.medianOnly = true; b.maxDepth = 0;
+		std::fill(nodeBuf.begin(), nodeBuf.end(), 0.0f);
+		rootRef = b.build(0, b.prims.size(), 0, 0, mn, mx);
+	}
 }
 
 // =================================================================================================

@@ -695,9 +695,14 @@ __device__ __forceinline__ void lbvh_store_child_box(float* node16, int slot, co
 
 // bottom-up: every leaf writes its box into its parent's slot; the second child to arrive at a node unites the two and climbs
 __global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, float* nodes /* 16 floats per inner node */, const int* __restrict__ parentOfInner,
-	const int* __restrict__ parentOfLeaf, int* arrived, float* rootBox) {
+	const int* __restrict__ parentOfLeaf, int* arrived, float* rootBox, int* maxDepth) {
 	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
 	if (leaf >= numLeaves) return;
+	{	// depth of this leaf = upper bound of the traversal stack a ray can need on its way here
+		int depth = 1, up = parentOfLeaf[leaf] >> 1;
+		while ((up = parentOfInner[up]) >= 0) { up >>= 1; depth++; }
+		if (depth > 92) atomicMax(maxDepth, depth);
+	}
 	float lo[3], hi[3];
 #pragma unroll
 	for (int a = 0; a < 3; a++) { lo[a] = leafBox[6 * (size_t)leaf + a]; hi[a] = leafBox[6 * (size_t)leaf + 3 + a]; }
@@ -769,14 +774,20 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 		D.rootRef = ~(int)(numTris - 1);          // leafRef = (0 << 1) | (count - 1)
 	}
 	else {
-		int *pInner = nullptr, *pLeaf = nullptr, *arrived = nullptr;
-		BUILD_TRY(tmp.alloc(&pInner, numInner)); BUILD_TRY(tmp.alloc(&pLeaf, numLeaves)); BUILD_TRY(tmp.alloc(&arrived, numInner));
+		int *pInner = nullptr, *pLeaf = nullptr, *arrived = nullptr, *dDepth = nullptr;
+		BUILD_TRY(tmp.alloc(&pInner, numInner)); BUILD_TRY(tmp.alloc(&pLeaf, numLeaves)); BUILD_TRY(tmp.alloc(&arrived, numInner)); BUILD_TRY(tmp.alloc(&dDepth, 1));
 		BUILD_TRY(cudaMemsetAsync(arrived, 0, sizeof(int) * (size_t)numInner, st));
+		BUILD_TRY(cudaMemsetAsync(dDepth, 0, sizeof(int), st));
 		k_lbvh_tree<<<(unsigned)((numInner + 255) / 256), 256, 0, st>>>(codesSorted, perLeaf, numLeaves, numTris, (float4*)dNodes, pInner, pLeaf);
-		k_lbvh_fit<<<blocksL, 256, 0, st>>>(numLeaves, leafBox, (float*)dNodes, pInner, pLeaf, arrived, dRoot);
+		k_lbvh_fit<<<blocksL, 256, 0, st>>>(numLeaves, leafBox, (float*)dNodes, pInner, pLeaf, arrived, dRoot, dDepth);
 		BUILD_TRY(cudaGetLastError());
+		int depth = 0;
 		BUILD_TRY(cudaMemcpyAsync(root, dRoot, sizeof(root), cudaMemcpyDeviceToHost, st));
+		BUILD_TRY(cudaMemcpyAsync(&depth, dDepth, sizeof(int), cudaMemcpyDeviceToHost, st));
 		BUILD_TRY(cudaStreamSynchronize(st));
+		// the kernels keep at most kBvhStack (96) postponed subtrees; a radix tree deeper than 92 levels needs > 2^29 triangles sharing one Morton
+		// cell and is refused rather than traversed wrongly (rto_scene_create_bvh builds a balanced tree for such input)
+		if (depth > 92) return rto_fail(RTO_ERR_UNSUPPORTED, "BVH build on the device: tree depth %d exceeds the traversal stack; use rto_scene_create_bvh", depth);
 		D.rootRef = 0;
 	}
 	for (int a = 0; a < 3; a++) { D.rootLo[a] = root[a]; D.rootHi[a] = root[3 + a]; }

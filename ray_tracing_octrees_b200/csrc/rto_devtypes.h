@@ -37,7 +37,7 @@ struct OctDev {
 constexpr uint32_t kOctLeaf = 0x80000000u;
 constexpr uint32_t kOctSolid = 0x40000000u;
 constexpr int kMaxOctDepth = 32;
-constexpr int kBvhStack = 64;
+constexpr int kBvhStack = 96;       // deepest tree the builders hand out: 92 levels (host SAH falls back to a balanced tree, device LBVH refuses)
 constexpr float kMissT = 1e30f;
 constexpr float kBelowMissT = 9.99999940e29f;    // the largest float below 1e30f (rto_init checks the bit pattern)
 constexpr float kMinPositive = 1.40129846e-45f;  // the smallest positive (denormal) float, bit pattern 0x00000001 (rto_init checks)

@@ -327,3 +327,42 @@ def test_city_block_octree_and_mesh_vs_oracle(gpu, checker):
             _cmp_frames({k: fa[k][sl] for k in fa}, oc_ref.render(rcam, 0, y0, y0 + 2), "city mode A rows %d cam %d/%d" % (y0, theta, phi))
             _cmp_frames({k: fb[k][sl] for k in fb}, oc_ref.render(rcam, 1, y0, y0 + 2), "city mode B rows %d cam %d/%d" % (y0, theta, phi))
             _cmp_frames({k: fm[k][sl] for k in fm}, m_ref.render(rcam, 1, bias, y0, y0 + 2), "city mesh rows %d cam %d/%d" % (y0, theta, phi), allow_frac=1e-3)
+
+
+def test_deep_trees_stay_within_the_traversal_stack(gpu, monkeypatch):
+    """The kernels keep a fixed number of postponed subtrees.  A SAH tree deeper than the builders' limit is replaced by a balanced
+    median-split tree over the same triangles; forcing that fallback (RTO_BVH_MAX_DEPTH) must not change a single result."""
+    rto = gpu
+    grid = rto.generate_test_volume(32)
+    tris = rto.marching_cubes_mesh(grid, rto.create_octree_from_voxel_grid(grid))
+    cam, _ = rto.Camera.from_degrees(30, 40, 1.2).consts(45.0, 1.0, 160, 160)
+    bias = 1e-3 * grid.voxel_size
+    a = rto.Scene.bvh(tris).render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias)
+    monkeypatch.setenv("RTO_BVH_MAX_DEPTH", "6")            # any SAH tree over 7 936 triangles is deeper than 6
+    sc = rto.Scene.bvh(tris)
+    monkeypatch.delenv("RTO_BVH_MAX_DEPTH")
+    b = sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias)
+    c = sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS | rto.FLAG_NO_PRUNE, bias)
+    for k in ("id", "t", "rgba"):
+        assert_bit_equal(a[k], b[k], "median-split fallback " + k)
+        assert_bit_equal(a[k], c[k], "exact replay " + k)
+    # strongly graded sizes (each triangle 1.2x smaller and closer to the origin than the last): whatever shape the builders give
+    # the tree, pruned, exact and device-built traversals agree
+    n = 64
+    k = np.arange(n, dtype=np.float64)
+    x = (1.2 ** -k * 1.0e5).astype(np.float32)
+    s = (x * np.float32(0.15)).astype(np.float32)
+    tris = np.zeros((n, 9), np.float32)
+    tris[:, 0] = x; tris[:, 3] = x + s; tris[:, 6] = x; tris[:, 7] = s
+    sc, dev = rto.Scene.bvh(tris), rto.Scene.bvh_device(tris)
+    rng = np.random.default_rng(3)
+    pick = rng.integers(0, n, 2048)
+    target = np.stack([x[pick] + s[pick] * 0.25, s[pick] * 0.25, np.zeros(len(pick), np.float32)], 1).astype(np.float32)
+    origin = (target + np.array([0.3, 0.2, 5.0], np.float32) * s[pick, None]).astype(np.float32)
+    d = (target - origin).astype(np.float32)
+    t0, i0 = sc.trace_rays(origin, d, rto.MODE_BVH, rto.FLAG_NO_PRUNE)
+    t1, i1 = sc.trace_rays(origin, d, rto.MODE_BVH, 0)
+    t2, i2 = dev.trace_rays(origin, d, rto.MODE_BVH, 0)
+    assert (i0 >= 0).mean() > 0.5                           # (the rule's |det| >= 1e-8 rejects the very smallest triangles)
+    assert np.array_equal(i0, i1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    assert np.array_equal(i0, i2) and np.array_equal(t0.view(np.uint32), t2.view(np.uint32))
