@@ -416,15 +416,19 @@ struct SahBuilder {
 };
 } // namespace
 
-void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef) {
+void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef, float& growOut) {
 	SahBuilder b; b.out = &nodeBuf;
 	nodeBuf.clear();
 	// one primitive per triangle, in reference leaf order (position p == tie-break rank of the closest-hit rule); its box is the
-	// triangle's own box grown by 2^-16 of the scene's extent on every side, far more than the rounding of the Moller-Trumbore
-	// test can move a hit and far less than a triangle
+	// triangle's own box grown by 2^-18 of the scene's extent on every side (more costs shadow rays, which start 1e-3 voxels above a
+	// surface and must not start inside its boxes; less would come too close to the rounding of the Moller-Trumbore test), far more than the rounding of the Moller-Trumbore
+	// test can move a hit and than the fused node tests of the kernels can move a plane, far less than a
+	// triangle
 	float ext = 0.0f;
 	if (!h.nodes.empty()) for (int k = 0; k < 3; k++) ext = std::max(ext, std::max(std::fabs(h.nodes[0].mn[k]), std::fabs(h.nodes[0].mx[k])));
-	const float grow = ext * (1.0f / 65536.0f);
+	int lg = 18; if (const char* e = getenv("RTO_BVH_GROW_LOG2")) { int v = atoi(e); if (v >= 8 && v <= 22) lg = v; }      // tuning aid
+	const float grow = std::ldexp(ext, -lg);
+	growOut = grow;
 	b.prims.resize(h.numTris);
 	for (size_t p = 0; p < h.numTris; p++) {
 		const RtoTriangle& t = h.tris[h.order[p]];

@@ -87,7 +87,7 @@ void rto_build_bvh_layout(const RtoHostBvh& h, BvhLayout& L) {
 	// BVH::query, and a binned-SAH topology for the production closest-hit / shadow traversal
 	rto_build_reference_topology(h, L.refNodes, L.refRoot);
 	static const bool refTopology = getenv("RTO_BVH_REFERENCE_TOPOLOGY") != nullptr;     // tuning aid: trace through the reference's tree
-	if (!refTopology) rto_build_fast_topology(h, L.fastNodes, L.fastRoot);
+	if (!refTopology) rto_build_fast_topology(h, L.fastNodes, L.fastRoot, L.fastGrow);
 	L.tris.assign(std::max<size_t>(h.numTris, 1) * 16, 0.0f);
 	for (const HostBvhNode& n : h.nodes) {              // every triangle carries the exact box of its reference leaf (floats 10..15)
 		if (n.left >= 0) continue;

@@ -629,7 +629,7 @@ __global__ void k_lbvh_codes(const RtoTriangle* __restrict__ tris, size_t n, con
 }
 
 // triangle records in sorted order (v0, e1, e2, id: rto_kernels.cuh TriV) and the exact box of every leaf (two neighbours)
-__global__ void k_lbvh_leaves(const RtoTriangle* __restrict__ tris, const uint32_t* __restrict__ order, size_t n, int perLeaf, float4* __restrict__ rec, float* __restrict__ leafBox /* 6 per leaf */) {
+__global__ void k_lbvh_leaves(const RtoTriangle* __restrict__ tris, const uint32_t* __restrict__ order, size_t n, int perLeaf, float grow, float4* __restrict__ rec, float* __restrict__ leafBox /* 6 per leaf */) {
 	const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const size_t numLeaves = (n + perLeaf - 1) / perLeaf;
 	if (leaf >= numLeaves) return;
@@ -646,7 +646,7 @@ __global__ void k_lbvh_leaves(const RtoTriangle* __restrict__ tris, const uint32
 		rec[4 * p + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
 #pragma unroll
-	for (int a = 0; a < 3; a++) { leafBox[6 * leaf + a] = lo[a]; leafBox[6 * leaf + 3 + a] = hi[a]; }
+	for (int a = 0; a < 3; a++) { leafBox[6 * leaf + a] = lo[a] - grow; leafBox[6 * leaf + 3 + a] = hi[a] + grow; }     // conservative boxes: BvhDev::grow
 }
 
 // common-prefix length of the keys of leaves i and j (key = Morton code of the leaf's first triangle, ties broken by index)
@@ -729,7 +729,7 @@ __global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, flo
 int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	cudaStream_t st = s->stream;
 	BvhDev D{};
-	D.numTris = (int)numTris; D.rootRef = -1; D.leafBox = 0;
+	D.numTris = (int)numTris; D.rootRef = -1; D.leafBox = 0; D.grow = 0.0f;
 	s->numPrims = numTris;
 	if (numTris == 0) { s->bvh = D; s->bvhFast = D; s->numNodes = 0; return RTO_OK; }
 	if (numTris >= (size_t)1 << 30) return rto_fail(RTO_ERR_UNSUPPORTED, "BVH build on the device: more than 2^30 triangles");
@@ -766,7 +766,18 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	if ((rc = rto_scene_alloc(s, &dNodes, (size_t)(numInner > 0 ? numInner : 1) * 64))) return rc;
 	float* leafBox = nullptr; float* dRoot = nullptr;
 	BUILD_TRY(tmp.alloc(&leafBox, 6 * (size_t)numLeaves)); BUILD_TRY(tmp.alloc(&dRoot, 6));
-	k_lbvh_leaves<<<blocksL, 256, 0, st>>>(dTris, order, numTris, perLeaf, (float4*)dRec, leafBox);
+	// leaf boxes grown by 2^-18 of the scene extent: the kernels' fused node tests need conservative boxes (rto_kernels.cuh slab_oct)
+	float grow = 0.0f;
+	{
+		int hb[6];
+		BUILD_TRY(cudaMemcpyAsync(hb, dBounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+		BUILD_TRY(cudaStreamSynchronize(st));
+		for (int a = 0; a < 6; a++) { int i = hb[a] >= 0 ? hb[a] : hb[a] ^ 0x7fffffff; float f; std::memcpy(&f, &i, 4); grow = std::max(grow, std::fabs(f)); }
+		int lg = 18; if (const char* e = getenv("RTO_BVH_GROW_LOG2")) { int v = atoi(e); if (v >= 8 && v <= 22) lg = v; }      // tuning aid
+		grow = std::ldexp(grow, -lg);
+	}
+	D.grow = grow;
+	k_lbvh_leaves<<<blocksL, 256, 0, st>>>(dTris, order, numTris, perLeaf, grow, (float4*)dRec, leafBox);
 	float root[6];
 	if (numInner == 0) {
 		BUILD_TRY(cudaMemcpyAsync(root, leafBox, sizeof(root), cudaMemcpyDeviceToHost, st));

@@ -224,10 +224,10 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
 	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "BVH upload failed: %s", cudaGetErrorString(e)); }
 	D.nodes = (const float4*)dN; D.tris = (const float4*)dT;
-	D.leafBox = 0;
+	D.leafBox = 0; D.grow = 0.0f;
 	s->bvh = D;
 	s->bvhFast = D;
-	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = L.fastRoot; s->bvhFast.leafBox = 1; }
+	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = L.fastRoot; s->bvhFast.leafBox = 1; s->bvhFast.grow = L.fastGrow; }
 	*out = s;
 	return RTO_OK;
 }

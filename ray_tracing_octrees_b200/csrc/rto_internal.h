@@ -35,7 +35,7 @@ struct RtoHostBvh {
 //                       Trumbore rejects it too; the visit order changes, and the closest-hit rule is order independent.  Tight
 //                       per-triangle boxes cut the Moller-Trumbore tests (the block that runs with the fewest lanes) by a third.
 void rto_build_reference_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef);
-void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef);
+void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef, float& grow);
 
 // ---- device layouts, built on the host (host_layouts.cpp) and uploaded verbatim by rto_device.cu --------------
 struct OctLayout {
@@ -52,6 +52,7 @@ int rto_build_octree_layout(const RtoGpuNode* nodes, size_t numNodes, OctLayout&
 struct BvhLayout {
 	std::vector<float> refNodes, fastNodes, tris;     // 16 floats per inner node; 16 floats per triangle in leaf order: v0, v1 - v0, v2 - v0, id in [9], box of its reference leaf in [10..15]
 	int32_t refRoot = -1, fastRoot = -1;
+	float fastGrow = 0.0f;                             // how far the fast topology's leaf boxes were grown (BvhDev::grow)
 	float rootLo[3] = { 0, 0, 0 }, rootHi[3] = { 0, 0, 0 };
 };
 void rto_build_bvh_layout(const RtoHostBvh& h, BvhLayout& out);

@@ -107,11 +107,13 @@ RTO_DEV Ray gen_ray(const RtoCamera& c, int px, int py) {
 // ------------------------------------------------------------------------------------------------
 struct RayBox {            // per-ray constants of BVH::query (BVH.cpp:107-113)
 	V3 o, inv; bool nx, ny, nz;
+	V3 noi;                // -(o * inv), for the fused conservative node test
 };
 RTO_DEV RayBox make_raybox(V3 o, V3 d) {
 	RayBox r; r.o = o;
 	r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 	r.nx = r.inv.x < 0; r.ny = r.inv.y < 0; r.nz = r.inv.z < 0;
+	r.noi = -(o * r.inv);
 	return r;
 }
 
@@ -169,15 +171,19 @@ RTO_DEV bool moller_trumbore(const TriV& tri, V3 o, V3 d, float& tOut) {
 	return true;
 }
 
-// Octant-specialised form: with the signs of 1/d known at compile time (OCT bit a set <=> 1/d negative on axis a) the near and
-// far plane of every axis are known, so the selects of BVH.cpp:78-86 disappear and the running max/min collapse into 3-input
-// min/max (FMNMX3 on sm_100).  Same six subtractions and products as slab_ref, hence the same tmin/tmax when no NaN arises
-// (1/d finite and non-zero).  A warp of primary rays almost always shares one octant, and every shadow ray does.
+// Octant-specialised CONSERVATIVE form for trees whose boxes are grown (BvhDev::grow > 0).  With the signs of 1/d known at compile
+// time (OCT bit a set <=> 1/d negative on axis a) the near and far plane of every axis are known, so the selects of BVH.cpp:78-86
+// disappear and the running max/min collapse into 3-input min/max (FMNMX3 on sm_100); and because no decision the reference
+// makes hangs on these boxes any more -- candidates are decided at the leaf, by the exact box of the reference leaf and the exact
+// Moller-Trumbore test -- each plane distance is ONE fused multiply-add, plane * (1/d) - o * (1/d), instead of a subtraction and
+// a product.  Compared with (plane - o) * (1/d) the fused form is off by at most the rounding of o * (1/d), which equals moving
+// the plane by |o| * 2^-24: bvh_fused_ok() admits a ray only when that is below grow / 4 (an origin within 16 scene extents).  A warp of primary rays almost
+// always shares one octant, and every shadow ray does.
 template <int OCT>
-RTO_DEV bool slab_oct(V3 o, V3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float tcap, float& tEntry) {
-	float t0x = (((OCT & 1) ? hix : lox) - o.x) * inv.x, t1x = (((OCT & 1) ? lox : hix) - o.x) * inv.x;
-	float t0y = (((OCT & 2) ? hiy : loy) - o.y) * inv.y, t1y = (((OCT & 2) ? loy : hiy) - o.y) * inv.y;
-	float t0z = (((OCT & 4) ? hiz : loz) - o.z) * inv.z, t1z = (((OCT & 4) ? loz : hiz) - o.z) * inv.z;
+RTO_DEV bool slab_oct(V3 noi, V3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float tcap, float& tEntry) {
+	float t0x = fmaf((OCT & 1) ? hix : lox, inv.x, noi.x), t1x = fmaf((OCT & 1) ? lox : hix, inv.x, noi.x);
+	float t0y = fmaf((OCT & 2) ? hiy : loy, inv.y, noi.y), t1y = fmaf((OCT & 2) ? loy : hiy, inv.y, noi.y);
+	float t0z = fmaf((OCT & 4) ? hiz : loz, inv.z, noi.z), t1z = fmaf((OCT & 4) ? loz : hiz, inv.z, noi.z);
 	float tmin = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), 0.0f);
 	// tcap = FLT_MAX gives intersectAABB's tmax; tcap = the pruning distance (< FLT_MAX) folds "entry <= tcap" into the same
 	// comparison: tmin <= min(tmax, FLT_MAX) && tmin <= tcap  <=>  tmin <= min(tmax, tcap)
@@ -186,8 +192,13 @@ RTO_DEV bool slab_oct(V3 o, V3 inv, float lox, float loy, float loz, float hix, 
 	return !(tmax < tmin);
 }
 constexpr int kOctGeneric = 8;
-RTO_DEV int ray_octant(const RayBox& rb) {
-	if (ray_needs_exact_box(rb)) return kOctGeneric;
+RTO_DEV bool bvh_fused_ok(const BvhDev& S, const RayBox& rb) {
+	const float far = fmaxf(fmaxf(fabsf(rb.o.x), fabsf(rb.o.y)), fabsf(rb.o.z));
+	return S.grow > 0.0f && far * (1.0f / 4194304.0f) <= S.grow;      // |o| * 2^-24 <= grow / 4 (NaN origins fail the test)
+}
+// 0..7: fused octant-specialised node tests; kOctGeneric: the reference's exact select form
+RTO_DEV int ray_octant(const BvhDev& S, const RayBox& rb) {
+	if (ray_needs_exact_box(rb) || !bvh_fused_ok(S, rb)) return kOctGeneric;
 	return (rb.nx ? 1 : 0) | (rb.ny ? 2 : 0) | (rb.nz ? 4 : 0);
 }
 
@@ -196,8 +207,8 @@ RTO_DEV int ray_octant(const RayBox& rb) {
 template <int OCT>
 RTO_DEV void node_boxes(const RayBox& rb, float4 a, float4 b, float4 c, float tcap, bool& h0, bool& h1, float& e0, float& e1) {
 	if (OCT < kOctGeneric) {
-		h0 = slab_oct<OCT>(rb.o, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, tcap, e0);
-		h1 = slab_oct<OCT>(rb.o, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, tcap, e1);
+		h0 = slab_oct<OCT>(rb.noi, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, tcap, e0);
+		h1 = slab_oct<OCT>(rb.noi, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, tcap, e1);
 	}
 	else {
 		h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0) && (e0 <= tcap);
@@ -213,8 +224,7 @@ RTO_DEV bool ref_leaf_box_passes(const BvhDev& S, const RayBox& rb, int pos, flo
 	float2 c = RTO_LDG(reinterpret_cast<const float2*>(rec + 2) + 1);
 	float4 d = RTO_LDG(rec + 3);
 	float e;
-	if (OCT < kOctGeneric) return slab_oct<OCT>(rb.o, rb.inv, c.x, c.y, d.x, d.y, d.z, d.w, tcap, e);
-	return slab_ref(rb, c.x, c.y, d.x, d.y, d.z, d.w, e) && (e <= tcap);
+	return slab_ref(rb, c.x, c.y, d.x, d.y, d.z, d.w, e) && (e <= tcap);       // the reference's own arithmetic: this one decides
 }
 
 // Closest hit.  Result = min over the reference's candidate set of (t, position in candidate order), i.e. the
@@ -283,7 +293,7 @@ RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos
 	float te;
 	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return;
 	if (!PRUNE) { bvh_closest_loop<false, kOctGeneric>(S, rb, o, d, bestT, bestPos); return; }      // verification path: one generic loop
-	switch (ray_octant(rb)) {
+	switch (ray_octant(S, rb)) {
 	case 0: bvh_closest_loop<PRUNE, 0>(S, rb, o, d, bestT, bestPos); break;
 	case 1: bvh_closest_loop<PRUNE, 1>(S, rb, o, d, bestT, bestPos); break;
 	case 2: bvh_closest_loop<PRUNE, 2>(S, rb, o, d, bestT, bestPos); break;
@@ -340,7 +350,7 @@ RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 	RayBox rb = make_raybox(o, d);
 	float te;
 	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return false;
-	switch (ray_octant(rb)) {
+	switch (ray_octant(S, rb)) {
 	case 0: return bvh_any_loop<0>(S, rb, o, d);
 	case 1: return bvh_any_loop<1>(S, rb, o, d);
 	case 2: return bvh_any_loop<2>(S, rb, o, d);
