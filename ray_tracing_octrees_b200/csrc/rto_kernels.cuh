@@ -194,7 +194,9 @@ RTO_DEV bool slab_oct(V3 noi, V3 inv, float lox, float loy, float loz, float hix
 constexpr int kOctGeneric = 8;
 RTO_DEV bool bvh_fused_ok(const BvhDev& S, const RayBox& rb) {
 	const float far = fmaxf(fmaxf(fabsf(rb.o.x), fabsf(rb.o.y)), fabsf(rb.o.z));
-	return S.grow > 0.0f && far * (1.0f / 4194304.0f) <= S.grow;      // |o| * 2^-24 <= grow / 4 (NaN origins fail the test)
+	// o / d must not overflow either (a direction component below ~1e-35): inf - inf would make the fused form miss boxes
+	const bool finite = fabsf(rb.noi.x) <= FLT_MAX && fabsf(rb.noi.y) <= FLT_MAX && fabsf(rb.noi.z) <= FLT_MAX;
+	return S.grow > 0.0f && finite && far * (1.0f / 4194304.0f) <= S.grow;      // |o| * 2^-24 <= grow / 4 (NaN origins fail the test)
 }
 // 0..7: fused octant-specialised node tests; kOctGeneric: the reference's exact select form
 RTO_DEV int ray_octant(const BvhDev& S, const RayBox& rb) {

@@ -366,3 +366,43 @@ def test_deep_trees_stay_within_the_traversal_stack(gpu, monkeypatch):
     assert (i0 >= 0).mean() > 0.5                           # (the rule's |det| >= 1e-8 rejects the very smallest triangles)
     assert np.array_equal(i0, i1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
     assert np.array_equal(i0, i2) and np.array_equal(t0.view(np.uint32), t2.view(np.uint32))
+
+
+def test_bvh_awkward_rays_match_the_exact_replay(gpu):
+    """Rays that leave the fast paths of the production traversal -- zero, denormal-small and huge direction components (1/d zero,
+    infinite or overflowing in o/d), origins far outside (beyond the fused tests' admission range), inside the mesh and on
+    vertices -- must give exactly what the exact replay of BVH::query (RTO_FLAG_NO_PRUNE, reference tree, select-form tests) gives."""
+    rto = gpu
+    grid = rto.generate_test_volume(32)
+    tris = rto.marching_cubes_mesh(grid, rto.create_octree_from_voxel_grid(grid))
+    sc = rto.Scene.bvh(tris)
+    rng = np.random.default_rng(11)
+    n = 20000
+    o = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    d = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    kinds = rng.integers(0, 8, n)
+    ax = rng.integers(0, 3, n)
+    small = np.array([0.0, -0.0, 1e-36, -1e-36, 1e-20, 1e-42, 3e38, -3e38], np.float32)
+    for i in range(n):
+        k = kinds[i]
+        if k == 0:
+            d[i, ax[i]] = small[rng.integers(0, 6)]                       # one (near-)zero component
+        elif k == 1:
+            d[i] = 0; d[i, ax[i]] = rng.choice([-1.0, 1.0])               # axis-parallel
+        elif k == 2:
+            o[i] *= np.float32(30.0)                                      # beyond the fused tests' admission range (16 scene extents), aimed at the scene
+            d[i] = -o[i] + rng.normal(0, 0.3, 3)
+        elif k == 3:
+            o[i] = rng.uniform(-0.1, 0.1, 3)                              # inside the hollow sphere
+        elif k == 4:
+            o[i] = tris[rng.integers(0, len(tris)), 0:3]                  # on a vertex
+        elif k == 5:
+            d[i, ax[i]] = small[6 + rng.integers(0, 2)]                   # one huge component
+        elif k == 6:
+            o[i, ax[i]] = np.float32(3e37); d[i, ax[i]] = np.float32(-1.0); d[i, (ax[i] + 1) % 3] = np.float32(1e-30)   # o/d overflows
+    t0, i0 = sc.trace_rays(o, d, rto.MODE_BVH, rto.FLAG_NO_PRUNE)
+    t1, i1 = sc.trace_rays(o, d, rto.MODE_BVH, 0)
+    assert (i0 >= 0).sum() > 1000
+    bad = np.nonzero(i0 != i1)[0]
+    assert len(bad) == 0, "%d rays differ, first: o=%s d=%s exact=(%d, %g) fast=(%d, %g)" % (len(bad), o[bad[0]], d[bad[0]], i0[bad[0]], t0[bad[0]], i1[bad[0]], t1[bad[0]])
+    assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
