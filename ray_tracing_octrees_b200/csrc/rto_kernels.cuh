@@ -984,10 +984,18 @@ __device__ __forceinline__ bool pixel_of_thread(const RenderArgs& A, const RtoCa
 	return true;
 }
 
+// Frame planes are written once and never read by the kernels: streaming stores (evict-first) keep the 400 MB a launch writes
+// from pushing the scene out of L2.
 RTO_DEV void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, float t) {
+#if defined(__CUDA_ARCH__) && !defined(RTO_NO_STREAMING_STORES)
+	if (A.rgba) __stcs(A.rgba + pix, make_float4(color.x, color.y, color.z, 1.0f));
+	if (A.hitId) __stcs(A.hitId + pix, id);
+	if (A.t) __stcs(A.t + pix, t);
+#else
 	if (A.rgba) A.rgba[pix] = make_float4(color.x, color.y, color.z, 1.0f);
 	if (A.hitId) A.hitId[pix] = id;
 	if (A.t) A.t[pix] = t;
+#endif
 }
 
 #ifndef RTO_BVH_MIN_BLOCKS
