@@ -251,7 +251,7 @@ struct Builder {
 		size_t mid = m / 2;                             // BVH.cpp:63
 		size_t li = nodeIdx + 1, ri = li + subtreeNodes(mid);
 		nd.left = (int32_t)li; nd.right = (int32_t)ri; nd.count = 0;
-		if (depth < 3 && m > 20000) {
+		if (depth < 5 && m > 20000) {                    // up to 32 subtrees in flight
 			std::thread th([=] { build(lo, lo + mid, li, depth + 1); });
 			build(lo + mid, hi, ri, depth + 1);
 			th.join();
