@@ -803,6 +803,7 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	}
 	for (int a = 0; a < 3; a++) { D.rootLo[a] = root[a]; D.rootHi[a] = root[3 + a]; }
 	D.nodes = (const float4*)dNodes; D.tris = (const float4*)dRec;
+	D.exactNodes = D.nodes; D.exactRoot = D.rootRef; D.exactLeafBox = 0;
 	s->bvh = D; s->bvhFast = D;
 	s->numNodes = (size_t)numLeaves + (size_t)numInner;
 	s->deviceBuiltBvh = true;

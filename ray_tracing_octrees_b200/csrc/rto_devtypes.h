@@ -15,6 +15,9 @@ struct BvhDev {
 	                         // e2 = v2 - v0, lo/hi = the exact box of the REFERENCE leaf the triangle belongs to
 	int   rootRef;           // >= 0: inner node index; < 0: ~leafRef, leafRef = (firstPos << 1) | (count - 1)
 	int   numTris;
+	const float4* exactNodes; // the tree rays take when they are not admitted to the fused tests (rto_kernels.cuh bvh_fused_ok): the reference-
+	int   exactRoot;          // shaped tree with exact boxes and the reference's leaves (host route), or this tree itself (device route)
+	int   exactLeafBox;       // leafBox of that tree
 	float grow;              // > 0: every box of this tree below the root is a conservative one (leaf boxes grown by `grow` on each side), so
 	                         // the node tests may use fused multiply-adds (rto_kernels.cuh slab_oct); 0: exact boxes, exact tests only
 	int   leafBox;           // 1: the tree's leaves are single triangles under (inflated) boxes of their own, and a triangle is a candidate

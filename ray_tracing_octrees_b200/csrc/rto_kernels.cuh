@@ -304,7 +304,11 @@ RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos
 	case 5: bvh_closest_loop<PRUNE, 5>(S, rb, o, d, bestT, bestPos); break;
 	case 6: bvh_closest_loop<PRUNE, 6>(S, rb, o, d, bestT, bestPos); break;
 	case 7: bvh_closest_loop<PRUNE, 7>(S, rb, o, d, bestT, bestPos); break;
-	default: bvh_closest_loop<PRUNE, kOctGeneric>(S, rb, o, d, bestT, bestPos); break;
+	default: {
+		// not admitted to the fused tests (zero / infinite 1/d, far origin): the reference's own arithmetic on the exact tree
+		BvhDev E = S; E.nodes = S.exactNodes; E.rootRef = S.exactRoot; E.leafBox = S.exactLeafBox; E.grow = 0.0f;
+		bvh_closest_loop<PRUNE, kOctGeneric>(E, rb, o, d, bestT, bestPos);
+		break; }
 	}
 }
 
@@ -361,7 +365,9 @@ RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 	case 5: return bvh_any_loop<5>(S, rb, o, d);
 	case 6: return bvh_any_loop<6>(S, rb, o, d);
 	case 7: return bvh_any_loop<7>(S, rb, o, d);
-	default: return bvh_any_loop<kOctGeneric>(S, rb, o, d);
+	default: {
+		BvhDev E = S; E.nodes = S.exactNodes; E.rootRef = S.exactRoot; E.leafBox = S.exactLeafBox; E.grow = 0.0f;
+		return bvh_any_loop<kOctGeneric>(E, rb, o, d); }
 	}
 }
 

@@ -68,6 +68,7 @@ void* emu_bvh_create(const RtoTriangle* tris, size_t n) {
 	for (int k = 0; k < 3; k++) { D.rootLo[k] = e->L.rootLo[k]; D.rootHi[k] = e->L.rootHi[k]; }
 	D.nodes = (const float4*)e->L.refNodes.data(); D.tris = (const float4*)e->L.tris.data();
 	D.leafBox = 0; D.grow = 0.0f;
+	D.exactNodes = D.nodes; D.exactRoot = D.rootRef; D.exactLeafBox = 0;
 	e->ref = D; e->fast = D;
 	if (!e->L.fastNodes.empty()) { e->fast.nodes = (const float4*)e->L.fastNodes.data(); e->fast.rootRef = e->L.fastRoot; e->fast.leafBox = 1; e->fast.grow = e->L.fastGrow; }
 	return e;

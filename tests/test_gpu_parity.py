@@ -390,7 +390,7 @@ def test_bvh_awkward_rays_match_the_exact_replay(gpu):
         elif k == 1:
             d[i] = 0; d[i, ax[i]] = rng.choice([-1.0, 1.0])               # axis-parallel
         elif k == 2:
-            o[i] *= np.float32(30.0)                                      # beyond the fused tests' admission range (16 scene extents), aimed at the scene
+            o[i] *= np.float32(30.0 if i % 2 else 3000.0)                 # beyond the fused tests' admission range (16 scene extents), aimed at the scene
             d[i] = -o[i] + rng.normal(0, 0.3, 3)
         elif k == 3:
             o[i] = rng.uniform(-0.1, 0.1, 3)                              # inside the hollow sphere
