@@ -144,8 +144,11 @@ RTO_API void rto_host_free(void* p);
 RTO_API int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3],
 	float voxelSize, RtoScene** out);
 
-/* Replaces "build a BVH, keep it for queries": builds the reference-shaped tree on the host
- * (or takes `prebuilt`), flattens it to the GPU layout and uploads triangles + nodes once. */
+/* Replaces "build a BVH, keep it for queries": builds the reference-shaped tree on the host (or takes `prebuilt`) and uploads
+ * (a) that tree, for rto_bvh_query, rto_render_stats and RTO_FLAG_NO_PRUNE, and (b) the production tree the renders walk: a SAH
+ * tree over single triangles whose records carry the box of their reference leaf, so that the candidate rule of BVH::query
+ * ("every triangle of a leaf whose box passes intersectAABB") is applied exactly while the tree itself is free to be a good one
+ * (DESIGN.md section 3).  Hit ids, t and colours equal the reference CPU path's bit for bit. */
 RTO_API int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt /* may be NULL */,
 	RtoScene** out);
 
