@@ -121,6 +121,18 @@ RTO_API int rto_host_bvh_export(const RtoHostBvh* bvh, float* boxes6, int32_t* m
 RTO_API int rto_host_camera_orbit(float theta, float phi, float radius, const float target[3],
 	float fovDeg, float aspect, int width, int height, RtoCamera* out, float* view16 /* may be NULL */);
 
+/* proj * view as RayTracerBVH::renderSceneComputeWithCulling forms it (RayTracerBVH.cpp:733-734): glm::perspective(radians(fovDeg),
+ * aspect, zNear, zFar) times the view matrix of rto_host_camera_orbit; the reference passes zNear 0.01, zFar 5000. */
+RTO_API int rto_host_view_proj(const float view16[16], float fovDeg, float aspect, float zNear, float zFar, float viewProj16[16]);
+
+/* The CPU part of RayTracerBVH::renderSceneComputeWithCulling (RayTracerBVH.cpp:724-813 over Frustum.cpp:5-93), the variant the
+ * reference's main loop actually calls (main.cpp:1357): every node whose world box, grown by `margin` (the reference passes 150),
+ * lies entirely behind a frustum plane is dropped, the rest is compacted in index order and child indices are remapped (-1 for a
+ * dropped child).  The result is the array the compute shader traverses; upload it with rto_scene_create_octree and render with
+ * RTO_MODE_OCTREE_GLSL: hit ids are then indices into the CULLED array, newToOld (optional) maps them back.  malloc'ed; rto_host_free. */
+RTO_API int rto_host_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize,
+	const float viewProj16[16], float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut /* may be NULL */);
+
 /* loadVoxelGrid / saveVoxelGrid, CacheUtils.cpp:5-59 (sceneCache.bin: 3 x int32 dims, 4 x float, size_t n, bytes). */
 RTO_API int rto_host_grid_load(const char* path, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut);
 RTO_API int rto_host_grid_save(const char* path, const int dims[3], const float minAndVoxel[4], const uint8_t* voxels);
@@ -172,6 +184,10 @@ RTO_API int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int di
 /* rto_host_csv_voxelize with the fill on the GPU (one warp per face); same grid, bit for bit. */
 RTO_API int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize,
 	int dims[3], float minAndVoxel[4], uint8_t** voxelsOut);
+
+/* rto_host_frustum_cull on the GPU (test, prefix sum, compaction + remap); same arrays. */
+RTO_API int rto_device_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize,
+	const float viewProj16[16], float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut /* may be NULL */);
 
 /* BVH scene built on the device: the fast, NOT reference-shaped route (linear BVH: Morton sort, leaves of two neighbours, radix
  * tree, exact union boxes).  BVH::build's tree depends on std::sort's order on equal centroids (BVH.cpp:58-60) and cannot be

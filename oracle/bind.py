@@ -65,6 +65,7 @@ class Backend:
             "render_octree": (C.c_double, [vp, C.POINTER(CamConsts), i32, i32, i32, vp, vp, vp, vp, i32]),
             "octree_rayskip": (None, [vp, vp, vp, sz, f32, f32, vp, vp]),
             "num_threads": (i32, []),
+            "cull_nodes": (sz, [vp, f32, f32, f32, vp, f32, f32, i32, i32, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, prefix + name)
@@ -147,6 +148,16 @@ class Octree:
             raise RuntimeError("BFS order check against RayTracerBVH::setOctree failed: %d" % n)
         self.num_nodes = n
         return n
+
+    def cull(self, theta_deg, phi_deg, radius, fov_deg=45.0, aspect=16.0 / 9.0, width=1920, height=1080, target=(0, 0, 0)):
+        """The node array RayTracerBVH::renderSceneComputeWithCulling(camera, w, h, aspect, fov, true) uploads (RayTracerBVH.cpp:724-813)."""
+        tgt = np.asarray(target, np.float32)
+        th, ph = float(np.deg2rad(np.float32(theta_deg))), float(np.deg2rad(np.float32(phi_deg)))
+        n = self.L.cull_nodes(self.h, th, ph, radius, _p(tgt), fov_deg, aspect, width, height, None)
+        out = np.zeros((n, 15), np.int32)
+        if n:
+            self.L.cull_nodes(self.h, th, ph, radius, _p(tgt), fov_deg, aspect, width, height, _p(out))
+        return out
 
     def flat(self):
         out = np.zeros((self.num_nodes, 15), np.int32)

@@ -88,6 +88,7 @@ void freeRec(ONode* n) { if (!n) return; for (auto* c : n->child) freeRec(c); de
 
 struct Octree {
 	Grid g; ONode* root = nullptr; std::vector<GNode> flat; std::unordered_map<const ONode*, int> index;
+	std::vector<GNode> culled;       // result of the last orc_cull_nodes (render mode 2 traverses it)
 	~Octree() { freeRec(root); }
 	void build() {                   // createOctreeFromVoxelGrid, OctreeVoxel.cpp:765-778
 		if (g.dx == 0 || g.dy == 0 || g.dz == 0) return;
@@ -389,6 +390,59 @@ void orc_camera_consts(float theta, float phi, float radius, const float* target
 	if (view16) std::memcpy(view16, view, 64);
 }
 
+// ---- frustum culling: restatement of the CPU part of RayTracerBVH::renderSceneComputeWithCulling (RayTracerBVH.cpp:724-813) over
+// Frustum (Frustum.cpp:5-93), glm::perspective (matrix_clip_space.inl:249-262) and glm's mat4 * mat4 (type_mat4x4.inl:630-648).
+// Returns the number of nodes kept; out (may be null) receives the compacted, remapped array (15 ints per node).
+size_t orc_cull_nodes(void* hv, float theta, float phi, float radius, const float* target, float fovDeg, float aspect, int w, int h, int32_t* out) {
+	Octree* o = (Octree*)hv;
+	(void)w; (void)h;
+	V3 tgt = v3(target[0], target[1], target[2]);
+	V3 eye = radius * v3(std::cos(theta) * std::sin(phi), std::sin(theta), std::cos(theta) * std::cos(phi)) + tgt;   // Camera.cpp:13-17
+	float view[16];
+	lookAtRH(eye, tgt, v3(0, 1, 0), view);
+	float P[16] = { 0 };                                                             // glm::perspective(radians(fovDeg), aspect, 0.01f, 5000.f), :733
+	const float zn = 0.01f, zf = 5000.f, th = std::tan(fovDeg * 0.01745329251994329576923690768489f / 2.0f);
+	P[0] = 1.0f / (aspect * th); P[5] = 1.0f / th; P[10] = -(zf + zn) / (zf - zn); P[11] = -1.0f; P[14] = -(2.0f * zf * zn) / (zf - zn);
+	float M[16];                                                                     // proj * view
+	for (int j = 0; j < 4; j++) for (int r = 0; r < 4; r++)
+		M[j * 4 + r] = ((P[r] * view[j * 4] + P[4 + r] * view[j * 4 + 1]) + P[8 + r] * view[j * 4 + 2]) + P[12 + r] * view[j * 4 + 3];
+	float pl[6][4];                                                                  // Frustum.cpp:5-48: left, right, bottom, top, near, far
+	for (int i = 0; i < 6; i++) {
+		int row = i / 2; bool plus = (i % 2) == 0;
+		for (int c = 0; c < 4; c++) pl[i][c] = plus ? M[c * 4 + 3] + M[c * 4 + row] : M[c * 4 + 3] - M[c * 4 + row];
+		float len = std::sqrt(dot(v3(pl[i][0], pl[i][1], pl[i][2]), v3(pl[i][0], pl[i][1], pl[i][2])));
+		for (int c = 0; c < 4; c++) pl[i][c] /= len;
+	}
+	const std::vector<GNode>& flat = o->flat;
+	std::vector<int> newIdx(flat.size(), -1);
+	int kept = 0;
+	const float margin = 150.0f;                                                     // :746
+	for (size_t i = 0; i < flat.size(); i++) {
+		const GNode& n = flat[i];
+		V3 mn = v3(o->g.minX + n.x * o->g.voxel, o->g.minY + n.y * o->g.voxel, o->g.minZ + n.z * o->g.voxel);      // :737-742
+		float s = n.size * o->g.voxel;
+		V3 mx = v3(mn.x + s, mn.y + s, mn.z + s);
+		V3 emn = v3(mn.x - margin, mn.y - margin, mn.z - margin), emx = v3(mx.x + margin, mx.y + margin, mx.z + margin);   // Frustum.cpp:58-59
+		bool outside = false;
+		for (int k = 0; k < 6 && !outside; k++) {
+			V3 p = v3(pl[k][0] > 0 ? emx.x : emn.x, pl[k][1] > 0 ? emx.y : emn.y, pl[k][2] > 0 ? emx.z : emn.z);
+			if (dot(v3(pl[k][0], pl[k][1], pl[k][2]), p) + pl[k][3] < 0) outside = true;
+		}
+		if (!outside) newIdx[i] = kept++;
+	}
+	o->culled.assign((size_t)kept, GNode());
+	{
+		for (size_t i = 0; i < flat.size(); i++) {
+			if (newIdx[i] < 0) continue;
+			GNode n = flat[i];
+			if (!n.isLeaf) for (int c = 0; c < 8; c++) { int oc = n.child[c]; n.child[c] = (oc >= 0 && oc < (int)flat.size() && newIdx[oc] >= 0) ? newIdx[oc] : -1; }   // :783-799
+			o->culled[(size_t)newIdx[i]] = n;
+		}
+	}
+	if (out && kept) std::memcpy(out, o->culled.data(), (size_t)kept * sizeof(GNode));
+	return (size_t)kept;
+}
+
 // ---- octree -----------------------------------------------------------------------------------------
 void* orc_grid_create(int dx, int dy, int dz, float minX, float minY, float minZ, float voxel, const uint8_t* data) {
 	Octree* o = new Octree();
@@ -525,7 +579,7 @@ double orc_render_octree(void* h, const Cam* cam, int mode, int y0, int y1, floa
 				}
 			}
 			else {
-				HitB r = traverseGLSL(oc->flat, gridMin, oc->g.voxel, o, d);
+				HitB r = traverseGLSL(mode == 2 ? oc->culled : oc->flat, gridMin, oc->g.voxel, o, d);
 				sVisits += (uint64_t)r.steps;
 				if (r.hit) { tRes = r.t; id = r.id; color = shadeLambert(r.normal); }
 			}

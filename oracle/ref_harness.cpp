@@ -61,6 +61,40 @@ static void installGLStubs() {
 	glad_glDeleteBuffers = stubDeleteBuffers;
 }
 
+// Stubs for everything RayTracerBVH::renderSceneComputeWithCulling touches (RayTracerBVH.cpp:706-892), so that its CPU part -- the
+// frustum test of every node, the compaction and the child-index remap (:724-813) -- runs headless.  The SSBO re-upload (:808-812)
+// is captured: that byte array is exactly what the compute shader would traverse.
+static std::vector<uint8_t> g_lastBufferData;
+static void APIENTRY captureBufferData(GLenum, GLsizeiptr size, const void* data, GLenum) {
+	g_lastBufferData.assign((const uint8_t*)data, (const uint8_t*)data + (data ? size : 0));
+}
+static void APIENTRY stubGenTextures(GLsizei n, GLuint* t) { for (GLsizei i = 0; i < n; i++) t[i] = 7u + (GLuint)i; }
+static void APIENTRY stubActiveTexture(GLenum) {}
+static void APIENTRY stubBindTexture(GLenum, GLuint) {}
+static void APIENTRY stubTexImage2D(GLenum, GLint, GLint, GLsizei, GLsizei, GLint, GLenum, GLenum, const void*) {}
+static void APIENTRY stubTexParameteri(GLenum, GLenum, GLint) {}
+static void APIENTRY stubUseProgram(GLuint) {}
+static void APIENTRY stubBindImageTexture(GLuint, GLuint, GLint, GLboolean, GLint, GLenum, GLenum) {}
+static GLint APIENTRY stubGetUniformLocation(GLuint, const GLchar*) { return 0; }
+static void APIENTRY stubUniform1i(GLint, GLint) {}
+static void APIENTRY stubUniform1f(GLint, GLfloat) {}
+static void APIENTRY stubUniform3f(GLint, GLfloat, GLfloat, GLfloat) {}
+static void APIENTRY stubUniformMatrix4fv(GLint, GLsizei, GLboolean, const GLfloat*) {}
+static void APIENTRY stubDispatchCompute(GLuint, GLuint, GLuint) {}
+static void APIENTRY stubMemoryBarrier(GLbitfield) {}
+static void APIENTRY stubBindVertexArray(GLuint) {}
+static void APIENTRY stubDrawArrays(GLenum, GLint, GLsizei) {}
+static void installRenderStubs() {
+	installGLStubs();
+	glad_glBufferData = captureBufferData;
+	glad_glGenTextures = stubGenTextures; glad_glActiveTexture = stubActiveTexture; glad_glBindTexture = stubBindTexture;
+	glad_glTexImage2D = stubTexImage2D; glad_glTexParameteri = stubTexParameteri; glad_glUseProgram = stubUseProgram;
+	glad_glBindImageTexture = stubBindImageTexture; glad_glGetUniformLocation = stubGetUniformLocation;
+	glad_glUniform1i = stubUniform1i; glad_glUniform1f = stubUniform1f; glad_glUniform3f = stubUniform3f;
+	glad_glUniformMatrix4fv = stubUniformMatrix4fv; glad_glDispatchCompute = stubDispatchCompute; glad_glMemoryBarrier = stubMemoryBarrier;
+	glad_glBindVertexArray = stubBindVertexArray; glad_glDrawArrays = stubDrawArrays;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Handles
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +207,26 @@ void ref_octree_free(void* hv) {
 }
 
 // ---- camera: real Camera + glm::inverse ------------------------------------------------------
+// The REAL RayTracerBVH::renderSceneComputeWithCulling(camera, w, h, aspect, fovDeg, true) (RayTracerBVH.cpp:706-892) up to its GL
+// dispatch: returns the number of nodes of the culled array it uploaded; out (may be null) receives them, 15 ints each.
+// Call with out == nullptr first to learn the count.  Needs ref_octree_build before.
+size_t ref_cull_nodes(void* hv, float theta, float phi, float radius, const float* target, float fovDeg, float aspect, int w, int h, int32_t* out) {
+	RefOctree* o = (RefOctree*)hv;
+	if (!o->tracer) return 0;
+	installRenderStubs();
+	o->tracer->m_computeInited = true; o->tracer->m_computeProg = 1; o->tracer->m_fsqProg = 1;
+	Camera cam(theta, phi, radius);
+	cam.setTarget(glm::vec3(target[0], target[1], target[2]));
+	g_lastBufferData.clear();
+	std::streambuf* keepOut = std::cout.rdbuf(nullptr);
+	o->tracer->renderSceneComputeWithCulling(cam, w, h, aspect, fovDeg, true);
+	std::cout.rdbuf(keepOut);
+	installGLStubs();
+	size_t n = g_lastBufferData.size() / sizeof(GPUNodes);
+	if (out) std::memcpy(out, g_lastBufferData.data(), n * sizeof(GPUNodes));
+	return n;
+}
+
 void ref_camera_consts(float theta, float phi, float radius, const float* target, float fovDeg, float aspect,
 	int w, int h, RefCamConsts* out, float* view16) {
 	Camera cam(theta, phi, radius);
@@ -444,7 +498,9 @@ double ref_render_octree(void* hv, const RefCamConsts* cam, int mode, int y0, in
 	float* rgba, int32_t* leafId, float* tOut, uint64_t* stats, int nthreads) {
 	RefOctree* h = (RefOctree*)hv;
 	const int W = cam->width;
-	const std::vector<GPUNodes>& nodes = h->tracer->m_flatNodes;
+	// mode 2: the GLSL traversal over the frustum-culled array the last ref_cull_nodes call made renderSceneComputeWithCulling build
+	const std::vector<GPUNodes>& nodes = (mode == 2) ? h->tracer->m_visibleNodes : h->tracer->m_flatNodes;
+	if (mode == 2) mode = 1;
 	const glm::vec3 gridMin(h->grid.minX, h->grid.minY, h->grid.minZ);
 	const float voxelSize = h->grid.voxelSize;
 	uint64_t sVisits = 0, sMismatch = 0;

@@ -47,6 +47,9 @@ SIGNATURES = {
     "rto_host_bvh_num_nodes": (_sz, [_vp]),
     "rto_host_bvh_export": (_i, [_vp, _vp, _vp, _sz]),
     "rto_host_camera_orbit": (_i, [_f, _f, _f, _vp, _f, _f, _i, _i, C.POINTER(RtoCamera), _vp]),
+    "rto_host_view_proj": (_i, [_vp, _f, _f, _f, _f, _vp]),
+    "rto_host_frustum_cull": (_i, [_vp, _sz, _vp, _f, _vp, _f, _pp, C.POINTER(_sz), _pp]),
+    "rto_device_frustum_cull": (_i, [_vp, _sz, _vp, _f, _vp, _f, _pp, C.POINTER(_sz), _pp]),
     "rto_host_grid_load": (_i, [C.c_char_p, _vp, _vp, _pp]),
     "rto_host_grid_save": (_i, [C.c_char_p, _vp, _vp, _vp]),
     "rto_host_csv_voxelize": (_i, [C.c_char_p, C.c_char_p, _f, _vp, _vp, _pp]),

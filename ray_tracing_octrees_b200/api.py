@@ -97,6 +97,25 @@ def create_octree_from_voxel_grid(grid):
     return _take(ptr, n.value, np.int32, (n.value, 15))
 
 
+def view_proj(view16, fov_deg, aspect, z_near=0.01, z_far=5000.0):
+    """proj * view of renderSceneComputeWithCulling (RayTracerBVH.cpp:733-734) as 16 floats, column-major."""
+    v = np.ascontiguousarray(view16, np.float32).ravel()
+    out = np.zeros(16, np.float32)
+    check(lib().rto_host_view_proj(_p(v), float(fov_deg), float(aspect), float(z_near), float(z_far), _p(out)))
+    return out
+
+
+def frustum_cull(nodes, grid, view_proj16, margin=150.0, device=False):
+    """The node array renderSceneComputeWithCulling uploads (RayTracerBVH.cpp:724-813) -> (culled (m, 15) int32, new_to_old (m,) int32)."""
+    nodes = np.ascontiguousarray(nodes, np.int32).reshape(-1, 15)
+    vp = np.ascontiguousarray(view_proj16, np.float32).ravel()
+    ptr, back = C.c_void_p(), C.c_void_p()
+    n = C.c_size_t()
+    fn = lib().rto_device_frustum_cull if device else lib().rto_host_frustum_cull
+    check(fn(_p(nodes), len(nodes), _p(grid.min), float(grid.voxel_size), _p(vp), float(margin), C.byref(ptr), C.byref(n), C.byref(back)))
+    return _take(ptr, n.value, np.int32, (n.value, 15)), _take(back, n.value, np.int32, (n.value,))
+
+
 def create_octree_on_device(grid):
     """Same array as create_octree_from_voxel_grid, built on the GPU (rto_device_octree_build)."""
     ptr = C.c_void_p()

@@ -16,6 +16,7 @@
 #include "rto_internal.h"
 #include "mc_tables.h"
 #include "rto_voxelize.h"
+#include "rto_frustum.h"
 
 #include <algorithm>
 #include <atomic>
@@ -660,5 +661,62 @@ extern "C" int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv,
 		for (auto& t : th) t.join();
 	}
 	*voxelsOut = vox;
+	return RTO_OK;
+}
+
+// =================================================================================================
+// Frustum culling of the flattened octree: RayTracerBVH::renderSceneComputeWithCulling, CPU part (RayTracerBVH.cpp:724-813)
+// =================================================================================================
+// proj * view with glm::perspective(radians(fovDeg), aspect, zNear, zFar) (matrix_clip_space.inl:249-262, RH, depth -1..1) and
+// glm's mat4 * mat4 (type_mat4x4.inl:630-648: ((A0*b0 + A1*b1) + A2*b2) + A3*b3 per column).
+extern "C" int rto_host_view_proj(const float view16[16], float fovDeg, float aspect, float zNear, float zFar, float viewProj16[16]) {
+	if (!view16 || !viewProj16) return rto_fail(RTO_ERR_INVALID, "rto_host_view_proj: null argument");
+	const float fovy = fovDeg * 0.01745329251994329576923690768489f;      // glm::radians
+	const float tanHalf = std::tan(fovy / 2.0f);
+	float P[16] = { 0 };
+	P[0] = 1.0f / (aspect * tanHalf);
+	P[5] = 1.0f / tanHalf;
+	P[10] = -(zFar + zNear) / (zFar - zNear);
+	P[11] = -1.0f;
+	P[14] = -(2.0f * zFar * zNear) / (zFar - zNear);
+	for (int j = 0; j < 4; j++)
+		for (int r = 0; r < 4; r++) {
+			float acc = P[0 * 4 + r] * view16[j * 4 + 0];
+			acc = acc + P[1 * 4 + r] * view16[j * 4 + 1];
+			acc = acc + P[2 * 4 + r] * view16[j * 4 + 2];
+			acc = acc + P[3 * 4 + r] * view16[j * 4 + 3];
+			viewProj16[j * 4 + r] = acc;
+		}
+	return RTO_OK;
+}
+
+extern "C" int rto_host_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, const float viewProj16[16],
+	float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut) {
+	if (!culledOut || !numCulled) return rto_fail(RTO_ERR_INVALID, "rto_host_frustum_cull: null output");
+	*culledOut = nullptr; *numCulled = 0;
+	if (newToOldOut) *newToOldOut = nullptr;
+	if (numNodes == 0) return RTO_OK;
+	if (!nodes || !gridMin || !viewProj16) return rto_fail(RTO_ERR_INVALID, "rto_host_frustum_cull: null input");
+	const FrustumPlanes F = frustum_from_view_proj(viewProj16);
+	std::vector<int32_t> newIndex(numNodes, -1);
+	size_t visible = 0;
+	for (size_t i = 0; i < numNodes; i++) if (frustum_node_visible(F, nodes[i], gridMin, voxelSize, margin)) newIndex[i] = (int32_t)visible++;
+	if (visible == 0) return RTO_OK;
+	RtoGpuNode* out = (RtoGpuNode*)std::malloc(visible * sizeof(RtoGpuNode));
+	int32_t* back = newToOldOut ? (int32_t*)std::malloc(visible * sizeof(int32_t)) : nullptr;
+	if (!out || (newToOldOut && !back)) { std::free(out); std::free(back); return rto_fail(RTO_ERR_ALLOC, "rto_host_frustum_cull: out of memory"); }
+	for (size_t i = 0; i < numNodes; i++) {
+		if (newIndex[i] < 0) continue;
+		RtoGpuNode n = nodes[i];
+		if (!n.isLeaf)                                       // children of leaves are copied as they are (:788)
+			for (int c = 0; c < 8; c++) {
+				int32_t oc = n.child[c];
+				n.child[c] = (oc >= 0 && (size_t)oc < numNodes && newIndex[oc] >= 0) ? newIndex[oc] : -1;
+			}
+		out[newIndex[i]] = n;
+		if (back) back[newIndex[i]] = (int32_t)i;
+	}
+	*culledOut = out; *numCulled = visible;
+	if (newToOldOut) *newToOldOut = back;
 	return RTO_OK;
 }

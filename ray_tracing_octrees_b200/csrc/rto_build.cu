@@ -12,6 +12,7 @@
 #include "rto_scene.cuh"
 #include "mc_tables.h"
 #include "rto_voxelize.h"
+#include "rto_frustum.h"
 
 #include <cub/cub.cuh>
 #include <cfloat>
@@ -908,5 +909,82 @@ extern "C" int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCs
 	if (st) cudaStreamDestroy(st);
 	if (e != cudaSuccess) { std::free(host); return rto_fail(RTO_ERR_CUDA, "rto_device_csv_voxelize: %s", cudaGetErrorString(e)); }
 	*voxelsOut = host;
+	return RTO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Frustum culling on the device: the per-node test, the compaction and the child remap of RayTracerBVH.cpp:724-813 (the reference
+// runs them on one CPU thread every time the frustum is refreshed).  Same arrays as rto_host_frustum_cull.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct CullArgs { FrustumPlanes F; float gmin[3]; float voxel; float margin; };
+
+__global__ void k_cull_flags(const RtoGpuNode* __restrict__ nodes, size_t n, CullArgs A, int* __restrict__ flag) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	flag[i] = frustum_node_visible(A.F, nodes[i], A.gmin, A.voxel, A.margin) ? 1 : 0;
+}
+__global__ void k_cull_emit(const RtoGpuNode* __restrict__ nodes, size_t n, const int* __restrict__ flag, const int* __restrict__ ex,
+	RtoGpuNode* __restrict__ out, int32_t* __restrict__ newToOld) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !flag[i]) return;
+	RtoGpuNode nd = nodes[i];
+	if (!nd.isLeaf)
+		for (int c = 0; c < 8; c++) {
+			const int oc = nd.child[c];
+			nd.child[c] = (oc >= 0 && (size_t)oc < n && flag[oc]) ? ex[oc] : -1;
+		}
+	out[ex[i]] = nd;
+	newToOld[ex[i]] = (int32_t)i;
+}
+} // namespace
+
+extern "C" int rto_device_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, const float viewProj16[16],
+	float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut) {
+	if (!culledOut || !numCulled) return rto_fail(RTO_ERR_INVALID, "rto_device_frustum_cull: null output");
+	*culledOut = nullptr; *numCulled = 0;
+	if (newToOldOut) *newToOldOut = nullptr;
+	if (numNodes == 0) return RTO_OK;
+	if (!nodes || !gridMin || !viewProj16) return rto_fail(RTO_ERR_INVALID, "rto_device_frustum_cull: null input");
+	if (numNodes >= (size_t)0x7fffff00) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_device_frustum_cull: too many nodes");
+	int rc = rto_require_device(); if (rc) return rc;
+	CullArgs A; A.F = frustum_from_view_proj(viewProj16);
+	for (int k = 0; k < 3; k++) A.gmin[k] = gridMin[k];
+	A.voxel = voxelSize; A.margin = margin;
+	DevPool pool;
+	cudaStream_t st = nullptr;
+	BUILD_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	RtoGpuNode *dIn = nullptr, *dOut = nullptr; int *flag = nullptr, *ex = nullptr; int32_t* dBack = nullptr; uint8_t* tmp = nullptr;
+	RtoGpuNode* host = nullptr; int32_t* back = nullptr;
+	auto fail = [&](int code) { cudaStreamSynchronize(st); cudaStreamDestroy(st); std::free(host); std::free(back); return code; };
+#define CULL_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(rto_fail(RTO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_))); } while (0)
+	CULL_TRY(pool.alloc(&dIn, numNodes)); CULL_TRY(pool.alloc(&flag, numNodes)); CULL_TRY(pool.alloc(&ex, numNodes));
+	CULL_TRY(cudaMemcpyAsync(dIn, nodes, numNodes * sizeof(RtoGpuNode), cudaMemcpyHostToDevice, st));
+	const unsigned blocks = (unsigned)((numNodes + 255) / 256);
+	k_cull_flags<<<blocks, 256, 0, st>>>(dIn, numNodes, A, flag);
+	size_t tmpBytes = 0;
+	CULL_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, flag, ex, (int)numNodes, st));
+	CULL_TRY(pool.alloc(&tmp, tmpBytes));
+	CULL_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, flag, ex, (int)numNodes, st));
+	int lastEx = 0, lastFlag = 0;
+	CULL_TRY(cudaMemcpyAsync(&lastEx, ex + (numNodes - 1), 4, cudaMemcpyDeviceToHost, st));
+	CULL_TRY(cudaMemcpyAsync(&lastFlag, flag + (numNodes - 1), 4, cudaMemcpyDeviceToHost, st));
+	CULL_TRY(cudaStreamSynchronize(st));
+	const size_t visible = (size_t)lastEx + (size_t)lastFlag;
+	if (visible == 0) { cudaStreamDestroy(st); return RTO_OK; }
+	CULL_TRY(pool.alloc(&dOut, visible)); CULL_TRY(pool.alloc(&dBack, visible));
+	k_cull_emit<<<blocks, 256, 0, st>>>(dIn, numNodes, flag, ex, dOut, dBack);
+	CULL_TRY(cudaGetLastError());
+	host = (RtoGpuNode*)std::malloc(visible * sizeof(RtoGpuNode));
+	back = (int32_t*)std::malloc(visible * sizeof(int32_t));
+	if (!host || !back) return fail(rto_fail(RTO_ERR_ALLOC, "rto_device_frustum_cull: out of host memory"));
+	CULL_TRY(cudaMemcpyAsync(host, dOut, visible * sizeof(RtoGpuNode), cudaMemcpyDeviceToHost, st));
+	CULL_TRY(cudaMemcpyAsync(back, dBack, visible * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	CULL_TRY(cudaStreamSynchronize(st));
+#undef CULL_TRY
+	cudaStreamDestroy(st);
+	*culledOut = host; *numCulled = visible;
+	if (newToOldOut) *newToOldOut = back; else std::free(back);
 	return RTO_OK;
 }

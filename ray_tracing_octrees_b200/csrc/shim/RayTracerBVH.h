@@ -23,14 +23,16 @@ struct Framebuffer {                       // host copy of one frame: row 0 = to
 class RayTracerBVH {
 public:
 	RayTracerBVH() = default;
-	~RayTracerBVH() { rto_scene_destroy(m_scene); }
+	~RayTracerBVH() { rto_scene_destroy(m_scene); rto_scene_destroy(m_culled); }
 	RayTracerBVH(const RayTracerBVH&) = delete;
 	RayTracerBVH& operator=(const RayTracerBVH&) = delete;
 
 	// RayTracerBVH.cpp:430-505: BFS flatten (root = 0, discovery order) and upload.  setOctree(nullptr, ...) clears.
 	void setOctree(OctreeNode* root, const VoxelGrid& grid) {
-		m_flatNodes.clear();
+		m_flatNodes.clear(); m_visibleToFlat.clear();
 		rto_scene_destroy(m_scene); m_scene = nullptr; m_mode = RTO_MODE_OCTREE_GLSL;
+		rto_scene_destroy(m_culled); m_culled = nullptr;
+		m_gridMin[0] = grid.minX; m_gridMin[1] = grid.minY; m_gridMin[2] = grid.minZ; m_voxelSize = grid.voxelSize;
 		if (!root) return;
 		std::queue<OctreeNode*> q; std::unordered_map<OctreeNode*, int> index;
 		q.push(root); index[root] = 0;
@@ -52,20 +54,40 @@ public:
 			std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error());
 	}
 	// extension: ray cast a triangle soup through the reference-shaped BVH
-	void setMesh(const BVH& bvh, float sceneScale) { rto_scene_destroy(m_scene); m_scene = nullptr; m_external = bvh.scene(); m_mode = RTO_MODE_BVH; m_shadowBias = 1e-3f * sceneScale; }
+	void setMesh(const BVH& bvh, float sceneScale) { rto_scene_destroy(m_scene); m_scene = nullptr; rto_scene_destroy(m_culled); m_culled = nullptr; m_culledEmpty = false; m_external = bvh.scene(); m_mode = RTO_MODE_BVH; m_shadowBias = 1e-3f * sceneScale; }
 
 	void ensureComputeInitialized() { if (!m_inited && rto_init(0) == RTO_OK) m_inited = true; else if (!m_inited) std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); }
-	void setFrustumCullingEnabled(bool) {}                                 // culling changes hit results; parity path is unculled
+	void setFrustumCullingEnabled(bool on) { m_cullingEnabled = on; }       // RayTracerBVH.h:44 (stored, like the reference; the culling call below does not consult it either)
 	void setTraversalMode(int mode) { m_mode = mode; }                      // RTO_MODE_OCTREE_GLSL (reference shader) or RTO_MODE_OCTREE_SKIP
 	void setShadows(bool on) { m_flags = on ? RTO_FLAG_SHADOWS : 0u; }
 
 	// RayTracerBVH.cpp:614-704.  Like the reference, errors are printed and the frame is left untouched.
 	void renderSceneCompute(const Camera& camera, int width, int height, float aspect, float fovDeg) { render(camera, width, height, aspect, fovDeg, m_frame); }
-	void renderSceneComputeWithCulling(const Camera& camera, int width, int height, float aspect, float fovDeg, bool) { renderSceneCompute(camera, width, height, aspect, fovDeg); }
+	// RayTracerBVH.cpp:706-892.  With updateFrustum the node array is culled against the camera's frustum (margin 150), compacted and
+	// re-uploaded (:724-813), here on the GPU; like the reference's SSBO, the culled array then stays the one every later render
+	// traverses until the next update or setOctree.  frame().hitId indexes that array; visibleToFlat() maps it back to flatNodes().
+	void renderSceneComputeWithCulling(const Camera& camera, int width, int height, float aspect, float fovDeg, bool updateFrustum) {
+		if (updateFrustum && m_scene && !m_flatNodes.empty()) {
+			RtoCamera cam; rto_shim::mat4 viewM; float vp[16];
+			const float* view = reinterpret_cast<const float*>(&viewM);
+			RtoGpuNode* culled = nullptr; size_t n = 0; int32_t* back = nullptr;
+			if (camera.consts(fovDeg, aspect, width, height, cam, &viewM) == RTO_OK && rto_host_view_proj(view, fovDeg, aspect, 0.01f, 5000.f, vp) == RTO_OK &&
+				rto_device_frustum_cull(reinterpret_cast<const RtoGpuNode*>(m_flatNodes.data()), m_flatNodes.size(), m_gridMin, m_voxelSize, vp, 150.0f, &culled, &n, &back) == RTO_OK) {
+				rto_scene_destroy(m_culled); m_culled = nullptr;
+				m_visibleToFlat.assign(back, back + n);
+				if (n && rto_scene_create_octree(culled, n, m_gridMin, m_voxelSize, &m_culled) != RTO_OK) std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error());
+				m_culledEmpty = (n == 0);
+			}
+			else std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error());
+			rto_host_free(culled); rto_host_free(back);
+		}
+		renderSceneCompute(camera, width, height, aspect, fovDeg);
+	}
+	const std::vector<int32_t>& visibleToFlat() const { return m_visibleToFlat; }
 	bool render(const Camera& camera, int width, int height, float aspect, float fovDeg, Framebuffer& fb) {
-		RtoScene* sc = m_scene ? m_scene : m_external;
+		RtoScene* sc = m_culled ? m_culled : (m_scene ? m_scene : m_external);
 		if (!m_inited) { std::fprintf(stderr, "[RayTracerBVH] Compute pipeline not initialized or failed.\n"); return false; }
-		if (!sc) return false;                                             // no data: skip (RayTracerBVH.cpp:624-627)
+		if (!sc || (m_culledEmpty && m_scene)) return false;               // no data (or everything culled): skip (RayTracerBVH.cpp:624-627)
 		RtoCamera cam;
 		if (camera.consts(fovDeg, aspect, width, height, cam, nullptr) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
 		fb.width = width; fb.height = height;
@@ -80,6 +102,10 @@ public:
 private:
 	std::vector<GPUNodes> m_flatNodes;
 	RtoScene* m_scene = nullptr;
+	RtoScene* m_culled = nullptr;         // the frustum-culled array of the last renderSceneComputeWithCulling(..., true)
+	std::vector<int32_t> m_visibleToFlat;
+	float m_gridMin[3] = { 0, 0, 0 }, m_voxelSize = 1.0f;
+	bool m_cullingEnabled = false, m_culledEmpty = false;
 	RtoScene* m_external = nullptr;       // owned by a BVH (setMesh)
 	int m_mode = RTO_MODE_OCTREE_GLSL;
 	unsigned m_flags = 0;

@@ -29,6 +29,10 @@ int main() {
 	if (tracer.render(cam, 160, 120, 160.f / 120.f, 45.f, fb)) {
 		size_t hits = 0; for (int id : fb.hitId) hits += id >= 0;
 		std::printf("octree frame: %zu of %zu pixels hit\n", hits, fb.hitId.size());
+		// the call the reference's main loop makes (main.cpp:1357): cull against the frustum, then render the culled array
+		tracer.renderSceneComputeWithCulling(cam, 160, 120, 160.f / 120.f, 45.f, true);
+		size_t chits = 0; for (int id : tracer.frame().hitId) chits += id >= 0;
+		std::printf("culled frame: %zu of %zu nodes visible, %zu pixels hit\n", tracer.visibleToFlat().size(), tracer.flatNodes().size(), chits);
 		try {
 			tracer.setMesh(bvh, grid.voxelSize); tracer.setShadows(true);
 			if (tracer.render(cam, 160, 120, 160.f / 120.f, 45.f, fb)) { hits = 0; for (int id : fb.hitId) hits += id >= 0; std::printf("mesh frame: %zu of %zu pixels hit\n", hits, fb.hitId.size()); }

@@ -29,3 +29,8 @@ def test_shim_renders_on_gpu(rto, tmp_path):
     out = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "octree frame:" in out.stdout and "mesh frame:" in out.stdout and "BVH::query candidates:" in out.stdout
+    # the sphere scene spans one unit: with the reference's culling margin of 150 every node stays, so the culled frame equals the plain one
+    import re
+    plain = int(re.search(r"octree frame: (\d+) of", out.stdout).group(1))
+    m = re.search(r"culled frame: (\d+) of (\d+) nodes visible, (\d+) pixels hit", out.stdout)
+    assert m and m.group(1) == m.group(2) == "6025" and int(m.group(3)) == plain
