@@ -243,6 +243,17 @@ RTO_API int rto_bvh_query(RtoScene* scene, const float* origins, const float* di
 RTO_API int rto_render_stats(RtoScene* scene, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias,
 	int y0, int y1, uint64_t stats[5]);
 
+/* VolumeRaycastRenderer's per-frame use of octreeRaySkip (VolumeRaycastRenderer.cpp:1598-1664): 49 probe rays (7 x 7 over the central
+ * +-0.2 of NDC, unprojected through inverse(perspective(45 deg, aspect, 0.1, 5000)) and inverse(view)) are traced with
+ * octreeRaySkip semantics on the GPU; the 15th percentile of the valid results, times 0.75, blended 0.4 : 0.6 with
+ * lastSkipDistance (the reference keeps that in a function-local static) is the distance the volume ray marcher may skip.
+ * probeT (optional) receives the 49 raw results. */
+RTO_API int rto_octree_skip_distance(RtoScene* scene, const float view16[16], const float camPos[3], float aspect,
+	float lastSkipDistance, float* skipDistanceOut, float* probeT /* may be NULL */);
+/* The two host halves of it: the 49 rays (origins / dirs: 147 floats each) and the percentile + blend. */
+RTO_API int rto_host_skip_probe_rays(const float view16[16], const float camPos[3], float aspect, float* origins, float* dirs);
+RTO_API float rto_host_skip_distance_from_probes(const float* t, int count, float lastSkipDistance);
+
 RTO_API int rto_scene_sync(RtoScene* scene);
 /* Device time in milliseconds of the most recent rto_render / rto_render_batch on this scene
  * (CUDA events on the scene's stream around the kernels only).  Synchronises. */

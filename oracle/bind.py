@@ -66,6 +66,7 @@ class Backend:
             "octree_rayskip": (None, [vp, vp, vp, sz, f32, f32, vp, vp]),
             "num_threads": (i32, []),
             "cull_nodes": (sz, [vp, f32, f32, f32, vp, f32, f32, i32, i32, vp]),
+            "skip_distance": (f32, [vp, f32, f32, f32, vp, f32, f32, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, prefix + name)
@@ -158,6 +159,13 @@ class Octree:
         if n:
             self.L.cull_nodes(self.h, th, ph, radius, _p(tgt), fov_deg, aspect, width, height, _p(out))
         return out
+
+    def skip_distance(self, theta_deg, phi_deg, radius, aspect, last=0.0, target=(0, 0, 0)):
+        """VolumeRaycastRenderer.cpp:1598-1664 -> (skip distance, 49 probe t, origins (49,3), dirs (49,3))."""
+        tgt = np.asarray(target, np.float32)
+        t, o, d = np.zeros(49, np.float32), np.zeros((49, 3), np.float32), np.zeros((49, 3), np.float32)
+        v = self.L.skip_distance(self.h, float(np.deg2rad(np.float32(theta_deg))), float(np.deg2rad(np.float32(phi_deg))), radius, _p(tgt), aspect, last, _p(t), _p(o), _p(d))
+        return float(v), t, o, d
 
     def flat(self):
         out = np.zeros((self.num_nodes, 15), np.int32)

@@ -390,6 +390,40 @@ void orc_camera_consts(float theta, float phi, float radius, const float* target
 	if (view16) std::memcpy(view16, view, 64);
 }
 
+// ---- skip-distance estimate: restatement of VolumeRaycastRenderer.cpp:1598-1664 (49 probe rays through octreeRaySkip, 15th percentile
+// x 0.75, temporal blend 0.4 : 0.6); glm::perspective, glm::inverse and mat4 * vec4 in glm's operation order.
+float orc_skip_distance(void* hv, float theta, float phi, float radius, const float* target, float aspect, float last, float* tOut, float* oOut, float* dOut) {
+	Octree* oc = (Octree*)hv;
+	V3 tgt = v3(target[0], target[1], target[2]);
+	V3 ro = radius * v3(std::cos(theta) * std::sin(phi), std::sin(theta), std::cos(theta) * std::cos(phi)) + tgt;
+	float V[16], P[16] = { 0 }, invV[16], invP[16];
+	lookAtRH(ro, tgt, v3(0, 1, 0), V);
+	const float zn = 0.1f, zf = 5000.0f, th = std::tan(45.0f * 0.01745329251994329576923690768489f / 2.0f);       // :1608
+	P[0] = 1.0f / (aspect * th); P[5] = 1.0f / th; P[10] = -(zf + zn) / (zf - zn); P[11] = -1.0f; P[14] = -(2.0f * zf * zn) / (zf - zn);
+	inverse4(V, invV); inverse4(P, invP);
+	auto mul = [](const float* m, const float* v, float* o) { for (int r = 0; r < 4; r++) o[r] = (m[r] * v[0] + m[4 + r] * v[1]) + (m[8 + r] * v[2] + m[12 + r] * v[3]); };
+	std::vector<float> valid;
+	int k = 0;
+	for (int y = 0; y < 7; y++) for (int x = 0; x < 7; x++, k++) {
+		float ndcX = ((float)x / 6 - 0.5f) * 2.0f * 0.2f, ndcY = ((float)y / 6 - 0.5f) * 2.0f * 0.2f;            // :1619-1620
+		float clip[4] = { ndcX, ndcY, 1.0f, 1.0f }, vp[4], wp[4];
+		mul(invP, clip, vp);
+		float w = vp[3]; for (int c = 0; c < 4; c++) vp[c] /= w;                                                   // :1625
+		mul(invV, vp, wp);
+		V3 rd = normalize(v3(wp[0], wp[1], wp[2]) - ro);
+		const ONode* leaf = nullptr; uint64_t visits = 0;
+		float t = raySkip(oc->root, ro, rd, 0.0f, 1e30f, oc->g, leaf, visits);
+		if (tOut) tOut[k] = t;
+		if (oOut) { oOut[3 * k] = ro.x; oOut[3 * k + 1] = ro.y; oOut[3 * k + 2] = ro.z; }
+		if (dOut) { dOut[3 * k] = rd.x; dOut[3 * k + 1] = rd.y; dOut[3 * k + 2] = rd.z; }
+		if (t < 1e30f && t > 0.0f) valid.push_back(t);
+	}
+	float skip = 0.0f;
+	if (!valid.empty()) { std::sort(valid.begin(), valid.end()); int idx = std::max(0, (int)(valid.size() * 0.15f)); skip = valid[idx]; skip *= 0.75f; }   // :1646-1654
+	const float blend = 0.4f;
+	return last * blend + skip * (1.0f - blend);                                                                    // :1657-1661
+}
+
 // ---- frustum culling: restatement of the CPU part of RayTracerBVH::renderSceneComputeWithCulling (RayTracerBVH.cpp:724-813) over
 // Frustum (Frustum.cpp:5-93), glm::perspective (matrix_clip_space.inl:249-262) and glm's mat4 * mat4 (type_mat4x4.inl:630-648).
 // Returns the number of nodes kept; out (may be null) receives the compacted, remapped array (15 ints per node).

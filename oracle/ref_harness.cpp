@@ -227,6 +227,50 @@ size_t ref_cull_nodes(void* hv, float theta, float phi, float radius, const floa
 	return n;
 }
 
+// The skip-distance estimate of VolumeRaycastRenderer::drawRaycast (VolumeRaycastRenderer.cpp:1598-1664).  That function is GL code
+// from top to bottom and cannot be called headless, so its 60 lines around the octreeRaySkip calls are restated here with the same
+// glm expressions; the 49 octreeRaySkip calls themselves are the reference's own function.  `last` plays the role of the
+// function-local static lastSkipDistance.  tOut (49), o, d (147 each) may be null.
+float ref_skip_distance(void* hv, float theta, float phi, float radius, const float* target, float aspect, float last, float* tOut, float* oOut, float* dOut) {
+	RefOctree* h = (RefOctree*)hv;
+	Camera cam(theta, phi, radius);
+	cam.setTarget(glm::vec3(target[0], target[1], target[2]));
+	float skipDistance = 0.0f;
+	const int gridSize = 7; const float sampleOffset = 0.2f;
+	std::vector<float> validSkipDistances;
+	glm::mat4 V = cam.getView();
+	glm::mat4 P = glm::perspective(glm::radians(45.0f), aspect, 0.1f, 5000.0f);
+	glm::mat4 invV = glm::inverse(V);
+	glm::mat4 invP = glm::inverse(P);
+	glm::vec3 ro = cam.getPos();
+	int k = 0;
+	for (int y = 0; y < gridSize; y++) {
+		for (int x = 0; x < gridSize; x++, k++) {
+			float ndcX = ((float)x / (gridSize - 1) - 0.5f) * 2.0f * sampleOffset;
+			float ndcY = ((float)y / (gridSize - 1) - 0.5f) * 2.0f * sampleOffset;
+			glm::vec4 clipPos(ndcX, ndcY, 1.f, 1.f);
+			glm::vec4 viewPos = invP * clipPos;
+			viewPos /= viewPos.w;
+			glm::vec4 worldPos4 = invV * viewPos;
+			glm::vec3 rd = glm::normalize(glm::vec3(worldPos4) - ro);
+			float raySkip = octreeRaySkip(h->root, ro, rd, 0.0f, 1e30f, h->grid);
+			if (tOut) tOut[k] = raySkip;
+			if (oOut) { oOut[3 * k] = ro.x; oOut[3 * k + 1] = ro.y; oOut[3 * k + 2] = ro.z; }
+			if (dOut) { dOut[3 * k] = rd.x; dOut[3 * k + 1] = rd.y; dOut[3 * k + 2] = rd.z; }
+			if (raySkip < 1e30f && raySkip > 0.0f) validSkipDistances.push_back(raySkip);
+		}
+	}
+	if (!validSkipDistances.empty()) {
+		std::sort(validSkipDistances.begin(), validSkipDistances.end());
+		int safeIndex = std::max(0, (int)(validSkipDistances.size() * 0.15f));
+		skipDistance = validSkipDistances[safeIndex];
+		skipDistance *= 0.75f;
+	}
+	float blendFactor = 0.4f;
+	skipDistance = last * blendFactor + skipDistance * (1.0f - blendFactor);
+	return skipDistance;
+}
+
 void ref_camera_consts(float theta, float phi, float radius, const float* target, float fovDeg, float aspect,
 	int w, int h, RefCamConsts* out, float* view16) {
 	Camera cam(theta, phi, radius);

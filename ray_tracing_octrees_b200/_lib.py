@@ -71,6 +71,9 @@ SIGNATURES = {
     "rto_trace_rays": (_i, [_vp, _i, _u32, _vp, _vp, _sz, _f, _f, _vp, _vp, _i]),
     "rto_bvh_query": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "rto_render_stats": (_i, [_vp, C.POINTER(RtoCamera), _i, _u32, _f, _i, _i, _vp]),
+    "rto_octree_skip_distance": (_i, [_vp, _vp, _vp, _f, _f, C.POINTER(_f), _vp]),
+    "rto_host_skip_probe_rays": (_i, [_vp, _vp, _f, _vp, _vp]),
+    "rto_host_skip_distance_from_probes": (_f, [_vp, _i, _f]),
     "rto_scene_sync": (_i, [_vp]),
     "rto_scene_last_kernel_ms": (_i, [_vp, C.POINTER(_f)]),
     "rto_scene_launch_count": (_u64, [_vp]),

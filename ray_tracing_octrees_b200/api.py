@@ -116,6 +116,20 @@ def frustum_cull(nodes, grid, view_proj16, margin=150.0, device=False):
     return _take(ptr, n.value, np.int32, (n.value, 15)), _take(back, n.value, np.int32, (n.value,))
 
 
+def skip_probe_rays(view16, cam_pos, aspect):
+    """The 49 probe rays of VolumeRaycastRenderer.cpp:1618-1629 -> (origins (49, 3), dirs (49, 3))."""
+    v = np.ascontiguousarray(view16, np.float32).ravel()
+    p = np.ascontiguousarray(cam_pos, np.float32).ravel()
+    o, d = np.zeros((49, 3), np.float32), np.zeros((49, 3), np.float32)
+    check(lib().rto_host_skip_probe_rays(_p(v), _p(p), float(aspect), _p(o), _p(d)))
+    return o, d
+
+
+def skip_distance_from_probes(t, last=0.0):
+    t = np.ascontiguousarray(t, np.float32).ravel()
+    return float(lib().rto_host_skip_distance_from_probes(_p(t), len(t), float(last)))
+
+
 def create_octree_on_device(grid):
     """Same array as create_octree_from_voxel_grid, built on the GPU (rto_device_octree_build)."""
     ptr = C.c_void_p()
@@ -250,6 +264,15 @@ class Scene:
         check(lib().rto_scene_create_bvh_from_grid(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min),
                                                    float(grid.voxel_size), C.byref(h)))
         return Scene(h)
+
+    def skip_distance(self, view16, cam_pos, aspect, last=0.0):
+        """VolumeRaycastRenderer's skip-distance estimate (VolumeRaycastRenderer.cpp:1598-1664) -> (distance, 49 probe results)."""
+        v = np.ascontiguousarray(view16, np.float32).ravel()
+        p = np.ascontiguousarray(cam_pos, np.float32).ravel()
+        out = C.c_float()
+        probes = np.zeros(49, np.float32)
+        check(lib().rto_octree_skip_distance(self.h, _p(v), _p(p), float(aspect), float(last), C.byref(out), _p(probes)))
+        return out.value, probes
 
     def info(self):
         kind, compact = C.c_int(), C.c_int()

@@ -458,18 +458,8 @@ void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, i
 // =================================================================================================
 // Camera constants
 // =================================================================================================
-extern "C" int rto_host_camera_orbit(float theta, float phi, float radius, const float target[3], float fovDeg, float aspect,
-	int width, int height, RtoCamera* out, float* view16) {
-	if (!out || !target) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: null argument");
-	if (width <= 0 || height <= 0) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: bad image size");
-	V3 tgt = mk3(target[0], target[1], target[2]);
-	V3 eye = radius * mk3(cosf(theta) * sinf(phi), sinf(theta), cosf(theta) * cosf(phi)) + tgt;    // Camera.cpp:13-17
-	// glm::lookAtRH(eye, target, (0,1,0))
-	V3 f = normalize3(tgt - eye);
-	V3 s = normalize3(cross3(f, mk3(0.0f, 1.0f, 0.0f)));
-	V3 u = cross3(s, f);
-	float m[16] = { s.x, u.x, -f.x, 0.0f,  s.y, u.y, -f.y, 0.0f,  s.z, u.z, -f.z, 0.0f,  -dot3(s, eye), -dot3(u, eye), dot3(f, eye), 1.0f };
-	// glm::inverse(mat4): cofactor expansion, same grouping as glm/detail/func_matrix.inl compute_inverse<4,4>
+// glm::inverse(mat4): cofactor expansion, same grouping as glm/detail/func_matrix.inl compute_inverse<4,4>; column-major m[c * 4 + r]
+static void glm_inverse4(const float* m, float* outInv) {
 	auto M = [&](int c, int r) { return m[c * 4 + r]; };
 	float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3), c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3), c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
 	float c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3), c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3), c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
@@ -491,7 +481,37 @@ extern "C" int rto_host_camera_orbit(float theta, float phi, float radius, const
 	}
 	float det = (M(0, 0) * inv[0] + M(0, 1) * inv[4]) + (M(0, 2) * inv[8] + M(0, 3) * inv[12]);
 	float ood = 1.0f / det;
-	for (int i = 0; i < 16; i++) out->invView[i] = inv[i] * ood;
+	for (int i = 0; i < 16; i++) outInv[i] = inv[i] * ood;
+}
+
+// glm::perspective(radians(fovDeg), aspect, zNear, zFar): matrix_clip_space.inl:249-262 (RH, depth -1..1)
+static void glm_perspective(float fovDeg, float aspect, float zNear, float zFar, float* P) {
+	const float fovy = fovDeg * 0.01745329251994329576923690768489f;      // glm::radians
+	const float tanHalf = std::tan(fovy / 2.0f);
+	for (int i = 0; i < 16; i++) P[i] = 0.0f;
+	P[0] = 1.0f / (aspect * tanHalf);
+	P[5] = 1.0f / tanHalf;
+	P[10] = -(zFar + zNear) / (zFar - zNear);
+	P[11] = -1.0f;
+	P[14] = -(2.0f * zFar * zNear) / (zFar - zNear);
+}
+// glm mat4 * vec4: (m0 * v0 + m1 * v1) + (m2 * v2 + m3 * v3), type_mat4x4.inl:561-572
+static void glm_mul_m4v4(const float* m, const float* v, float* out) {
+	for (int r = 0; r < 4; r++) out[r] = (m[r] * v[0] + m[4 + r] * v[1]) + (m[8 + r] * v[2] + m[12 + r] * v[3]);
+}
+
+extern "C" int rto_host_camera_orbit(float theta, float phi, float radius, const float target[3], float fovDeg, float aspect,
+	int width, int height, RtoCamera* out, float* view16) {
+	if (!out || !target) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: null argument");
+	if (width <= 0 || height <= 0) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: bad image size");
+	V3 tgt = mk3(target[0], target[1], target[2]);
+	V3 eye = radius * mk3(cosf(theta) * sinf(phi), sinf(theta), cosf(theta) * cosf(phi)) + tgt;    // Camera.cpp:13-17
+	// glm::lookAtRH(eye, target, (0,1,0))
+	V3 f = normalize3(tgt - eye);
+	V3 s = normalize3(cross3(f, mk3(0.0f, 1.0f, 0.0f)));
+	V3 u = cross3(s, f);
+	float m[16] = { s.x, u.x, -f.x, 0.0f,  s.y, u.y, -f.y, 0.0f,  s.z, u.z, -f.z, 0.0f,  -dot3(s, eye), -dot3(u, eye), dot3(f, eye), 1.0f };
+	glm_inverse4(m, out->invView);
 	out->camPos[0] = eye.x; out->camPos[1] = eye.y; out->camPos[2] = eye.z;
 	float fovRad = fovDeg * 0.01745329251994329576923690768489f;     // glm::radians
 	out->tanHalfFov = tanf(fovRad * 0.5f);
@@ -671,14 +691,8 @@ extern "C" int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv,
 // glm's mat4 * mat4 (type_mat4x4.inl:630-648: ((A0*b0 + A1*b1) + A2*b2) + A3*b3 per column).
 extern "C" int rto_host_view_proj(const float view16[16], float fovDeg, float aspect, float zNear, float zFar, float viewProj16[16]) {
 	if (!view16 || !viewProj16) return rto_fail(RTO_ERR_INVALID, "rto_host_view_proj: null argument");
-	const float fovy = fovDeg * 0.01745329251994329576923690768489f;      // glm::radians
-	const float tanHalf = std::tan(fovy / 2.0f);
-	float P[16] = { 0 };
-	P[0] = 1.0f / (aspect * tanHalf);
-	P[5] = 1.0f / tanHalf;
-	P[10] = -(zFar + zNear) / (zFar - zNear);
-	P[11] = -1.0f;
-	P[14] = -(2.0f * zFar * zNear) / (zFar - zNear);
+	float P[16];
+	glm_perspective(fovDeg, aspect, zNear, zFar, P);
 	for (int j = 0; j < 4; j++)
 		for (int r = 0; r < 4; r++) {
 			float acc = P[0 * 4 + r] * view16[j * 4 + 0];
@@ -719,4 +733,48 @@ extern "C" int rto_host_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, c
 	*culledOut = out; *numCulled = visible;
 	if (newToOldOut) *newToOldOut = back;
 	return RTO_OK;
+}
+
+// =================================================================================================
+// The probe rays of VolumeRaycastRenderer's skip-distance estimate (VolumeRaycastRenderer.cpp:1598-1629): a 7 x 7 grid over the
+// central +-0.2 of NDC, unprojected through inverse(perspective(45 deg, aspect, 0.1, 5000)) and inverse(view).
+// =================================================================================================
+extern "C" int rto_host_skip_probe_rays(const float view16[16], const float camPos[3], float aspect, float* origins, float* dirs) {
+	if (!view16 || !camPos || !origins || !dirs) return rto_fail(RTO_ERR_INVALID, "rto_host_skip_probe_rays: null argument");
+	float P[16], invP[16], invV[16];
+	glm_perspective(45.0f, aspect, 0.1f, 5000.0f, P);
+	glm_inverse4(view16, invV);
+	glm_inverse4(P, invP);
+	const int gridSize = 7; const float sampleOffset = 0.2f;
+	V3 ro = mk3(camPos[0], camPos[1], camPos[2]);
+	int k = 0;
+	for (int y = 0; y < gridSize; y++)
+		for (int x = 0; x < gridSize; x++, k++) {
+			float ndcX = ((float)x / (gridSize - 1) - 0.5f) * 2.0f * sampleOffset;
+			float ndcY = ((float)y / (gridSize - 1) - 0.5f) * 2.0f * sampleOffset;
+			float clip[4] = { ndcX, ndcY, 1.0f, 1.0f }, vpos[4], wpos[4];
+			glm_mul_m4v4(invP, clip, vpos);
+			const float w = vpos[3];
+			for (int c = 0; c < 4; c++) vpos[c] = vpos[c] / w;
+			glm_mul_m4v4(invV, vpos, wpos);
+			V3 rd = normalize3(mk3(wpos[0], wpos[1], wpos[2]) - ro);
+			origins[3 * k] = ro.x; origins[3 * k + 1] = ro.y; origins[3 * k + 2] = ro.z;
+			dirs[3 * k] = rd.x; dirs[3 * k + 1] = rd.y; dirs[3 * k + 2] = rd.z;
+		}
+	return RTO_OK;
+}
+
+// 15th percentile of the valid probe results, 75 % of it, blended with the previous frame's value (VolumeRaycastRenderer.cpp:1646-1663)
+extern "C" float rto_host_skip_distance_from_probes(const float* t, int count, float lastSkipDistance) {
+	std::vector<float> valid;
+	for (int i = 0; i < count; i++) if (t[i] < 1e30f && t[i] > 0.0f) valid.push_back(t[i]);
+	float skip = 0.0f;
+	if (!valid.empty()) {
+		std::sort(valid.begin(), valid.end());
+		int safeIndex = std::max(0, (int)(valid.size() * 0.15f));
+		skip = valid[safeIndex];
+		skip *= 0.75f;
+	}
+	const float blendFactor = 0.4f;
+	return lastSkipDistance * blendFactor + skip * (1.0f - blendFactor);
 }

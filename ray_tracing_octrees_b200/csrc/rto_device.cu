@@ -424,3 +424,18 @@ extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dir
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	return RTO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// VolumeRaycastRenderer's per-frame use of octreeRaySkip (VolumeRaycastRenderer.cpp:1598-1664): 49 probe rays -> one start distance
+// ------------------------------------------------------------------------------------------------
+extern "C" int rto_octree_skip_distance(RtoScene* s, const float view16[16], const float camPos[3], float aspect, float lastSkipDistance,
+	float* skipDistanceOut, float* probeT /* 49 floats, may be NULL */) {
+	if (!s || !skipDistanceOut) return rto_fail(RTO_ERR_INVALID, "rto_octree_skip_distance: null argument");
+	if (s->kind == RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "rto_octree_skip_distance: scene is not an octree");
+	float o[49 * 3], d[49 * 3], t[49];
+	int rc = rto_host_skip_probe_rays(view16, camPos, aspect, o, d); if (rc) return rc;
+	rc = rto_trace_rays(s, RTO_MODE_OCTREE_SKIP, 0, o, d, 49, 0.0f, 1e30f, t, nullptr, RTO_MEM_HOST); if (rc) return rc;
+	if (probeT) std::memcpy(probeT, t, sizeof(t));
+	*skipDistanceOut = rto_host_skip_distance_from_probes(t, 49, lastSkipDistance);
+	return RTO_OK;
+}
