@@ -107,6 +107,19 @@ RTO_API int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ
 	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
 	RtoTriangle** trisOut, size_t* numTris);
 
+/* The Adaptive Dual Contouring mesh (the triangle soup of configuration C4): renderOctree (main.cpp:95-208) calling
+ * AdaptiveDualContouringRenderer::render -> createTriangles (AdaptiveDualContouringRenderer.cpp:489-803 with createFaceTriangles
+ * :805-1088, gatherHermiteData :1090-1144, generateDualVertex :1146-1234, calculateIntersection :1236-1357, cellContainsSurface
+ * :1367-1530, QEFSolver :46-160) on every leaf in depth-first order.  The renderer's dual-vertex cache makes the result depend on
+ * that order; this builder keeps the order and gives the same triangles in the same sequence, bit for bit, with the expensive
+ * per-cell work spread over all host threads.  viewProj16 == NULL: every leaf is visited; otherwise subtrees whose box, grown by
+ * extraMargin (the reference passes 50), is outside the frustum of viewProj16 (rto_host_view_proj with zNear 0.01, zFar 5000) are
+ * skipped like renderOctree does.  Octrees wider than 1024 voxels are refused (the reference's cell keys alias beyond 10 bits per
+ * axis).  malloc'ed; rto_host_free. */
+RTO_API int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
+	const float* viewProj16 /* may be NULL */, float extraMargin, RtoTriangle** trisOut, size_t* numTris);
+
 /* BVH::BVH(const std::vector<Triangle>&) (BVH.cpp:19-71): same tree (median split, longest axis, std::sort
  * by centroid, leaves <= 2 triangles).  The triangle array must outlive the handle (the reference keeps raw
  * pointers too, BVH.cpp:21-25). */

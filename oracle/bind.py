@@ -68,7 +68,8 @@ class Backend:
             "cull_nodes": (sz, [vp, f32, f32, f32, vp, f32, f32, i32, i32, vp]),
             "skip_distance": (f32, [vp, f32, f32, f32, vp, f32, f32, vp, vp, vp]),
         }
-        for name, (res, args) in sig.items():
+        optional = {"dc_mesh_from_octree": (vp, [vp, vp, f32])}
+        for name, (res, args) in list(sig.items()) + [kv for kv in optional.items() if hasattr(L, prefix + kv[0])]:
             fn = getattr(L, prefix + name)
             fn.restype, fn.argtypes = res, args
             setattr(self, name, fn)
@@ -192,6 +193,11 @@ class Octree:
 
     def mesh(self):
         return Mesh(self.L, handle=self.L.mesh_from_octree(self.h))
+
+    def dc_mesh(self, view_proj=None, margin=50.0):
+        """renderOctree (main.cpp:95-208) over AdaptiveDualContouringRenderer::render: the DC triangle soup; view_proj None = no culling."""
+        vp = None if view_proj is None else np.ascontiguousarray(view_proj, np.float32).ravel()
+        return Mesh(self.L, handle=self.L.dc_mesh_from_octree(self.h, _p(vp), float(margin)))
 
     def free(self):
         if self.h:

@@ -12,6 +12,7 @@
 //   BVH::BVH / BVH::query                       453-skeleton/BVH.cpp:19-113
 //   Camera::getView / getPos                    453-skeleton/Camera.cpp:11-29
 //   loadVoxelGrid                               453-skeleton/CacheUtils.cpp:33-59
+//   AdaptiveDualContouringRenderer::render      453-skeleton/AdaptiveDualContouringRenderer.cpp:489-1530 (createTriangles per leaf)
 //   loadCSVDataIntoVoxelGrid (CSV voxeliser)    453-skeleton/BuildingLoader.cpp:153-290
 //   glm 0.9.9.7 arithmetic                      thirdparty/glm-0.9.9.7
 //
@@ -33,6 +34,8 @@
 #undef private
 
 #include "Renderer.h"
+#include "AdaptiveDualContouringRenderer.h"
+#include "Frustum.h"
 #include "CacheUtils.h"
 #include "Camera.h"
 
@@ -345,6 +348,49 @@ void* ref_mesh_from_octree(void* hv) {
 	RefMesh* m = new RefMesh();
 	m->tris.resize(mct.size());
 	for (size_t i = 0; i < mct.size(); i++) { m->tris[i].v0 = mct[i].v[0]; m->tris[i].v1 = mct[i].v[1]; m->tris[i].v2 = mct[i].v[2]; }
+	return m;
+}
+
+// The Dual-Contouring mesh as the application produces it: renderOctree (main.cpp:95-208) walks the octree depth first (children 0..7),
+// skips every node whose box (+ extraMargin) is outside the frustum and calls AdaptiveDualContouringRenderer::render on each leaf, one
+// after the other on the calling thread (the renderer's thread pool is never fed by this path), so the renderer's dual-vertex cache
+// fills in that order.  main.cpp is the GL application and cannot be compiled here; its 30-line traversal lambda (main.cpp:152-187)
+// is restated below with the same glm expressions, everything it calls is the reference's own code.  The compute-shader attempt of
+// render() (taken only when the root itself is a leaf) is disabled: there is no GL context.
+// viewProj16 == NULL: no culling (every leaf is visited).
+void* ref_dc_mesh_from_octree(void* hv, const float* viewProj16, float extraMargin) {
+	RefOctree* h = (RefOctree*)hv;
+	AdaptiveDualContouringRenderer dc;
+	dc.m_useComputeShader = false;
+	dc.m_useAdaptiveLOD = true;
+	dc.m_detailThreshold = 0.1f;
+	std::vector<MCTriangle> result;
+	Frustum* frustum = nullptr;
+	if (viewProj16) { glm::mat4 VP; std::memcpy(&VP[0][0], viewProj16, 64); frustum = new Frustum(VP); }
+	const VoxelGrid& grid = h->grid;
+	Renderer& renderer = dc;
+	std::function<void(const OctreeNode*)> traverse = [&](const OctreeNode* node) {
+		if (!node) return;
+		float voxelSize = grid.voxelSize;
+		glm::vec3 minPoint(grid.minX + node->x * voxelSize, grid.minY + node->y * voxelSize, grid.minZ + node->z * voxelSize);
+		glm::vec3 maxPoint = minPoint + glm::vec3(node->size * voxelSize);
+		if (frustum) {
+			int frustumTest = frustum->testAABB(minPoint, maxPoint, extraMargin);
+			if (frustumTest == -1) return;
+		}
+		if (node->isLeaf) {
+			auto tris = renderer.render(node, grid, node->x, node->y, node->z, node->size);
+			if (!tris.empty()) result.insert(result.end(), tris.begin(), tris.end());
+		}
+		else {
+			for (auto child : node->children) traverse(child);
+		}
+	};
+	traverse(h->root);
+	delete frustum;
+	RefMesh* m = new RefMesh();
+	m->tris.resize(result.size());
+	for (size_t i = 0; i < result.size(); i++) { m->tris[i].v0 = result[i].v[0]; m->tris[i].v1 = result[i].v[1]; m->tris[i].v2 = result[i].v[2]; }
 	return m;
 }
 

@@ -1,0 +1,63 @@
+"""Adaptive Dual Contouring mesh (rto_host_dc_mesh) against the reference's own AdaptiveDualContouringRenderer.cpp (compiled in place,
+driven by renderOctree's traversal) and against golden checksums generated from it (tests/golden/make_golden_dc.py).  Bit-exact:
+same triangles, same order.  The builder keeps the reference's visit order (its dual-vertex cache makes the mesh depend on it)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+from dc_cases import CASES, GOLDEN, SLOW_IN_REFERENCE, make_grid, view_proj_for
+
+META = json.load(open(os.path.join(GOLDEN, "golden_dc.json")))
+
+
+def build(rto, case):
+    dims, gmin, voxel, data = make_grid(case)
+    g = rto.VoxelGrid(dims, gmin, voxel, data)
+    return g, rto.create_octree_from_voxel_grid(g)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_dc_mesh_equals_the_golden_checksums(rto, name):
+    case, want = CASES[name], META[name]
+    g, nodes = build(rto, case)
+    vp = None if want["view_proj"] is None else np.array(want["view_proj"], np.float32)
+    got = rto.dual_contouring_mesh(g, nodes, vp, case.get("margin", 50.0))
+    assert len(nodes) == want["nodes"]
+    assert len(got) == want["tris"]
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want["sha"]
+    if name == "sphere32":
+        assert_bit_equal(got, np.load(os.path.join(GOLDEN, "golden_dc_sphere32.npz"))["tris"], "sphere32 DC triangles")
+
+
+@pytest.mark.parametrize("name", sorted(set(CASES) - SLOW_IN_REFERENCE))
+def test_dc_mesh_equals_the_compiled_reference(rto, ref, name):
+    case = CASES[name]
+    dims, gmin, voxel, data = make_grid(case)
+    oc = ref.octree(dims, gmin, voxel, data); oc.build()
+    g, nodes = build(rto, case)
+    vp = view_proj_for(ref, case)
+    if vp is not None:                       # the host view-projection equals the one the golden file recorded
+        assert_bit_equal(vp, np.array(META[name]["view_proj"], np.float32), "view_proj")
+    want = oc.dc_mesh(vp, case.get("margin", 50.0)).tris()
+    got = rto.dual_contouring_mesh(g, nodes, vp, case.get("margin", 50.0))
+    oc.free()
+    assert_bit_equal(got, want, name)
+
+
+def test_dc_mesh_refuses_octrees_beyond_the_reference_key_range(rto):
+    """Cell keys are x << 20 | y << 10 | z in the reference (AdaptiveDualContouringRenderer.cpp:553-555): they alias past 1024 voxels."""
+    nodes = np.zeros((1, 15), np.int32)
+    nodes[0, 3] = 2048; nodes[0, 4] = 1; nodes[0, 7:] = -1
+    g = rto.VoxelGrid((1, 1, 1), (0, 0, 0), 1.0, np.zeros(1, np.uint8))
+    with pytest.raises(rto.RtoError):
+        rto.dual_contouring_mesh(g, nodes)
+
+
+def test_dc_mesh_of_nothing(rto):
+    g = rto.VoxelGrid((4, 4, 4), (0, 0, 0), 1.0, np.zeros(64, np.uint8))
+    assert len(rto.dual_contouring_mesh(g, np.zeros((0, 15), np.int32))) == 0
+    assert len(rto.dual_contouring_mesh(g, rto.create_octree_from_voxel_grid(g))) == 0
