@@ -33,6 +33,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 #include <vector>
 
@@ -411,6 +413,9 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 	std::vector<std::vector<Hermite>> scratch((size_t)nthreads);
 	std::vector<Hermite> seqScratch;
 
+	const bool verbose = std::getenv("RTO_DC_VERBOSE") != nullptr;
+	double tSurf = 0, tRec = 0, tSeq = 0; size_t nSurf = 0, nLate = 0;
+	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const size_t kBlock = (size_t)1 << 18;
 	std::vector<uint8_t> surf;
 	std::vector<LeafRec> recs;
@@ -418,6 +423,7 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 	for (size_t b0 = 0; b0 < order.size(); b0 += kBlock) {
 		const size_t bn = std::min(kBlock, order.size() - b0);
 		// 2a. which leaves of the block contain surface (createTriangles' second early-out, :542-545)
+		double tA = now();
 		surf.assign(bn, 0);
 		parallelFor(bn, 2048, nthreads, [&](size_t lo, size_t hi, int) {
 			for (size_t i = lo; i < hi; i++) {
@@ -425,6 +431,7 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 				surf[i] = cellContainsSurface(g, n.x, n.y, n.z, n.size) ? 1 : 0;
 			}
 		});
+		double tB = now();
 		recIndex.clear();
 		for (size_t i = 0; i < bn; i++) if (surf[i]) { recIndex.push_back((uint32_t)i); int32_t nd = order[b0 + i]; if (slotOf[nd] == -1) slotOf[nd] = -2; }
 		recs.resize(recIndex.size());
@@ -472,6 +479,7 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 				}
 			}
 		});
+		double tC = now();
 		// 3. the cache protocol, in visit order
 		auto cached = [&](int32_t node, V3& v) { int32_t s = slotOf[node]; if (s < 0) return false; v = cacheVal[(size_t)s]; return true; };
 		auto store = [&](int32_t node, V3 v) { slotOf[node] = (int32_t)cacheVal.size(); cacheVal.push_back(v); };
@@ -491,7 +499,7 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 			const size_t before = out.size();
 			V3 cellVertex;
 			if (!cached(R.node, cellVertex)) {
-				cellVertex = (R.memoMask & 1) ? R.memo[0] : dualVertex(g, x0, y0, z0, size, seqScratch);
+				if (R.memoMask & 1) cellVertex = R.memo[0]; else { cellVertex = dualVertex(g, x0, y0, z0, size, seqScratch); nLate++; }
 				store(R.node, cellVertex);
 			}
 			for (int dir = 0; dir < 3; dir++)
@@ -506,7 +514,7 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 						V3 v;
 						if (!cached(k, v)) {
 							if (R.memoMask & (1u << o)) v = R.memo[o];
-							else v = dualVertex(g, x0 - ((o & 1) ? size : 0), y0 - ((o & 2) ? size : 0), z0 - ((o & 4) ? size : 0), size, seqScratch);
+							else { v = dualVertex(g, x0 - ((o & 1) ? size : 0), y0 - ((o & 2) ? size : 0), z0 - ((o & 4) ? size : 0), size, seqScratch); nLate++; }
 							store(k, v);
 						}
 						adj[cnt++] = v;
@@ -544,8 +552,10 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 				}
 			}
 		}
-		// leaves marked "will cache itself" all did
+		tSurf += tB - tA; tRec += tC - tB; tSeq += now() - tC; nSurf += recs.size();
 	}
+	if (verbose) std::fprintf(stderr, "rto_host_dc_mesh: %zu leaves visited, %zu with surface, %zu triangles; surface test %.2f s, records %.2f s (%d threads), replay %.2f s, %zu vertices computed in the replay\n",
+		order.size(), nSurf, out.size(), tSurf, tRec, nthreads, tSeq, nLate);
 	if (out.empty()) return RTO_OK;
 	RtoTriangle* buf = (RtoTriangle*)std::malloc(out.size() * sizeof(RtoTriangle));
 	if (!buf) return rto_fail(RTO_ERR_ALLOC, "rto_host_dc_mesh: out of memory");

@@ -114,18 +114,46 @@ private:
 	Framebuffer m_frame;
 };
 
-inline std::vector<MCTriangle> rto_shim_marching_cubes(const OctreeNode* root, const VoxelGrid& grid) {
-	std::vector<MCTriangle> out;
-	if (!root) return out;
-	// flatten for librto (any order works for the mesh as long as child links are consistent: use BFS like setOctree)
-	std::vector<RtoGpuNode> flat; std::vector<const OctreeNode*> order; std::unordered_map<const OctreeNode*, int> index;
-	order.push_back(root); index[root] = 0;
+// flatten a pointer tree for librto (any order works for the meshers as long as child links are consistent: BFS like setOctree)
+inline std::vector<RtoGpuNode> rto_shim_flatten(const OctreeNode* root) {
+	std::vector<RtoGpuNode> flat; std::vector<const OctreeNode*> order;
+	if (!root) return flat;
+	order.push_back(root);
 	for (size_t i = 0; i < order.size(); i++) {
 		const OctreeNode* nd = order[i];
 		RtoGpuNode g{ nd->x, nd->y, nd->z, nd->size, nd->isLeaf ? 1 : 0, nd->isSolid ? 1 : 0, nd->isUniform ? 1 : 0, { -1, -1, -1, -1, -1, -1, -1, -1 } };
-		if (!nd->isLeaf) for (int c = 0; c < 8; c++) if (nd->children[c]) { index[nd->children[c]] = (int)order.size(); g.child[c] = (int)order.size(); order.push_back(nd->children[c]); }
+		if (!nd->isLeaf) for (int c = 0; c < 8; c++) if (nd->children[c]) { g.child[c] = (int)order.size(); order.push_back(nd->children[c]); }
 		flat.push_back(g);
 	}
+	return flat;
+}
+
+// renderOctree(root, grid, dcRenderer, camera, aspect, extraMargin) (main.cpp:95-208) for the Dual-Contouring renderer: the triangle
+// soup AdaptiveDualContouringRenderer::createTriangles emits leaf by leaf, in the same order, as the Triangles BVH takes
+// (main.cpp:1275 -> BVH).  viewProj16 (column-major proj * view, e.g. rto_host_view_proj(view, 45, aspect, 0.01, 5000)) culls like
+// renderOctree; nullptr visits every leaf.  The reference passes extraMargin 50.
+inline std::vector<Triangle> rto_shim_dual_contouring(const OctreeNode* root, const VoxelGrid& grid, const float* viewProj16 = nullptr, float extraMargin = 50.0f) {
+	std::vector<Triangle> out;
+	if (!root) return out;
+	std::vector<RtoGpuNode> flat = rto_shim_flatten(root);
+	RtoTriangle* tris = nullptr; size_t n = 0;
+	float gmin[3] = { grid.minX, grid.minY, grid.minZ };
+	if (rto_host_dc_mesh(reinterpret_cast<const uint8_t*>(grid.data.data()), grid.dimX, grid.dimY, grid.dimZ, gmin, grid.voxelSize, flat.data(), flat.size(),
+		viewProj16, extraMargin, &tris, &n) != RTO_OK) { std::fprintf(stderr, "[AdaptiveDualContouringRenderer] %s\n", rto_last_error()); return out; }
+	out.resize(n);
+	for (size_t i = 0; i < n; i++) {
+		out[i].v0 = rto_shim::vec3(tris[i].v0[0], tris[i].v0[1], tris[i].v0[2]);
+		out[i].v1 = rto_shim::vec3(tris[i].v1[0], tris[i].v1[1], tris[i].v1[2]);
+		out[i].v2 = rto_shim::vec3(tris[i].v2[0], tris[i].v2[1], tris[i].v2[2]);
+	}
+	rto_host_free(tris);
+	return out;
+}
+
+inline std::vector<MCTriangle> rto_shim_marching_cubes(const OctreeNode* root, const VoxelGrid& grid) {
+	std::vector<MCTriangle> out;
+	if (!root) return out;
+	std::vector<RtoGpuNode> flat = rto_shim_flatten(root);
 	RtoTriangle* tris = nullptr; size_t n = 0;
 	float gmin[3] = { grid.minX, grid.minY, grid.minZ };
 	if (rto_host_mc_mesh(reinterpret_cast<const uint8_t*>(grid.data.data()), grid.dimX, grid.dimY, grid.dimZ, gmin, grid.voxelSize, flat.data(), flat.size(), &tris, &n) != RTO_OK) return out;

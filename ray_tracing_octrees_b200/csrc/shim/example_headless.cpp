@@ -24,6 +24,8 @@ int main() {
 	tracer.ensureComputeInitialized();
 	tracer.setOctree(root, grid);
 	std::printf("octree nodes %zu, triangles %zu, bvh nodes %zu\n", tracer.flatNodes().size(), tris.size(), rto_host_bvh_num_nodes(bvh.host()));
+	std::vector<Triangle> dc = rto_shim_dual_contouring(root, grid);      // the other mesher of the application (main.cpp:1275)
+	std::printf("dual contouring triangles %zu\n", dc.size());
 	Camera cam(0.5235988f, 0.6981317f, 1.2f);
 	Framebuffer fb;
 	if (tracer.render(cam, 160, 120, 160.f / 120.f, 45.f, fb)) {

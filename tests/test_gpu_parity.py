@@ -329,6 +329,33 @@ def test_city_block_octree_and_mesh_vs_oracle(gpu, checker):
             _cmp_frames({k: fm[k][sl] for k in fm}, m_ref.render(rcam, 1, bias, y0, y0 + 2), "city mesh rows %d cam %d/%d" % (y0, theta, phi), allow_frac=1e-3)
 
 
+def test_dual_contouring_mesh_renders_like_the_oracle(gpu, checker, dt_grid_path):
+    """C4-shaped path at a size the oracle finishes in seconds: Dual-Contouring soups (rto_host_dc_mesh, bit-identical to the reference's
+    mesher: tests/test_dc_mesh.py) of a 192^3 city-block grid and of the DT grid through the BVH kernel with shadows, against the
+    oracle's BVH::query + Moller-Trumbore on the same triangles.  DC soups are harder on the tie rules than Marching-Cubes soups:
+    quads are split along a diagonal both triangles share and neighbouring cells emit coincident triangles."""
+    rto = gpu
+    W, H = 640, 360
+    for name, grid, radius in (("city", rto.city_block_grid(192, 777, 12), 0.9 * 192), ("dt", rto.VoxelGrid.load(dt_grid_path), 0.6 * 4250)):
+        nodes = rto.create_octree_from_voxel_grid(grid)
+        tris = rto.dual_contouring_mesh(grid, nodes)
+        sc = rto.Scene.bvh(tris)
+        m_ref = checker.mesh(tris); m_ref.build()
+        bias = 1e-3 * grid.voxel_size
+        for theta, phi in ((35, 40), (60, 190)):
+            cam, _ = rto.Camera.from_degrees(theta, phi, radius).consts(45.0, float(np.float32(W) / np.float32(H)), W, H)
+            rcam, _ = checker.camera(theta, phi, radius, width=W, height=H)
+            fm = sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, bias)
+            fx = sc.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS | rto.FLAG_NO_PRUNE, bias)
+            assert (fm["id"] >= 0).mean() > 0.05
+            for y0 in range(2, H, 45):
+                sl = slice(y0 * W, (y0 + 2) * W)
+                want = m_ref.render(rcam, 1, bias, y0, y0 + 2)
+                _cmp_frames({k: fx[k][sl] for k in fx}, want, "%s DC exact replay rows %d cam %d/%d" % (name, y0, theta, phi))
+                _cmp_frames({k: fm[k][sl] for k in fm}, want, "%s DC rows %d cam %d/%d" % (name, y0, theta, phi), allow_frac=1e-3)
+        m_ref.free()
+
+
 def test_deep_trees_stay_within_the_traversal_stack(gpu, monkeypatch):
     """The kernels keep a fixed number of postponed subtrees.  A SAH tree deeper than the builders' limit is replaced by a balanced
     median-split tree over the same triangles; forcing that fallback (RTO_BVH_MAX_DEPTH) must not change a single result."""

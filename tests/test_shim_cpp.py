@@ -22,6 +22,7 @@ def test_shim_compiles_and_host_part_runs(rto, tmp_path):
     out = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "octree nodes 6025, triangles 7768, bvh nodes 8191" in out.stdout      # same counts as the oracle on sphere-32
+    assert "dual contouring triangles 4113" in out.stdout                         # tests/golden/golden_dc.json
 
 
 @pytest.mark.gpu

@@ -93,6 +93,28 @@ def main():
         rep["C4 city 1024^3 MC mesh (DC mesher out of scope) BVH 4K primary+shadow (4 frames)"] = dict(
             tris=len(tris), octree_nodes=len(nodes), grid_octree_mc_s=t1 - t0, bvh_build_upload_s=t2 - t1, device_MB=sc.info()["device_bytes"] / 1e6,
             **timed(sc, cams, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3, 2160, 3840, reps=3))
+    if want("C4DC"):
+        # C4 as BASELINE.json names it: the Adaptive Dual Contouring mesh (rto_host_dc_mesh == the reference's createTriangles per leaf)
+        t0 = time.time()
+        g = rto.city_block_grid(1024, 4321, 64)
+        nodes = rto.create_octree_on_device(g)
+        t1 = time.time()
+        tris = rto.dual_contouring_mesh(g, nodes)
+        t2 = time.time()
+        cams = cams_orbit(35, 0.9 * 1024, 3840, 2160, 4)
+        if os.environ.get("RTO_C4DC_HOST_TREE", "1") == "1":
+            sc = rto.Scene.bvh(tris)
+            t3 = time.time()
+            rep["C4 city 1024^3 Dual-Contouring mesh BVH 4K primary+shadow (4 frames), reference-shaped tree + SAH"] = dict(
+                tris=len(tris), octree_nodes=len(nodes), grid_octree_s=t1 - t0, dc_mesh_s=t2 - t1, bvh_build_upload_s=t3 - t2, device_MB=sc.info()["device_bytes"] / 1e6,
+                **timed(sc, cams, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3, 2160, 3840, reps=3))
+            del sc
+        t3 = time.time()
+        sd = rto.Scene.bvh_device(tris)
+        t4 = time.time()
+        rep["C4 city 1024^3 Dual-Contouring mesh BVH 4K primary+shadow (4 frames), device-built LBVH"] = dict(
+            tris=len(tris), dc_mesh_s=t2 - t1, bvh_build_upload_s=t4 - t3, device_MB=sd.info()["device_bytes"] / 1e6,
+            **timed(sd, cams, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3, 2160, 3840, reps=3))
     for k, v in rep.items():
         print("%-90s %8.0f Mrays/s  %7.3f ms  hit %.2f" % (k, v["Mrays_s"], v["ms"], v["hit_fraction"]))
     json.dump(rep, open(args.out, "w"), indent=1)
