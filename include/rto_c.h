@@ -119,6 +119,11 @@ RTO_API int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ
 RTO_API int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
 	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
 	const float* viewProj16 /* may be NULL */, float extraMargin, RtoTriangle** trisOut, size_t* numTris);
+/* The same mesh by replaying the reference's cache protocol leaf by leaf (the cross-check of rto_host_dc_mesh's order-free
+ * formulation, and its way out if the fallback rounds did not settle). */
+RTO_API int rto_host_dc_mesh_replay(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
+	const float* viewProj16 /* may be NULL */, float extraMargin, RtoTriangle** trisOut, size_t* numTris);
 
 /* BVH::BVH(const std::vector<Triangle>&) (BVH.cpp:19-71): same tree (median split, longest axis, std::sort
  * by centroid, leaves <= 2 triangles).  The triangle array must outlive the handle (the reference keeps raw

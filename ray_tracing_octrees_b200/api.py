@@ -157,15 +157,16 @@ def marching_cubes_mesh(grid, nodes):
     return _take(ptr, n.value, np.float32, (n.value, 9))
 
 
-def dual_contouring_mesh(grid, nodes, view_proj=None, margin=50.0):
+def dual_contouring_mesh(grid, nodes, view_proj=None, margin=50.0, algo="default"):
     """-> (m, 9) float32: the Adaptive Dual Contouring triangle soup in the reference's emission order (renderOctree over
     AdaptiveDualContouringRenderer::createTriangles, main.cpp:95-208); view_proj (16 floats, see view_proj()) culls like renderOctree."""
     nodes = np.ascontiguousarray(nodes, np.int32)
     vp = None if view_proj is None else np.ascontiguousarray(view_proj, np.float32).ravel()
     ptr = C.c_void_p()
     n = C.c_size_t()
-    check(lib().rto_host_dc_mesh(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min), grid.voxel_size,
-                                 _p(nodes), len(nodes), _p(vp), float(margin), C.byref(ptr), C.byref(n)))
+    fn = {"default": lib().rto_host_dc_mesh, "replay": lib().rto_host_dc_mesh_replay}[algo]
+    check(fn(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min), grid.voxel_size,
+             _p(nodes), len(nodes), _p(vp), float(margin), C.byref(ptr), C.byref(n)))
     return _take(ptr, n.value, np.float32, (n.value, 9))
 
 

@@ -20,12 +20,14 @@ def build(rto, case):
     return g, rto.create_octree_from_voxel_grid(g)
 
 
+@pytest.mark.parametrize("algo", ["default", "replay"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_dc_mesh_equals_the_golden_checksums(rto, name):
+def test_dc_mesh_equals_the_golden_checksums(rto, name, algo):
+    """Both host formulations (order-free first-toucher minima; replay of the cache protocol in visit order) against the reference's output."""
     case, want = CASES[name], META[name]
     g, nodes = build(rto, case)
     vp = None if want["view_proj"] is None else np.array(want["view_proj"], np.float32)
-    got = rto.dual_contouring_mesh(g, nodes, vp, case.get("margin", 50.0))
+    got = rto.dual_contouring_mesh(g, nodes, vp, case.get("margin", 50.0), algo=algo)
     assert len(nodes) == want["nodes"]
     assert len(got) == want["tris"]
     assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want["sha"]
@@ -55,6 +57,17 @@ def test_dc_mesh_refuses_octrees_beyond_the_reference_key_range(rto):
     g = rto.VoxelGrid((1, 1, 1), (0, 0, 0), 1.0, np.zeros(1, np.uint8))
     with pytest.raises(rto.RtoError):
         rto.dual_contouring_mesh(g, nodes)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_dc_formulations_agree_on_random_grids(rto, seed):
+    """Noise grids make every boundary leaf a fallback candidate and chain the fallback rounds of the order-free formulation."""
+    rng = np.random.default_rng(100 + seed)
+    dims = tuple(int(x) for x in rng.integers(2, 48, 3))
+    p = [0.01, 0.05, 0.2, 0.5, 0.7, 0.9, 0.99, 0.35][seed]
+    g = rto.VoxelGrid(dims, (1.0, -2.0, 0.5), 0.25, (rng.random(dims[0] * dims[1] * dims[2]) < p).astype(np.uint8))
+    nodes = rto.create_octree_from_voxel_grid(g)
+    assert_bit_equal(rto.dual_contouring_mesh(g, nodes), rto.dual_contouring_mesh(g, nodes, algo="replay"), "seed %d" % seed)
 
 
 def test_dc_mesh_of_nothing(rto):
