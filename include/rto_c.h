@@ -203,6 +203,14 @@ RTO_API int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int di
 RTO_API int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize,
 	int dims[3], float minAndVoxel[4], uint8_t** voxelsOut);
 
+/* The Adaptive Dual Contouring mesh extracted on the GPU: same arguments and same result as rto_host_dc_mesh (same triangles, same
+ * order, bit for bit).  The reference's visit-order-dependent vertex cache is resolved without a sequential pass: every cache key
+ * takes the vertex of its first toucher, found as an atomic minimum over (Morton position of the visiting leaf, kind of touch),
+ * and the boundary fallback (createFaceTriangles) is settled in rounds (csrc/rto_dc.cu).  malloc'ed; rto_host_free. */
+RTO_API int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
+	const float* viewProj16 /* may be NULL */, float extraMargin, RtoTriangle** trisOut, size_t* numTris);
+
 /* rto_host_frustum_cull on the GPU (test, prefix sum, compaction + remap); same arrays. */
 RTO_API int rto_device_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize,
 	const float viewProj16[16], float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut /* may be NULL */);

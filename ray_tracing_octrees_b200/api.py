@@ -164,7 +164,7 @@ def dual_contouring_mesh(grid, nodes, view_proj=None, margin=50.0, algo="default
     vp = None if view_proj is None else np.ascontiguousarray(view_proj, np.float32).ravel()
     ptr = C.c_void_p()
     n = C.c_size_t()
-    fn = {"default": lib().rto_host_dc_mesh, "replay": lib().rto_host_dc_mesh_replay}[algo]
+    fn = {"default": lib().rto_host_dc_mesh, "replay": lib().rto_host_dc_mesh_replay, "device": lib().rto_device_dc_mesh}[algo]
     check(fn(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min), grid.voxel_size,
              _p(nodes), len(nodes), _p(vp), float(margin), C.byref(ptr), C.byref(n)))
     return _take(ptr, n.value, np.float32, (n.value, 9))

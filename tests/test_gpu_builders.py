@@ -151,3 +151,38 @@ def test_device_bvh_edge_cases(rto, grids):
     with pytest.raises(rto.RtoError) as err:
         dev.stats(cam, rto.MODE_BVH, 0, 0.0)
     assert err.value.code == 6
+
+
+# ---- Dual Contouring mesh on the GPU (rto_dc.cu) -------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", NAMES)
+def test_device_dc_mesh_equals_host(rto, grids, name):
+    """Same triangles in the same order as rto_host_dc_mesh (which tests/test_dc_mesh.py pins to the reference's own mesher)."""
+    g = grids[name]
+    nodes = rto.create_octree_from_voxel_grid(g)
+    assert_bit_equal(rto.dual_contouring_mesh(g, nodes, algo="device"), rto.dual_contouring_mesh(g, nodes), "DC triangles " + name)
+
+
+def test_device_dc_mesh_equals_the_golden_checksums(rto, grids):
+    """Every case of tests/golden/golden_dc.json (generated from the reference's AdaptiveDualContouringRenderer.cpp), culled walks included."""
+    import hashlib, json, os
+    from dc_cases import CASES, GOLDEN, make_grid
+    meta = json.load(open(os.path.join(GOLDEN, "golden_dc.json")))
+    for name in sorted(CASES):
+        case, want = CASES[name], meta[name]
+        dims, gmin, voxel, data = make_grid(case)
+        g = rto.VoxelGrid(dims, gmin, voxel, data)
+        nodes = rto.create_octree_from_voxel_grid(g)
+        vp = None if want["view_proj"] is None else np.array(want["view_proj"], np.float32)
+        got = rto.dual_contouring_mesh(g, nodes, vp, case.get("margin", 50.0), algo="device")
+        assert len(got) == want["tris"], name
+        assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want["sha"], name
+
+
+def test_device_dc_mesh_fallback_rounds(rto, grids):
+    """Noise grids: most boundary leaves fall back and their cached centres change what later leaves see (several rounds)."""
+    rng = np.random.default_rng(5)
+    for p in (0.05, 0.3, 0.6, 0.95):
+        d = tuple(int(x) for x in rng.integers(5, 40, 3))
+        g = rto.VoxelGrid(d, (0.5, -1.0, 2.0), 0.3, (rng.random(d[0] * d[1] * d[2]) < p).astype(np.uint8))
+        nodes = rto.create_octree_from_voxel_grid(g)
+        assert_bit_equal(rto.dual_contouring_mesh(g, nodes, algo="device"), rto.dual_contouring_mesh(g, nodes, algo="replay"), "noise p=%g" % p)

@@ -101,6 +101,11 @@ def main():
         t1 = time.time()
         tris = rto.dual_contouring_mesh(g, nodes)
         t2 = time.time()
+        tdev = rto.dual_contouring_mesh(g, nodes, algo="device")
+        t2d = time.time()
+        rep["C4 Dual-Contouring mesh extraction, host (all threads) vs device (incl. grid + node upload and triangle read-back)"] = dict(
+            ms=0.0, Mrays_s=0.0, hit_fraction=0.0, host_s=t2 - t1, device_s=t2d - t2, identical=bool(tris.shape == tdev.shape and np.array_equal(tris.view(np.uint32), tdev.view(np.uint32))))
+        del tdev
         cams = cams_orbit(35, 0.9 * 1024, 3840, 2160, 4)
         if os.environ.get("RTO_C4DC_HOST_TREE", "1") == "1":
             sc = rto.Scene.bvh(tris)
