@@ -227,6 +227,10 @@ RTO_API int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTris,
  * triangle soup rto_host_mc_mesh / rto_device_mc_mesh return for the same grid. */
 RTO_API int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ,
 	const float gridMin[3], float voxelSize, RtoScene** out);
+/* The same with the Adaptive Dual Contouring mesher in the middle (the pipeline configuration C4 names): grid -> octree -> DC mesh
+ * (rto_device_dc_mesh's triangles and order; viewProj16 / extraMargin as there) -> linear BVH, nothing leaves the device. */
+RTO_API int rto_scene_create_bvh_from_grid_dc(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, const float* viewProj16 /* may be NULL */, float extraMargin, RtoScene** out);
 
 /* Diagnostic: the compact device layout of an octree scene (desc: numNodes + 8 words, up: (numNodes + 7) / 8 + 1 words,
  * inner: 4 words per internal node); any pointer may be NULL.  Lets tests compare the two construction routes. */

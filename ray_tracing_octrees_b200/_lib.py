@@ -65,6 +65,7 @@ SIGNATURES = {
     "rto_device_mc_mesh": (_i, [_vp, _i, _i, _i, _vp, _f, _pp, C.POINTER(_sz)]),
     "rto_scene_create_bvh_device": (_i, [_vp, _sz, _pp]),
     "rto_scene_create_bvh_from_grid": (_i, [_vp, _i, _i, _i, _vp, _f, _pp]),
+    "rto_scene_create_bvh_from_grid_dc": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _f, _pp]),
     "rto_scene_octree_layout_read": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_sz)]),
     "rto_scene_destroy": (None, [_vp]),
     "rto_scene_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -278,6 +278,15 @@ class Scene:
                                                    float(grid.voxel_size), C.byref(h)))
         return Scene(h)
 
+    @staticmethod
+    def bvh_from_grid_dc(grid, view_proj=None, margin=50.0):
+        """Voxel grid -> octree -> Dual-Contouring mesh -> linear BVH, all on the GPU (rto_scene_create_bvh_from_grid_dc)."""
+        vp = None if view_proj is None else np.ascontiguousarray(view_proj, np.float32).ravel()
+        h = C.c_void_p()
+        check(lib().rto_scene_create_bvh_from_grid_dc(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min),
+                                                      float(grid.voxel_size), _p(vp), float(margin), C.byref(h)))
+        return Scene(h)
+
     def skip_distance(self, view16, cam_pos, aspect, last=0.0):
         """VolumeRaycastRenderer's skip-distance estimate (VolumeRaycastRenderer.cpp:1598-1664) -> (distance, 49 probe results)."""
         v = np.ascontiguousarray(view16, np.float32).ravel()

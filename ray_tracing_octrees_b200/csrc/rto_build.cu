@@ -852,6 +852,34 @@ extern "C" int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, i
 	return RTO_OK;
 }
 
+// The pipeline configuration C4 names, entirely on the device: grid -> octree -> Adaptive Dual Contouring mesh (rto_dc.cu: the reference's
+// triangles in the reference's order) -> linear BVH.  Hit ids index the soup rto_device_dc_mesh / rto_host_dc_mesh return for the
+// same arguments.
+extern "C" int rto_scene_create_bvh_from_grid_dc(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const float* viewProj16, float extraMargin, RtoScene** out) {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid_dc: null output");
+	*out = nullptr;
+	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid_dc: empty grid");
+	RtoScene* s = nullptr;
+	int rc = rto_scene_new(&s); if (rc) return rc;
+	s->kind = RTO_MODE_BVH;
+	{
+		OctBuild B;
+		RtoTriangle* dTris = nullptr; size_t numTris = 0;
+		rc = oct_pyramid(B, voxels, false, dimX, dimY, dimZ, s->stream);
+		if (!rc && (1 << B.rootLevel) > 1024) rc = rto_fail(RTO_ERR_UNSUPPORTED, "rto_scene_create_bvh_from_grid_dc: grid larger than 1024 voxels per axis (the reference's cell keys alias there)");
+		if (!rc) rc = oct_emit(B, false, true, s->stream);
+		if (!rc) rc = rto_dc_extract_device(B.dVoxels, dimX, dimY, dimZ, gridMin, voxelSize, B.nodes, B.numNodes, viewProj16, extraMargin, s->stream, &dTris, &numTris, nullptr, nullptr);
+		if (!rc) rc = lbvh_build(s, dTris, numTris);
+		if (!rc) { cudaError_t e = cudaStreamSynchronize(s->stream); if (e != cudaSuccess) rc = rto_fail(RTO_ERR_CUDA, "scene build on the device failed: %s", cudaGetErrorString(e)); }
+		else cudaStreamSynchronize(s->stream);
+		if (dTris) cudaFree(dTris);
+	}
+	if (rc) { rto_scene_destroy(s); return rc; }
+	*out = s;
+	return RTO_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // CSV voxeliser, fill on the device: the files are parsed on the host (rto_csv_load), one warp rasterises one

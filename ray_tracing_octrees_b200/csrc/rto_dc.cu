@@ -163,31 +163,15 @@ inline unsigned blocksFor(size_t n, int threads) { return (unsigned)((n + thread
 
 } // namespace
 
-extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) {
-	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_device_dc_mesh: null output");
-	*trisOut = nullptr; *numTris = 0;
-	if (numNodes == 0) return RTO_OK;
-	if (!voxels || !nodes || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_device_dc_mesh: bad input");
-	if (nodes[0].size > 1024) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_device_dc_mesh: octree larger than 1024 voxels per axis (the reference's cell keys alias there)");
-	if (numNodes >= ((size_t)1 << 31)) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_device_dc_mesh: too many nodes");
-	int rc = rto_require_device(); if (rc) return rc;
-	const bool verbose = std::getenv("RTO_DC_VERBOSE") != nullptr;
-	cudaStream_t st = nullptr;
-	DC_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-	struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } guard{ st };
+// The mesh of a grid and node array that already live on the device; *dTrisOut is cudaMalloc'ed and belongs to the caller.
+int rto_dc_extract_device(const uint8_t* dVox, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const RtoGpuNode* dNodes, size_t numNodes, const float* viewProj16, float extraMargin, cudaStream_t st,
+	RtoTriangle** dTrisOut, size_t* numTris, size_t* numLeavesOut, int* roundsOut) {
+	*dTrisOut = nullptr; *numTris = 0;
+	if (numLeavesOut) *numLeavesOut = 0;
+	if (roundsOut) *roundsOut = 0;
+	if (numNodes >= ((size_t)1 << 31)) return rto_fail(RTO_ERR_UNSUPPORTED, "Dual Contouring on the device: too many nodes");
 	Pool pool;
-	cudaEvent_t ev0, ev1;
-	DC_TRY(cudaEventCreate(&ev0)); DC_TRY(cudaEventCreate(&ev1));
-	struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evGuard{ ev0, ev1 };
-
-	// uploads: the grid and the node array
-	const size_t nvox = (size_t)dimX * dimY * dimZ;
-	uint8_t* dVox = nullptr; RtoGpuNode* dNodes = nullptr;
-	DC_TRY(pool.alloc(&dVox, nvox)); DC_TRY(pool.alloc(&dNodes, numNodes));
-	DC_TRY(cudaMemcpyAsync(dVox, voxels, nvox, cudaMemcpyHostToDevice, st));
-	DC_TRY(cudaMemcpyAsync(dNodes, nodes, numNodes * sizeof(RtoGpuNode), cudaMemcpyHostToDevice, st));
-	DC_TRY(cudaEventRecord(ev0, st));
 	const Grid g{ dVox, dimX, dimY, dimZ, gridMin[0], gridMin[1], gridMin[2], voxelSize };
 	WalkArgs W; std::memset(&W, 0, sizeof(W));
 	W.cull = viewProj16 ? 1 : 0;
@@ -209,6 +193,7 @@ extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 	DC_TRY(cudaStreamSynchronize(st));
 	const size_t numRecs = (size_t)numRecsI;
 	pool.free_now(tmp); pool.free_now(flag);
+	if (numLeavesOut) *numLeavesOut = numRecs;
 	if (numRecs == 0) return RTO_OK;
 	uint32_t* keys = nullptr; uint32_t* keysSorted = nullptr; int32_t* recNode = nullptr;
 	DC_TRY(pool.alloc(&keys, numRecs)); DC_TRY(pool.alloc(&keysSorted, numRecs)); DC_TRY(pool.alloc(&recNode, numRecs));
@@ -237,7 +222,7 @@ extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 	// 3. rounds
 	int rounds = 0;
 	for (;; rounds++) {
-		if (rounds > 64) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_device_dc_mesh: fallback rounds did not settle (use rto_host_dc_mesh_replay)");
+		if (rounds > 64) return rto_fail(RTO_ERR_UNSUPPORTED, "Dual Contouring on the device: fallback rounds did not settle (use rto_host_dc_mesh_replay)");
 		DC_TRY(cudaMemcpyAsync(first, firstAB, numNodes * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
 		if (rounds > 0) k_dc_touch_fallback<<<blocksFor(numRecs, 128), 128, 0, st>>>(g, dNodes, recNode, numRecs, fallback, first);
 		k_dc_vertices<<<blocksFor(numNodes, 64), 64, 0, st>>>(g, dNodes, numNodes, first, firstPrev, val);
@@ -250,6 +235,7 @@ extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 		if (!changed) break;
 		uint8_t* t = fallback; fallback = fallbackNew; fallbackNew = t;
 	}
+	if (roundsOut) *roundsOut = rounds;
 
 	// 4. counts, scan, emission
 	unsigned long long* counts = nullptr; unsigned long long* offsets = nullptr;
@@ -268,9 +254,41 @@ extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 	pool.free_now(tmp); pool.free_now(firstAB); pool.free_now(first); pool.free_now(firstPrev);
 	if (total == 0) return RTO_OK;
 	RtoTriangle* dTris = nullptr;
-	DC_TRY(pool.alloc(&dTris, total));
+	DC_TRY(cudaMalloc((void**)&dTris, total * sizeof(RtoTriangle)));
 	k_dc_emit<<<blocksFor(numRecs, 128), 128, 0, st>>>(g, dNodes, recNode, numRecs, edgeMask, tgt, val, fallback, offsets, counts, dTris);
-	DC_TRY(cudaGetLastError());
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) { cudaFree(dTris); return rto_fail(RTO_ERR_CUDA, "Dual Contouring on the device: %s", cudaGetErrorString(e)); }
+	*dTrisOut = dTris; *numTris = total;
+	return RTO_OK;
+}
+
+extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) {
+	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_device_dc_mesh: null output");
+	*trisOut = nullptr; *numTris = 0;
+	if (numNodes == 0) return RTO_OK;
+	if (!voxels || !nodes || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_device_dc_mesh: bad input");
+	if (nodes[0].size > 1024) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_device_dc_mesh: octree larger than 1024 voxels per axis (the reference's cell keys alias there)");
+	int rc = rto_require_device(); if (rc) return rc;
+	const bool verbose = std::getenv("RTO_DC_VERBOSE") != nullptr;
+	cudaStream_t st = nullptr;
+	DC_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } guard{ st };
+	Pool pool;
+	cudaEvent_t ev0, ev1;
+	DC_TRY(cudaEventCreate(&ev0)); DC_TRY(cudaEventCreate(&ev1));
+	struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evGuard{ ev0, ev1 };
+	const size_t nvox = (size_t)dimX * dimY * dimZ;
+	uint8_t* dVox = nullptr; RtoGpuNode* dNodes = nullptr;
+	DC_TRY(pool.alloc(&dVox, nvox)); DC_TRY(pool.alloc(&dNodes, numNodes));
+	DC_TRY(cudaMemcpyAsync(dVox, voxels, nvox, cudaMemcpyHostToDevice, st));
+	DC_TRY(cudaMemcpyAsync(dNodes, nodes, numNodes * sizeof(RtoGpuNode), cudaMemcpyHostToDevice, st));
+	DC_TRY(cudaEventRecord(ev0, st));
+	RtoTriangle* dTris = nullptr; size_t total = 0, leaves = 0; int rounds = 0;
+	rc = rto_dc_extract_device(dVox, dimX, dimY, dimZ, gridMin, voxelSize, dNodes, numNodes, viewProj16, extraMargin, st, &dTris, &total, &leaves, &rounds);
+	if (rc || total == 0) return rc;
+	pool.blocks.push_back(dTris);
 	DC_TRY(cudaEventRecord(ev1, st));
 	RtoTriangle* host = (RtoTriangle*)std::malloc(total * sizeof(RtoTriangle));
 	if (!host) return rto_fail(RTO_ERR_ALLOC, "rto_device_dc_mesh: out of host memory");
@@ -279,7 +297,7 @@ extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 	if (e != cudaSuccess) { std::free(host); return rto_fail(RTO_ERR_CUDA, "rto_device_dc_mesh: %s", cudaGetErrorString(e)); }
 	if (verbose) {
 		float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
-		std::fprintf(stderr, "rto_device_dc_mesh: %zu leaves with surface, %zu triangles, %d extra rounds, %.1f ms on the device between upload and read-back\n", numRecs, total, rounds, ms);
+		std::fprintf(stderr, "rto_device_dc_mesh: %zu leaves with surface, %zu triangles, %d extra rounds, %.1f ms on the device between upload and read-back\n", leaves, total, rounds, ms);
 	}
 	*trisOut = host; *numTris = total;
 	return RTO_OK;

@@ -33,3 +33,9 @@ int rto_scene_new(RtoScene** out);                             // stream, events
 int rto_scene_alloc(RtoScene* s, void** p, size_t bytes);      // device memory owned by the scene
 int rto_scene_adopt(RtoScene* s, void* p, size_t bytes);       // take ownership of an existing cudaMalloc'ed block
 int rto_scene_scratch(RtoScene* s, int slot, size_t bytes, void** p);
+
+// Dual Contouring on the device (rto_dc.cu) for a grid and a node array that already live there; *dTrisOut is cudaMalloc'ed and
+// belongs to the caller.  Synchronises the stream.
+int rto_dc_extract_device(const uint8_t* dVox, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const RtoGpuNode* dNodes, size_t numNodes, const float* viewProj16, float extraMargin, cudaStream_t st,
+	RtoTriangle** dTrisOut, size_t* numTris, size_t* numLeavesOut, int* roundsOut);

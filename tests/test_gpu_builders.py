@@ -186,3 +186,20 @@ def test_device_dc_mesh_fallback_rounds(rto, grids):
         g = rto.VoxelGrid(d, (0.5, -1.0, 2.0), 0.3, (rng.random(d[0] * d[1] * d[2]) < p).astype(np.uint8))
         nodes = rto.create_octree_from_voxel_grid(g)
         assert_bit_equal(rto.dual_contouring_mesh(g, nodes, algo="device"), rto.dual_contouring_mesh(g, nodes, algo="replay"), "noise p=%g" % p)
+
+
+@pytest.mark.parametrize("name", ["sphere32", "city128", "dt"])
+def test_scene_from_grid_dc_equals_scene_from_the_dc_soup(rto, grids, name):
+    """grid -> octree -> DC mesh -> linear BVH without leaving the device renders exactly like the linear BVH over rto_host_dc_mesh's soup."""
+    g = grids[name]
+    nodes = rto.create_octree_from_voxel_grid(g)
+    tris = rto.dual_contouring_mesh(g, nodes)
+    a, b = rto.Scene.bvh_from_grid_dc(g), rto.Scene.bvh_device(tris)
+    assert a.info()["prims"] == b.info()["prims"] == len(tris)
+    ext = float(max(g.dims)) * g.voxel_size
+    centre = tuple(float(g.min[i]) + 0.5 * g.dims[i] * g.voxel_size for i in range(3))
+    cam, _ = rto.Camera.from_degrees(35, 40, 1.1 * ext, centre).consts(45.0, 1.5, 384, 256)
+    fa, fb = a.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3 * g.voxel_size), b.render(cam, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3 * g.voxel_size)
+    assert (fa["id"] >= 0).any()
+    for k in ("id", "t", "rgba"):
+        assert_bit_equal(fa[k], fb[k], "%s %s" % (name, k))

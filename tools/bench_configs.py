@@ -107,6 +107,13 @@ def main():
             ms=0.0, Mrays_s=0.0, hit_fraction=0.0, host_s=t2 - t1, device_s=t2d - t2, identical=bool(tris.shape == tdev.shape and np.array_equal(tris.view(np.uint32), tdev.view(np.uint32))))
         del tdev
         cams = cams_orbit(35, 0.9 * 1024, 3840, 2160, 4)
+        t5 = time.time()
+        sg = rto.Scene.bvh_from_grid_dc(g)
+        t6 = time.time()
+        rep["C4 city 1024^3: grid -> octree -> Dual-Contouring mesh -> linear BVH entirely on the device, 4K primary+shadow (4 frames)"] = dict(
+            tris=sg.info()["prims"], scene_from_grid_s=t6 - t5, device_MB=sg.info()["device_bytes"] / 1e6,
+            **timed(sg, cams, rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3, 2160, 3840, reps=3))
+        del sg
         if os.environ.get("RTO_C4DC_HOST_TREE", "1") == "1":
             sc = rto.Scene.bvh(tris)
             t3 = time.time()
