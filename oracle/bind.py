@@ -68,8 +68,8 @@ class Backend:
             "cull_nodes": (sz, [vp, f32, f32, f32, vp, f32, f32, i32, i32, vp]),
             "skip_distance": (f32, [vp, f32, f32, f32, vp, f32, f32, vp, vp, vp]),
         }
-        optional = {"dc_mesh_from_octree": (vp, [vp, vp, f32])}
-        for name, (res, args) in list(sig.items()) + [kv for kv in optional.items() if hasattr(L, prefix + kv[0])]:
+        sig["dc_mesh_from_octree"] = (vp, [vp, vp, f32])
+        for name, (res, args) in sig.items():
             fn = getattr(L, prefix + name)
             fn.restype, fn.argtypes = res, args
             setattr(self, name, fn)

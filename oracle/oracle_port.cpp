@@ -5,7 +5,7 @@
 // function cites the reference lines it follows.  Parity status: PINNED -- tests/test_oracle_pinning.py
 // compares this port with oracle/_ref/libref.so (the reference's own translation units compiled in
 // place) wherever the reference has real code (octree build, BFS flatten, octreeRaySkip, localMC mesh,
-// BVH build/query, Camera) and against the golden vectors under tests/golden/ generated from it.
+// the Dual-Contouring mesh, BVH build/query, Camera) and against the golden vectors under tests/golden/ generated from it.
 // For the pieces the reference does not have (Moller-Trumbore closest hit, shadow rays, GLSL traversal
 // on a CPU) the written-down rules of SURVEY.md section 8c are the specification; both this port and
 // oracle/ref_harness.cpp (which uses real glm types) implement them and must agree bit for bit.
@@ -635,10 +635,334 @@ void orc_octree_rayskip(void* h, const float* o3, const float* d3, size_t n, flo
 	}
 }
 
+// ---- Adaptive Dual Contouring: renderOctree (main.cpp:95-208) over AdaptiveDualContouringRenderer::createTriangles -----------------
+// Literal, sequential restatement of AdaptiveDualContouringRenderer.cpp with the reference's two maps: g_octreeMap (every node under
+// x << 20 | y << 10 | z in buildOctreeRec's insertion order, OctreeVoxel.cpp:551-553, 712-713: a child 0 overwrites its parent) and
+// dualVertexCache (first writer wins).  The edge-intersection cache holds pure values and is left out.
+struct DcPort {
+	const Grid& g;
+	std::unordered_map<long long, const ONode*> octreeMap;
+	std::unordered_map<long long, V3> dualVertexCache;
+	struct Hermite { V3 position, normal; };
+	explicit DcPort(const Grid& grid) : g(grid) {}
+	static long long key(int x, int y, int z) { return ((long long)x << 20) | ((long long)y << 10) | (long long)z; }
+	void fillMap(const ONode* n) { if (!n) return; octreeMap[key(n->x, n->y, n->z)] = n; for (auto* c : n->child) fillMap(c); }
+	bool filled(int x, int y, int z) const { return g.data[(size_t)x + (size_t)y * g.dx + (size_t)z * ((size_t)g.dx * g.dy)] == 1; }
+	bool inb(int x, int y, int z) const { return !(x < 0 || y < 0 || z < 0 || x >= g.dx || y >= g.dy || z >= g.dz); }
+	V3 gridToWorld(int x, int y, int z) const { return v3(g.minX + x * g.voxel, g.minY + y * g.voxel, g.minZ + z * g.voxel); }     // :1359-1365
+	static V3 clampv(V3 x, V3 lo, V3 hi) { return v3(fmin2(fmax2(x.x, lo.x), hi.x), fmin2(fmax2(x.y, lo.y), hi.y), fmin2(fmax2(x.z, lo.z), hi.z)); }
+	static V3 mixv(V3 x, V3 y, float a) { return x * (1.0f - a) + y * a; }                                                          // func_common.inl:104-112
+
+	Hermite calculateIntersection(int x1, int y1, int z1, int x2, int y2, int z2) const {                                          // :1236-1357
+		bool isFilled1 = filled(x1, y1, z1), isFilled2 = filled(x2, y2, z2);
+		float v1 = isFilled1 ? -1.0f : 1.0f, v2 = isFilled2 ? -1.0f : 1.0f;
+		V3 p1 = gridToWorld(x1, y1, z1), p2 = gridToWorld(x2, y2, z2);
+		float t = v1 / (v1 - v2);
+		t = fmin2(fmax2(t, 0.0f), 1.0f);
+		V3 position = p1 + t * (p2 - p1);
+		int dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;                                     // always one unit step along one axis here
+		auto getScalar = [&](int x, int y, int z) -> float { if (!inb(x, y, z)) return 1.0f; return filled(x, y, z) ? -1.0f : 1.0f; };
+		V3 normal = v3((float)dx, (float)dy, (float)dz);
+		if (dx != 0) normal = v3(0.0f, getScalar(x1, y1 + 1, z1) - getScalar(x1, y1 - 1, z1), getScalar(x1, y1, z1 + 1) - getScalar(x1, y1, z1 - 1));
+		else if (dy != 0) normal = v3(getScalar(x1 + 1, y1, z1) - getScalar(x1 - 1, y1, z1), 0.0f, getScalar(x1, y1, z1 + 1) - getScalar(x1, y1, z1 - 1));
+		else normal = v3(getScalar(x1 + 1, y1, z1) - getScalar(x1 - 1, y1, z1), getScalar(x1, y1 + 1, z1) - getScalar(x1, y1 - 1, z1), 0.0f);
+		if (dot(normal, normal) < 1e-10) normal = v3((float)dx, (float)dy, (float)dz);
+		else normal = normalize(normal);
+		float dotProduct = normal.x * dx + normal.y * dy + normal.z * dz;
+		if ((dotProduct > 0) == isFilled2) normal = -normal;
+		return Hermite{ position, normal };
+	}
+	std::vector<Hermite> gatherHermiteData(int x0, int y0, int z0, int size) const {                                              // :1090-1144
+		int maxX = std::min(x0 + size, g.dx - 1), maxY = std::min(y0 + size, g.dy - 1), maxZ = std::min(z0 + size, g.dz - 1);
+		int minX = std::max(x0, 0), minY = std::max(y0, 0), minZ = std::max(z0, 0);
+		int stride = (size > 8) ? 2 : 1;
+		if (size <= 4) stride = 1;
+		std::vector<Hermite> points;
+		for (int z = minZ; z <= maxZ; z += stride) for (int y = minY; y <= maxY; y += stride) for (int x = minX; x <= maxX; x += stride) {
+			bool currentFilled = filled(x, y, z);
+			const int dirs[3][3] = { {1, 0, 0}, {0, 1, 0}, {0, 0, 1} };
+			for (int d = 0; d < 3; d++) {
+				int nx = x + dirs[d][0], ny = y + dirs[d][1], nz = z + dirs[d][2];
+				if (!inb(nx, ny, nz)) continue;
+				if (currentFilled != filled(nx, ny, nz)) points.push_back(calculateIntersection(x, y, z, nx, ny, nz));
+			}
+		}
+		return points;
+	}
+	struct Qef {                                                                                                                   // :46-160
+		float ata[3][3] = { {0, 0, 0}, {0, 0, 0}, {0, 0, 0} }; V3 atb = v3(0, 0, 0), pointSum = v3(0, 0, 0); int numPoints = 0;
+		void addPoint(V3 point, V3 normalIn) {
+			V3 n = normalize(normalIn);
+			const float c[3] = { n.x, n.y, n.z };
+			for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) ata[i][j] += c[i] * c[j];
+			float d = -dot(n, point);
+			atb.x += n.x * d; atb.y += n.y * d; atb.z += n.z * d;
+			pointSum = pointSum + point; numPoints++;
+		}
+		V3 solve(V3 cellCenter, float cellSize) const {
+			V3 masspoint = (numPoints > 0) ? pointSum / (float)numPoints : cellCenter;
+			if (numPoints <= 2) return masspoint;
+			float m[3][3];
+			for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[i][j] = ata[i][j];
+			m[0][0] += 0.3f; m[1][1] += 0.3f; m[2][2] += 0.3f;
+			auto det3 = [&]() { return m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) - m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2]) + m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]); };   // func_matrix.inl:211-220
+			bool invertible = true;
+			float inv[3][3];
+			if (std::abs(det3()) < 1e-10) invertible = false;
+			else {
+				float ood = 1.0f / det3();                                                                                         // func_matrix.inl:269-291
+				inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * ood; inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * ood; inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * ood;
+				inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * ood; inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * ood; inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * ood;
+				inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * ood; inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * ood; inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * ood;
+				for (int i = 0; i < 3 && invertible; i++) for (int j = 0; j < 3 && invertible; j++)
+					if (std::isnan(inv[i][j]) || std::isinf(inv[i][j]) || std::abs(inv[i][j]) > 1e6) invertible = false;
+			}
+			if (invertible) {
+				V3 solution = v3(inv[0][0] * atb.x + inv[1][0] * atb.y + inv[2][0] * atb.z, inv[0][1] * atb.x + inv[1][1] * atb.y + inv[2][1] * atb.z, inv[0][2] * atb.x + inv[1][2] * atb.y + inv[2][2] * atb.z);
+				solution = masspoint + 0.7f * (solution - masspoint);
+				if (!std::isnan(solution.x) && !std::isnan(solution.y) && !std::isnan(solution.z)) {
+					V3 dl = masspoint - solution;
+					if (dot(dl, dl) < cellSize * cellSize) return mixv(solution, masspoint, 0.2f);
+				}
+			}
+			return masspoint;
+		}
+	};
+	V3 generateDualVertex(const std::vector<Hermite>& hermiteData, V3 cellCenter, float cellSize) const {                          // :1146-1234
+		if (hermiteData.empty()) return cellCenter;
+		V3 halfSize = v3(cellSize * 0.5f, cellSize * 0.5f, cellSize * 0.5f);
+		V3 minBound = cellCenter - halfSize, maxBound = cellCenter + halfSize;
+		float inset = cellSize * 0.001f;
+		minBound = minBound + v3(inset, inset, inset); maxBound = maxBound - v3(inset, inset, inset);
+		V3 massPoint = v3(0, 0, 0);
+		for (const auto& hp : hermiteData) massPoint = massPoint + hp.position;
+		massPoint = massPoint / (float)hermiteData.size();
+		V3 avgNormal = v3(0, 0, 0);
+		for (const auto& hp : hermiteData) avgNormal = avgNormal + hp.normal;
+		if (std::sqrt(dot(avgNormal, avgNormal)) > 0.0001f) {
+			avgNormal = normalize(avgNormal);
+			V3 a = v3(std::fabs(avgNormal.x), std::fabs(avgNormal.y), std::fabs(avgNormal.z));
+			float maxComp = fmax2(fmax2(a.x, a.y), a.z);
+			if (maxComp > 0.85f) {
+				if (a.x == maxComp) avgNormal = v3(avgNormal.x > 0 ? 1.0f : -1.0f, 0, 0);
+				else if (a.y == maxComp) avgNormal = v3(0, avgNormal.y > 0 ? 1.0f : -1.0f, 0);
+				else avgNormal = v3(0, 0, avgNormal.z > 0 ? 1.0f : -1.0f);
+				V3 planePoint = v3(0, 0, 0); int planePointCount = 0;
+				for (const auto& hp : hermiteData) if (dot(normalize(hp.normal), avgNormal) > 0.7f) { planePoint = planePoint + hp.position; planePointCount++; }
+				if (planePointCount > 0) {
+					planePoint = planePoint / (float)planePointCount;
+					float d = -dot(avgNormal, planePoint);
+					float t = -(dot(avgNormal, cellCenter) + d);
+					return clampv(cellCenter + t * avgNormal, minBound, maxBound);
+				}
+			}
+		}
+		Qef qef;
+		for (const auto& hp : hermiteData) qef.addPoint(hp.position, hp.normal);
+		V3 c = (minBound + maxBound) * 0.5f;                                                                                       // solveConstrained, :151-161
+		V3 qefSolution = clampv(qef.solve(c, maxBound.x - minBound.x), minBound, maxBound);
+		return mixv(qefSolution, massPoint, 0.1f);
+	}
+	bool cellContainsSurface(int x0, int y0, int z0, int size) const {                                                            // :1367-1530
+		int maxX = std::min(x0 + size, g.dx), maxY = std::min(y0 + size, g.dy), maxZ = std::min(z0 + size, g.dz);
+		int minX = std::max(x0, 0), minY = std::max(y0, 0), minZ = std::max(z0, 0);
+		if (minX >= maxX || minY >= maxY || minZ >= maxZ) return false;
+		bool anyFilled = false, anyEmpty = false;
+		const int corners[8][3] = { {minX, minY, minZ}, {maxX - 1, minY, minZ}, {maxX - 1, maxY - 1, minZ}, {minX, maxY - 1, minZ},
+			{minX, minY, maxZ - 1}, {maxX - 1, minY, maxZ - 1}, {maxX - 1, maxY - 1, maxZ - 1}, {minX, maxY - 1, maxZ - 1} };
+		for (int i = 0; i < 8; i++) {
+			if (!inb(corners[i][0], corners[i][1], corners[i][2])) continue;
+			if (filled(corners[i][0], corners[i][1], corners[i][2])) anyFilled = true; else anyEmpty = true;
+			if (anyFilled && anyEmpty) return true;
+		}
+		for (int dir = 0; dir < 3; dir++) {
+			int stride = std::max(1, size / 4);
+			for (int offset = 0; offset < size; offset += stride) {
+				int lo[3] = { minX, minY, minZ }, hi[3] = { maxX, maxY, maxZ }, dim[3] = { g.dx, g.dy, g.dz };
+				int p[3];                                                // the two axes other than dir step along the diagonal
+				bool skip = false;
+				for (int a = 0; a < 3; a++) if (a != dir) { p[a] = lo[a] + offset; if (p[a] >= hi[a]) skip = true; }
+				if (skip) continue;
+				for (int side = 0; side < 2; side++) {                   // the face at min, then the face at max
+					int c1 = side == 0 ? lo[dir] - 1 : hi[dir] - 1, c2 = side == 0 ? lo[dir] : hi[dir];
+					if (c1 >= 0 && c2 < dim[dir]) {
+						int q1[3] = { p[0], p[1], p[2] }, q2[3] = { p[0], p[1], p[2] };
+						q1[dir] = c1; q2[dir] = c2;
+						if (filled(q1[0], q1[1], q1[2]) != filled(q2[0], q2[1], q2[2])) return true;
+					}
+				}
+			}
+		}
+		if (size <= 4)
+			for (int z = minZ; z < maxZ - 1; z++) for (int y = minY; y < maxY - 1; y++) for (int x = minX; x < maxX - 1; x++) {
+				bool s = filled(x, y, z);
+				if (s != filled(x + 1, y, z) || s != filled(x, y + 1, z) || s != filled(x, y, z + 1)) return true;
+			}
+		return false;
+	}
+	static void pushIfArea(std::vector<Tri>& out, V3 a, V3 b, V3 c) {                                                             // :727-739
+		V3 cr = cross(b - a, c - a);
+		if (0.5f * std::sqrt(dot(cr, cr)) > 1e-6f) out.push_back(Tri{ a, b, c });
+	}
+	void createFaceTriangles(const ONode* node, int x0, int y0, int z0, int size, std::vector<Tri>& triangles) {                  // :805-1088
+		long long cellKey = key(x0, y0, z0);
+		V3 cellVertex;
+		auto it = dualVertexCache.find(cellKey);
+		if (it != dualVertexCache.end()) cellVertex = it->second;
+		else { cellVertex = gridToWorld(x0, y0, z0) + v3(size * 0.5f * g.voxel, size * 0.5f * g.voxel, size * 0.5f * g.voxel); dualVertexCache[cellKey] = cellVertex; }
+		const int faceDirections[6][3] = { {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1} };
+		for (int face = 0; face < 6; face++) {
+			int nx = x0 + faceDirections[face][0] * size, ny = y0 + faceDirections[face][1] * size, nz = z0 + faceDirections[face][2] * size;
+			if (!inb(nx, ny, nz)) continue;
+			bool currentSolid = node->solid, neighborSolid = false;
+			long long neighborKey = key(nx, ny, nz);
+			auto nodeIt = octreeMap.find(neighborKey);
+			bool leafThere = nodeIt != octreeMap.end() && nodeIt->second->leaf;
+			if (leafThere) {
+				int adjSize = nodeIt->second->size;
+				if (std::max(size, adjSize) > std::min(size, adjSize) * 2) continue;
+				neighborSolid = nodeIt->second->solid;
+			}
+			else {
+				int cx = std::min(std::max(nx + size / 2, 0), g.dx - 1), cy = std::min(std::max(ny + size / 2, 0), g.dy - 1), cz = std::min(std::max(nz + size / 2, 0), g.dz - 1);
+				neighborSolid = filled(cx, cy, cz);
+			}
+			if (currentSolid == neighborSolid) continue;
+			V3 neighborVertex; bool hasNeighborVertex = false;
+			if (leafThere) { auto f = dualVertexCache.find(neighborKey); if (f != dualVertexCache.end()) { neighborVertex = f->second; hasNeighborVertex = true; } }
+			if (!hasNeighborVertex) { neighborVertex = gridToWorld(nx, ny, nz) + v3(size * 0.5f * g.voxel, size * 0.5f * g.voxel, size * 0.5f * g.voxel); dualVertexCache[neighborKey] = neighborVertex; }
+			float halfSize = size * g.voxel * 0.5f;
+			V3 faceNormal = v3((float)faceDirections[face][0], (float)faceDirections[face][1], (float)faceDirections[face][2]);
+			V3 faceCenter = (cellVertex + neighborVertex) * 0.5f;
+			V3 tangent1, tangent2;
+			if (std::fabs(faceNormal.x) > 0.5f) { tangent1 = v3(0, 1, 0); tangent2 = v3(0, 0, 1); }
+			else if (std::fabs(faceNormal.y) > 0.5f) { tangent1 = v3(1, 0, 0); tangent2 = v3(0, 0, 1); }
+			else { tangent1 = v3(1, 0, 0); tangent2 = v3(0, 1, 0); }
+			const int divisions = 2;
+			std::vector<V3> gridPoints;
+			for (int i = 0; i <= divisions; i++) {
+				float u = i / float(divisions);
+				for (int j = 0; j <= divisions; j++) {
+					float v = j / float(divisions);
+					float mappedU = 2.0f * u - 1.0f, mappedV = 2.0f * v - 1.0f;
+					V3 point = faceCenter + tangent1 * (mappedU * halfSize) + tangent2 * (mappedV * halfSize);
+					float distFromCenter = std::sqrt(mappedU * mappedU + mappedV * mappedV);
+					float bulge = 0.05f * halfSize * (1.0f - distFromCenter * distFromCenter);
+					point = point + faceNormal * bulge;
+					gridPoints.push_back(point);
+				}
+			}
+			for (int pass = 0; pass < 2; pass++)
+				for (int i = 0; i < divisions; i++) for (int j = 0; j < divisions; j++) {
+					int idx00 = i * (divisions + 1) + j, idx10 = (i + 1) * (divisions + 1) + j, idx01 = i * (divisions + 1) + (j + 1), idx11 = (i + 1) * (divisions + 1) + (j + 1);
+					if (pass == 0) {
+						triangles.push_back(Tri{ cellVertex, gridPoints[idx00], gridPoints[idx10] }); triangles.push_back(Tri{ cellVertex, gridPoints[idx10], gridPoints[idx11] });
+						triangles.push_back(Tri{ cellVertex, gridPoints[idx11], gridPoints[idx01] }); triangles.push_back(Tri{ cellVertex, gridPoints[idx01], gridPoints[idx00] });
+					}
+					else {
+						triangles.push_back(Tri{ neighborVertex, gridPoints[idx10], gridPoints[idx00] }); triangles.push_back(Tri{ neighborVertex, gridPoints[idx11], gridPoints[idx10] });
+						triangles.push_back(Tri{ neighborVertex, gridPoints[idx01], gridPoints[idx11] }); triangles.push_back(Tri{ neighborVertex, gridPoints[idx00], gridPoints[idx01] });
+					}
+				}
+		}
+	}
+	void createTriangles(const ONode* node, int x0, int y0, int z0, int size, std::vector<Tri>& result) {                         // :528-803
+		std::vector<Tri> triangles;
+		if (!node || !node->leaf) return;
+		if (!cellContainsSurface(x0, y0, z0, size)) return;
+		float cellSizeWorld = size * g.voxel;
+		V3 cellCenter = gridToWorld(x0, y0, z0) + v3(size * 0.5f * g.voxel, size * 0.5f * g.voxel, size * 0.5f * g.voxel);
+		long long cellKey = key(x0, y0, z0);
+		V3 cellVertex = cellCenter;
+		auto it = dualVertexCache.find(cellKey);
+		if (it != dualVertexCache.end()) cellVertex = it->second;
+		else {
+			std::vector<Hermite> hermiteData = gatherHermiteData(x0, y0, z0, size);
+			if (!hermiteData.empty()) cellVertex = generateDualVertex(hermiteData, cellCenter, cellSizeWorld);
+			dualVertexCache[cellKey] = cellVertex;
+		}
+		static const int edgeDirections[3][3] = { {1, 0, 0}, {0, 1, 0}, {0, 0, 1} };
+		for (int dir = 0; dir < 3; dir++) for (int edge = 0; edge < 4; edge++) {
+			int ex1 = x0, ey1 = y0, ez1 = z0;
+			if (dir == 0) { ey1 += (edge & 1) ? size : 0; ez1 += (edge & 2) ? size : 0; }
+			else if (dir == 1) { ex1 += (edge & 1) ? size : 0; ez1 += (edge & 2) ? size : 0; }
+			else { ex1 += (edge & 1) ? size : 0; ey1 += (edge & 2) ? size : 0; }
+			int ex2 = ex1 + edgeDirections[dir][0] * size, ey2 = ey1 + edgeDirections[dir][1] * size, ez2 = ez1 + edgeDirections[dir][2] * size;
+			if (!inb(ex1, ey1, ez1) || !inb(ex2, ey2, ez2)) continue;
+			if (filled(ex1, ey1, ez1) == filled(ex2, ey2, ez2)) continue;
+			std::vector<V3> adjacent;
+			adjacent.push_back(cellVertex);
+			for (int adjIdx = 1; adjIdx < 4; adjIdx++) {
+				int adjX = x0, adjY = y0, adjZ = z0;
+				if (dir == 0) { if (adjIdx == 1) adjY = ey1 - size; else if (adjIdx == 2) adjZ = ez1 - size; else { adjY = ey1 - size; adjZ = ez1 - size; } }
+				else if (dir == 1) { if (adjIdx == 1) adjX = ex1 - size; else if (adjIdx == 2) adjZ = ez1 - size; else { adjX = ex1 - size; adjZ = ez1 - size; } }
+				else { if (adjIdx == 1) adjX = ex1 - size; else if (adjIdx == 2) adjY = ey1 - size; else { adjX = ex1 - size; adjY = ey1 - size; } }
+				if (!inb(adjX, adjY, adjZ)) continue;
+				long long k = key(adjX, adjY, adjZ);
+				auto nodeIt = octreeMap.find(k);
+				if (nodeIt == octreeMap.end() || !nodeIt->second->leaf) continue;
+				int adjSize = nodeIt->second->size, mySize = node->size;
+				if (std::max(mySize, adjSize) > std::min(mySize, adjSize) * 2) continue;
+				V3 adjVertex;
+				auto found = dualVertexCache.find(k);
+				if (found != dualVertexCache.end()) adjVertex = found->second;
+				else {
+					V3 adjCenter = gridToWorld(adjX, adjY, adjZ) + v3(size * 0.5f * g.voxel, size * 0.5f * g.voxel, size * 0.5f * g.voxel);
+					std::vector<Hermite> adjHermite = gatherHermiteData(adjX, adjY, adjZ, size);
+					adjVertex = !adjHermite.empty() ? generateDualVertex(adjHermite, adjCenter, cellSizeWorld) : adjCenter;
+					dualVertexCache[k] = adjVertex;
+				}
+				adjacent.push_back(adjVertex);
+			}
+			if (adjacent.size() == 3) pushIfArea(triangles, adjacent[0], adjacent[1], adjacent[2]);
+			else if (adjacent.size() >= 4) { pushIfArea(triangles, adjacent[0], adjacent[1], adjacent[2]); pushIfArea(triangles, adjacent[0], adjacent[2], adjacent[3]); }
+		}
+		if (triangles.empty() && (x0 == 0 || y0 == 0 || z0 == 0 || (x0 + size) >= g.dx || (y0 + size) >= g.dy || (z0 + size) >= g.dz))
+			createFaceTriangles(node, x0, y0, z0, size, triangles);
+		result.insert(result.end(), triangles.begin(), triangles.end());
+	}
+};
+
 // ---- mesh + BVH -------------------------------------------------------------------------------------
 void* orc_mesh_from_octree(void* h) {
 	Octree* oc = (Octree*)h; Mesh* m = new Mesh();
 	mcRender(oc->g, oc->root, 0, 0, 0, oc->root->size, m->tris);
+	return m;
+}
+// renderOctree's traverse lambda (main.cpp:152-187): depth first, children 0..7, nodes whose box + extraMargin is outside the frustum
+// of viewProj16 (column-major proj * view; NULL: no culling) are dropped with their subtrees; every leaf goes through createTriangles.
+void* orc_dc_mesh_from_octree(void* h, const float* viewProj16, float extraMargin) {
+	Octree* oc = (Octree*)h; Mesh* m = new Mesh();
+	if (!oc->root) return m;
+	DcPort dc(oc->g);
+	dc.fillMap(oc->root);
+	float pl[6][4];
+	if (viewProj16) for (int i = 0; i < 6; i++) {                                   // Frustum.cpp:5-48
+		int row = i / 2; bool plus = (i % 2) == 0;
+		for (int c = 0; c < 4; c++) pl[i][c] = plus ? viewProj16[c * 4 + 3] + viewProj16[c * 4 + row] : viewProj16[c * 4 + 3] - viewProj16[c * 4 + row];
+		float len = std::sqrt(dot(v3(pl[i][0], pl[i][1], pl[i][2]), v3(pl[i][0], pl[i][1], pl[i][2])));
+		for (int c = 0; c < 4; c++) pl[i][c] /= len;
+	}
+	struct Walk {
+		Octree* oc; DcPort& dc; Mesh* m; const float* vp; float (*pl)[4]; float margin;
+		void go(const ONode* n) {
+			if (!n) return;
+			if (vp) {                                                                   // Frustum::testAABB == -1, Frustum.cpp:52-75
+				const Grid& g = oc->g;
+				V3 mn = v3(g.minX + n->x * g.voxel, g.minY + n->y * g.voxel, g.minZ + n->z * g.voxel);
+				float s = n->size * g.voxel;
+				V3 mx = v3(mn.x + s, mn.y + s, mn.z + s);
+				V3 emn = v3(mn.x - margin, mn.y - margin, mn.z - margin), emx = v3(mx.x + margin, mx.y + margin, mx.z + margin);
+				for (int k = 0; k < 6; k++) {
+					V3 p = v3(pl[k][0] > 0 ? emx.x : emn.x, pl[k][1] > 0 ? emx.y : emn.y, pl[k][2] > 0 ? emx.z : emn.z);
+					if (dot(v3(pl[k][0], pl[k][1], pl[k][2]), p) + pl[k][3] < 0) return;
+				}
+			}
+			if (n->leaf) dc.createTriangles(n, n->x, n->y, n->z, n->size, m->tris);
+			else for (auto* c : n->child) go(c);
+		}
+	} walk{ oc, dc, m, viewProj16, pl, extraMargin };
+	walk.go(oc->root);
 	return m;
 }
 void* orc_mesh_from_tris(const float* xyz9, size_t n) { Mesh* m = new Mesh(); m->tris.resize(n); std::memcpy((void*)m->tris.data(), xyz9, n * 36); return m; }

@@ -50,6 +50,19 @@ def test_dc_mesh_equals_the_compiled_reference(rto, ref, name):
     assert_bit_equal(got, want, name)
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_port_restatement_equals_the_golden_checksums(port, name):
+    """oracle/oracle_port.cpp's literal, sequential restatement of the mesher (the checker where libref.so is absent) is pinned to the
+    reference's output too."""
+    case, want = CASES[name], META[name]
+    oc = port.octree(*make_grid(case)); oc.build()
+    vp = None if want["view_proj"] is None else np.array(want["view_proj"], np.float32)
+    got = oc.dc_mesh(vp, case.get("margin", 50.0)).tris()
+    oc.free()
+    assert len(got) == want["tris"]
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want["sha"]
+
+
 def test_dc_mesh_refuses_octrees_beyond_the_reference_key_range(rto):
     """Cell keys are x << 20 | y << 10 | z in the reference (AdaptiveDualContouringRenderer.cpp:553-555): they alias past 1024 voxels."""
     nodes = np.zeros((1, 15), np.int32)
