@@ -52,7 +52,7 @@ def main():
         oc = rto.Scene.octree(nodes, g.min, g.voxel_size)
         for mode, name in ((rto.MODE_OCTREE_SKIP, "A octreeRaySkip"), (rto.MODE_OCTREE_GLSL, "B GLSL")):
             rep["C1 sphere128 octree mode %s 1024x768 (8 frames)" % name] = dict(nodes=len(nodes), **timed(oc, cams, mode, 0, 0.0, 768, 1024))
-    if want("C2") or want("C5"):
+    if want("C2") or want("C5") or want("C2DC"):
         g = rto.VoxelGrid.load(DT_GRID)
         nodes = rto.create_octree_from_voxel_grid(g)
         tris = rto.marching_cubes_mesh(g, nodes)
@@ -67,6 +67,13 @@ def main():
             cams = cams_orbit(35, 0.6 * 4250, 1920, 1080, 8)
             for mode, name in ((rto.MODE_OCTREE_SKIP, "A octreeRaySkip"), (rto.MODE_OCTREE_GLSL, "B GLSL")):
                 rep["DT octree mode %s 1080p (8 frames)" % name] = dict(nodes=len(nodes), **timed(oc, cams, mode, 0, 0.0, 1080, 1920))
+        if want("C2DC"):
+            dct = rto.dual_contouring_mesh(g, nodes)
+            sdc = rto.Scene.bvh(dct)
+            for name, (th, ph, r) in {"far": (35, 40, 0.6 * 4250), "near": (60, 10, 0.35 * 4250)}.items():
+                cams = [rto.Camera.from_degrees(th, ph, r).consts(45.0, float(np.float32(1920) / np.float32(1080)), 1920, 1080)[0]] * 8
+                rep["C2 DT Dual-Contouring mesh BVH primary+shadow 1080p camera %s (8 frames)" % name] = dict(tris=len(dct), **timed(sdc, cams, rto.MODE_BVH, rto.FLAG_SHADOWS, bias, 1080, 1920))
+            del sdc
         if want("C5"):
             cams = cams_orbit(35, 0.6 * 4250, 3840, 2160, 16, phi0=0.0)
             rep["C5 DT mesh 4K orbit primary+shadow (16 of 64 frames per launch)"] = timed(sc, cams, rto.MODE_BVH, rto.FLAG_SHADOWS, bias, 2160, 3840, reps=3)

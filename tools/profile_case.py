@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One named case rendered a few times -- the target of `ncu -k regex:k_render -s 2 -c 1` captures and of quick A/B timing.
-    python tools/profile_case.py CASE [--reps N]      CASE in dt-bvh, dt-bvh-primary, dt-octA, dt-octB, c3-octA, c3-octB, c1-bvh"""
+    python tools/profile_case.py CASE [--reps N]      CASE in dt-bvh, dt-bvh-primary, dt-dcbvh, dt-octA, dt-octB, c3-octA, c3-octB, c3-dcbvh, c1-bvh, c3-dcbuild, c4-dcbuild"""
 import argparse, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,8 +30,21 @@ def main():
     else:
         g = rto.generate_test_volume(128)
         radius, theta, W, H = 1.2, 30, 1024, 768
+    if a.case.endswith("-dcbuild"):
+        # scene construction only: grid -> octree -> Dual-Contouring mesh -> linear BVH on the device (launch-list target)
+        if a.case.startswith("c4"):
+            g = rto.city_block_grid(1024, 4321, 64)
+        import time
+        for r in range(2):
+            t0 = time.time(); sc = rto.Scene.bvh_from_grid_dc(g); dt = time.time() - t0
+            print("%s: scene from grid in %.3f s, %d triangles" % (a.case, dt, sc.info()["prims"]))
+            del sc
+        return
     nodes = rto.create_octree_from_voxel_grid(g)
-    if "bvh" in a.case:
+    if "dcbvh" in a.case:
+        sc = rto.Scene.bvh(rto.dual_contouring_mesh(g, nodes))
+        mode, flags, bias = rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3 * g.voxel_size
+    elif "bvh" in a.case:
         sc = rto.Scene.bvh(rto.marching_cubes_mesh(g, nodes))
         mode = rto.MODE_BVH
         if "primary" not in a.case and not a.case.startswith("c1"):
