@@ -119,6 +119,18 @@ RTO_API int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ
 RTO_API int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ,
 	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
 	const float* viewProj16 /* may be NULL */, float extraMargin, RtoTriangle** trisOut, size_t* numTris);
+/* rto_host_dc_mesh that also returns the normal the reference stores with each triangle (MCTriangle::normal, the same vector three
+ * times): normalize(cross(v1 - v0, v2 - v0)), negated when the emitting leaf is solid; the face normal for the fans of the boundary
+ * fallback.  normalsOut: 3 floats per triangle, malloc'ed. */
+RTO_API int rto_host_dc_mesh_normals(const uint8_t* voxels, int dimX, int dimY, int dimZ,
+	const float gridMin[3], float voxelSize, const RtoGpuNode* nodes, size_t numNodes,
+	const float* viewProj16 /* may be NULL */, float extraMargin, RtoTriangle** trisOut, float** normalsOut, size_t* numTris);
+/* The application's triangle cache (saveTriangleCache / loadTriangleCache, main.cpp:27-67; triangle_cache/dc_triangles_<hash>.bin):
+ * size_t count, then count x MCTriangle { vec3 v[3]; vec3 normal[3]; } (72 bytes).  save: normals3 holds one normal per triangle
+ * (written three times) or is NULL (the flat normal of the geometry, what localMC stores).  load: normals9Out (optional) receives
+ * the three stored normals of every triangle.  malloc'ed; rto_host_free. */
+RTO_API int rto_host_tricache_save(const char* path, const RtoTriangle* tris, const float* normals3 /* may be NULL */, size_t numTris);
+RTO_API int rto_host_tricache_load(const char* path, RtoTriangle** trisOut, float** normals9Out /* may be NULL */, size_t* numTris);
 /* The same mesh by replaying the reference's cache protocol leaf by leaf (the cross-check of rto_host_dc_mesh's order-free
  * formulation, and its way out if the fallback rounds did not settle). */
 RTO_API int rto_host_dc_mesh_replay(const uint8_t* voxels, int dimX, int dimY, int dimZ,

@@ -69,6 +69,8 @@ class Backend:
             "skip_distance": (f32, [vp, f32, f32, f32, vp, f32, f32, vp, vp, vp]),
         }
         sig["dc_mesh_from_octree"] = (vp, [vp, vp, f32])
+        if hasattr(L, prefix + "dc_mesh_full"):          # the compiled reference only: MCTriangles with their normals
+            sig["dc_mesh_full"] = (sz, [vp, vp, f32, vp, sz])
         for name, (res, args) in sig.items():
             fn = getattr(L, prefix + name)
             fn.restype, fn.argtypes = res, args
@@ -198,6 +200,16 @@ class Octree:
         """renderOctree (main.cpp:95-208) over AdaptiveDualContouringRenderer::render: the DC triangle soup; view_proj None = no culling."""
         vp = None if view_proj is None else np.ascontiguousarray(view_proj, np.float32).ravel()
         return Mesh(self.L, handle=self.L.dc_mesh_from_octree(self.h, _p(vp), float(margin)))
+
+    def dc_mesh_full(self, view_proj=None, margin=50.0):
+        """The MCTriangles of the Dual-Contouring run, (m, 18): 3 vertices + 3 normals (compiled reference only)."""
+        vp = None if view_proj is None else np.ascontiguousarray(view_proj, np.float32).ravel()
+        out = np.zeros((1 << 16, 18), np.float32)
+        n = self.L.dc_mesh_full(self.h, _p(vp), float(margin), _p(out), len(out))
+        if n > len(out):
+            out = np.zeros((n, 18), np.float32)
+            self.L.dc_mesh_full(self.h, _p(vp), float(margin), _p(out), n)
+        return out[:n].copy()
 
     def free(self):
         if self.h:

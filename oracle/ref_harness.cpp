@@ -358,7 +358,7 @@ void* ref_mesh_from_octree(void* hv) {
 // is restated below with the same glm expressions, everything it calls is the reference's own code.  The compute-shader attempt of
 // render() (taken only when the root itself is a leaf) is disabled: there is no GL context.
 // viewProj16 == NULL: no culling (every leaf is visited).
-void* ref_dc_mesh_from_octree(void* hv, const float* viewProj16, float extraMargin) {
+static std::vector<MCTriangle> refDcTriangles(void* hv, const float* viewProj16, float extraMargin) {
 	RefOctree* h = (RefOctree*)hv;
 	AdaptiveDualContouringRenderer dc;
 	dc.m_useComputeShader = false;
@@ -388,10 +388,22 @@ void* ref_dc_mesh_from_octree(void* hv, const float* viewProj16, float extraMarg
 	};
 	traverse(h->root);
 	delete frustum;
+	return result;
+}
+void* ref_dc_mesh_from_octree(void* hv, const float* viewProj16, float extraMargin) {
+	std::vector<MCTriangle> result = refDcTriangles(hv, viewProj16, extraMargin);
 	RefMesh* m = new RefMesh();
 	m->tris.resize(result.size());
 	for (size_t i = 0; i < result.size(); i++) { m->tris[i].v0 = result[i].v[0]; m->tris[i].v1 = result[i].v[1]; m->tris[i].v2 = result[i].v[2]; }
 	return m;
+}
+// The same run with the MCTriangles whole (3 vertices + 3 normals = 18 floats each, the record of the triangle cache, main.cpp:27-67).
+// Returns the count; fills out18 when cap is large enough.
+size_t ref_dc_mesh_full(void* hv, const float* viewProj16, float extraMargin, float* out18, size_t cap) {
+	std::vector<MCTriangle> result = refDcTriangles(hv, viewProj16, extraMargin);
+	static_assert(sizeof(MCTriangle) == 72, "MCTriangle must be 18 floats");
+	if (out18 && cap >= result.size() && !result.empty()) std::memcpy(out18, result.data(), result.size() * 72);
+	return result.size();
 }
 
 void* ref_mesh_from_tris(const float* xyz9, size_t n) {

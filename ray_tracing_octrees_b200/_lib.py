@@ -44,6 +44,9 @@ SIGNATURES = {
     "rto_host_mc_mesh": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _sz, _pp, C.POINTER(_sz)]),
     "rto_host_dc_mesh": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _sz, _vp, _f, _pp, C.POINTER(_sz)]),
     "rto_host_dc_mesh_replay": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _sz, _vp, _f, _pp, C.POINTER(_sz)]),
+    "rto_host_dc_mesh_normals": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _sz, _vp, _f, _pp, _pp, C.POINTER(_sz)]),
+    "rto_host_tricache_save": (_i, [C.c_char_p, _vp, _vp, _sz]),
+    "rto_host_tricache_load": (_i, [C.c_char_p, _pp, _pp, C.POINTER(_sz)]),
     "rto_device_dc_mesh": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _sz, _vp, _f, _pp, C.POINTER(_sz)]),
     "rto_host_bvh_build": (_i, [_vp, _sz, _pp]),
     "rto_host_bvh_free": (None, [_vp]),

@@ -170,6 +170,32 @@ def dual_contouring_mesh(grid, nodes, view_proj=None, margin=50.0, algo="default
     return _take(ptr, n.value, np.float32, (n.value, 9))
 
 
+def dual_contouring_mesh_with_normals(grid, nodes, view_proj=None, margin=50.0):
+    """-> ((m, 9) triangles, (m, 3) normals): rto_host_dc_mesh_normals, the MCTriangles of the reference's mesher."""
+    nodes = np.ascontiguousarray(nodes, np.int32)
+    vp = None if view_proj is None else np.ascontiguousarray(view_proj, np.float32).ravel()
+    ptr, nptr = C.c_void_p(), C.c_void_p()
+    n = C.c_size_t()
+    check(lib().rto_host_dc_mesh_normals(_p(grid.data), grid.dims[0], grid.dims[1], grid.dims[2], _p(grid.min), grid.voxel_size,
+                                         _p(nodes), len(nodes), _p(vp), float(margin), C.byref(ptr), C.byref(nptr), C.byref(n)))
+    return _take(ptr, n.value, np.float32, (n.value, 9)), _take(nptr, n.value, np.float32, (n.value, 3))
+
+
+def save_triangle_cache(path, tris, normals=None):
+    """saveTriangleCache (main.cpp:27-45): size_t count + count x MCTriangle (72 bytes)."""
+    tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+    nm = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    check(lib().rto_host_tricache_save(os.fsencode(path), _p(tris), _p(nm), len(tris)))
+
+
+def load_triangle_cache(path):
+    """loadTriangleCache (main.cpp:48-67) -> ((m, 9) triangles, (m, 9) stored normals)."""
+    ptr, nptr = C.c_void_p(), C.c_void_p()
+    n = C.c_size_t()
+    check(lib().rto_host_tricache_load(os.fsencode(path), C.byref(ptr), C.byref(nptr), C.byref(n)))
+    return _take(ptr, n.value, np.float32, (n.value, 9)), _take(nptr, n.value, np.float32, (n.value, 9))
+
+
 class Camera:
     """Orbit camera (Camera.h:5-44): theta / phi in radians, radius, target."""
 

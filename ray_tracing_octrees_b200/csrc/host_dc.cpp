@@ -110,8 +110,9 @@ void atomicMinU64(std::atomic<unsigned long long>& a, unsigned long long v) {
 // until it repeats.  A leaf's triangles depend only on touches made before it in the walk, so each round gets a longer prefix of
 // the walk right, and a set that repeats is the reference's (it starts empty and normally repeats after one round).
 // =================================================================================================================================
-extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) {
+static int dcMeshOrderFree(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, float** normalsOut, size_t* numTris) {
+	if (normalsOut) *normalsOut = nullptr;
 	int rc = checkArgs("rto_host_dc_mesh", voxels, gridMin, nodes, numNodes, trisOut, numTris);
 	if (rc || numNodes == 0) return rc;
 	const Grid g{ voxels, dimX, dimY, dimZ, gridMin[0], gridMin[1], gridMin[2], voxelSize };
@@ -157,7 +158,10 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 	int rounds = 0;
 	size_t numFallback = 0, vertices = 0;
 	for (;; rounds++) {
-		if (rounds > 64) return rto_host_dc_mesh_replay(voxels, dimX, dimY, dimZ, gridMin, voxelSize, nodes, numNodes, viewProj16, extraMargin, trisOut, numTris);
+		if (rounds > 64) {
+			if (normalsOut) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_host_dc_mesh_normals: fallback rounds did not settle");
+			return rto_host_dc_mesh_replay(voxels, dimX, dimY, dimZ, gridMin, voxelSize, nodes, numNodes, viewProj16, extraMargin, trisOut, numTris);
+		}
 		parallelFor(numNodes, 1 << 16, nthreads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; i++) first[i] = firstAB[i].load(std::memory_order_relaxed); });
 		// touches of the assumed fallback leaves (kind 2), sequentially: they are few
 		for (size_t r = 0; r < recs.size(); r++) if (fallback[r]) {
@@ -211,27 +215,100 @@ extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 		recs.size(), total, numFallback, rounds, vertices, t1 - t0, t2 - t1, t3 - t2, nthreads);
 	if (total == 0) return RTO_OK;
 	RtoTriangle* buf = (RtoTriangle*)std::malloc(total * sizeof(RtoTriangle));
-	if (!buf) return rto_fail(RTO_ERR_ALLOC, "rto_host_dc_mesh: out of memory");
+	V3* nbuf = normalsOut ? (V3*)std::malloc(total * sizeof(V3)) : nullptr;
+	if (!buf || (normalsOut && !nbuf)) { std::free(buf); std::free(nbuf); return rto_fail(RTO_ERR_ALLOC, "rto_host_dc_mesh: out of memory"); }
 	parallelFor(recs.size(), 4096, nthreads, [&](size_t lo, size_t hi, int) {
 		for (size_t r = lo; r < hi; r++) {
 			if (offset[r + 1] == offset[r]) continue;
 			const LeafRec& R = recs[r];
 			const RtoGpuNode& n = nodes[R.node];
 			RtoTriangle* out = buf + offset[r];
+			V3* nrm = nbuf ? nbuf + offset[r] : nullptr;
 			V3 vtx[8];
 			for (int o = 0; o < 7; o++) if (R.tgt[o] >= 0) vtx[o] = val[(size_t)R.tgt[o]];
-			out += edgeTriangles(R.edgeMask, R.tgt, vtx, out);
+			const int ne = edgeTriangles(R.edgeMask, R.tgt, vtx, out, nrm, n.isSolid != 0);
+			out += ne; if (nrm) nrm += ne;
 			if (fallback[r])
 				for (int face = 0; face < 6; face++) {
 					int nx, ny, nz; int32_t k;
 					if (!fallbackFace(g, nodes, n, face, nx, ny, nz, k)) continue;
 					const V3 neighborVertex = k >= 0 ? val[(size_t)k] : g.centre(nx, ny, nz, n.size);
-					faceFan(vtx[0], neighborVertex, face, n.size, voxelSize, out);
-					out += 32;
+					faceFan(vtx[0], neighborVertex, face, n.size, voxelSize, out, nrm, n.isSolid != 0);
+					out += 32; if (nrm) nrm += 32;
 				}
 		}
 	});
 	*trisOut = buf; *numTris = total;
+	if (normalsOut) *normalsOut = reinterpret_cast<float*>(nbuf);
+	return RTO_OK;
+}
+
+extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) {
+	return dcMeshOrderFree(voxels, dimX, dimY, dimZ, gridMin, voxelSize, nodes, numNodes, viewProj16, extraMargin, trisOut, nullptr, numTris);
+}
+
+extern "C" int rto_host_dc_mesh_normals(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, float** normalsOut, size_t* numTris) {
+	if (!normalsOut) return rto_fail(RTO_ERR_INVALID, "rto_host_dc_mesh_normals: null output");
+	return dcMeshOrderFree(voxels, dimX, dimY, dimZ, gridMin, voxelSize, nodes, numNodes, viewProj16, extraMargin, trisOut, normalsOut, numTris);
+}
+
+// =================================================================================================================================
+// The triangle cache of the application (main.cpp:27-67, written after every Dual-Contouring run and read back instead of meshing):
+// size_t count, then count x MCTriangle { vec3 v[3]; vec3 normal[3]; } = 72 bytes each.
+// =================================================================================================================================
+extern "C" int rto_host_tricache_save(const char* path, const RtoTriangle* tris, const float* normals3, size_t numTris) {
+	if (!path || (numTris && !tris)) return rto_fail(RTO_ERR_INVALID, "rto_host_tricache_save: null argument");
+	FILE* f = std::fopen(path, "wb");
+	if (!f) return rto_fail(RTO_ERR_IO, "rto_host_tricache_save: cannot open %s", path);
+	const size_t n = numTris;
+	bool ok = std::fwrite(&n, sizeof(n), 1, f) == 1;
+	std::vector<float> rec((size_t)18 * 4096);
+	for (size_t i0 = 0; i0 < n && ok; i0 += 4096) {
+		const size_t m = std::min<size_t>(4096, n - i0);
+		for (size_t i = 0; i < m; i++) {
+			float* r = rec.data() + 18 * i;
+			std::memcpy(r, &tris[i0 + i], 36);
+			V3 nm;
+			if (normals3) nm = mk3(normals3[3 * (i0 + i)], normals3[3 * (i0 + i) + 1], normals3[3 * (i0 + i) + 2]);
+			else {       // flat normal of the geometry, what localMC stores (OctreeVoxel.cpp:863-870)
+				const float* v = tris[i0 + i].v0;
+				nm = normalize3(cross3(mk3(v[3], v[4], v[5]) - mk3(v[0], v[1], v[2]), mk3(v[6], v[7], v[8]) - mk3(v[0], v[1], v[2])));
+			}
+			for (int k = 0; k < 3; k++) { r[9 + 3 * k] = nm.x; r[10 + 3 * k] = nm.y; r[11 + 3 * k] = nm.z; }
+		}
+		ok = std::fwrite(rec.data(), 72, m, f) == m;
+	}
+	ok = (std::fclose(f) == 0) && ok;
+	return ok ? RTO_OK : rto_fail(RTO_ERR_IO, "rto_host_tricache_save: write to %s failed", path);
+}
+
+extern "C" int rto_host_tricache_load(const char* path, RtoTriangle** trisOut, float** normals9Out, size_t* numTris) {
+	if (!path || !trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_host_tricache_load: null argument");
+	*trisOut = nullptr; *numTris = 0; if (normals9Out) *normals9Out = nullptr;
+	FILE* f = std::fopen(path, "rb");
+	if (!f) return rto_fail(RTO_ERR_IO, "rto_host_tricache_load: cannot open %s", path);
+	size_t n = 0;
+	if (std::fread(&n, sizeof(n), 1, f) != 1) { std::fclose(f); return rto_fail(RTO_ERR_IO, "rto_host_tricache_load: %s is truncated", path); }
+	std::fseek(f, 0, SEEK_END);
+	const long bytes = std::ftell(f);
+	if (bytes < 0 || (size_t)bytes < 8 || ((size_t)bytes - 8) / 72 < n) { std::fclose(f); return rto_fail(RTO_ERR_IO, "rto_host_tricache_load: %s holds fewer than the %zu triangles it announces", path, n); }
+	std::fseek(f, 8, SEEK_SET);
+	if (n == 0) { std::fclose(f); return RTO_OK; }
+	RtoTriangle* t = (RtoTriangle*)std::malloc(n * sizeof(RtoTriangle));
+	float* nm = normals9Out ? (float*)std::malloc(n * 36) : nullptr;
+	if (!t || (normals9Out && !nm)) { std::free(t); std::free(nm); std::fclose(f); return rto_fail(RTO_ERR_ALLOC, "rto_host_tricache_load: out of memory"); }
+	std::vector<float> rec((size_t)18 * 4096);
+	bool ok = true;
+	for (size_t i0 = 0; i0 < n && ok; i0 += 4096) {
+		const size_t m = std::min<size_t>(4096, n - i0);
+		ok = std::fread(rec.data(), 72, m, f) == m;
+		for (size_t i = 0; i < m && ok; i++) { std::memcpy(&t[i0 + i], rec.data() + 18 * i, 36); if (nm) std::memcpy(nm + 9 * (i0 + i), rec.data() + 18 * i + 9, 36); }
+	}
+	std::fclose(f);
+	if (!ok) { std::free(t); std::free(nm); return rto_fail(RTO_ERR_IO, "rto_host_tricache_load: read from %s failed", path); }
+	*trisOut = t; *numTris = n; if (normals9Out) *normals9Out = nm;
 	return RTO_OK;
 }
 

@@ -339,7 +339,10 @@ RTO_HD bool hasArea(V3 a, V3 b, V3 c) {
 
 // The triangles createTriangles emits for the 12 edges of one leaf (:586-787) given the dual vertices its cache look-ups return:
 // vtx[0] the leaf's own, vtx[o] the joinable neighbour's at offset o (tgt[o] >= 0).  out == nullptr: count only.
-RTO_HD int edgeTriangles(uint32_t edgeMask, const int32_t tgt[8], const V3 vtx[8], RtoTriangle* out) {
+// nrm (may be null, only with out): the flat normal the reference stores three times per MCTriangle, normalize(cross(e1, e2)), negated
+// when the emitting leaf is solid (:730-734).
+RTO_HD V3 flatNormal(V3 a, V3 b, V3 c, bool flip) { V3 n = normalize3(cross3(b - a, c - a)); return flip ? -n : n; }
+RTO_HD int edgeTriangles(uint32_t edgeMask, const int32_t tgt[8], const V3 vtx[8], RtoTriangle* out, V3* nrm = nullptr, bool flip = false) {
 	int n = 0;
 	for (int dir = 0; dir < 3; dir++)
 		for (int edge = 0; edge < 4; edge++) {
@@ -352,8 +355,8 @@ RTO_HD int edgeTriangles(uint32_t edgeMask, const int32_t tgt[8], const V3 vtx[8
 				adj[cnt++] = vtx[o];
 			}
 			if (cnt >= 3) {
-				if (hasArea(adj[0], adj[1], adj[2])) { if (out) putTri(out + n, adj[0], adj[1], adj[2]); n++; }
-				if (cnt >= 4 && hasArea(adj[0], adj[2], adj[3])) { if (out) putTri(out + n, adj[0], adj[2], adj[3]); n++; }
+				if (hasArea(adj[0], adj[1], adj[2])) { if (out) putTri(out + n, adj[0], adj[1], adj[2]); if (nrm) nrm[n] = flatNormal(adj[0], adj[1], adj[2], flip); n++; }
+				if (cnt >= 4 && hasArea(adj[0], adj[2], adj[3])) { if (out) putTri(out + n, adj[0], adj[2], adj[3]); if (nrm) nrm[n] = flatNormal(adj[0], adj[2], adj[3], flip); n++; }
 			}
 		}
 	return n;
@@ -387,7 +390,8 @@ RTO_HD bool fallbackFace(const Grid& g, const RtoGpuNode* nodes, const RtoGpuNod
 }
 
 // The 32 triangles of one face of createFaceTriangles (:906-1084): two bulged fans of 16 over a 3 x 3 point grid
-RTO_HD void faceFan(V3 cellVertex, V3 neighborVertex, int face, int size, float vs, RtoTriangle* out) {
+// nrm (may be null): the face normal, pointing away from the solid side for the cell's fan and the other way for the neighbour's (:936-940)
+RTO_HD void faceFan(V3 cellVertex, V3 neighborVertex, int face, int size, float vs, RtoTriangle* out, V3* nrm = nullptr, bool currentSolid = false) {
 	const int fx = face == 0 ? 1 : (face == 1 ? -1 : 0), fy = face == 2 ? 1 : (face == 3 ? -1 : 0), fz = face == 4 ? 1 : (face == 5 ? -1 : 0);
 	const float halfSize = float(size) * vs * 0.5f;
 	const V3 faceNormal = mk3(float(fx), float(fy), float(fz));
@@ -428,6 +432,11 @@ RTO_HD void faceFan(V3 cellVertex, V3 neighborVertex, int face, int size, float 
 			putTri(out + t++, neighborVertex, gridPoints[idx01], gridPoints[idx11]);
 			putTri(out + t++, neighborVertex, gridPoints[idx00], gridPoints[idx01]);
 		}
+	if (nrm) {
+		V3 normal = faceNormal;
+		if (!currentSolid) normal = -normal;
+		for (int i = 0; i < 16; i++) { nrm[i] = normal; nrm[16 + i] = -normal; }
+	}
 }
 
 // ---- the order of renderOctree's walk, as a number ------------------------------------------------------------------------

@@ -87,3 +87,48 @@ def test_dc_mesh_of_nothing(rto):
     g = rto.VoxelGrid((4, 4, 4), (0, 0, 0), 1.0, np.zeros(64, np.uint8))
     assert len(rto.dual_contouring_mesh(g, np.zeros((0, 15), np.int32))) == 0
     assert len(rto.dual_contouring_mesh(g, rto.create_octree_from_voxel_grid(g))) == 0
+
+
+@pytest.mark.parametrize("name", ["sphere32", "sphere48_culled", "noise_half", "noise_dense", "boxes_ragged", "dt_culled_near"])
+def test_dc_normals_equal_the_reference_mctriangles(rto, ref, name):
+    """rto_host_dc_mesh_normals: the normal stored with every MCTriangle (flat normal, negated for solid leaves; face normals for the
+    fallback fans, signed zeros included), against the reference's own records."""
+    case = CASES[name]
+    dims, gmin, voxel, data = make_grid(case)
+    oc = ref.octree(dims, gmin, voxel, data); oc.build()
+    g, nodes = build(rto, case)
+    vp = view_proj_for(ref, case)
+    want = oc.dc_mesh_full(vp, case.get("margin", 50.0))
+    oc.free()
+    tris, normals = rto.dual_contouring_mesh_with_normals(g, nodes, vp, case.get("margin", 50.0))
+    assert_bit_equal(tris, want[:, :9], name + " vertices")
+    for k in range(3):
+        assert_bit_equal(normals, want[:, 9 + 3 * k:12 + 3 * k], name + " normal %d" % k)
+
+
+def test_triangle_cache_file_round_trip(rto, tmp_path):
+    """saveTriangleCache / loadTriangleCache (main.cpp:27-67): size_t count + count x 72-byte MCTriangle."""
+    case = CASES["sphere32"]
+    g, nodes = build(rto, case)
+    tris, normals = rto.dual_contouring_mesh_with_normals(g, nodes)
+    path = str(tmp_path / "dc_triangles_1.bin")
+    rto.save_triangle_cache(path, tris, normals)
+    raw = open(path, "rb").read()
+    want = np.concatenate([tris, normals, normals, normals], axis=1).astype(np.float32)
+    assert raw == np.uint64(len(tris)).tobytes() + want.tobytes()
+    t2, n2 = rto.load_triangle_cache(path)
+    assert_bit_equal(t2, tris, "tris"); assert_bit_equal(n2, want[:, 9:], "normals")
+    # no normals given: the flat normal of the geometry (what localMC stores with Marching-Cubes triangles)
+    rto.save_triangle_cache(path, tris[:10])
+    t3, n3 = rto.load_triangle_cache(path)
+    e1, e2 = tris[:10, 3:6] - tris[:10, 0:3], tris[:10, 6:9] - tris[:10, 0:3]
+    c = np.cross(e1.astype(np.float64), e2.astype(np.float64)); c /= np.linalg.norm(c, axis=1, keepdims=True)
+    assert len(t3) == 10 and np.allclose(n3[:, :3], c, atol=1e-5) and np.array_equal(n3[:, :3], n3[:, 3:6])
+    # truncated and missing files are errors, an empty cache is not
+    open(path, "wb").write(raw[:100])
+    with pytest.raises(rto.RtoError):
+        rto.load_triangle_cache(path)
+    with pytest.raises(rto.RtoError):
+        rto.load_triangle_cache(str(tmp_path / "nope.bin"))
+    rto.save_triangle_cache(path, np.zeros((0, 9), np.float32))
+    assert len(rto.load_triangle_cache(path)[0]) == 0
