@@ -82,6 +82,8 @@ typedef enum RtoMode {
 
 #define RTO_FLAG_SHADOWS      1u   /* BVH scenes: one shadow ray per primary hit towards normalize(1,1,1) */
 #define RTO_FLAG_NO_PRUNE     2u   /* BVH scenes: visit every box the reference's queryNode visits (no t-pruning) */
+#define RTO_FLAG_SORT_RAYS    4u   /* rto_trace_rays: trace the list in coherence order (octant, Morton cell of the entry point into the
+                                      scene box, coarse direction; radix sort on the device); results are the same, in the caller's order */
 
 typedef struct RtoScene RtoScene;          /* device-resident scene (BVH or octree), one CUDA stream each */
 typedef struct RtoHostBvh RtoHostBvh;      /* host BVH identical in shape to the reference's BVH */

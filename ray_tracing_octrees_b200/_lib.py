@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "librto_%s.so" % os.environ["RTO_LIB_VARIANT"] if 
 
 RTO_OK = 0
 MODE_BVH, MODE_OCTREE_SKIP, MODE_OCTREE_GLSL = 0, 1, 2
-FLAG_SHADOWS, FLAG_NO_PRUNE = 1, 2
+FLAG_SHADOWS, FLAG_NO_PRUNE, FLAG_SORT_RAYS = 1, 2, 4
 MEM_HOST, MEM_DEVICE = 0, 1
 
 

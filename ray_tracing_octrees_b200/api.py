@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 from . import _lib as L
-from ._lib import (FLAG_NO_PRUNE, FLAG_SHADOWS, MEM_DEVICE, MEM_HOST, MODE_BVH, MODE_OCTREE_GLSL, MODE_OCTREE_SKIP,
+from ._lib import (FLAG_NO_PRUNE, FLAG_SHADOWS, FLAG_SORT_RAYS, MEM_DEVICE, MEM_HOST, MODE_BVH, MODE_OCTREE_GLSL, MODE_OCTREE_SKIP,
                    RtoCamera, RtoError, RtoFrame, check, lib)
 
 MISS_T = np.float32(1e30)
@@ -385,6 +385,10 @@ class Scene:
         ids = np.empty(len(o), np.int32)
         check(lib().rto_trace_rays(self.h, mode, flags, _p(o), _p(d), len(o), tmin, tmax, _p(t), _p(ids), MEM_HOST))
         return t, ids
+
+    def trace_rays_device(self, o_ptr, d_ptr, n, mode, flags, t_ptr, id_ptr, tmin=0.0, tmax=1e30):
+        """rto_trace_rays on device-resident ray lists and outputs (raw device addresses); asynchronous on the scene's stream."""
+        check(lib().rto_trace_rays(self.h, mode, flags, C.c_void_p(o_ptr), C.c_void_p(d_ptr), n, tmin, tmax, C.c_void_p(t_ptr), C.c_void_p(id_ptr), MEM_DEVICE))
 
     def query(self, origins, dirs):
         """BVH::query for many rays -> (offsets int64 (n+1,), triangle ids int32) in the reference's candidate order."""

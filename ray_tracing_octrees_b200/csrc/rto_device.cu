@@ -4,6 +4,7 @@
 // There is no CPU fallback in this file: every entry point that traces rays requires a CUDA device.
 #include "rto_scene.cuh"
 #include "rto_kernels.cuh"
+#include <cub/cub.cuh>
 
 #include <cstdarg>
 #include <cstdio>
@@ -371,8 +372,30 @@ extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float
 		if (idOut) { if ((rc = scene_scratch(s, 2, numRays * 4, &p))) return rc; dI = (int32_t*)p; }
 	}
 	unsigned blocks = (unsigned)((numRays + 127) / 128);
-	if (s->kind == RTO_MODE_BVH) k_trace_bvh<<<blocks, 128, 0, s->stream>>>((flags & RTO_FLAG_NO_PRUNE) ? s->bvh : s->bvhFast, flags, dO, dD, numRays, dT, dI);
-	else k_trace_octree<<<blocks, 128, 0, s->stream>>>(s->oct, mode, dO, dD, numRays, tMin, tMax, dT, dI);
+	const uint32_t* perm = nullptr;
+	CUDA_TRY(cudaEventRecord(s->evStart, s->stream));          // rto_scene_last_kernel_ms: key generation + sort + trace
+	if ((flags & RTO_FLAG_SORT_RAYS) && numRays > 1) {
+		// ray coherence sorting: trace the rays in the order of their sort keys (rto_kernels.cuh k_ray_sort_keys); results land at each ray's own index
+		if (numRays >= ((size_t)1 << 31)) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_trace_rays: RTO_FLAG_SORT_RAYS takes fewer than 2^31 rays");
+		float lo[3], hi[3];
+		if (s->kind == RTO_MODE_BVH) for (int a = 0; a < 3; a++) { lo[a] = s->bvhFast.rootLo[a]; hi[a] = s->bvhFast.rootHi[a]; }
+		else for (int a = 0; a < 3; a++) { lo[a] = s->oct.gmin[a]; hi[a] = s->oct.gmin[a] + (float)s->oct.rootSize * s->oct.voxel; }
+		void *k0 = nullptr, *k1 = nullptr, *i0 = nullptr, *i1 = nullptr, *tmp = nullptr;
+		if ((rc = scene_scratch(s, 4, numRays * 8, &k0))) return rc;
+		if ((rc = scene_scratch(s, 5, numRays * 8, &i0))) return rc;
+		k1 = (uint32_t*)k0 + numRays; i1 = (uint32_t*)i0 + numRays;
+		size_t tmpBytes = 0;
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (uint32_t*)k0, (uint32_t*)k1, (uint32_t*)i0, (uint32_t*)i1, (int)numRays, 0, 32, s->stream));
+		if ((rc = scene_scratch(s, 6, tmpBytes, &tmp))) return rc;
+		k_ray_sort_keys<<<(unsigned)((numRays + 255) / 256), 256, 0, s->stream>>>(dO, dD, numRays, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], (uint32_t*)k0, (uint32_t*)i0);
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, (uint32_t*)k0, (uint32_t*)k1, (uint32_t*)i0, (uint32_t*)i1, (int)numRays, 0, 32, s->stream));
+		perm = (const uint32_t*)i1;
+		s->launches += 2;
+	}
+	if (s->kind == RTO_MODE_BVH) k_trace_bvh<<<blocks, 128, 0, s->stream>>>((flags & RTO_FLAG_NO_PRUNE) ? s->bvh : s->bvhFast, flags, dO, dD, numRays, dT, dI, perm);
+	else k_trace_octree<<<blocks, 128, 0, s->stream>>>(s->oct, mode, dO, dD, numRays, tMin, tMax, dT, dI, perm);
+	CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
+	s->timed = true;
 	s->launches++;
 	CUDA_TRY(cudaGetLastError());
 	if (host) {

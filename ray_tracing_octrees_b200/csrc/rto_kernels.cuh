@@ -1057,10 +1057,35 @@ __global__ void __launch_bounds__(128, MODE == RTO_MODE_OCTREE_SKIP ? 6 : RTO_OC
 // ------------------------------------------------------------------------------------------------
 // Explicit ray lists
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_trace_octree(OctDev S, int mode, const float* __restrict__ o3, const float* __restrict__ d3, size_t n,
-	float tMin, float tMax, float* tOut, int* idOut) {
+// Ray coherence sorting for explicit ray lists (RTO_FLAG_SORT_RAYS): key = octant of the direction (3 bits), Morton code of the point
+// where the ray meets the scene box (7 bits per axis) and a coarse direction (4 + 4 bits).  Rays that share a key start in the same
+// 1/128 cell of the scene and point the same way, so neighbouring lanes walk the same nodes.  The arithmetic here only decides the
+// ORDER in which rays are traced (perm); every ray is traced by the same code and its result lands at its own index.
+__global__ void __launch_bounds__(256) k_ray_sort_keys(const float* __restrict__ o3, const float* __restrict__ d3, size_t n,
+	float lox, float loy, float loz, float hix, float hiy, float hiz, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
+	float ox = o3[3 * i], oy = o3[3 * i + 1], oz = o3[3 * i + 2], dx = d3[3 * i], dy = d3[3 * i + 1], dz = d3[3 * i + 2];
+	float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+	float t0 = fmaxf(fmaxf(fminf((lox - ox) * ix, (hix - ox) * ix), fminf((loy - oy) * iy, (hiy - oy) * iy)), fmaxf(fminf((loz - oz) * iz, (hiz - oz) * iz), 0.0f));
+	if (!(t0 >= 0.0f && t0 < 3.0e38f)) t0 = 0.0f;
+	float px = ox + t0 * dx, py = oy + t0 * dy, pz = oz + t0 * dz;
+	auto cell = [](float p, float lo, float hi) { float u = (p - lo) / (hi - lo) * 128.0f; int c = (int)u; return (uint32_t)(c < 0 || !(u == u) ? 0 : (c > 127 ? 127 : c)); };
+	auto spread = [](uint32_t v) { v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu; v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+	uint32_t m = spread(cell(px, lox, hix)) | (spread(cell(py, loy, hiy)) << 1) | (spread(cell(pz, loz, hiz)) << 2);
+	float len = sqrtf(dx * dx + dy * dy + dz * dz);
+	float ax = fabsf(dx) / len, ay = fabsf(dy) / len;
+	uint32_t qa = (uint32_t)fminf(fmaxf(ax * 16.0f, 0.0f), 15.0f), qb = (uint32_t)fminf(fmaxf(ay * 16.0f, 0.0f), 15.0f);
+	uint32_t oct = (dx < 0 ? 1u : 0u) | (dy < 0 ? 2u : 0u) | (dz < 0 ? 4u : 0u);
+	keys[i] = (oct << 29) | ((m & 0x1fffffu) << 8) | (qa << 4) | qb;
+	idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(128) k_trace_octree(OctDev S, int mode, const float* __restrict__ o3, const float* __restrict__ d3, size_t n,
+	float tMin, float tMax, float* tOut, int* idOut, const uint32_t* __restrict__ perm) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (perm) i = perm[i];
 	V3 o = mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
 	OctHit h = oct_trace<false>(S, mode, o, d, tMin, tMax);
 	if (tOut) tOut[i] = h.t;
@@ -1068,9 +1093,10 @@ __global__ void __launch_bounds__(128) k_trace_octree(OctDev S, int mode, const 
 }
 
 __global__ void __launch_bounds__(128) k_trace_bvh(BvhDev S, unsigned flags, const float* __restrict__ o3, const float* __restrict__ d3, size_t n,
-	float* tOut, int* idOut) {
+	float* tOut, int* idOut, const uint32_t* __restrict__ perm) {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
+	if (perm) i = perm[i];
 	V3 o = mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
 	float bestT; int bestPos;
 	if (flags & RTO_FLAG_NO_PRUNE) bvh_closest<false>(S, o, d, bestT, bestPos); else bvh_closest<true>(S, o, d, bestT, bestPos);

@@ -433,3 +433,27 @@ def test_bvh_awkward_rays_match_the_exact_replay(gpu):
     bad = np.nonzero(i0 != i1)[0]
     assert len(bad) == 0, "%d rays differ, first: o=%s d=%s exact=(%d, %g) fast=(%d, %g)" % (len(bad), o[bad[0]], d[bad[0]], i0[bad[0]], t0[bad[0]], i1[bad[0]], t1[bad[0]])
     assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+
+
+def test_ray_coherence_sorting_changes_nothing_but_the_order(gpu, dt_scene):
+    """RTO_FLAG_SORT_RAYS traces an explicit ray list in the order of a device radix sort on (octant, Morton cell of the entry point,
+    coarse direction); every result must land at its ray's own index with the same bits, for all three traversals, including rays
+    that miss the scene box, start inside it, or have zero direction components."""
+    rto = gpu
+    g, sc, oc = dt_scene["grid"], dt_scene["bvh"], dt_scene["oct"]
+    rng = np.random.default_rng(11)
+    n = 200_000
+    ext = np.array(g.dims, np.float32) * np.float32(g.voxel_size)
+    lo = np.array(g.min, np.float32)
+    o = (lo + (rng.random((n, 3)).astype(np.float32) * 3 - 1) * ext).astype(np.float32)            # inside and around the grid
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[::17, 0] = 0.0; d[::23, 1] = 0.0; d[::29, 2] = 0.0
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    for scene, mode in ((sc, rto.MODE_BVH), (oc, rto.MODE_OCTREE_SKIP), (oc, rto.MODE_OCTREE_GLSL)):
+        t0, i0 = scene.trace_rays(o, d, mode)
+        t1, i1 = scene.trace_rays(o, d, mode, flags=rto.FLAG_SORT_RAYS)
+        assert (i0 >= 0).mean() > 0.02
+        assert np.array_equal(i0, i1)
+        assert_bit_equal(t0, t1, "t mode %d" % mode)
+    t1, i1 = sc.trace_rays(o[:1], d[:1], rto.MODE_BVH, flags=rto.FLAG_SORT_RAYS)                     # a single ray is not sorted
+    assert i1[0] == sc.trace_rays(o[:1], d[:1], rto.MODE_BVH)[1][0]
