@@ -41,7 +41,12 @@ def main():
             del sc
         return
     nodes = rto.create_octree_from_voxel_grid(g)
-    if "dcbvh" in a.case:
+    if "devbvh" in a.case:          # the device-built tree over the Marching-Cubes soup (RTO_DEVICE_BVH=lbvh: radix tree instead of clustering)
+        import time
+        tris = rto.marching_cubes_mesh(g, nodes)
+        t0 = time.time(); sc = rto.Scene.bvh_device(tris); print("device BVH over %d triangles built in %.3f s" % (len(tris), time.time() - t0))
+        mode, flags, bias = rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3 * g.voxel_size
+    elif "dcbvh" in a.case:
         sc = rto.Scene.bvh(rto.dual_contouring_mesh(g, nodes))
         mode, flags, bias = rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3 * g.voxel_size
     elif "bvh" in a.case:
