@@ -726,124 +726,6 @@ __global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, flo
 	}
 }
 
-// ---- PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) over the Morton-sorted leaves -----------------------------
-// The radix tree above splits where Morton prefixes change, whatever the boxes look like.  PLOC builds the tree bottom-up instead:
-// every cluster looks at its `radius` neighbours on either side in Morton order for the one whose union with it has the smallest
-// surface area, clusters that chose each other merge into an inner node, the list is compacted, and the round repeats until one
-// cluster is left.  Same leaves, same records, same node layout and the same exact union boxes as the radix tree; the topology is
-// what a surface-area heuristic would pick locally.  Deterministic: node indices come from prefix sums, ties go to the lower index.
-constexpr int kPlocMaxRadius = 32;
-
-__device__ __forceinline__ float ploc_union_area(const float* a, const float* b) {
-	const float dx = fmaxf(a[3], b[3]) - fminf(a[0], b[0]), dy = fmaxf(a[4], b[4]) - fminf(a[1], b[1]), dz = fmaxf(a[5], b[5]) - fminf(a[2], b[2]);
-	return dx * dy + dy * dz + dz * dx;
-}
-
-__global__ void __launch_bounds__(256) k_ploc_nearest(const float* __restrict__ box, int n, int radius, int* __restrict__ nn) {
-	__shared__ float tile[(256 + 2 * kPlocMaxRadius) * 6];
-	const int base = blockIdx.x * 256 - radius, count = 256 + 2 * radius;
-	for (int k = threadIdx.x; k < count * 6; k += 256) {
-		const int c = base + k / 6;
-		tile[k] = (c >= 0 && c < n) ? box[6 * (size_t)c + k % 6] : 0.0f;
-	}
-	__syncthreads();
-	const int i = blockIdx.x * 256 + threadIdx.x;
-	if (i >= n) return;
-	const float* mine = tile + 6 * (threadIdx.x + radius);
-	float best = FLT_MAX; int bestJ = -1;
-	for (int o = -radius; o <= radius; o++) {
-		const int j = i + o;
-		if (o == 0 || j < 0 || j >= n) continue;
-		const float a = ploc_union_area(mine, tile + 6 * (threadIdx.x + radius + o));
-		if (a < best) { best = a; bestJ = j; }            // ascending j: ties keep the lower index
-	}
-	nn[i] = bestJ;
-}
-
-// low 32 bits: the cluster stays in the list (everything but the higher partner of a merging pair); high 32 bits: it leads a merge
-__global__ void k_ploc_flags(const int* __restrict__ nn, int n, unsigned long long* __restrict__ flags) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const int j = nn[i];
-	const bool mutual = j >= 0 && nn[j] == i;
-	flags[i] = (mutual && i > j ? 0ull : 1ull) | (mutual && i < j ? (1ull << 32) : 0ull);
-}
-
-__global__ void k_ploc_merge(const float* __restrict__ box, const int* __restrict__ ref, const int* __restrict__ height, const int* __restrict__ nn, int n,
-	const unsigned long long* __restrict__ ex, int nodesBase, float* __restrict__ outBox, int* __restrict__ outRef, int* __restrict__ outHeight, float* __restrict__ nodes) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const int j = nn[i];
-	const bool mutual = j >= 0 && nn[j] == i;
-	if (mutual && i > j) return;
-	const size_t pos = (size_t)(ex[i] & 0xffffffffull);
-	float b[6];
-#pragma unroll
-	for (int k = 0; k < 6; k++) b[k] = box[6 * (size_t)i + k];
-	int r = ref[i], h = height[i];
-	if (mutual) {
-		const int node = nodesBase + (int)(ex[i] >> 32);
-		float* n16 = nodes + 16 * (size_t)node;
-		float c[6];
-#pragma unroll
-		for (int k = 0; k < 6; k++) { c[k] = box[6 * (size_t)j + k]; n16[k] = b[k]; n16[6 + k] = c[k]; }
-		n16[12] = __int_as_float(r); n16[13] = __int_as_float(ref[j]); n16[14] = 0.0f; n16[15] = 0.0f;
-#pragma unroll
-		for (int k = 0; k < 3; k++) { b[k] = fminf(b[k], c[k]); b[3 + k] = fmaxf(b[3 + k], c[3 + k]); }
-		r = node; h = max(h, height[j]) + 1;
-	}
-#pragma unroll
-	for (int k = 0; k < 6; k++) outBox[6 * pos + k] = b[k];
-	outRef[pos] = r; outHeight[pos] = h;
-}
-
-__global__ void k_ploc_init(int numLeaves, int perLeaf, size_t numTris, int* __restrict__ ref, int* __restrict__ height) {
-	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
-	if (leaf >= numLeaves) return;
-	const size_t p = perLeaf * (size_t)leaf;
-	const int cnt = (perLeaf == 2 && p + 1 < numTris) ? 2 : 1;
-	ref[leaf] = ~(int)((p << 1) | (size_t)(cnt - 1));
-	height[leaf] = 0;
-}
-
-// leafBox: 6 floats per leaf in Morton order (consumed); nodes: numLeaves - 1 records of 16 floats.  Returns root index, box, height.
-int ploc_build(DevPool& tmp, float* leafBox, int numLeaves, int perLeaf, size_t numTris, float* nodes, int radius, cudaStream_t st,
-	int* rootRef, float root[6], int* rootHeight, int* roundsOut) {
-	float* boxA = leafBox; float* boxB = nullptr; int *refA = nullptr, *refB = nullptr, *hA = nullptr, *hB = nullptr, *nn = nullptr;
-	unsigned long long *flags = nullptr, *ex = nullptr;
-	BUILD_TRY(tmp.alloc(&boxB, 6 * (size_t)numLeaves)); BUILD_TRY(tmp.alloc(&refA, numLeaves)); BUILD_TRY(tmp.alloc(&refB, numLeaves));
-	BUILD_TRY(tmp.alloc(&hA, numLeaves)); BUILD_TRY(tmp.alloc(&hB, numLeaves)); BUILD_TRY(tmp.alloc(&nn, numLeaves));
-	BUILD_TRY(tmp.alloc(&flags, numLeaves)); BUILD_TRY(tmp.alloc(&ex, numLeaves));
-	size_t scanBytes = 0; uint8_t* scanTmp = nullptr;
-	BUILD_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, flags, ex, numLeaves, st));
-	BUILD_TRY(tmp.alloc(&scanTmp, scanBytes));
-	k_ploc_init<<<(unsigned)((numLeaves + 255) / 256), 256, 0, st>>>(numLeaves, perLeaf, numTris, refA, hA);
-	int n = numLeaves, nodesUsed = 0, rounds = 0;
-	while (n > 1) {
-		const unsigned blocks = (unsigned)((n + 255) / 256);
-		k_ploc_nearest<<<blocks, 256, 0, st>>>(boxA, n, radius, nn);
-		k_ploc_flags<<<blocks, 256, 0, st>>>(nn, n, flags);
-		BUILD_TRY(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, flags, ex, n, st));
-		k_ploc_merge<<<blocks, 256, 0, st>>>(boxA, refA, hA, nn, n, ex, nodesUsed, boxB, refB, hB, nodes);
-		BUILD_TRY(cudaGetLastError());
-		unsigned long long lastEx = 0, lastFlag = 0;
-		BUILD_TRY(cudaMemcpyAsync(&lastEx, ex + (n - 1), 8, cudaMemcpyDeviceToHost, st));
-		BUILD_TRY(cudaMemcpyAsync(&lastFlag, flags + (n - 1), 8, cudaMemcpyDeviceToHost, st));
-		BUILD_TRY(cudaStreamSynchronize(st));
-		const unsigned long long tot = lastEx + lastFlag;
-		const int merges = (int)(tot >> 32), kept = (int)(tot & 0xffffffffull);
-		if (merges <= 0 || kept != n - merges) return rto_fail(RTO_ERR_CUDA, "BVH build on the device: clustering round made no progress");
-		nodesUsed += merges; n = kept; rounds++;
-		std::swap(boxA, boxB); std::swap(refA, refB); std::swap(hA, hB);
-	}
-	BUILD_TRY(cudaMemcpyAsync(root, boxA, 24, cudaMemcpyDeviceToHost, st));
-	BUILD_TRY(cudaMemcpyAsync(rootRef, refA, 4, cudaMemcpyDeviceToHost, st));
-	BUILD_TRY(cudaMemcpyAsync(rootHeight, hA, 4, cudaMemcpyDeviceToHost, st));
-	BUILD_TRY(cudaStreamSynchronize(st));
-	if (roundsOut) *roundsOut = rounds;
-	return RTO_OK;
-}
-
 // tris: device array of numTris RtoTriangle (reference emission order, index == hit id).  Fills s->bvh / s->bvhFast.
 int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	cudaStream_t st = s->stream;
@@ -857,10 +739,6 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	// Moller-Trumbore tests, the block that runs with the fewest lanes) or 2 (RTO_LBVH_LEAF=2, tuning aid)
 	static const int perLeaf = [] { const char* e = getenv("RTO_LBVH_LEAF"); return (e && e[0] == '2') ? 2 : 1; }();
 	const int numLeaves = (int)((numTris + perLeaf - 1) / perLeaf), numInner = numLeaves - 1;
-	static const int plocRadius = [] {
-		const char* e = getenv("RTO_DEVICE_BVH"); if (e && !strcmp(e, "lbvh")) return 0;
-		int r = 16; if (const char* q = getenv("RTO_PLOC_RADIUS")) { int v = atoi(q); if (v >= 1 && v <= kPlocMaxRadius) r = v; }
-		return r; }();
 	int* dBounds = nullptr;
 	BUILD_TRY(tmp.alloc(&dBounds, 6));
 	{
@@ -907,18 +785,7 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 		BUILD_TRY(cudaStreamSynchronize(st));
 		D.rootRef = ~(int)(numTris - 1);          // leafRef = (0 << 1) | (count - 1)
 	}
-	bool built = false;
-	if (numInner > 0 && plocRadius > 0) {
-		// default: locally-ordered clustering over the sorted leaves (better boxes than the radix tree; RTO_DEVICE_BVH=lbvh selects the latter)
-		int rootRef = 0, height = 0, rounds = 0;
-		float* boxCopy = nullptr;                         // the clustering consumes its input; the radix tree below may still need the leaf boxes
-		BUILD_TRY(tmp.alloc(&boxCopy, 6 * (size_t)numLeaves));
-		BUILD_TRY(cudaMemcpyAsync(boxCopy, leafBox, 24 * (size_t)numLeaves, cudaMemcpyDeviceToDevice, st));
-		rc = ploc_build(tmp, boxCopy, numLeaves, perLeaf, numTris, (float*)dNodes, plocRadius, st, &rootRef, root, &height, &rounds);
-		if (rc) return rc;
-		if (height <= 92) { D.rootRef = rootRef; built = true; }      // deeper than the traversal stack allows: fall back to the radix tree
-	}
-	if (numInner > 0 && !built) {
+	else {
 		int *pInner = nullptr, *pLeaf = nullptr, *arrived = nullptr, *dDepth = nullptr;
 		BUILD_TRY(tmp.alloc(&pInner, numInner)); BUILD_TRY(tmp.alloc(&pLeaf, numLeaves)); BUILD_TRY(tmp.alloc(&arrived, numInner)); BUILD_TRY(tmp.alloc(&dDepth, 1));
 		BUILD_TRY(cudaMemsetAsync(arrived, 0, sizeof(int) * (size_t)numInner, st));

@@ -41,7 +41,7 @@ def main():
             del sc
         return
     nodes = rto.create_octree_from_voxel_grid(g)
-    if "devbvh" in a.case:          # the device-built tree over the Marching-Cubes soup (RTO_DEVICE_BVH=lbvh: radix tree instead of clustering)
+    if "devbvh" in a.case:          # the device-built tree over the Marching-Cubes soup 
         import time
         tris = rto.marching_cubes_mesh(g, nodes)
         t0 = time.time(); sc = rto.Scene.bvh_device(tris); print("device BVH over %d triangles built in %.3f s" % (len(tris), time.time() - t0))
