@@ -1005,7 +1005,9 @@ RTO_DEV void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, floa
 }
 
 #ifndef RTO_BVH_MIN_BLOCKS
-#define RTO_BVH_MIN_BLOCKS 12     // 40 registers, 48 warps per SM: 4 % faster than the unconstrained 48-register build, 16 blocks (32 registers) is slower
+#define RTO_BVH_MIN_BLOCKS 10     // 48 registers, 40 warps per SM.  Re-measured on the final kernel (8 x 1080p, C2 / primary only / 512^3 city / sphere):
+                                  // 10 blocks 1.716 / 1.187 / 2.573 / 0.493 ms, 12 blocks (40 registers) 1.732 / 1.217 / 2.570 / 0.506, 8 blocks (58 registers, no
+                                  // spills) 1.838 / 1.224 / 2.857 / 0.503; 14-16 blocks (32 registers) is slower still
 #endif
 template <bool SHADOWS, bool PRUNE>
 __global__ void __launch_bounds__(128, RTO_BVH_MIN_BLOCKS) k_render_bvh(BvhDev S, RenderArgs A) {
