@@ -1040,10 +1040,13 @@ __global__ void __launch_bounds__(128, RTO_BVH_MIN_BLOCKS) k_render_bvh(BvhDev S
 // One instantiation per traversal mode so that each gets its own register budget: the mode-A walk wants ~80 registers (it
 // spills at 64), the lighter mode-B walk runs better with 8 resident blocks per SM (64 registers).
 #ifndef RTO_OCT_B_MIN_BLOCKS
-#define RTO_OCT_B_MIN_BLOCKS 8
+#define RTO_OCT_B_MIN_BLOCKS 12    // re-measured: 12 blocks 2.12 / 3.31 ms, 8 blocks 2.20 / 3.45, 10 blocks 2.15 / 3.38, 14-16 blocks 2.18 / 3.41
+#endif
+#ifndef RTO_OCT_A_MIN_BLOCKS
+#define RTO_OCT_A_MIN_BLOCKS 8     // re-measured (DT / 512^3 city, 8 x 1080p): 8 blocks 2.60 / 4.14 ms, 6 blocks 2.66 / 4.25, 10 blocks 2.62 / 4.17, 4-5 and 12 slower
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(128, MODE == RTO_MODE_OCTREE_SKIP ? 6 : RTO_OCT_B_MIN_BLOCKS) k_render_octree(OctDev S, RenderArgs A) {
+__global__ void __launch_bounds__(128, MODE == RTO_MODE_OCTREE_SKIP ? RTO_OCT_A_MIN_BLOCKS : RTO_OCT_B_MIN_BLOCKS) k_render_octree(OctDev S, RenderArgs A) {
 	const int mode = MODE;
 	RtoCamera cam = A.cam0;
 	if (A.cams) cam = A.cams[blockIdx.z];
