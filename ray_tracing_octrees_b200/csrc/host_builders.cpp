@@ -410,7 +410,8 @@ struct SahBuilder {
 			r1 = build(mid, hi, idx + (mid - lo), depth + 1, rmn, rmx);
 		}
 		float* d = &(*out)[idx * 16];
-		std::memcpy(d, lmn, 12); std::memcpy(d + 3, lmx, 12); std::memcpy(d + 6, rmn, 12); std::memcpy(d + 9, rmx, 12);
+		// paired layout (BvhDev::paired): plane k of child 0 and of child 1 side by side, k = lo x, lo y, lo z, hi x, hi y, hi z
+		for (int k = 0; k < 3; k++) { d[2 * k] = lmn[k]; d[2 * k + 1] = rmn[k]; d[6 + 2 * k] = lmx[k]; d[6 + 2 * k + 1] = rmx[k]; }
 		std::memcpy(&d[12], &r0, 4); std::memcpy(&d[13], &r1, 4);
 		return (int32_t)idx;
 	}

@@ -690,8 +690,8 @@ __global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int perLeaf, int
 }
 
 __device__ __forceinline__ void lbvh_store_child_box(float* node16, int slot, const float lo[3], const float hi[3]) {
-	float* d = node16 + 6 * slot;
-	d[0] = lo[0]; d[1] = lo[1]; d[2] = lo[2]; d[3] = hi[0]; d[4] = hi[1]; d[5] = hi[2];
+	// paired layout (BvhDev::paired): plane k of both children side by side
+	for (int k = 0; k < 3; k++) { node16[2 * k + slot] = lo[k]; node16[6 + 2 * k + slot] = hi[k]; }
 }
 
 // bottom-up: every leaf writes its box into its parent's slot; the second child to arrive at a node unites the two and climbs
@@ -714,9 +714,9 @@ __global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, flo
 		lbvh_store_child_box(n16, slot, lo, hi);
 		__threadfence();
 		if (atomicAdd(arrived + node, 1) == 0) return;          // the sibling subtree is not finished yet: its thread will continue
-		volatile float* other = n16 + 6 * (slot ^ 1);
+		volatile float* other = n16 + (slot ^ 1);
 #pragma unroll
-		for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], other[a]); hi[a] = fmaxf(hi[a], other[3 + a]); }
+		for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], other[2 * a]); hi[a] = fmaxf(hi[a], other[6 + 2 * a]); }
 		link = parentOfInner[node];
 		if (link < 0) {
 #pragma unroll
@@ -730,7 +730,7 @@ __global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, flo
 int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 	cudaStream_t st = s->stream;
 	BvhDev D{};
-	D.numTris = (int)numTris; D.rootRef = -1; D.leafBox = 0; D.grow = 0.0f;
+	D.numTris = (int)numTris; D.rootRef = -1; D.leafBox = 0; D.grow = 0.0f; D.paired = 1; D.exactPaired = 1;
 	s->numPrims = numTris;
 	if (numTris == 0) { s->bvh = D; s->bvhFast = D; s->numNodes = 0; return RTO_OK; }
 	if (numTris >= (size_t)1 << 30) return rto_fail(RTO_ERR_UNSUPPORTED, "BVH build on the device: more than 2^30 triangles");

@@ -225,11 +225,11 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
 	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "BVH upload failed: %s", cudaGetErrorString(e)); }
 	D.nodes = (const float4*)dN; D.tris = (const float4*)dT;
-	D.leafBox = 0; D.grow = 0.0f;
+	D.leafBox = 0; D.grow = 0.0f; D.paired = 0; D.exactPaired = 0;
 	D.exactNodes = D.nodes; D.exactRoot = D.rootRef; D.exactLeafBox = 0;
 	s->bvh = D;
 	s->bvhFast = D;
-	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = L.fastRoot; s->bvhFast.leafBox = 1; s->bvhFast.grow = L.fastGrow; }
+	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = L.fastRoot; s->bvhFast.leafBox = 1; s->bvhFast.grow = L.fastGrow; s->bvhFast.paired = 1; }
 	*out = s;
 	return RTO_OK;
 }

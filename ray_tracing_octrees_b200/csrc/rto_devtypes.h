@@ -24,6 +24,10 @@ struct BvhDev {
 	                         // only if the box of its reference leaf (in its record) passes intersectAABB: tested at the leaf.
 	                         // 0: the tree's leaves are the reference's leaves and their boxes were tested in the parent node.
 	float rootLo[3], rootHi[3];
+	int   paired;            // node layout of `nodes`: 0 = child 0's box then child 1's ([lo0.xyz hi0.x][hi0.yz lo1.xy][lo1.z hi1.xyz]); 1 = the two children
+	                         // interleaved plane by plane ([lo0.x lo1.x lo0.y lo1.y][lo0.z lo1.z hi0.x hi1.x][hi0.y hi1.y hi0.z hi1.z]), so that the same plane of both
+	                         // children sits in one 64-bit register pair and one packed FFMA2 (fma.rn.f32x2, sm_100) tests it for both
+	int   exactPaired;       // the same for `exactNodes`
 };
 
 struct OctDev {

@@ -204,13 +204,52 @@ RTO_DEV int ray_octant(const BvhDev& S, const RayBox& rb) {
 	return (rb.nx ? 1 : 0) | (rb.ny ? 2 : 0) | (rb.nz ? 4 : 0);
 }
 
+// packed fp32 x 2 fused multiply-add: one FFMA2 on sm_100 (fma.rn.f32x2), two fmaf elsewhere (tests/emu).  Each half is an IEEE fma.
+RTO_DEV float2 fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+	unsigned long long ra, rb, rc, rd;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+	asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+	asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+	float2 d;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+	return d;
+#else
+	return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+// per-ray constants of the paired node test: 1/d and -o/d of every axis twice
+struct RayBox2 { float2 ix, iy, iz, nx, ny, nz; };
+RTO_DEV RayBox2 make_raybox2(const RayBox& rb) {
+	RayBox2 r;
+	r.ix = make_float2(rb.inv.x, rb.inv.x); r.iy = make_float2(rb.inv.y, rb.inv.y); r.iz = make_float2(rb.inv.z, rb.inv.z);
+	r.nx = make_float2(rb.noi.x, rb.noi.x); r.ny = make_float2(rb.noi.y, rb.noi.y); r.nz = make_float2(rb.noi.z, rb.noi.z);
+	return r;
+}
+// slab_oct for both children of a node in the paired layout (BvhDev::paired): six FFMA2 instead of twelve FFMA
+template <int OCT>
+RTO_DEV void slab_oct_pair(const RayBox2& r, float4 a, float4 b, float4 c, float tcap, bool& h0, bool& h1, float& e0, float& e1) {
+	const float2 loX = make_float2(a.x, a.y), loY = make_float2(a.z, a.w), loZ = make_float2(b.x, b.y);
+	const float2 hiX = make_float2(b.z, b.w), hiY = make_float2(c.x, c.y), hiZ = make_float2(c.z, c.w);
+	const float2 t0x = fma2((OCT & 1) ? hiX : loX, r.ix, r.nx), t1x = fma2((OCT & 1) ? loX : hiX, r.ix, r.nx);
+	const float2 t0y = fma2((OCT & 2) ? hiY : loY, r.iy, r.ny), t1y = fma2((OCT & 2) ? loY : hiY, r.iy, r.ny);
+	const float2 t0z = fma2((OCT & 4) ? hiZ : loZ, r.iz, r.nz), t1z = fma2((OCT & 4) ? loZ : hiZ, r.iz, r.nz);
+	e0 = fmaxf(fmaxf(fmaxf(t0x.x, t0y.x), t0z.x), 0.0f);
+	e1 = fmaxf(fmaxf(fmaxf(t0x.y, t0y.y), t0z.y), 0.0f);
+	const float x0 = fminf(fminf(fminf(t1x.x, t1y.x), t1z.x), tcap), x1 = fminf(fminf(fminf(t1x.y, t1y.y), t1z.y), tcap);
+	h0 = !(x0 < e0); h1 = !(x1 < e1);
+}
+
 // both child boxes of an inner node (layout in BvhDev)
 // h0/h1: the child's box passes intersectAABB and is entered no later than tcap (tcap = FLT_MAX: no pruning)
+// Trees with grown boxes (the only ones the fused tests run on) are stored in the paired layout; the reference-shaped tree is not.
 template <int OCT>
-RTO_DEV void node_boxes(const RayBox& rb, float4 a, float4 b, float4 c, float tcap, bool& h0, bool& h1, float& e0, float& e1) {
-	if (OCT < kOctGeneric) {
-		h0 = slab_oct<OCT>(rb.noi, rb.inv, a.x, a.y, a.z, a.w, b.x, b.y, tcap, e0);
-		h1 = slab_oct<OCT>(rb.noi, rb.inv, b.z, b.w, c.x, c.y, c.z, c.w, tcap, e1);
+RTO_DEV void node_boxes(const RayBox& rb, const RayBox2& rb2, int paired, float4 a, float4 b, float4 c, float tcap, bool& h0, bool& h1, float& e0, float& e1) {
+	if (OCT < kOctGeneric) slab_oct_pair<OCT>(rb2, a, b, c, tcap, h0, h1, e0, e1);
+	else if (paired) {
+		h0 = slab_ref(rb, a.x, a.z, b.x, b.z, c.x, c.z, e0) && (e0 <= tcap);
+		h1 = slab_ref(rb, a.y, a.w, b.y, b.w, c.y, c.w, e1) && (e1 <= tcap);
 	}
 	else {
 		h0 = slab_ref(rb, a.x, a.y, a.z, a.w, b.x, b.y, e0) && (e0 <= tcap);
@@ -237,6 +276,7 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 	StackEnt stack[kBvhStack];                 // one 8-byte local store / load per push / pop
 	int sp = 0;
 	int cur = S.rootRef;
+	const RayBox2 rb2 = make_raybox2(rb);
 	float tcut = kMissT * kPruneSlack;
 	// (a per-step warp vote that re-joins the lanes, the change that made the octree mode-A walk 2x faster, costs 5-9 % here)
 	{
@@ -248,7 +288,7 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 				float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
 				float e0, e1;
 				bool h0, h1;
-				node_boxes<OCT>(rb, a, b, c, PRUNE ? tcut : FLT_MAX, h0, h1, e0, e1);
+				node_boxes<OCT>(rb, rb2, S.paired, a, b, c, PRUNE ? tcut : FLT_MAX, h0, h1, e0, e1);
 				int r0 = f2i(r.x), r1 = f2i(r.y);
 				if (h0 && h1) {
 					bool swap = PRUNE && (e1 < e0);
@@ -306,7 +346,7 @@ RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos
 	case 7: bvh_closest_loop<PRUNE, 7>(S, rb, o, d, bestT, bestPos); break;
 	default: {
 		// not admitted to the fused tests (zero / infinite 1/d, far origin): the reference's own arithmetic on the exact tree
-		BvhDev E = S; E.nodes = S.exactNodes; E.rootRef = S.exactRoot; E.leafBox = S.exactLeafBox; E.grow = 0.0f;
+		BvhDev E = S; E.nodes = S.exactNodes; E.rootRef = S.exactRoot; E.leafBox = S.exactLeafBox; E.grow = 0.0f; E.paired = S.exactPaired;
 		bvh_closest_loop<PRUNE, kOctGeneric>(E, rb, o, d, bestT, bestPos);
 		break; }
 	}
@@ -318,6 +358,7 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 	int stackRef[kBvhStack];
 	int sp = 0;
 	int cur = S.rootRef;
+	const RayBox2 rb2 = make_raybox2(rb);
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
@@ -325,7 +366,7 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
 			float e0, e1;
 			bool h0, h1;
-			node_boxes<OCT>(rb, a, b, c, FLT_MAX, h0, h1, e0, e1);
+			node_boxes<OCT>(rb, rb2, S.paired, a, b, c, FLT_MAX, h0, h1, e0, e1);
 			int r0 = f2i(r.x), r1 = f2i(r.y);
 			if (h0 && h1) {
 				bool swap = e1 < e0;
@@ -366,7 +407,7 @@ RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 	case 6: return bvh_any_loop<6>(S, rb, o, d);
 	case 7: return bvh_any_loop<7>(S, rb, o, d);
 	default: {
-		BvhDev E = S; E.nodes = S.exactNodes; E.rootRef = S.exactRoot; E.leafBox = S.exactLeafBox; E.grow = 0.0f;
+		BvhDev E = S; E.nodes = S.exactNodes; E.rootRef = S.exactRoot; E.leafBox = S.exactLeafBox; E.grow = 0.0f; E.paired = S.exactPaired;
 		return bvh_any_loop<kOctGeneric>(E, rb, o, d); }
 	}
 }

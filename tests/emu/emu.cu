@@ -67,10 +67,10 @@ void* emu_bvh_create(const RtoTriangle* tris, size_t n) {
 	D.numTris = (int)n; D.rootRef = e->L.refRoot;
 	for (int k = 0; k < 3; k++) { D.rootLo[k] = e->L.rootLo[k]; D.rootHi[k] = e->L.rootHi[k]; }
 	D.nodes = (const float4*)e->L.refNodes.data(); D.tris = (const float4*)e->L.tris.data();
-	D.leafBox = 0; D.grow = 0.0f;
+	D.leafBox = 0; D.grow = 0.0f; D.paired = 0; D.exactPaired = 0;
 	D.exactNodes = D.nodes; D.exactRoot = D.rootRef; D.exactLeafBox = 0;
 	e->ref = D; e->fast = D;
-	if (!e->L.fastNodes.empty()) { e->fast.nodes = (const float4*)e->L.fastNodes.data(); e->fast.rootRef = e->L.fastRoot; e->fast.leafBox = 1; e->fast.grow = e->L.fastGrow; }
+	if (!e->L.fastNodes.empty()) { e->fast.nodes = (const float4*)e->L.fastNodes.data(); e->fast.rootRef = e->L.fastRoot; e->fast.leafBox = 1; e->fast.grow = e->L.fastGrow; e->fast.paired = 1; }
 	return e;
 }
 void emu_bvh_free(void* h) { delete (EmuBvh*)h; }

@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
 	RtoTriangle* tris; size_t nt; rto_host_mc_mesh(vox.data(), dims[0], dims[1], dims[2], mv, mv[3], nodes, nn, &tris, &nt);
 	RtoHostBvh* hb; rto_host_bvh_build(tris, nt, &hb);
 	BvhLayout L; rto_build_bvh_layout(*hb, L);
-	BvhDev S; S.numTris = (int)nt; S.rootRef = L.fastRoot; S.leafBox = 1; S.grow = L.fastGrow; S.exactNodes = (const float4*)L.refNodes.data(); S.exactRoot = L.refRoot; S.exactLeafBox = 0; S.nodes = (const float4*)L.fastNodes.data(); S.tris = (const float4*)L.tris.data();
+	BvhDev S; S.numTris = (int)nt; S.rootRef = L.fastRoot; S.leafBox = 1; S.grow = L.fastGrow; S.paired = 1; S.exactPaired = 0; S.exactNodes = (const float4*)L.refNodes.data(); S.exactRoot = L.refRoot; S.exactLeafBox = 0; S.nodes = (const float4*)L.fastNodes.data(); S.tris = (const float4*)L.tris.data();
 	for (int k = 0; k < 3; k++) { S.rootLo[k] = L.rootLo[k]; S.rootHi[k] = L.rootHi[k]; }
 	printf("tris %zu\n", nt);
 	const int W = 1920, H = 1080;
