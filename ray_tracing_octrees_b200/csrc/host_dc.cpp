@@ -65,19 +65,31 @@ int handOver(const char* who, const std::vector<RtoTriangle>& out, RtoTriangle**
 	return RTO_OK;
 }
 
-// the visit order of renderOctree's traverse lambda (main.cpp:152-187): depth first, children 0..7, frustum-culled subtrees dropped
+// the visit order of renderOctree's traverse lambda (main.cpp:152-187): depth first, children 0..7, frustum-culled subtrees dropped.
+// The subtrees three levels below the root are walked on separate threads and their leaf lists joined in order.
 void visitOrder(const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, const float gridMin[3], float voxelSize, float extraMargin, std::vector<int32_t>& order) {
 	FrustumPlanes F;
 	if (viewProj16) F = frustum_from_view_proj(viewProj16);
-	std::vector<int32_t> stack; stack.push_back(0);
-	while (!stack.empty()) {
-		int32_t i = stack.back(); stack.pop_back();
-		if (i < 0 || (size_t)i >= numNodes) continue;
-		const RtoGpuNode& n = nodes[i];
-		if (viewProj16 && !frustum_node_visible(F, n, gridMin, voxelSize, extraMargin)) continue;
-		if (n.isLeaf) order.push_back(i);
-		else for (int c = 7; c >= 0; c--) stack.push_back(n.child[c]);
-	}
+	auto walk = [&](int32_t root, int depthLimit, std::vector<int32_t>& leaves, std::vector<int32_t>* cut) {
+		std::vector<std::pair<int32_t, int>> stack; stack.emplace_back(root, 0);
+		while (!stack.empty()) {
+			auto [i, depth] = stack.back(); stack.pop_back();
+			if (i < 0 || (size_t)i >= numNodes) continue;
+			const RtoGpuNode& n = nodes[i];
+			if (cut && depth == depthLimit) { cut->push_back(i); leaves.push_back(-(int32_t)cut->size()); continue; }     // placeholder -(task + 1)
+			if (viewProj16 && !frustum_node_visible(F, n, gridMin, voxelSize, extraMargin)) continue;
+			if (n.isLeaf) leaves.push_back(i);
+			else for (int c = 7; c >= 0; c--) stack.emplace_back(n.child[c], depth + 1);
+		}
+	};
+	std::vector<int32_t> top, tasks;
+	walk(0, 3, top, &tasks);
+	std::vector<std::vector<int32_t>> parts(tasks.size());
+	parallelFor(tasks.size(), 1, hostThreads(), [&](size_t lo, size_t hi, int) { for (size_t t = lo; t < hi; t++) walk(tasks[t], 0, parts[t], nullptr); });
+	size_t total = 0;
+	for (int32_t v : top) total += v >= 0 ? 1 : parts[(size_t)(-v - 1)].size();
+	order.reserve(total);
+	for (int32_t v : top) { if (v >= 0) order.push_back(v); else { const auto& p = parts[(size_t)(-v - 1)]; order.insert(order.end(), p.begin(), p.end()); } }
 }
 
 UniformBox boxOf(const RtoGpuNode& n) { UniformBox u; u.x0 = n.x; u.y0 = n.y; u.z0 = n.z; u.size = n.size; return u; }
