@@ -203,3 +203,28 @@ def test_scene_from_grid_dc_equals_scene_from_the_dc_soup(rto, grids, name):
     assert (fa["id"] >= 0).any()
     for k in ("id", "t", "rgba"):
         assert_bit_equal(fa[k], fb[k], "%s %s" % (name, k))
+
+
+def test_device_built_tree_exact_path_and_no_prune(rto, grids):
+    """Rays that are not admitted to the fused node tests (zero direction components, far origins) and RTO_FLAG_NO_PRUNE walk the
+    device-built tree with the reference's select-form box test; that tree is stored in the paired node layout, which this path has
+    to unpack.  Same hit distances as the host route's scene (ids may differ at exact ties only)."""
+    g = grids["sphere32"]
+    nodes = rto.create_octree_from_voxel_grid(g)
+    tris = rto.marching_cubes_mesh(g, nodes)
+    dev, host = rto.Scene.bvh_device(tris), rto.Scene.bvh(tris)
+    rng = np.random.default_rng(3)
+    n = 20000
+    o = (rng.random((n, 3)).astype(np.float32) * 3 - 1.5).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[::2, rng.integers(0, 3)] = 0.0                       # every second ray has a zero component: reciprocal is infinite
+    d[::5] = np.array([0, 0, -1], np.float32)              # axis-parallel rays
+    o[::7] *= 4000.0                                       # origins thousands of scene extents away
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    for flags in (0, rto.FLAG_NO_PRUNE):
+        td, idd = dev.trace_rays(o, d, rto.MODE_BVH, flags=flags)
+        th, idh = host.trace_rays(o, d, rto.MODE_BVH, flags=flags)
+        assert (idh >= 0).sum() > 500
+        assert np.array_equal(idd >= 0, idh >= 0)
+        assert_bit_equal(td, th, "t flags %d" % flags)
+        assert (idd != idh).mean() < 1e-3
