@@ -270,6 +270,59 @@ RTO_API int rto_render(RtoScene* scene, const RtoCamera* cam, int mode, uint32_t
 RTO_API int rto_render_batch(RtoScene* scene, const RtoCamera* cams, int numCams, int mode, uint32_t flags,
 	float shadowBias, int y0, int y1, const RtoFrame* frame);
 
+/* ---- compact frames: 4 bytes per pixel out of the trace kernel ---------------------------------------------------------------------
+ * Colour, hit id and t of a pixel of a BVH scene are pure functions of (camera, pixel, hit triangle, shadow bit).  rto_render_codes
+ * writes only that: one 32-bit word per pixel (0 = miss, else (position of the hit triangle in the scene's leaf order + 1) |
+ * shadowed << 31), in the kernel's TILE order (the 128 pixels of a 16 x 8 block are consecutive: a warp writes one full 128-byte line,
+ * which is what makes the destination usable across NVLink), and rto_resolve_codes rebuilds the three planes of RtoFrame from the
+ * words with the same ray generation, the same Moller-Trumbore arithmetic on the same triangle record and the same shading: the planes
+ * equal those of rto_render_batch bit for bit (tests/test_gpu_codes.py).  The words are meaningful to any scene built from the same
+ * triangles by the same route (scenes replicated over the GPUs of a box), not across different scenes.
+ * This is the path's one exchange step (the reference keeps its frame in a GL texture on the one GPU it has, RayTracerBVH.cpp:815-887):
+ * a GPU that traces frames for another one ships 4 bytes per pixel instead of 24.
+ * y0 must be a multiple of 8 and y1 a multiple of 8 or the image height.  `codes` addresses frame 0 of the code buffer; the call fills
+ * frames [firstFrame, firstFrame + numCams), rto_codes_frame_words(width, height) words each.  `stream` is a cudaStream_t of the scene's
+ * device, or NULL for the scene's own stream.  Both calls only enqueue (rto_resolve_codes with RTO_MEM_HOST also copies and waits). */
+RTO_API size_t rto_codes_frame_words(int width, int height);
+RTO_API int rto_render_codes(RtoScene* scene, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, int y0, int y1,
+	uint32_t* codes /* device-accessible: local, peer or IPC-mapped memory */, size_t firstFrame, void* stream);
+RTO_API int rto_resolve_codes(RtoScene* scene, const RtoCamera* cams, int numCams, int y0, int y1, const uint32_t* codes, size_t firstFrame,
+	const RtoFrame* frame /* planes indexed from (frame 0 of this call, row y0) */, void* stream);
+
+/* Exchange memory: a device buffer GPUs of the same box write hit codes into.  Same process: allocate on the receiving device and let
+ * the senders enable peer access (rto_group_* does).  Other processes (one process per GPU): pass the 64-byte handle over any channel and
+ * map it with rto_exchange_open (CUDA IPC; the mapping is an ordinary device pointer for rto_render_codes). */
+typedef struct RtoIpcHandle { unsigned char bytes[64]; } RtoIpcHandle;
+RTO_API int rto_exchange_alloc(size_t bytes, void** devPtr, RtoIpcHandle* handleOut /* may be NULL */);
+RTO_API int rto_exchange_free(void* devPtr);
+RTO_API int rto_exchange_open(const RtoIpcHandle* handle, void** devPtr);
+RTO_API int rto_exchange_close(void* devPtr);
+
+/* ---- device groups: several GPUs of one box behind one handle (one process, one host thread) ----------------------------------------
+ * What the reference's main loop would call instead of one renderSceneCompute per frame (main.cpp:1357-1363) when the box has more
+ * than one GPU: the scene is replicated on every device (trees built once on the host), the rows of a batch of frames are dealt to the
+ * devices in contiguous ranges, every device but the first writes hit codes straight into the first device's memory from its trace
+ * kernel (NVLink peer stores), and the first device expands them into the caller's planes on a second stream while it traces its own
+ * share.  Shares follow the measured time of every device.  The planes equal rto_render_batch's bit for bit.
+ * frame->memory: RTO_MEM_DEVICE = memory of devices[0] (the call only enqueues; order your own work after rto_group_stream() or call
+ * rto_group_sync), RTO_MEM_HOST = copied and waited for. */
+typedef struct RtoGroup RtoGroup;
+RTO_API int rto_group_create(const int* devices, int numDevices, RtoGroup** out);
+RTO_API void rto_group_destroy(RtoGroup* group);
+RTO_API int rto_group_size(const RtoGroup* group);
+/* rto_scene_create_bvh on every device of the group (`prebuilt` as there). */
+RTO_API int rto_group_scene_bvh(RtoGroup* group, const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt /* may be NULL */);
+/* The replica on devices[member] (owned by the group). */
+RTO_API RtoScene* rto_group_scene(RtoGroup* group, int member);
+RTO_API int rto_group_render_batch(RtoGroup* group, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, const RtoFrame* frame);
+/* enabled: adapt the shares to the measured times (default on); weights (optional, one per device): shares to start from or to keep;
+ * chunks: launches per device and batch, so that the first device expands chunk c while chunk c + 1 is traced (default 4; 0 = keep). */
+RTO_API int rto_group_set_balancing(RtoGroup* group, int enabled, const float* weights /* may be NULL */, int chunks);
+/* Device time of the last batch on every device (the first device: its own trace, with the expansion running beside it).  Waits. */
+RTO_API int rto_group_last_ms(RtoGroup* group, float* msPerDevice);
+RTO_API void* rto_group_stream(const RtoGroup* group);
+RTO_API int rto_group_sync(RtoGroup* group);
+
 /* Explicit ray list (origins/directions 3 floats each, directions need not be unit), for edge cases and as the
  * batched counterpart of single-ray calls: octree scenes return what octreeRaySkip(root, ro, rd, tMin, tMax, grid)
  * returns (mode A) or the GLSL traversal's closestT (mode B); BVH scenes the closest MT hit. */

@@ -84,6 +84,23 @@ SIGNATURES = {
     "rto_scene_sync": (_i, [_vp]),
     "rto_scene_last_kernel_ms": (_i, [_vp, C.POINTER(_f)]),
     "rto_scene_launch_count": (_u64, [_vp]),
+    "rto_codes_frame_words": (_sz, [_i, _i]),
+    "rto_render_codes": (_i, [_vp, _vp, _i, _u32, _f, _i, _i, _vp, _sz, _vp]),
+    "rto_resolve_codes": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, C.POINTER(RtoFrame), _vp]),
+    "rto_exchange_alloc": (_i, [_sz, _pp, _vp]),
+    "rto_exchange_free": (_i, [_vp]),
+    "rto_exchange_open": (_i, [_vp, _pp]),
+    "rto_exchange_close": (_i, [_vp]),
+    "rto_group_create": (_i, [_vp, _i, _pp]),
+    "rto_group_destroy": (None, [_vp]),
+    "rto_group_size": (_i, [_vp]),
+    "rto_group_scene_bvh": (_i, [_vp, _vp, _sz, _vp]),
+    "rto_group_scene": (_vp, [_vp, _i]),
+    "rto_group_render_batch": (_i, [_vp, _vp, _i, _u32, _f, C.POINTER(RtoFrame)]),
+    "rto_group_set_balancing": (_i, [_vp, _i, _vp, _i]),
+    "rto_group_last_ms": (_i, [_vp, _vp]),
+    "rto_group_stream": (_vp, [_vp]),
+    "rto_group_sync": (_i, [_vp]),
 }
 
 _lib = None

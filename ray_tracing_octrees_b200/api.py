@@ -372,6 +372,38 @@ class Scene:
         fr = RtoFrame(rgba_ptr, id_ptr, t_ptr, MEM_HOST)
         check(lib().rto_render_batch(self.h, arr, len(cams), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
 
+    def render_codes(self, cams, flags, shadow_bias, codes_ptr, first_frame=0, y0=0, y1=None, stream=None):
+        """rto_render_codes: trace rows [y0, y1) of the cameras and write one 32-bit hit code per pixel (tile order) into the code
+        buffer at device address codes_ptr (local, peer or IPC-mapped memory).  Asynchronous."""
+        if isinstance(cams, RtoCamera):
+            cams = [cams]
+        arr = cams if isinstance(cams, C.Array) else (RtoCamera * len(cams))(*cams)
+        y1 = arr[0].height if y1 is None else y1
+        check(lib().rto_render_codes(self.h, arr, len(arr), flags, shadow_bias, y0, y1, C.c_void_p(codes_ptr), first_frame, C.c_void_p(stream or 0)))
+
+    def resolve_codes(self, cams, codes_ptr, first_frame=0, y0=0, y1=None, rgba_ptr=None, id_ptr=None, t_ptr=None, memory=MEM_DEVICE, stream=None):
+        """rto_resolve_codes: rebuild the planes of rows [y0, y1) of the cameras from hit codes (bit-identical to a direct render)."""
+        if isinstance(cams, RtoCamera):
+            cams = [cams]
+        arr = cams if isinstance(cams, C.Array) else (RtoCamera * len(cams))(*cams)
+        y1 = arr[0].height if y1 is None else y1
+        fr = RtoFrame(rgba_ptr, id_ptr, t_ptr, memory)
+        check(lib().rto_resolve_codes(self.h, arr, len(arr), y0, y1, C.c_void_p(codes_ptr), first_frame, C.byref(fr), C.c_void_p(stream or 0)))
+
+    def render_via_codes(self, cam, flags=0, shadow_bias=0.0):
+        """One frame through the compact path (codes on the device, planes rebuilt from them) -> host arrays like render()."""
+        words = codes_frame_words(cam.width, cam.height)
+        buf = ExchangeBuffer(words * 4)
+        try:
+            self.render_codes(cam, flags, shadow_bias, buf.ptr)
+            n = cam.width * cam.height
+            out = dict(rgba=np.empty((n, 4), np.float32), id=np.empty(n, np.int32), t=np.empty(n, np.float32))
+            self.resolve_codes(cam, buf.ptr, rgba_ptr=_p(out["rgba"]), id_ptr=_p(out["id"]), t_ptr=_p(out["t"]), memory=MEM_HOST)
+        finally:
+            self.sync()
+            buf.close()
+        return out
+
     def stats(self, cam, mode, flags=0, shadow_bias=0.0, y0=0, y1=None):
         y1 = cam.height if y1 is None else y1
         st = np.zeros(5, np.uint64)
@@ -405,6 +437,105 @@ class Scene:
     def close(self):
         if self.h:
             lib().rto_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def codes_frame_words(width, height):
+    """32-bit words of one frame's hit-code plane (tile order, padded to whole 16 x 8 blocks)."""
+    return int(lib().rto_codes_frame_words(width, height))
+
+
+class ExchangeBuffer:
+    """Device memory other GPUs of the box write hit codes into (rto_exchange_*): allocate on the receiving device and hand
+    `handle` (64 bytes) to the other processes, or map another process's buffer with ExchangeBuffer.open(handle)."""
+
+    def __init__(self, nbytes=0, _mapped=None):
+        self.ptr, self.handle, self.mapped = None, None, _mapped is not None
+        if _mapped is not None:
+            self.ptr = _mapped
+            return
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        check(lib().rto_exchange_alloc(nbytes, C.byref(p), h))
+        self.ptr, self.handle, self.nbytes = p.value, bytes(h), nbytes
+
+    @staticmethod
+    def open(handle):
+        h = (C.c_ubyte * 64).from_buffer_copy(bytes(handle))
+        p = C.c_void_p()
+        check(lib().rto_exchange_open(h, C.byref(p)))
+        return ExchangeBuffer(_mapped=p.value)
+
+    def close(self):
+        if self.ptr:
+            check((lib().rto_exchange_close if self.mapped else lib().rto_exchange_free)(C.c_void_p(self.ptr)))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """Several GPUs of one box behind one handle (rto_group_*): scene replicated, rows of a batch dealt to the devices, hit codes
+    written into the first device's memory over NVLink and expanded there."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = C.c_void_p()
+        check(lib().rto_group_create(devs, len(devices), C.byref(self.h)))
+        self.devices = list(devices)
+        self._keep = ()
+
+    def set_mesh(self, tris, prebuilt=None):
+        tris = prebuilt.tris if prebuilt is not None else np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        check(lib().rto_group_scene_bvh(self.h, _p(tris), len(tris), prebuilt.h if prebuilt is not None else None))
+        self._keep = (tris, prebuilt)
+
+    def set_balancing(self, enabled=True, weights=None, chunks=0):
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        check(lib().rto_group_set_balancing(self.h, int(enabled), _p(w), chunks))
+
+    def render(self, cams, flags=0, shadow_bias=0.0):
+        """Host-memory render of whole frames -> dict(rgba (F, n, 4), id (F, n), t (F, n))."""
+        if isinstance(cams, RtoCamera):
+            cams = [cams]
+        arr = (RtoCamera * len(cams))(*cams)
+        n = cams[0].width * cams[0].height
+        out = dict(rgba=np.empty((len(cams), n, 4), np.float32), id=np.empty((len(cams), n), np.int32), t=np.empty((len(cams), n), np.float32))
+        fr = RtoFrame(_p(out["rgba"]), _p(out["id"]), _p(out["t"]), MEM_HOST)
+        check(lib().rto_group_render_batch(self.h, arr, len(cams), flags, shadow_bias, C.byref(fr)))
+        return out
+
+    def render_device(self, cams, flags, shadow_bias, rgba_ptr, id_ptr, t_ptr):
+        """Enqueue a batch writing planes in the first device's memory (asynchronous; sync() or order after `stream`)."""
+        arr = cams if isinstance(cams, C.Array) else (RtoCamera * len(cams))(*cams)
+        fr = RtoFrame(rgba_ptr, id_ptr, t_ptr, MEM_DEVICE)
+        check(lib().rto_group_render_batch(self.h, arr, len(arr), flags, shadow_bias, C.byref(fr)))
+
+    def last_ms(self):
+        ms = np.zeros(len(self.devices), np.float32)
+        check(lib().rto_group_last_ms(self.h, _p(ms)))
+        return ms
+
+    @property
+    def stream(self):
+        return lib().rto_group_stream(self.h)
+
+    def sync(self):
+        check(lib().rto_group_sync(self.h))
+
+    def close(self):
+        if self.h:
+            lib().rto_group_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):
@@ -481,16 +612,19 @@ def generate_test_volume(dim):
 def city_block_grid(dim, seed, blocks, max_height=None):
     """Synthetic city-block voxel grid: `blocks` x `blocks` lots on the x-z ground plane,
     a building on a lot with p = 0.7, footprint inset U{1..4} voxels, height U{8..max_height} voxels (y up), voxel 1.0,
-    grid min = -dim/2.  Deterministic for a given (dim, seed, blocks) via numpy's PCG64."""
-    rng = np.random.Generator(np.random.PCG64(seed))
+    grid min = -dim/2.  RNG: std::mt19937(seed), three raw 32-bit draws r0, r1, r2 per lot in (z-lot, x-lot) order:
+    present = r0 < floor(0.7 * 2^32), inset = 1 + r1 % 4, height = 8 + r2 % (max_height - 7).  (numpy's RandomState(seed) is the
+    same generator with the same seeding, so a C++ caller reproduces the grid with <random> alone.)"""
     lot = dim // blocks
     max_height = (3 * dim) // 4 if max_height is None else max_height
+    raw = np.random.RandomState(seed).randint(0, 2 ** 32, size=3 * blocks * blocks, dtype=np.uint32).astype(np.uint64).reshape(blocks, blocks, 3)
     vol = np.zeros((dim, dim, dim), np.uint8)            # [z, y, x]
     for bz in range(blocks):
         for bx in range(blocks):
-            present = rng.random() < 0.7
-            inset = int(rng.integers(1, 5))
-            height = int(rng.integers(8, max_height + 1))
+            r0, r1, r2 = (int(v) for v in raw[bz, bx])
+            present = r0 < int(0.7 * 2 ** 32)
+            inset = 1 + r1 % 4
+            height = 8 + r2 % (max_height - 7)
             if not present or lot - 2 * inset <= 0:
                 continue
             x0, z0 = bx * lot + inset, bz * lot + inset

@@ -122,6 +122,7 @@ extern "C" void rto_scene_destroy(RtoScene* s) {
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (void* p : s->owned) cudaFree(p);
 	for (void* p : s->scratch) if (p) cudaFree(p);
+	for (auto& c : s->camRing) { if (c.host) cudaFreeHost(c.host); if (c.dev) cudaFree(c.dev); if (c.done) cudaEventDestroy(c.done); }
 	if (s->evStart) cudaEventDestroy(s->evStart);
 	if (s->evStop) cudaEventDestroy(s->evStop);
 	if (s->evFrame) cudaEventDestroy(s->evFrame);
@@ -194,24 +195,11 @@ extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes,
 // ------------------------------------------------------------------------------------------------
 // BVH upload: reference-shaped host tree -> child-boxes-in-parent nodes + leaf-ordered triangles
 // ------------------------------------------------------------------------------------------------
-extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, RtoScene** out) {
-	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null output");
-	*out = nullptr;
-	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null triangles");
-	int rc = require_device(); if (rc) return rc;
-	RtoHostBvh* ownedBvh = nullptr;
-	const RtoHostBvh* h = prebuilt;
-	if (!h) { rc = rto_host_bvh_build(tris, numTris, &ownedBvh); if (rc) return rc; h = ownedBvh; }
-	else if (h->numTris != numTris || h->tris != tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: prebuilt BVH belongs to another triangle array");
-
+// the device scene of a host-built layout, on the current device
+int rto_scene_from_bvh_layout(const BvhLayout& L, size_t numTris, size_t numRefNodes, RtoScene** out) {
 	RtoScene* s = nullptr;
-	rc = scene_new(&s);
-	if (rc) { rto_host_bvh_free(ownedBvh); return rc; }
-	s->kind = RTO_MODE_BVH; s->numPrims = numTris; s->numNodes = h->nodes.size();
-
-	BvhLayout L;
-	rto_build_bvh_layout(*h, L);
-	rto_host_bvh_free(ownedBvh);
+	int rc = scene_new(&s); if (rc) return rc;
+	s->kind = RTO_MODE_BVH; s->numPrims = numTris; s->numNodes = numRefNodes;
 	BvhDev& D = s->bvh;
 	D.numTris = (int)numTris;
 	for (int k = 0; k < 3; k++) { D.rootLo[k] = L.rootLo[k]; D.rootHi[k] = L.rootHi[k]; }
@@ -234,6 +222,29 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 	return RTO_OK;
 }
 
+// reference-shaped host tree (built here unless given) -> the two device topologies and the triangle records, on the host
+int rto_bvh_layout_from_tris(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, BvhLayout& L, size_t* numRefNodes) {
+	RtoHostBvh* ownedBvh = nullptr;
+	const RtoHostBvh* h = prebuilt;
+	if (!h) { int rc = rto_host_bvh_build(tris, numTris, &ownedBvh); if (rc) return rc; h = ownedBvh; }
+	else if (h->numTris != numTris || h->tris != tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: prebuilt BVH belongs to another triangle array");
+	int rc = RTO_OK;
+	try { rto_build_bvh_layout(*h, L); *numRefNodes = h->nodes.size(); }
+	catch (...) { rc = rto_fail(RTO_ERR_ALLOC, "rto_scene_create_bvh: out of host memory while building the device layout"); }
+	rto_host_bvh_free(ownedBvh);
+	return rc;
+}
+
+extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, RtoScene** out) {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null output");
+	*out = nullptr;
+	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null triangles");
+	int rc = require_device(); if (rc) return rc;
+	BvhLayout L; size_t numRefNodes = 0;
+	if ((rc = rto_bvh_layout_from_tris(tris, numTris, prebuilt, L, &numRefNodes))) return rc;
+	return rto_scene_from_bvh_layout(L, numTris, numRefNodes, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // rendering
 // ------------------------------------------------------------------------------------------------
@@ -248,18 +259,45 @@ static int check_mode(const RtoScene* s, int mode) {
 // Octree scenes: thread-per-pixel kernel.  (Other schedulings were built, measured and removed in round 1 -- for the BVH loop a
 // persistent per-lane refill kernel, a warp-phased while-while kernel and a per-step warp vote; for the octree walks a persistent
 // kernel refilling idle lanes from a pixel counter; see profiles/README.md.)
-static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCams, int mode) {
+static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCams, int mode, cudaStream_t st) {
 	dim3 block(128), grid((width + 15) / 16, (A.y1 - A.y0 + 7) / 8, numCams);
 	if (s->kind == RTO_MODE_BVH) {
 		bool sh = (A.flags & RTO_FLAG_SHADOWS) != 0, prune = (A.flags & RTO_FLAG_NO_PRUNE) == 0;
-		if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, s->stream>>>(s->bvhFast, A);
-		else if (prune) k_render_bvh<false, true><<<grid, block, 0, s->stream>>>(s->bvhFast, A);
-		else if (sh) k_render_bvh<true, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
-		else k_render_bvh<false, false><<<grid, block, 0, s->stream>>>(s->bvh, A);
+		if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, st>>>(s->bvhFast, A);
+		else if (prune) k_render_bvh<false, true><<<grid, block, 0, st>>>(s->bvhFast, A);
+		else if (sh) k_render_bvh<true, false><<<grid, block, 0, st>>>(s->bvh, A);
+		else k_render_bvh<false, false><<<grid, block, 0, st>>>(s->bvh, A);
 	}
-	else if (mode == RTO_MODE_OCTREE_SKIP) k_render_octree<RTO_MODE_OCTREE_SKIP><<<grid, block, 0, s->stream>>>(s->oct, A);
-	else k_render_octree<RTO_MODE_OCTREE_GLSL><<<grid, block, 0, s->stream>>>(s->oct, A);
+	else if (mode == RTO_MODE_OCTREE_SKIP) k_render_octree<RTO_MODE_OCTREE_SKIP><<<grid, block, 0, st>>>(s->oct, A);
+	else k_render_octree<RTO_MODE_OCTREE_GLSL><<<grid, block, 0, st>>>(s->oct, A);
 	s->launches++;
+	return RTO_OK;
+}
+
+// Camera array of a batched call: copied into a pinned slot of the scene's ring and from there to the device on `st`, so the call
+// returns without waiting for anything.  A slot is reused only after the kernel that read it has finished (release_cameras).
+static int stage_cameras(RtoScene* s, const RtoCamera* cams, int n, cudaStream_t st, int* slotOut, const RtoCamera** devOut) {
+	const int slot = s->camNext;
+	s->camNext = (s->camNext + 1) % RtoScene::kCamSlots;
+	RtoScene::CamSlot& c = s->camRing[slot];
+	if (!c.done) CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+	else CUDA_TRY(cudaEventSynchronize(c.done));
+	if (c.cap < n) {
+		if (c.host) cudaFreeHost(c.host);
+		if (c.dev) cudaFree(c.dev);
+		c.host = nullptr; c.dev = nullptr; c.cap = 0;
+		const int want = n < 64 ? 64 : n;
+		CUDA_TRY(cudaHostAlloc((void**)&c.host, sizeof(RtoCamera) * want, cudaHostAllocDefault));
+		CUDA_TRY(cudaMalloc((void**)&c.dev, sizeof(RtoCamera) * want));
+		c.cap = want;
+	}
+	std::memcpy(c.host, cams, sizeof(RtoCamera) * n);
+	CUDA_TRY(cudaMemcpyAsync(c.dev, c.host, sizeof(RtoCamera) * n, cudaMemcpyHostToDevice, st));
+	*slotOut = slot; *devOut = c.dev;
+	return RTO_OK;
+}
+static int release_cameras(RtoScene* s, int slot, cudaStream_t st) {
+	if (slot >= 0) CUDA_TRY(cudaEventRecord(s->camRing[slot].done, st));
 	return RTO_OK;
 }
 
@@ -276,13 +314,9 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 	const size_t npix = (size_t)numCams * (size_t)(y1 - y0) * W;
 	RenderArgs A{};
 	A.cam0 = cams[0]; A.cams = nullptr; A.y0 = y0; A.y1 = y1; A.shadowBias = shadowBias; A.flags = flags;
-	if (numCams > 1) {
-		void* dC = nullptr;
-		if ((rc = scene_scratch(s, 3, sizeof(RtoCamera) * numCams, &dC))) return rc;
-		CUDA_TRY(cudaMemcpyAsync(dC, cams, sizeof(RtoCamera) * numCams, cudaMemcpyHostToDevice, s->stream));
-		A.cams = (const RtoCamera*)dC;
-	}
 	const bool host = frame->memory == RTO_MEM_HOST;
+	int camSlot = -1;
+	if (numCams > 1 && !host) { if ((rc = stage_cameras(s, cams, numCams, s->stream, &camSlot, &A.cams))) return rc; }
 	if (host) {
 		void* p = nullptr;
 		if (frame->rgba) { if ((rc = scene_scratch(s, 0, npix * 16, &p))) return rc; A.rgba = (float4*)p; }
@@ -299,7 +333,7 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 			RenderArgs Ac = A;
 			Ac.cam0 = cams[c]; Ac.cams = nullptr;
 			Ac.rgba = A.rgba ? A.rgba + c * fpix : nullptr; Ac.hitId = A.hitId ? A.hitId + c * fpix : nullptr; Ac.t = A.t ? A.t + c * fpix : nullptr;
-			if ((rc = launch_render(s, Ac, W, 1, mode))) return rc;
+			if ((rc = launch_render(s, Ac, W, 1, mode, s->stream))) return rc;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(s->evFrame, s->stream));
 			CUDA_TRY(cudaStreamWaitEvent(s->copyStream, s->evFrame, 0));
@@ -313,8 +347,9 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 		CUDA_TRY(cudaStreamSynchronize(s->stream));
 		return RTO_OK;
 	}
-	if ((rc = launch_render(s, A, W, numCams, mode))) return rc;
+	if ((rc = launch_render(s, A, W, numCams, mode, s->stream))) return rc;
 	CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
+	if ((rc = release_cameras(s, camSlot, s->stream))) return rc;
 	s->timed = true;
 	CUDA_TRY(cudaGetLastError());
 	if (host) {
@@ -323,6 +358,136 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 		if (frame->t) CUDA_TRY(cudaMemcpyAsync(frame->t, A.t, npix * 4, cudaMemcpyDeviceToHost, s->stream));
 		CUDA_TRY(cudaStreamSynchronize(s->stream));
 	}
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hit codes: 4 bytes per pixel out of the trace kernel, planes rebuilt where they are wanted (rto_c.h "compact frames")
+// ------------------------------------------------------------------------------------------------
+static int check_rows(const char* who, const RtoCamera* cams, int numCams, int y0, int y1, bool tileAligned) {
+	if (!cams || numCams <= 0) return rto_fail(RTO_ERR_INVALID, "%s: no cameras", who);
+	const int W = cams[0].width, H = cams[0].height;
+	if (W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 >= y1) return rto_fail(RTO_ERR_INVALID, "%s: bad image size or row range [%d,%d) of %dx%d", who, y0, y1, W, H);
+	for (int c = 1; c < numCams; c++) if (cams[c].width != W || cams[c].height != H) return rto_fail(RTO_ERR_INVALID, "%s: all cameras must share one image size", who);
+	if (numCams > 65535) return rto_fail(RTO_ERR_INVALID, "%s: at most 65535 cameras per call", who);
+	if ((unsigned long long)numCams * (unsigned long long)(y1 - y0) * W >= 0xffffffffull) return rto_fail(RTO_ERR_UNSUPPORTED, "%s: more than 2^32 pixels in one call", who);
+	if (tileAligned && ((y0 & 7) || ((y1 & 7) && y1 != H))) return rto_fail(RTO_ERR_INVALID, "%s: with hit codes y0 must be a multiple of 8 and y1 a multiple of 8 or the image height", who);
+	return RTO_OK;
+}
+
+int rto_enqueue_render(RtoScene* s, const RtoCamera* cams, int numCams, int mode, uint32_t flags, float shadowBias, int y0, int y1,
+	float4* rgba, int32_t* hitId, float* t, uint32_t* codes, size_t codeFrame0, cudaStream_t st) {
+	RenderArgs A{};
+	A.cam0 = cams[0]; A.cams = nullptr; A.y0 = y0; A.y1 = y1; A.shadowBias = shadowBias; A.flags = flags;
+	A.rgba = rgba; A.hitId = hitId; A.t = t;
+	A.codes = codes; A.codeFrame0 = (unsigned)codeFrame0; A.codeTilesY = (unsigned)((cams[0].height + 7) / 8);
+	int slot = -1, rc;
+	if (numCams > 1 && (rc = stage_cameras(s, cams, numCams, st, &slot, &A.cams))) return rc;
+	if ((rc = launch_render(s, A, cams[0].width, numCams, mode, st))) return rc;
+	CUDA_TRY(cudaGetLastError());
+	return release_cameras(s, slot, st);
+}
+
+int rto_enqueue_resolve(RtoScene* s, const RtoCamera* cams, int numCams, int y0, int y1, const uint32_t* codes, size_t codeFrame0,
+	float4* rgba, int32_t* hitId, float* t, cudaStream_t st) {
+	RenderArgs A{};
+	A.cam0 = cams[0]; A.cams = nullptr; A.y0 = y0; A.y1 = y1;
+	A.rgba = rgba; A.hitId = hitId; A.t = t;
+	A.codes = const_cast<uint32_t*>(codes); A.codeFrame0 = (unsigned)codeFrame0; A.codeTilesY = (unsigned)((cams[0].height + 7) / 8);
+	int slot = -1, rc;
+	if (numCams > 1 && (rc = stage_cameras(s, cams, numCams, st, &slot, &A.cams))) return rc;
+	dim3 block(128), grid((cams[0].width + 15) / 16, (y1 - y0 + 7) / 8, numCams);
+	k_resolve_bvh<<<grid, block, 0, st>>>(s->bvhFast, A);
+	s->launches++;
+	CUDA_TRY(cudaGetLastError());
+	return release_cameras(s, slot, st);
+}
+
+extern "C" size_t rto_codes_frame_words(int width, int height) {
+	if (width <= 0 || height <= 0) return 0;
+	return (size_t)((width + 15) / 16) * (size_t)((height + 7) / 8) * 128;
+}
+
+extern "C" int rto_render_codes(RtoScene* s, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, int y0, int y1,
+	uint32_t* codes, size_t firstFrame, void* stream) {
+	if (!s || !codes) return rto_fail(RTO_ERR_INVALID, "rto_render_codes: null argument");
+	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render_codes: hit codes exist for BVH scenes only");
+	int rc = check_rows("rto_render_codes", cams, numCams, y0, y1, true); if (rc) return rc;
+	if (firstFrame + (size_t)numCams > 0xffffffffull) return rto_fail(RTO_ERR_INVALID, "rto_render_codes: frame index out of range");
+	CUDA_TRY(cudaSetDevice(s->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+	if (!stream) CUDA_TRY(cudaEventRecord(s->evStart, st));
+	if ((rc = rto_enqueue_render(s, cams, numCams, RTO_MODE_BVH, flags, shadowBias, y0, y1, nullptr, nullptr, nullptr, codes, firstFrame, st))) return rc;
+	if (!stream) { CUDA_TRY(cudaEventRecord(s->evStop, st)); s->timed = true; }
+	return RTO_OK;
+}
+
+extern "C" int rto_resolve_codes(RtoScene* s, const RtoCamera* cams, int numCams, int y0, int y1, const uint32_t* codes, size_t firstFrame,
+	const RtoFrame* frame, void* stream) {
+	if (!s || !codes || !frame) return rto_fail(RTO_ERR_INVALID, "rto_resolve_codes: null argument");
+	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_resolve_codes: hit codes exist for BVH scenes only");
+	int rc = check_rows("rto_resolve_codes", cams, numCams, y0, y1, true); if (rc) return rc;
+	if (frame->memory != RTO_MEM_HOST && frame->memory != RTO_MEM_DEVICE) return rto_fail(RTO_ERR_INVALID, "rto_resolve_codes: bad RtoFrame.memory");
+	CUDA_TRY(cudaSetDevice(s->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+	const bool host = frame->memory == RTO_MEM_HOST;
+	const size_t npix = (size_t)numCams * (size_t)(y1 - y0) * cams[0].width;
+	float4* rgba = (float4*)frame->rgba; int32_t* hid = frame->hitId; float* t = frame->t;
+	if (host) {
+		void* p = nullptr;
+		if (frame->rgba) { if ((rc = scene_scratch(s, 0, npix * 16, &p))) return rc; rgba = (float4*)p; }
+		if (frame->hitId) { if ((rc = scene_scratch(s, 1, npix * 4, &p))) return rc; hid = (int32_t*)p; }
+		if (frame->t) { if ((rc = scene_scratch(s, 2, npix * 4, &p))) return rc; t = (float*)p; }
+	}
+	if (!stream) CUDA_TRY(cudaEventRecord(s->evStart, st));
+	if ((rc = rto_enqueue_resolve(s, cams, numCams, y0, y1, codes, firstFrame, rgba, hid, t, st))) return rc;
+	if (!stream) { CUDA_TRY(cudaEventRecord(s->evStop, st)); s->timed = true; }
+	if (host) {
+		if (frame->rgba) CUDA_TRY(cudaMemcpyAsync(frame->rgba, rgba, npix * 16, cudaMemcpyDeviceToHost, st));
+		if (frame->hitId) CUDA_TRY(cudaMemcpyAsync(frame->hitId, hid, npix * 4, cudaMemcpyDeviceToHost, st));
+		if (frame->t) CUDA_TRY(cudaMemcpyAsync(frame->t, t, npix * 4, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	return RTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exchange memory: device buffers another GPU of the box writes hit codes into (same process: peer access; other process: CUDA IPC)
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(RtoIpcHandle) == sizeof(cudaIpcMemHandle_t), "RtoIpcHandle must hold a cudaIpcMemHandle_t");
+
+extern "C" int rto_exchange_alloc(size_t bytes, void** devPtr, RtoIpcHandle* handleOut) {
+	if (!devPtr) return rto_fail(RTO_ERR_INVALID, "rto_exchange_alloc: null output");
+	*devPtr = nullptr;
+	int rc = require_device(); if (rc) return rc;
+	void* p = nullptr;
+	cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
+	if (e != cudaSuccess) return rto_fail(RTO_ERR_ALLOC, "rto_exchange_alloc: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	if (handleOut) {
+		cudaIpcMemHandle_t h;
+		e = cudaIpcGetMemHandle(&h, p);
+		if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return rto_fail(RTO_ERR_CUDA, "rto_exchange_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+		std::memcpy(handleOut, &h, sizeof(h));
+	}
+	*devPtr = p;
+	return RTO_OK;
+}
+extern "C" int rto_exchange_free(void* devPtr) {
+	if (devPtr) CUDA_TRY(cudaFree(devPtr));
+	return RTO_OK;
+}
+extern "C" int rto_exchange_open(const RtoIpcHandle* handle, void** devPtr) {
+	if (!handle || !devPtr) return rto_fail(RTO_ERR_INVALID, "rto_exchange_open: null argument");
+	*devPtr = nullptr;
+	int rc = require_device(); if (rc) return rc;
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, handle, sizeof(h));
+	cudaError_t e = cudaIpcOpenMemHandle(devPtr, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) { cudaGetLastError(); *devPtr = nullptr; return rto_fail(RTO_ERR_CUDA, "rto_exchange_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); }
+	return RTO_OK;
+}
+extern "C" int rto_exchange_close(void* devPtr) {
+	if (devPtr) CUDA_TRY(cudaIpcCloseMemHandle(devPtr));
 	return RTO_OK;
 }
 

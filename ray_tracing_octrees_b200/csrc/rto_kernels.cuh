@@ -1019,7 +1019,20 @@ struct RenderArgs {
 	float4* rgba; int* hitId; float* t;
 	float shadowBias;
 	unsigned flags;
+	// compact hit codes (BVH scenes; include/rto_c.h rto_render_codes): one 32-bit word per pixel in TILE order -- the 128 pixels of a
+	// block are consecutive, so a warp writes (and rto_resolve_codes reads) one full 128-byte line; the destination may be the memory
+	// of another GPU (NVLink peer mapping), which is why the order is the kernel's own and not the image's.
+	uint32_t* codes;
+	unsigned codeFrame0;          // index, in the code buffer, of the frame blockIdx.z == 0 renders
+	unsigned codeTilesY;          // blocks per image column = (height + 7) / 8
 };
+
+// word of one pixel: 0 = miss, else (position of the hit triangle in the scene's leaf order + 1) | (shadowed << 31)
+constexpr uint32_t kCodeShadowBit = 0x80000000u;
+__device__ __forceinline__ size_t code_index(const RenderArgs& A) {
+	const size_t tile = ((size_t)(A.codeFrame0 + blockIdx.z) * A.codeTilesY + (size_t)(A.y0 >> 3) + blockIdx.y) * gridDim.x + blockIdx.x;
+	return tile * 128 + threadIdx.x;
+}
 
 __device__ __forceinline__ bool pixel_of_thread(const RenderArgs& A, const RtoCamera& cam, int& px, int& py, size_t& pix) {
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1074,8 +1087,35 @@ __global__ void __launch_bounds__(128, RTO_BVH_MIN_BLOCKS) k_render_bvh(BvhDev S
 			shadowed = bvh_any(S, so, sd);
 		}
 		color = shadowed ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
+		if (A.codes) __stcs(A.codes + code_index(A), (uint32_t)(bestPos + 1) | (shadowed ? kCodeShadowBit : 0u));
 	}
+	else if (A.codes) __stcs(A.codes + code_index(A), 0u);
 	store_pixel(A, pix, color, id, bestT);
+}
+
+// The frame planes from the hit codes: colour, hit id and t of a pixel are pure functions of (camera, pixel, hit triangle, shadow
+// bit) -- the same ray generation, the same Moller-Trumbore arithmetic on the same record and the same shading as k_render_bvh, so
+// the planes equal a direct render bit for bit.  Memory-bound: 4 bytes in, 24 bytes out per pixel.
+__global__ void __launch_bounds__(128) k_resolve_bvh(BvhDev S, RenderArgs A) {
+	RtoCamera cam = A.cam0;
+	if (A.cams) cam = A.cams[blockIdx.z];
+	int px, py; size_t pix;
+	if (!pixel_of_thread(A, cam, px, py, pix)) return;
+	const uint32_t code = __ldcs(A.codes + code_index(A));
+	V3 color = mk3(0.0f, 0.0f, 0.0f);
+	int id = -1;
+	float t = kMissT;
+	const int pos = (int)(code & ~kCodeShadowBit) - 1;
+	if (pos >= 0 && pos < S.numTris) {
+		Ray ray = gen_ray(cam, px, py);
+		TriV tri = load_tri(S.tris, pos);
+		id = tri.id;
+		if (!moller_trumbore(tri, ray.o, ray.d, t)) t = kMissT;      // cannot happen for a code this scene produced for this camera
+		V3 n = normalize3(cross3(tri.e1, tri.e2));
+		if (dot3(n, ray.d) > 0.0f) n = -n;
+		color = (code & kCodeShadowBit) ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
+	}
+	store_pixel(A, pix, color, id, t);
 }
 
 // One instantiation per traversal mode so that each gets its own register budget: the mode-A walk wants ~80 registers (it

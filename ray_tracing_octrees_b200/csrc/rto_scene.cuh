@@ -26,6 +26,11 @@ struct RtoScene {
 	void* scratch[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	size_t scratchBytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	int smCount = 0;
+	// camera arrays of batched calls: pinned host slot -> device slot, a ring so that a call never waits for the previous one's kernel
+	struct CamSlot { RtoCamera* host = nullptr; RtoCamera* dev = nullptr; int cap = 0; cudaEvent_t done = nullptr; };
+	static constexpr int kCamSlots = 16;
+	CamSlot camRing[kCamSlots];
+	int camNext = 0;
 	bool deviceBuiltBvh = false;      // linear BVH built on the device: the reference-shaped tree (BVH::query replay, work counters) does not exist
 };
 
@@ -33,6 +38,18 @@ int rto_scene_new(RtoScene** out);                             // stream, events
 int rto_scene_alloc(RtoScene* s, void** p, size_t bytes);      // device memory owned by the scene
 int rto_scene_adopt(RtoScene* s, void* p, size_t bytes);       // take ownership of an existing cudaMalloc'ed block
 int rto_scene_scratch(RtoScene* s, int slot, size_t bytes, void** p);
+
+// Enqueue a render of rows [y0, y1) of `numCams` cameras on `st` (a stream of the scene's device; the planes and the code buffer are
+// device-accessible addresses, any of them may be null; codes: BVH scenes only, see include/rto_c.h rto_render_codes), and the
+// expansion of hit codes into planes.  Camera arrays are staged through the scene's pinned ring.  Nothing here synchronises.
+int rto_enqueue_render(RtoScene* s, const RtoCamera* cams, int numCams, int mode, uint32_t flags, float shadowBias, int y0, int y1,
+	float4* rgba, int32_t* hitId, float* t, uint32_t* codes, size_t codeFrame0, cudaStream_t st);
+int rto_enqueue_resolve(RtoScene* s, const RtoCamera* cams, int numCams, int y0, int y1, const uint32_t* codes, size_t codeFrame0,
+	float4* rgba, int32_t* hitId, float* t, cudaStream_t st);
+// the device scene of a triangle soup on the CURRENT device from a layout built once on the host (rto_group.cu replicates it)
+struct BvhLayout;
+int rto_bvh_layout_from_tris(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, BvhLayout& L, size_t* numRefNodes);
+int rto_scene_from_bvh_layout(const BvhLayout& L, size_t numTris, size_t numRefNodes, RtoScene** out);
 
 // Dual Contouring on the device (rto_dc.cu) for a grid and a node array that already live there; *dTrisOut is cudaMalloc'ed and
 // belongs to the caller.  Synchronises the stream.

@@ -26,6 +26,29 @@ def rto():
 
 
 @pytest.fixture(scope="session")
+def gpu(rto):
+    """The product package on cuda:0 (fails, not skips, without a device: -m gpu tests are the parity tests proper)."""
+    rc = rto.lib().rto_init(0)
+    assert rc == 0, rto.lib().rto_last_error()
+    return rto
+
+
+@pytest.fixture(scope="session")
+def dt_scene(gpu, dt_grid_path):
+    """The DT Calgary scene of C2 / C5: the reference's voxel grid -> octree -> Marching-Cubes mesh -> BVH scene + octree scene."""
+    rto = gpu
+    grid = rto.VoxelGrid.load(dt_grid_path)
+    nodes = rto.create_octree_from_voxel_grid(grid)
+    tris = rto.marching_cubes_mesh(grid, nodes)
+    return dict(grid=grid, nodes=nodes, tris=tris, oct=rto.Scene.octree(nodes, grid.min, grid.voxel_size), bvh=rto.Scene.bvh(tris))
+
+
+@pytest.fixture(scope="session")
+def golden_fullsize():
+    return json.load(open(os.path.join(GOLDEN, "golden_fullsize.json")))
+
+
+@pytest.fixture(scope="session")
 def port():
     from oracle import bind
     return bind.port()

@@ -11,19 +11,18 @@ from conftest import assert_bit_equal, cam_from_dict
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def gpu(rto):
-    import ctypes
-    rc = rto.lib().rto_init(0)
-    assert rc == 0, rto.lib().rto_last_error()
-    return rto
+NEAR_TIE_FRAC = 1e-4        # BASELINE.json north_star: hit ids may differ at documented near-ties on at most 1e-4 of the pixels
 
 
-def _cmp_frames(got, want, what, allow_frac=0.0):
+def _cmp_frames(got, want, what, allow_frac=0.0, tally=None):
+    """ids equal (or, with tally = [bad, total], counted for a cap over everything compared), t and rgba bit-equal where ids agree."""
     n = len(want["id"])
     bad = got["id"] != want["id"]
     frac = bad.sum() / max(n, 1)
-    assert frac <= allow_frac, "%s: %d of %d ids differ" % (what, int(bad.sum()), n)
+    if tally is not None:
+        tally[0] += int(bad.sum()); tally[1] += n
+    else:
+        assert frac <= allow_frac, "%s: %d of %d ids differ" % (what, int(bad.sum()), n)
     ok = ~bad
     assert_bit_equal(got["t"][ok], want["t"][ok], what + " t")
     assert_bit_equal(got["rgba"][ok], want["rgba"][ok], what + " rgba")
@@ -73,15 +72,6 @@ def test_golden_sphere32_query_and_edge_rays(gpu, golden_sphere32):
     t, ids = oc.trace_rays(g["edge_o"], g["edge_d"], rto.MODE_OCTREE_SKIP)
     assert_bit_equal(t, g["edge_t"], "octreeRaySkip on axis-parallel rays")
     assert np.array_equal(ids, g["edge_id"])
-
-
-@pytest.fixture(scope="module")
-def dt_scene(gpu, dt_grid_path):
-    rto = gpu
-    grid = rto.VoxelGrid.load(dt_grid_path)
-    nodes = rto.create_octree_from_voxel_grid(grid)
-    tris = rto.marching_cubes_mesh(grid, nodes)
-    return dict(grid=grid, nodes=nodes, tris=tris, oct=rto.Scene.octree(nodes, grid.min, grid.voxel_size), bvh=rto.Scene.bvh(tris))
 
 
 @pytest.mark.parametrize("name", ["far", "near"])
@@ -267,15 +257,15 @@ def test_full_size_dt_1080p(gpu, dt_scene, checker, dt_grid_path):
     m_ref = oc_ref.mesh(); m_ref.build()
     rcam, _ = checker.camera(35, 40, 0.6 * 4250, width=1920, height=1080)
     assert bytes(rcam) == bytes(cam)
-    bad_total = 0
+    tally = [0, 0]
     for y0 in range(8, 1080, 135):
         want = m_ref.render(rcam, 1, bias, y0, y0 + 2)
         sl = slice(y0 * 1920, (y0 + 2) * 1920)
         got = {k: exact[k][sl] for k in ("rgba", "id", "t")}
         _cmp_frames(got, want, "dt exact rows %d" % y0)
         got = {k: full[k][sl] for k in ("rgba", "id", "t")}
-        bad_total += _cmp_frames(got, want, "dt pruned rows %d" % y0, allow_frac=1e-3)
-    assert bad_total <= 2
+        _cmp_frames(got, want, "dt pruned rows %d" % y0, tally=tally)
+    assert tally[0] <= NEAR_TIE_FRAC * tally[1], "pruned traversal vs oracle: %d of %d pixels differ" % tuple(tally)
 
 
 def test_full_size_sphere128_and_octree_modes(gpu, checker):
@@ -295,11 +285,13 @@ def test_full_size_sphere128_and_octree_modes(gpu, checker):
     fa, fb = oc.render(cam, rto.MODE_OCTREE_SKIP), oc.render(cam, rto.MODE_OCTREE_GLSL)
     # mode A returns a solid leaf at least as far as ... no ordering guarantee between modes, but both hit the same pixels
     assert np.array_equal(fa["id"] >= 0, fb["id"] >= 0)
+    tally = [0, 0]
     for y0 in range(5, 768, 96):
         sl = slice(y0 * 1024, (y0 + 3) * 1024)
-        _cmp_frames({k: full[k][sl] for k in full}, m_ref.render(rcam, 1, bias, y0, y0 + 3), "sphere bvh rows %d" % y0, allow_frac=1e-3)
+        _cmp_frames({k: full[k][sl] for k in full}, m_ref.render(rcam, 1, bias, y0, y0 + 3), "sphere bvh rows %d" % y0, tally=tally)
         _cmp_frames({k: fa[k][sl] for k in fa}, oc_ref.render(rcam, 0, y0, y0 + 3), "sphere mode A rows %d" % y0)
         _cmp_frames({k: fb[k][sl] for k in fb}, oc_ref.render(rcam, 1, y0, y0 + 3), "sphere mode B rows %d" % y0)
+    assert tally[0] <= NEAR_TIE_FRAC * tally[1], "pruned traversal vs oracle: %d of %d pixels differ" % tuple(tally)
 
 
 def test_city_block_octree_and_mesh_vs_oracle(gpu, checker):
@@ -316,6 +308,7 @@ def test_city_block_octree_and_mesh_vs_oracle(gpu, checker):
     m_ref = oc_ref.mesh(); m_ref.build()
     W, H = 640, 360
     bias = 1e-3 * grid.voxel_size
+    tally = [0, 0]
     for theta, phi in ((35, 40), (20, 90), (60, 180), (1, 0)):
         cam, _ = rto.Camera.from_degrees(theta, phi, 0.9 * 192).consts(45.0, float(np.float32(W) / np.float32(H)), W, H)
         rcam, _ = checker.camera(theta, phi, 0.9 * 192, width=W, height=H)
@@ -326,7 +319,8 @@ def test_city_block_octree_and_mesh_vs_oracle(gpu, checker):
             sl = slice(y0 * W, (y0 + 2) * W)
             _cmp_frames({k: fa[k][sl] for k in fa}, oc_ref.render(rcam, 0, y0, y0 + 2), "city mode A rows %d cam %d/%d" % (y0, theta, phi))
             _cmp_frames({k: fb[k][sl] for k in fb}, oc_ref.render(rcam, 1, y0, y0 + 2), "city mode B rows %d cam %d/%d" % (y0, theta, phi))
-            _cmp_frames({k: fm[k][sl] for k in fm}, m_ref.render(rcam, 1, bias, y0, y0 + 2), "city mesh rows %d cam %d/%d" % (y0, theta, phi), allow_frac=1e-3)
+            _cmp_frames({k: fm[k][sl] for k in fm}, m_ref.render(rcam, 1, bias, y0, y0 + 2), "city mesh rows %d cam %d/%d" % (y0, theta, phi), tally=tally)
+    assert tally[0] <= NEAR_TIE_FRAC * tally[1], "pruned traversal vs oracle: %d of %d pixels differ" % tuple(tally)
 
 
 def test_dual_contouring_mesh_renders_like_the_oracle(gpu, checker, dt_grid_path):
@@ -342,6 +336,7 @@ def test_dual_contouring_mesh_renders_like_the_oracle(gpu, checker, dt_grid_path
         sc = rto.Scene.bvh(tris)
         m_ref = checker.mesh(tris); m_ref.build()
         bias = 1e-3 * grid.voxel_size
+        tally = [0, 0]
         for theta, phi in ((35, 40), (60, 190)):
             cam, _ = rto.Camera.from_degrees(theta, phi, radius).consts(45.0, float(np.float32(W) / np.float32(H)), W, H)
             rcam, _ = checker.camera(theta, phi, radius, width=W, height=H)
@@ -352,7 +347,8 @@ def test_dual_contouring_mesh_renders_like_the_oracle(gpu, checker, dt_grid_path
                 sl = slice(y0 * W, (y0 + 2) * W)
                 want = m_ref.render(rcam, 1, bias, y0, y0 + 2)
                 _cmp_frames({k: fx[k][sl] for k in fx}, want, "%s DC exact replay rows %d cam %d/%d" % (name, y0, theta, phi))
-                _cmp_frames({k: fm[k][sl] for k in fm}, want, "%s DC rows %d cam %d/%d" % (name, y0, theta, phi), allow_frac=1e-3)
+                _cmp_frames({k: fm[k][sl] for k in fm}, want, "%s DC rows %d cam %d/%d" % (name, y0, theta, phi), tally=tally)
+        assert tally[0] <= NEAR_TIE_FRAC * tally[1], "%s: pruned traversal vs oracle: %d of %d pixels differ" % (name, tally[0], tally[1])
         m_ref.free()
 
 
