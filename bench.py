@@ -4,16 +4,23 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C2"): the DT Calgary scene -- the reference's voxelised sceneCache.bin (the DT
-CSVs are absent from the reference checkout, so its own voxel grid -> octree -> Marching-Cubes mesh, 487 832
-triangles, is the stand-in) -- ray cast through the reference-shaped BVH at 1920x1080, primary rays
-plus one shadow ray per primary hit.  One "step" = one batch of F orbit frames per GPU (camera theta 35 deg,
-radius 0.6*4250, phi advancing 360/64 deg per frame; ranks take disjoint phi ranges: frames shard, scene replicated).
+Workload (BASELINE.json configs[1], "C2"): the DT Calgary scene -- the reference's voxelised sceneCache.bin (the DT CSVs are absent
+from the reference checkout, so its own voxel grid -> octree -> Marching-Cubes mesh, 487 832 triangles, is the stand-in, SURVEY.md
+8d) -- ray cast through the reference-shaped BVH at 1920x1080, primary rays plus one shadow ray per primary hit, cameras on the
+64-position orbit (theta 35 deg, radius 0.6 * 4250, phi_k = 40 + 360 k / 64 deg).
 
-metric  Mrays/s = (primary + shadow rays traced by all ranks) / (max over ranks of the device time of the K steps).
-value   inputs (scene, cameras) resident in HBM, outputs written to HBM.
-e2e     the same metric through the public host API: cameras go host->device and the three frame planes
-        (rgba32f, hit id, t: 24 B/pixel) come back device->host into pinned buffers inside the timed region.
+One "step" = F orbit frames PER GPU (default 128 = two orbits), traced in launches of 16 frames per GPU.
+  N = 1   the frames are rendered straight into the frame planes (rgba32f + hit id + t, 24 B/pixel) in HBM.
+  N > 1   scene replicated, the rows of every 16 x N-frame batch are dealt to the ranks, and EVERY frame is delivered as full planes
+          in rank 0's HBM inside the timed region (BASELINE north_star: "only the framebuffer gather uses ... NVLink"): ranks != 0
+          write 4-byte hit codes straight into rank 0's memory from the trace kernel (CUDA-IPC peer stores over NVLink), rank 0
+          expands them into planes on a second stream (ray_tracing_octrees_b200/sharding.py GatheredRenderer; csrc/rto_group.cu is
+          the same thing for one process).  The comm-free number (every rank keeps its frames) is reported beside it.
+
+metric  Mrays/s = (primary + shadow rays of all frames of the K steps) / (max over ranks of the device time of the K steps).
+value   inputs (scene, cameras) resident, outputs in HBM (N > 1: all in rank 0's HBM).
+e2e     the same metric through the public host API: cameras go host->device and the three frame planes come back device->host
+        into pinned buffers inside the timed region (rto_render_batch(RTO_MEM_HOST), 8 frames per call).
 """
 import argparse
 import ctypes
@@ -31,17 +38,22 @@ sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
 THETA_DEG, RADIUS, FOV = 35.0, 0.6 * 4250.0, 45.0
-PHI0_DEG, PHI_STEP_DEG = 40.0, 360.0 / 64.0
+PHI0_DEG, PHI_STEP_DEG, ORBIT = 40.0, 360.0 / 64.0, 64
 DT_GRID = os.path.join(ROOT, "tests", "golden", "dt_sceneCache.bin.gz")
 METRIC = "Mrays/s primary+shadow (DT mesh, 1080p)"
+CONFIG = {"workload": "C2: DT Calgary mesh (Marching-Cubes soup of the reference's sceneCache.bin, 487832 triangles; the DT CSVs are absent "
+                      "from the checkout), BVH ray cast at 1920x1080, primary + shadow rays, 64-camera orbit",
+          "image": "1920x1080", "rays": "primary + one shadow ray per primary hit", "cameras": "orbit theta 35 deg, r 0.6*4250, phi 40 + 360k/64 deg"}
+DATA = "the reference's own voxelised DT Calgary grid (sceneCache.bin, committed gzip-compressed as tests/golden/dt_sceneCache.bin.gz) -> octree -> Marching-Cubes mesh; cameras synthetic"
+BATCH = 16            # frames per GPU per launch
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured", float(d.get("sm_max_mhz", 1965.0))
-    return 6650.0, "fallback", 1965.0
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
 class ClockSampler(threading.Thread):
@@ -55,7 +67,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -87,15 +99,6 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
-def orbit_cameras(rto, first_frame, count):
-    cams = []
-    aspect = float(np.float32(W) / np.float32(H))
-    for k in range(first_frame, first_frame + count):
-        cam, _ = rto.Camera.from_degrees(THETA_DEG, PHI0_DEG + PHI_STEP_DEG * (k % 64), RADIUS).consts(FOV, aspect, W, H)
-        cams.append(cam)
-    return cams
-
-
 # =====================================================================================================
 # reference arm: the reference's own CPU implementation (compiled in place -> oracle/_ref), else the port
 # =====================================================================================================
@@ -110,26 +113,22 @@ def run_reference(args, rank, world):
     mesh.build()
     cores = host_cores()
     bias = 1e-3 * oc.voxel
-    cam, _ = chk.camera(THETA_DEG, PHI0_DEG, RADIUS, width=W, height=H)
-    # per-step sample: one whole 1080p orbit frame (a fraction of a second on a many-core host)
-    rows, y0 = H, 0
 
-    def step(k):
-        c, _ = chk.camera(THETA_DEG, PHI0_DEG + PHI_STEP_DEG * (k % 64), RADIUS, width=W, height=H)
-        out = mesh.render(c, 1, bias, y0, y0 + rows, threads=cores)
-        return rows * W + int((out["id"] >= 0).sum()), out["sec"]
+    def step(k):       # per-step sample: one whole 1080p orbit frame (a fraction of a second on a many-core host)
+        c, _ = chk.camera(THETA_DEG, PHI0_DEG + PHI_STEP_DEG * (k % ORBIT), RADIUS, width=W, height=H)
+        out = mesh.render(c, 1, bias, 0, H, threads=cores)
+        return H * W + int((out["id"] >= 0).sum()), out["sec"]
     for k in range(args.warmup):
         step(k)
-    rays = 0
-    secs = 0.0
+    rays, secs = 0, 0.0
     for k in range(args.steps):
         r, s = step(args.warmup + k)
         rays += r
         secs += s
     v = rays / secs / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 DT-voxel MC mesh 487832 tris, BVH ray cast 1920x1080 primary+shadow", "sample": "one full 1080p orbit frame per step (ours: %d frames per step)" % args.frames},
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA,
+            "config": CONFIG, "step": "one full 1080p orbit frame (bounded sample of the workload; the CUDA arm traces %d frames per GPU per step)" % args.frames,
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": chk.kind,
                              "sample": "%d full 1080p orbit frames, BVH::query + Moller-Trumbore + shadow, OpenMP over scanlines" % args.steps},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -145,14 +144,16 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     from ray_tracing_octrees_b200 import build
     if rank == 0:
         build.build()
     if world > 1:
         dist.barrier()
     import ray_tracing_octrees_b200 as rto
+    from ray_tracing_octrees_b200 import sharding
     rc = rto.lib().rto_init(local_rank)
     if rc != 0:
         raise SystemExit("rto_init failed: " + rto.lib().rto_last_error().decode())
@@ -166,142 +167,210 @@ def run_ours(args, rank, world, local_rank):
     build_s = time.time() - t0
     bias = float(np.float32(1e-3) * np.float32(grid.voxel_size))
     flags = rto.FLAG_SHADOWS
-    F = args.frames
-    stream = torch.cuda.ExternalStream(scene.stream, device=torch.device("cuda", local_rank))
-    rgba = torch.empty((F, H, W, 4), dtype=torch.float32, device="cuda")
-    hid = torch.empty((F, H, W), dtype=torch.int32, device="cuda")
-    tt = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
+    F = max(BATCH, (args.frames // BATCH) * BATCH)
+    chunks = F // BATCH
+    stream = torch.cuda.ExternalStream(scene.stream, device=dev)
+    aspect = float(np.float32(W) / np.float32(H))
+    orbit = [rto.Camera.from_degrees(THETA_DEG, PHI0_DEG + PHI_STEP_DEG * k, RADIUS).consts(FOV, aspect, W, H)[0] for k in range(ORBIT)]
+    cam_cache = {}
 
-    def step_device(k):
-        cams = orbit_cameras(rto, (rank * args.steps_total + k) * F, F)
-        scene.render_device(cams, rto.MODE_BVH, flags, bias, 0, H, rgba.data_ptr(), hid.data_ptr(), tt.data_ptr())
-        return cams
+    def cam_array(start, n):
+        """ctypes array of the n orbit cameras from global frame index `start` (built once per distinct phase: nothing per step)."""
+        key = (start % ORBIT, n)
+        if key not in cam_cache:
+            cam_cache[key] = (rto.RtoCamera * n)(*[orbit[(start + j) % ORBIT] for j in range(n)])
+        return cam_cache[key]
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident ----------------------------------------------------------------------
+    # primary hits of every orbit camera (rays per frame = W*H + hits), counted once outside every timed region
+    tmp_id = torch.empty((BATCH, H, W), dtype=torch.int32, device=dev)
+    hits_of = []
+    for k0 in range(0, ORBIT, BATCH):
+        scene.render_device(cam_array(k0, BATCH), rto.MODE_BVH, flags, bias, 0, H, None, tmp_id.data_ptr(), None)
+        torch.cuda.synchronize()
+        hits_of += [int(x) for x in (tmp_id >= 0).flatten(1).sum(1).tolist()]
+    del tmp_id
+    rays_of = [W * H + h for h in hits_of]
+
+    def rays_in(start, n):
+        return sum(rays_of[(start + j) % ORBIT] for j in range(n))
+
+    # ---- planes: a ring of two batches (a batch is 16 frames per GPU; N > 1: all of them on rank 0) --------------------------
+    gathered = world > 1 and not args.comm_free_only
+    nb = BATCH * world if (gathered and rank == 0) else BATCH
+    ring = [dict(rgba=torch.empty((nb, H, W, 4), dtype=torch.float32, device=dev), id=torch.empty((nb, H, W), dtype=torch.int32, device=dev),
+                 t=torch.empty((nb, H, W), dtype=torch.float32, device=dev)) for _ in range(2)]
+    gr = None
+    if gathered:
+        gr = sharding.GatheredRenderer(rto, scene, W, H, BATCH * world, flags, bias, dev, transport=os.environ.get("RTO_GATHER_TRANSPORT", "auto"))
+
+    def step_local(k, rank_offset=True):
+        """comm-free: this rank's F frames of step k straight into its own planes."""
+        base = (k * world + (rank if rank_offset else 0)) * F
+        for c in range(chunks):
+            p = ring[c & 1]
+            scene.render_device(cam_array(base + c * BATCH, BATCH), rto.MODE_BVH, flags, bias, 0, H, p["rgba"].data_ptr(), p["id"].data_ptr(), p["t"].data_ptr())
+
+    def step_gathered(k):
+        """all ranks trace, every frame of the step ends up as planes on rank 0."""
+        base = k * world * F
+        for c in range(chunks):
+            p = ring[c & 1]
+            gr.render(cam_array(base + c * BATCH * world, BATCH * world), p["rgba"].data_ptr(), p["id"].data_ptr(), p["t"].data_ptr())
+
+    def timed(step_fn, steps, finish=None):
+        sync_all()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(stream)
+        end = torch.cuda.Event(enable_timing=True)
+        for k in range(steps):
+            step_fn(args.warmup + k)
+            ev[k + 1].record(stream)              # (per-step marks; on rank 0 the expansion of a step's last batch may still run beside the next step)
+        if finish:
+            finish()                              # rank 0: everything expanded
+        end.record(stream)
+        sync_all()
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        return ev[0].elapsed_time(end), per
+
+    # ---- calibration of the shares (N > 1) + warm-up ----------------------------------------------------------------------------
+    cal = None
+    if gathered:
+        p = ring[0]
+
+        def four_batches():       # back to back, so that rank 0's trace is measured with the expansion of the previous batch beside it
+            for c in range(4):
+                q = ring[c & 1]
+                gr.render(cam_array(c * BATCH * world, BATCH * world), q["rgba"].data_ptr(), q["id"].data_ptr(), q["t"].data_ptr())
+        cal = gr.calibrate(four_batches, rounds=8)
+    main_step = step_gathered if gathered else step_local
+    main_finish = gr.finish if gathered else None
     for k in range(args.warmup):
-        step_device(k)
+        main_step(k)
+    if main_finish:
+        main_finish()
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.25)
+    time.sleep(0.2)
     launches0 = scene.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rays = 0
-    kern_ms = []
-    sync_all()
-    ev0.record(stream)
-    for k in range(args.steps):
-        step_device(args.warmup + k)
-        if args.per_launch_timing:
-            kern_ms.append(scene.last_kernel_ms())
-    ev1.record(stream)
-    sync_all()
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms, per_step = timed(main_step, args.steps, main_finish)
     launches = scene.launch_count - launches0
     clocks = sampler.stop()
-    # rays actually traced: primaries + one shadow ray per primary hit (counted on the device, outside the timed region)
-    rays_per_step = []
-    for k in range(args.steps):
-        step_device(args.warmup + k)
-        torch.cuda.synchronize()
-        rays_per_step.append(F * W * H + int((hid >= 0).sum().item()))
-    rays = sum(rays_per_step)
+    rays_main = sum(rays_in((args.warmup + k) * world * F, world * F) for k in range(args.steps)) if gathered else \
+        sum(rays_in(((args.warmup + k) * world + rank) * F, F) for k in range(args.steps))
 
-    # ---- kernel duration for the roofline (CUDA events on the launching stream around each launch) ------------
-    if not kern_ms:
-        for k in range(min(args.steps, 5)):
-            step_device(args.warmup + k)
-            kern_ms.append(scene.last_kernel_ms())
-    kern_ms_avg = float(np.mean(kern_ms))
+    # ---- N > 1: the gathered planes equal a local render (last batch of the last step), and the comm-free number beside it ------
+    gather_check, comm_free = None, None
+    if gathered:
+        if rank == 0:
+            last = (args.warmup + args.steps - 1) * world * F + (chunks - 1) * BATCH * world
+            got = ring[(chunks - 1) & 1]
+            ref = dict(rgba=torch.empty_like(got["rgba"][:BATCH]), id=torch.empty_like(got["id"][:BATCH]), t=torch.empty_like(got["t"][:BATCH]))
+            same = True
+            for j in range(0, BATCH * world, BATCH):
+                scene.render_device(cam_array(last + j, BATCH), rto.MODE_BVH, flags, bias, 0, H, ref["rgba"].data_ptr(), ref["id"].data_ptr(), ref["t"].data_ptr())
+                torch.cuda.synchronize()
+                for key in ("rgba", "id", "t"):
+                    same = same and bool(torch.equal(got[key][j:j + BATCH].view(torch.int32), ref[key].view(torch.int32)))
+            gather_check = "bit-equal to a local render (%d frames)" % (BATCH * world) if same else "MISMATCH"
+            del ref
+        cf_ms, _ = timed(step_local, min(args.steps, 10))
+        comm_free = (cf_ms, sum(rays_in(((args.warmup + k) * world + rank) * F, F) for k in range(min(args.steps, 10))))
 
-    # ---- e2e: host API, pinned host buffers, H2D cameras + D2H frame planes inside the timed region ------------
-    h_rgba = torch.empty((F, H, W, 4), dtype=torch.float32).pin_memory()
-    h_id = torch.empty((F, H, W), dtype=torch.int32).pin_memory()
-    h_t = torch.empty((F, H, W), dtype=torch.float32).pin_memory()
+    # ---- kernel duration for the roofline (CUDA events on the launching stream around one launch of 16 frames) ------------------
+    kern_ms = []
+    p = ring[0]
+    for k in range(7):
+        scene.render_device(cam_array(k * BATCH, BATCH), rto.MODE_BVH, flags, bias, 0, H, p["rgba"].data_ptr(), p["id"].data_ptr(), p["t"].data_ptr())
+        kern_ms.append(scene.last_kernel_ms())
+    kern_ms_avg = float(np.mean(kern_ms[2:6]))          # launches 2..5 = camera phases 32, 48, 0, 16: the whole orbit once
+
+    # ---- e2e: host API, pinned host buffers, H2D cameras + D2H frame planes inside the timed region ---------------------------
+    EB = 8
+    h_rgba = torch.empty((EB, H, W, 4), dtype=torch.float32).pin_memory()
+    h_id = torch.empty((EB, H, W), dtype=torch.int32).pin_memory()
+    h_t = torch.empty((EB, H, W), dtype=torch.float32).pin_memory()
 
     def step_host(k):
-        cams = orbit_cameras(rto, (rank * args.steps_total + k) * F, F)
-        scene.render_host_ptrs(cams, rto.MODE_BVH, flags, bias, 0, H, h_rgba.data_ptr(), h_id.data_ptr(), h_t.data_ptr())
+        base = (k * world + rank) * F
+        for c in range(F // EB):
+            scene.render_host_ptrs(cam_array(base + c * EB, EB), rto.MODE_BVH, flags, bias, 0, H, h_rgba.data_ptr(), h_id.data_ptr(), h_t.data_ptr())
 
-    e2e_steps = max(1, min(args.steps, 10))
-    for k in range(2):
-        step_host(k)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    scene.render_host_ptrs(cam_array(0, EB), rto.MODE_BVH, flags, bias, 0, H, h_rgba.data_ptr(), h_id.data_ptr(), h_t.data_ptr())
     sync_all()
     te = time.perf_counter()
     for k in range(e2e_steps):
         step_host(args.warmup + k)                      # synchronous: returns when the planes are in host memory
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - te
-    e2e_rays = sum(rays_per_step[:e2e_steps])            # same frames as the device-timed steps
-    assert int((h_id >= 0).sum().item()) + F * W * H == rays_per_step[e2e_steps - 1], "host planes differ from device planes"
+    e2e_rays = sum(rays_in(((args.warmup + k) * world + rank) * F, F) for k in range(e2e_steps))
+    lastb = ((args.warmup + e2e_steps - 1) * world + rank) * F + F - EB
+    assert int((h_id >= 0).sum().item()) == sum(hits_of[(lastb + j) % ORBIT] for j in range(EB)), "host planes differ from device planes"
     if world > 1:
         dist.barrier()
 
     # ---- reduce over ranks: max time, sum rays ---------------------------------------------------------------
-    tvec = torch.tensor([dev_ms, e2e_s, kern_ms_avg], dtype=torch.float64, device="cuda")
-    rvec = torch.tensor([rays, e2e_rays, launches], dtype=torch.float64, device="cuda")
+    tvec = torch.tensor([dev_ms, e2e_s, kern_ms_avg, comm_free[0] if comm_free else 0.0], dtype=torch.float64, device=dev)
+    rvec = torch.tensor([0 if gathered else rays_main, e2e_rays, launches, comm_free[1] if comm_free else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
         dist.all_reduce(rvec, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, kern_ms_max = [float(x) for x in tvec.tolist()]
-    rays_all, e2e_rays_all, launches_all = [float(x) for x in rvec.tolist()]
-
-    # ---- optional: NCCL framebuffer gather to rank 0 (the one collective of the path), timed separately --------
-    gather = None
-    if world > 1:
-        from ray_tracing_octrees_b200 import sharding
-        sharding.gather_planes(hid, dst=0)                      # warm up the communicator
-        torch.cuda.synchronize(); dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for plane in (rgba, hid, tt):
-            sharding.gather_planes(plane, dst=0)
-        g1.record(); torch.cuda.synchronize()
-        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        nbytes = rgba.numel() * 4 + hid.numel() * 4 + tt.numel() * 4
-        gather = {"what": "all three planes of one step (F frames) from every rank to rank 0 over NCCL", "bytes_per_rank": nbytes,
-                  "ms": float(gms.item()), "GBps_into_rank0": nbytes * (world - 1) / (float(gms.item()) * 1e-3) / 1e9}
+    dev_ms_max, e2e_s_max, kern_ms_max, cf_ms_max = [float(x) for x in tvec.tolist()]
+    rays_all, e2e_rays_all, launches_all, cf_rays_all = [float(x) for x in rvec.tolist()]
+    if gathered:
+        rays_all = float(rays_main)                     # every rank counted the same global frames
 
     if rank != 0:
+        if gr:
+            gr.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_render_bvh<shadows, pruned>) --------------------------------------
-    # Algorithmic bytes/flops per ray are defined on the REFERENCE's structures: B box tests, C candidates,
-    # counted on the GPU by replaying the reference's visit pattern (rto_render_stats, checked against the oracle in tests):
+    # ---- roofline of the dominant kernel (k_render_bvh<shadows, pruned>), one launch = 16 frames ------------------------------
+    # Algorithmic bytes/flops per ray are defined on the REFERENCE's structures (SURVEY.md 8d): B box tests, C candidates, counted on
+    # the GPU by replaying the reference's visit pattern (rto_render_stats, checked against the oracle's counters in the tests):
     #   primary ray: 24 B + 36 C + 24 bytes, 18 B + 51 C + 60 flops;  shadow ray: 24 Bs + 36 Cs bytes, 18 Bs + 51 Cs flops.
-    cams = orbit_cameras(rto, args.warmup * F, F)
+    # The orbit's 64 cameras are sampled every 4th (16 of them = the cameras of an average launch).
     st = np.zeros(5, np.float64)
-    for c in cams:
-        st += scene.stats(c, rto.MODE_BVH, flags, bias).astype(np.float64)
-    prim = F * W * H
+    for k in range(0, ORBIT, 4):
+        st += scene.stats(orbit[k], rto.MODE_BVH, flags, bias).astype(np.float64)
+    prim = BATCH * W * H
     alg_bytes = 24 * st[0] + 36 * st[1] + 24 * prim + 24 * st[2] + 36 * st[3]
     alg_flops = 18 * st[0] + 51 * st[1] + 60 * prim + 18 * st[2] + 51 * st[3]
-    peak, peak_src, sm_max = load_peaks()
-    achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("k_render_bvh_bytes_per_launch")
-        except Exception:
-            traffic = None
+    hbm_peak, peak_src, sm_max = load_peaks()
     sms = ctypes.c_int()
     rto.lib().rto_device_info(ctypes.byref(sms), None, None, None, None)
     fp32_peak = sms.value * 128 * 2 * sm_max * 1e6 / 1e12
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src + " MEASURED_PEAKS.json hbm_gbs (burst copy)", "kernel": "k_render_bvh<shadows,pruned>",
-                "kernel_ms": kern_ms_avg, "algorithmic_bytes_per_launch": alg_bytes,
-                "per_primary_ray": {"box_tests": st[0] / prim, "candidates": st[1] / prim}, "shadow_rays_per_launch": st[4],
-                "fp32": {"achieved_tflops": alg_flops / (kern_ms_avg * 1e-3) / 1e12, "peak_tflops": fp32_peak, "frac": alg_flops / (kern_ms_avg * 1e-3) / 1e12 / fp32_peak},
-                "note": "scene (~64 MB) is L2-resident by design, so algorithmic bytes are served mostly from L2/L1; frac>1 of HBM is expected"}
+    ksec = kern_ms_avg * 1e-3
+    counters = {}
+    cp = os.path.join(ROOT, "profiles", "r02_bvh_counters.json")
+    if os.path.exists(cp):
+        try:
+            counters = json.load(open(cp))
+        except Exception:
+            counters = {}
+    traffic = counters.get("dram_bytes_per_launch")
+    roofline = {
+        # neither HBM nor the tensor cores bound this kernel (scene L1/L2-resident, no contraction): the limit it is nearest to is FP32
+        # instruction issue, so that is the one `frac` is quoted against (<= 1 by construction); the other limits are listed beside it.
+        "bound": "fp32-issue", "achieved": alg_flops / ksec / 1e12, "peak": fp32_peak, "unit": "TFLOP/s", "frac": alg_flops / ksec / 1e12 / fp32_peak,
+        "traffic": traffic, "kernel": "k_render_bvh<shadows,pruned>", "kernel_ms": kern_ms_avg, "frames_per_launch": BATCH,
+        "peak_source": "SMs x 128 lanes x 2 x sm_max_mhz (%d SMs, %.0f MHz)" % (sms.value, sm_max),
+        "definition": "algorithmic flops of the REFERENCE's structures (SURVEY.md 8d) per launch / kernel time; the production tree does fewer box and triangle tests than counted",
+        "hbm": {"achieved_GBps": (traffic / ksec / 1e9) if traffic else None, "peak_GBps": hbm_peak, "frac": (traffic / ksec / 1e9 / hbm_peak) if traffic else None,
+                "peak_source": peak_src, "compulsory_bytes_per_launch": prim * 24, "source": "profiles/r02_bvh_counters.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None},
+        "ncu": {k: counters.get(k) for k in ("issue_active_pct", "lanes_per_instruction", "alu_pipe_pct", "fma_pipe_pct", "l1_hit_pct", "l2_hit_pct",
+                                             "l2_throughput_pct", "dram_throughput_pct", "warp_instructions", "source")} if counters else None,
+        "algorithmic_intensity": {"bytes_per_launch": alg_bytes, "GBps": alg_bytes / ksec / 1e9, "flops_per_launch": alg_flops,
+                                  "note": "reference-defined bytes, served from L1/L2; not a fraction of any limit"},
+        "per_primary_ray": {"box_tests": st[0] / prim, "candidates": st[1] / prim}, "shadow_rays_per_launch": st[4]}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores ---------------------------
     cpu = None
@@ -328,21 +397,26 @@ def run_ours(args, rank, world, local_rank):
 
     value = rays_all / (dev_ms_max * 1e-3) / 1e6
     e2e_value = e2e_rays_all / e2e_s_max / 1e6
+    run = ({"frames_per_step_per_gpu": F, "frames_per_launch_per_gpu": BATCH, "triangles": int(len(tris)), "bvh_nodes": int(host_bvh.num_nodes),
+                "l2": "every launch writes %.0f MB of planes per GPU through L2 (126 MB), two plane sets alternate; scene resident by design" % (BATCH * W * H * 24 / 1e6),
+                "parallelism": ("rows of every %d-frame batch dealt to %d GPUs, scene replicated, all frames gathered on rank 0 (%s)" % (BATCH * world, world, gr.transport)) if gathered
+                else "frames sharded over %d GPU(s), scene replicated, no exchange" % world, "scene_build_s": build_s})
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "C2 DT-voxel MC mesh 487832 tris (sceneCache.bin stand-in for the absent DT CSVs), BVH ray cast 1920x1080 primary+shadow",
-                       "frames_per_step_per_gpu": F, "triangles": int(len(tris)), "bvh_nodes": int(host_bvh.num_nodes),
-                       "l2": "outputs %.0f MB/step written through L2 (126 MB) between repeats; scene resident by design" % (F * W * H * 24 / 1e6),
-                       "parallelism": "frames sharded over %d GPU(s), scene replicated" % world, "scene_build_s": build_s},
-            "clocks": clocks,
+            "ms_per_step": dev_ms_max / args.steps, "ms_per_step_median": float(np.median(per_step)), "timed_region_s": dev_ms_max * 1e-3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA, "config": CONFIG, "run": run, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": F * ctypes.sizeof(rto.RtoCamera), "d2h_bytes_per_step": F * W * H * 24,
-                    "steps": e2e_steps, "api": "rto_render_batch(RTO_MEM_HOST) into pinned host planes; per-frame D2H overlaps the next frame's kernel"},
-            "gpu_launches": int(launches_all),
-            "roofline": roofline, "cpu_baseline": cpu}
-    if gather:
-        line["nccl_gather"] = gather
+                    "steps": e2e_steps, "api": "rto_render_batch(RTO_MEM_HOST), %d frames per call into pinned host planes; per-frame D2H overlaps the next frame's kernel" % EB},
+            "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu}
+    if gathered:
+        line["gather"] = {"what": "every frame delivered as rgba32f + id + t planes in rank 0's HBM inside the timed region", "transport": gr.transport,
+                          "bytes_per_pixel_on_the_wire": 4, "check": gather_check, "shares": [round(w / sum(gr.weights), 4) for w in gr.weights],
+                          "calibration_ms": [[round(x, 3) for x in r] for r in (cal or [])][-2:],
+                          "into_rank0_GBps": (1.0 - gr.weights[0] / sum(gr.weights)) * world * F * args.steps * W * H * 4 / (dev_ms_max * 1e-3) / 1e9}
+        line["comm_free"] = {"value": cf_rays_all / (cf_ms_max * 1e-3) / 1e6, "unit": "Mrays/s", "steps": min(args.steps, 10),
+                             "what": "the same frames, every rank keeps its own planes (no exchange)"}
     print(json.dumps(line), flush=True)
+    if gr:
+        gr.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -353,15 +427,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=8, help="orbit frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=128, help="orbit frames per step per GPU (multiple of 16)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--per-launch-timing", action="store_true")
+    ap.add_argument("--comm-free-only", action="store_true", help="N > 1: skip the gather (round-1 behaviour)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    args.steps_total = args.steps + args.warmup
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -325,7 +325,9 @@ RTO_API int rto_group_sync(RtoGroup* group);
 
 /* Explicit ray list (origins/directions 3 floats each, directions need not be unit), for edge cases and as the
  * batched counterpart of single-ray calls: octree scenes return what octreeRaySkip(root, ro, rd, tMin, tMax, grid)
- * returns (mode A) or the GLSL traversal's closestT (mode B); BVH scenes the closest MT hit. */
+ * returns (mode A) or the GLSL traversal's closestT (mode B); BVH scenes the closest MT hit.  [tMin, tMax] is octreeRaySkip's
+ * interval; the GLSL traversal and the BVH hit rule have none: BVH scenes accept only tMin = 0, tMax >= 1e30 (RTO_ERR_INVALID
+ * otherwise).  memory: RTO_MEM_HOST or RTO_MEM_DEVICE for all four arrays. */
 RTO_API int rto_trace_rays(RtoScene* scene, int mode, uint32_t flags, const float* origins, const float* dirs, size_t numRays,
 	float tMin, float tMax, float* tOut, int32_t* idOut, int memory);
 

@@ -359,18 +359,18 @@ class Scene:
         """Enqueue a render of one camera or a list of cameras writing to device pointers (asynchronous)."""
         if isinstance(cams, RtoCamera):
             cams = [cams]
-        arr = (RtoCamera * len(cams))(*cams)
-        y1 = cams[0].height if y1 is None else y1
+        arr = cams if isinstance(cams, C.Array) else (RtoCamera * len(cams))(*cams)
+        y1 = arr[0].height if y1 is None else y1
         fr = RtoFrame(rgba_ptr, id_ptr, t_ptr, MEM_DEVICE)
-        check(lib().rto_render_batch(self.h, arr, len(cams), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
+        check(lib().rto_render_batch(self.h, arr, len(arr), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
 
     def render_host_ptrs(self, cams, mode, flags, shadow_bias, y0, y1, rgba_ptr, id_ptr, t_ptr):
         """Synchronous render into caller-owned HOST pointers (e.g. pinned torch tensors)."""
         if isinstance(cams, RtoCamera):
             cams = [cams]
-        arr = (RtoCamera * len(cams))(*cams)
+        arr = cams if isinstance(cams, C.Array) else (RtoCamera * len(cams))(*cams)
         fr = RtoFrame(rgba_ptr, id_ptr, t_ptr, MEM_HOST)
-        check(lib().rto_render_batch(self.h, arr, len(cams), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
+        check(lib().rto_render_batch(self.h, arr, len(arr), mode, flags, shadow_bias, y0, y1, C.byref(fr)))
 
     def render_codes(self, cams, flags, shadow_bias, codes_ptr, first_frame=0, y0=0, y1=None, stream=None):
         """rto_render_codes: trace rows [y0, y1) of the cameras and write one 32-bit hit code per pixel (tile order) into the code

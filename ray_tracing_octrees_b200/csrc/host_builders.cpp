@@ -83,9 +83,7 @@ void buildPyramid(const uint8_t* vox, int dx, int dy, int dz, int levels, Pyrami
 		int nthreads = (int)std::min<size_t>(hw, std::max<size_t>(1, ((size_t)cx * cy * cz) >> 16));
 		if (nthreads <= 1) slab(0, cz);
 		else {
-			std::vector<std::thread> th;
-			for (int t = 0; t < nthreads; t++) th.emplace_back(slab, (int)((int64_t)cz * t / nthreads), (int)((int64_t)cz * (t + 1) / nthreads));
-			for (auto& t : th) t.join();
+			rto_run_threads(nthreads, [&](int t) { slab((int)((int64_t)cz * t / nthreads), (int)((int64_t)cz * (t + 1) / nthreads)); });
 		}
 		P.data[l] = dst;
 	}
@@ -93,7 +91,7 @@ void buildPyramid(const uint8_t* vox, int dx, int dy, int dz, int levels, Pyrami
 
 } // namespace
 
-extern "C" int rto_host_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ, RtoGpuNode** nodesOut, size_t* numNodes) {
+extern "C" int rto_host_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ, RtoGpuNode** nodesOut, size_t* numNodes) try {
 	if (!nodesOut || !numNodes) return rto_fail(RTO_ERR_INVALID, "rto_host_octree_build: null output");
 	*nodesOut = nullptr; *numNodes = 0;
 	// createOctreeFromVoxelGrid returns nullptr for an empty grid (OctreeVoxel.cpp:766): zero nodes, still RTO_OK
@@ -136,7 +134,7 @@ extern "C" int rto_host_octree_build(const uint8_t* voxels, int dimX, int dimY, 
 	std::memcpy(out, nodes.data(), nodes.size() * sizeof(RtoGpuNode));
 	*nodesOut = out; *numNodes = nodes.size();
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_octree_build")
 
 // =================================================================================================
 // Marching cubes in the reference's emission order
@@ -184,7 +182,7 @@ inline void mcCell(const McGrid& g, int x, int y, int z, std::vector<RtoTriangle
 } // namespace
 
 extern "C" int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const RtoGpuNode* nodes, size_t numNodes, RtoTriangle** trisOut, size_t* numTris) {
+	const RtoGpuNode* nodes, size_t numNodes, RtoTriangle** trisOut, size_t* numTris) try {
 	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_host_mc_mesh: null output");
 	*trisOut = nullptr; *numTris = 0;
 	if (numNodes == 0) return RTO_OK;
@@ -213,7 +211,7 @@ extern "C" int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int d
 	std::memcpy(buf, out.data(), out.size() * sizeof(RtoTriangle));
 	*trisOut = buf; *numTris = out.size();
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_mc_mesh")
 
 // =================================================================================================
 // BVH with the reference's shape
@@ -252,18 +250,14 @@ struct Builder {
 		size_t mid = m / 2;                             // BVH.cpp:63
 		size_t li = nodeIdx + 1, ri = li + subtreeNodes(mid);
 		nd.left = (int32_t)li; nd.right = (int32_t)ri; nd.count = 0;
-		if (depth < 5 && m > 20000) {                    // up to 32 subtrees in flight
-			std::thread th([=] { build(lo, lo + mid, li, depth + 1); });
-			build(lo + mid, hi, ri, depth + 1);
-			th.join();
-		}
-		else { build(lo, lo + mid, li, depth + 1); build(lo + mid, hi, ri, depth + 1); }
+		// up to 32 subtrees in flight
+		rto_fork_join(depth < 5 && m > 20000, [=] { build(lo, lo + mid, li, depth + 1); }, [=] { build(lo + mid, hi, ri, depth + 1); });
 	}
 };
 
 } // namespace
 
-extern "C" int rto_host_bvh_build(const RtoTriangle* tris, size_t numTris, RtoHostBvh** out) {
+extern "C" int rto_host_bvh_build(const RtoTriangle* tris, size_t numTris, RtoHostBvh** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_build: null output");
 	*out = nullptr;
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_build: null triangles");
@@ -284,12 +278,12 @@ extern "C" int rto_host_bvh_build(const RtoTriangle* tris, size_t numTris, RtoHo
 	h->order.swap(b.idx);
 	*out = h;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_bvh_build")
 
 extern "C" void rto_host_bvh_free(RtoHostBvh* bvh) { delete bvh; }
 extern "C" size_t rto_host_bvh_num_nodes(const RtoHostBvh* bvh) { return bvh ? bvh->nodes.size() : 0; }
 
-extern "C" int rto_host_bvh_export(const RtoHostBvh* bvh, float* boxes6, int32_t* meta4, size_t capacity) {
+extern "C" int rto_host_bvh_export(const RtoHostBvh* bvh, float* boxes6, int32_t* meta4, size_t capacity) try {
 	if (!bvh || !boxes6 || !meta4) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_export: null argument");
 	if (capacity < bvh->nodes.size()) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_export: capacity too small");
 	for (size_t i = 0; i < bvh->nodes.size(); i++) {    // nodes are stored in pre-order already
@@ -301,7 +295,7 @@ extern "C" int rto_host_bvh_export(const RtoHostBvh* bvh, float* boxes6, int32_t
 		meta4[4 * i + 3] = (leaf && n.count > 1) ? (int32_t)bvh->order[n.first + 1] : -1;
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_bvh_export")
 
 // =================================================================================================
 // Device node arrays
@@ -400,15 +394,7 @@ struct SahBuilder {
 		}
 		float lmn[3], lmx[3], rmn[3], rmx[3];
 		int32_t r0, r1;
-		if (depth < 4 && hi - lo > 65536) {
-			std::thread th([&] { r0 = build(lo, mid, idx + 1, depth + 1, lmn, lmx); });
-			r1 = build(mid, hi, idx + (mid - lo), depth + 1, rmn, rmx);
-			th.join();
-		}
-		else {
-			r0 = build(lo, mid, idx + 1, depth + 1, lmn, lmx);
-			r1 = build(mid, hi, idx + (mid - lo), depth + 1, rmn, rmx);
-		}
+		rto_fork_join(depth < 4 && hi - lo > 65536, [&] { r0 = build(lo, mid, idx + 1, depth + 1, lmn, lmx); }, [&] { r1 = build(mid, hi, idx + (mid - lo), depth + 1, rmn, rmx); });
 		float* d = &(*out)[idx * 16];
 		// paired layout (BvhDev::paired): plane k of child 0 and of child 1 side by side, k = lo x, lo y, lo z, hi x, hi y, hi z
 		for (int k = 0; k < 3; k++) { d[2 * k] = lmn[k]; d[2 * k + 1] = rmn[k]; d[6 + 2 * k] = lmx[k]; d[6 + 2 * k + 1] = rmx[k]; }
@@ -502,7 +488,7 @@ static void glm_mul_m4v4(const float* m, const float* v, float* out) {
 }
 
 extern "C" int rto_host_camera_orbit(float theta, float phi, float radius, const float target[3], float fovDeg, float aspect,
-	int width, int height, RtoCamera* out, float* view16) {
+	int width, int height, RtoCamera* out, float* view16) try {
 	if (!out || !target) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: null argument");
 	if (width <= 0 || height <= 0) return rto_fail(RTO_ERR_INVALID, "rto_host_camera_orbit: bad image size");
 	V3 tgt = mk3(target[0], target[1], target[2]);
@@ -519,12 +505,12 @@ extern "C" int rto_host_camera_orbit(float theta, float phi, float radius, const
 	out->aspect = aspect; out->width = width; out->height = height;
 	if (view16) std::memcpy(view16, m, 64);
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_camera_orbit")
 
 // =================================================================================================
 // sceneCache.bin (CacheUtils.cpp:5-59)
 // =================================================================================================
-extern "C" int rto_host_grid_load(const char* path, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) {
+extern "C" int rto_host_grid_load(const char* path, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) try {
 	if (!path || !dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_host_grid_load: null argument");
 	*voxelsOut = nullptr;
 	FILE* f = std::fopen(path, "rb");
@@ -540,9 +526,9 @@ extern "C" int rto_host_grid_load(const char* path, int dims[3], float minAndVox
 	if (!ok) { std::free(buf); return rto_fail(RTO_ERR_IO, "rto_host_grid_load: truncated or inconsistent file"); }
 	*voxelsOut = buf;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_grid_load")
 
-extern "C" int rto_host_grid_save(const char* path, const int dims[3], const float minAndVoxel[4], const uint8_t* voxels) {
+extern "C" int rto_host_grid_save(const char* path, const int dims[3], const float minAndVoxel[4], const uint8_t* voxels) try {
 	if (!path || !dims || !minAndVoxel || !voxels) return rto_fail(RTO_ERR_INVALID, "rto_host_grid_save: null argument");
 	FILE* f = std::fopen(path, "wb");
 	if (!f) return rto_fail(RTO_ERR_IO, "rto_host_grid_save: cannot open file");
@@ -550,7 +536,7 @@ extern "C" int rto_host_grid_save(const char* path, const int dims[3], const flo
 	bool ok = std::fwrite(dims, 4, 3, f) == 3 && std::fwrite(minAndVoxel, 4, 4, f) == 4 && std::fwrite(&n, 8, 1, f) == 1 && std::fwrite(voxels, 1, n, f) == n;
 	ok = (std::fclose(f) == 0) && ok;
 	return ok ? RTO_OK : rto_fail(RTO_ERR_IO, "rto_host_grid_save: write failed");
-}
+} RTO_CATCH_ALL("rto_host_grid_save")
 
 extern "C" void rto_host_free(void* p) { std::free(p); }
 
@@ -651,7 +637,7 @@ int rto_csv_load(const char* vertsCsv, const char* facesCsv, float voxelSize, Cs
 	return RTO_OK;
 }
 
-extern "C" int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) {
+extern "C" int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) try {
 	if (!dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_host_csv_voxelize: null output");
 	*voxelsOut = nullptr; dims[0] = dims[1] = dims[2] = 0;
 	CsvScene S;
@@ -677,20 +663,18 @@ extern "C" int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv,
 	size_t nt = std::min<size_t>(hw, std::max<size_t>(1, S.tris.size() / 256));
 	if (nt <= 1) work(0, S.tris.size());
 	else {
-		std::vector<std::thread> th;
-		for (size_t k = 0; k < nt; k++) th.emplace_back(work, S.tris.size() * k / nt, S.tris.size() * (k + 1) / nt);
-		for (auto& t : th) t.join();
+		rto_run_threads((int)nt, [&](int k) { work(S.tris.size() * (size_t)k / nt, S.tris.size() * ((size_t)k + 1) / nt); });
 	}
 	*voxelsOut = vox;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_csv_voxelize")
 
 // =================================================================================================
 // Frustum culling of the flattened octree: RayTracerBVH::renderSceneComputeWithCulling, CPU part (RayTracerBVH.cpp:724-813)
 // =================================================================================================
 // proj * view with glm::perspective(radians(fovDeg), aspect, zNear, zFar) (matrix_clip_space.inl:249-262, RH, depth -1..1) and
 // glm's mat4 * mat4 (type_mat4x4.inl:630-648: ((A0*b0 + A1*b1) + A2*b2) + A3*b3 per column).
-extern "C" int rto_host_view_proj(const float view16[16], float fovDeg, float aspect, float zNear, float zFar, float viewProj16[16]) {
+extern "C" int rto_host_view_proj(const float view16[16], float fovDeg, float aspect, float zNear, float zFar, float viewProj16[16]) try {
 	if (!view16 || !viewProj16) return rto_fail(RTO_ERR_INVALID, "rto_host_view_proj: null argument");
 	float P[16];
 	glm_perspective(fovDeg, aspect, zNear, zFar, P);
@@ -703,10 +687,10 @@ extern "C" int rto_host_view_proj(const float view16[16], float fovDeg, float as
 			viewProj16[j * 4 + r] = acc;
 		}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_view_proj")
 
 extern "C" int rto_host_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, const float viewProj16[16],
-	float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut) {
+	float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut) try {
 	if (!culledOut || !numCulled) return rto_fail(RTO_ERR_INVALID, "rto_host_frustum_cull: null output");
 	*culledOut = nullptr; *numCulled = 0;
 	if (newToOldOut) *newToOldOut = nullptr;
@@ -734,13 +718,13 @@ extern "C" int rto_host_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, c
 	*culledOut = out; *numCulled = visible;
 	if (newToOldOut) *newToOldOut = back;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_frustum_cull")
 
 // =================================================================================================
 // The probe rays of VolumeRaycastRenderer's skip-distance estimate (VolumeRaycastRenderer.cpp:1598-1629): a 7 x 7 grid over the
 // central +-0.2 of NDC, unprojected through inverse(perspective(45 deg, aspect, 0.1, 5000)) and inverse(view).
 // =================================================================================================
-extern "C" int rto_host_skip_probe_rays(const float view16[16], const float camPos[3], float aspect, float* origins, float* dirs) {
+extern "C" int rto_host_skip_probe_rays(const float view16[16], const float camPos[3], float aspect, float* origins, float* dirs) try {
 	if (!view16 || !camPos || !origins || !dirs) return rto_fail(RTO_ERR_INVALID, "rto_host_skip_probe_rays: null argument");
 	float P[16], invP[16], invV[16];
 	glm_perspective(45.0f, aspect, 0.1f, 5000.0f, P);
@@ -763,7 +747,7 @@ extern "C" int rto_host_skip_probe_rays(const float view16[16], const float camP
 			dirs[3 * k] = rd.x; dirs[3 * k + 1] = rd.y; dirs[3 * k + 2] = rd.z;
 		}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_skip_probe_rays")
 
 // 15th percentile of the valid probe results, 75 % of it, blended with the previous frame's value (VolumeRaycastRenderer.cpp:1646-1663)
 extern "C" float rto_host_skip_distance_from_probes(const float* t, int count, float lastSkipDistance) {

@@ -38,10 +38,7 @@ namespace {
 template <class F> void parallelFor(size_t n, size_t grain, int nthreads, F&& body) {
 	if (nthreads <= 1 || n <= grain) { if (n) body(0, n, 0); return; }
 	std::atomic<size_t> next{ 0 };
-	std::vector<std::thread> th;
-	for (int t = 0; t < nthreads; t++)
-		th.emplace_back([&, t] { for (;;) { size_t lo = next.fetch_add(grain); if (lo >= n) break; body(lo, std::min(n, lo + grain), t); } });
-	for (auto& x : th) x.join();
+	rto_run_threads(nthreads, [&](int t) { for (;;) { size_t lo = next.fetch_add(grain); if (lo >= n) break; body(lo, std::min(n, lo + grain), t); } });
 }
 
 double nowSec() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -256,21 +253,21 @@ static int dcMeshOrderFree(const uint8_t* voxels, int dimX, int dimY, int dimZ, 
 }
 
 extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) {
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) try {
 	return dcMeshOrderFree(voxels, dimX, dimY, dimZ, gridMin, voxelSize, nodes, numNodes, viewProj16, extraMargin, trisOut, nullptr, numTris);
-}
+} RTO_CATCH_ALL("rto_host_dc_mesh")
 
 extern "C" int rto_host_dc_mesh_normals(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, float** normalsOut, size_t* numTris) {
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, float** normalsOut, size_t* numTris) try {
 	if (!normalsOut) return rto_fail(RTO_ERR_INVALID, "rto_host_dc_mesh_normals: null output");
 	return dcMeshOrderFree(voxels, dimX, dimY, dimZ, gridMin, voxelSize, nodes, numNodes, viewProj16, extraMargin, trisOut, normalsOut, numTris);
-}
+} RTO_CATCH_ALL("rto_host_dc_mesh_normals")
 
 // =================================================================================================================================
 // The triangle cache of the application (main.cpp:27-67, written after every Dual-Contouring run and read back instead of meshing):
 // size_t count, then count x MCTriangle { vec3 v[3]; vec3 normal[3]; } = 72 bytes each.
 // =================================================================================================================================
-extern "C" int rto_host_tricache_save(const char* path, const RtoTriangle* tris, const float* normals3, size_t numTris) {
+extern "C" int rto_host_tricache_save(const char* path, const RtoTriangle* tris, const float* normals3, size_t numTris) try {
 	if (!path || (numTris && !tris)) return rto_fail(RTO_ERR_INVALID, "rto_host_tricache_save: null argument");
 	FILE* f = std::fopen(path, "wb");
 	if (!f) return rto_fail(RTO_ERR_IO, "rto_host_tricache_save: cannot open %s", path);
@@ -294,9 +291,9 @@ extern "C" int rto_host_tricache_save(const char* path, const RtoTriangle* tris,
 	}
 	ok = (std::fclose(f) == 0) && ok;
 	return ok ? RTO_OK : rto_fail(RTO_ERR_IO, "rto_host_tricache_save: write to %s failed", path);
-}
+} RTO_CATCH_ALL("rto_host_tricache_save")
 
-extern "C" int rto_host_tricache_load(const char* path, RtoTriangle** trisOut, float** normals9Out, size_t* numTris) {
+extern "C" int rto_host_tricache_load(const char* path, RtoTriangle** trisOut, float** normals9Out, size_t* numTris) try {
 	if (!path || !trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_host_tricache_load: null argument");
 	*trisOut = nullptr; *numTris = 0; if (normals9Out) *normals9Out = nullptr;
 	FILE* f = std::fopen(path, "rb");
@@ -322,7 +319,7 @@ extern "C" int rto_host_tricache_load(const char* path, RtoTriangle** trisOut, f
 	if (!ok) { std::free(t); std::free(nm); return rto_fail(RTO_ERR_IO, "rto_host_tricache_load: read from %s failed", path); }
 	*trisOut = t; *numTris = n; if (normals9Out) *normals9Out = nm;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_host_tricache_load")
 
 // =================================================================================================================================
 // Replay formulation: the reference's cache protocol executed leaf by leaf in visit order, with the pure per-cell work prepared
@@ -334,7 +331,7 @@ extern "C" int rto_host_tricache_load(const char* path, RtoTriangle** trisOut, f
 //     speculation, only speed does.
 // =================================================================================================================================
 extern "C" int rto_host_dc_mesh_replay(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) {
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) try {
 	int rc = checkArgs("rto_host_dc_mesh_replay", voxels, gridMin, nodes, numNodes, trisOut, numTris);
 	if (rc || numNodes == 0) return rc;
 	const Grid g{ voxels, dimX, dimY, dimZ, gridMin[0], gridMin[1], gridMin[2], voxelSize };
@@ -412,4 +409,4 @@ extern "C" int rto_host_dc_mesh_replay(const uint8_t* voxels, int dimX, int dimY
 		}
 	}
 	return handOver("rto_host_dc_mesh_replay", out, trisOut, numTris);
-}
+} RTO_CATCH_ALL("rto_host_dc_mesh_replay")

@@ -42,6 +42,17 @@ int rto_build_octree_layout(const RtoGpuNode* nodes, size_t numNodes, OctLayout&
 			if (nodes[i].child[c] >= (int64_t)numNodes) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: node %zu child %d out of range", i, c);
 	L.numLeaves = 0;
 	for (size_t i = 0; i < numNodes; i++) L.numLeaves += nodes[i].isLeaf ? 1 : 0;
+	{	// in-degree <= 1 everywhere and 0 at the root  <=>  what can be reached from the root is a tree (no shared children, no cycles)
+		std::vector<uint8_t> refs(numNodes, 0);
+		L.isTree = true;
+		for (size_t i = 0; i < numNodes && L.isTree; i++)
+			for (int c = 0; c < 8; c++) {
+				const int32_t k = nodes[i].child[c];
+				if (k < 0) continue;
+				if (k == 0 || refs[k]) { L.isTree = false; break; }
+				refs[k] = 1;
+			}
+	}
 	L.compact = octree_is_compactable(nodes, numNodes);
 	if (!L.compact) {
 		L.padded.assign(numNodes * 16, -1);

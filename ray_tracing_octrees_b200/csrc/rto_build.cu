@@ -289,7 +289,7 @@ int oct_emit(OctBuild& B, bool wantCompact, bool wantNodes, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // C ABI: octree
 // ------------------------------------------------------------------------------------------------
-extern "C" int rto_device_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ, RtoGpuNode** nodesOut, size_t* numNodes) {
+extern "C" int rto_device_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ, RtoGpuNode** nodesOut, size_t* numNodes) try {
 	if (!nodesOut || !numNodes) return rto_fail(RTO_ERR_INVALID, "rto_device_octree_build: null output");
 	*nodesOut = nullptr; *numNodes = 0;
 	if (dimX == 0 || dimY == 0 || dimZ == 0) return RTO_OK;        // createOctreeFromVoxelGrid returns nullptr (OctreeVoxel.cpp:766)
@@ -315,10 +315,10 @@ extern "C" int rto_device_octree_build(const uint8_t* voxels, int dimX, int dimY
 	if (rc) return rc;
 	*nodesOut = host; *numNodes = B.numNodes;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_device_octree_build")
 
 extern "C" int rto_scene_create_octree_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	RtoScene** out) {
+	RtoScene** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree_from_grid: null output");
 	*out = nullptr;
 	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree_from_grid: empty grid (nothing to trace)");
@@ -340,11 +340,11 @@ extern "C" int rto_scene_create_octree_from_grid(const uint8_t* voxels, int dimX
 	rto_scene_adopt(s, B.desc, B.descWords * 4); rto_scene_adopt(s, B.up, B.upWords * 4); rto_scene_adopt(s, B.inner, B.innerRecs * 16);
 	*out = s;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_create_octree_from_grid")
 
 // Diagnostic: copies the compact device layout of an octree scene to the host (desc: numNodes + 8 words, up: (numNodes + 7) / 8 + 1
 // words, inner: 4 words per internal node); any pointer may be null.  Used by the tests to compare both construction routes.
-extern "C" int rto_scene_octree_layout_read(RtoScene* s, uint32_t* desc, int32_t* up, int32_t* inner4, size_t* numInnerOut) {
+extern "C" int rto_scene_octree_layout_read(RtoScene* s, uint32_t* desc, int32_t* up, int32_t* inner4, size_t* numInnerOut) try {
 	if (!s || s->kind == RTO_MODE_BVH || !s->oct.compact) return rto_fail(RTO_ERR_INVALID, "rto_scene_octree_layout_read: not a compact octree scene");
 	BUILD_TRY(cudaSetDevice(s->device));
 	const size_t n = s->numNodes, numInner = n > 1 ? (n - 1) / 8 : 0;
@@ -354,7 +354,7 @@ extern "C" int rto_scene_octree_layout_read(RtoScene* s, uint32_t* desc, int32_t
 	if (inner4) BUILD_TRY(cudaMemcpyAsync(inner4, s->oct.inner, (numInner ? numInner : 1) * 16, cudaMemcpyDeviceToHost, s->stream));
 	BUILD_TRY(cudaStreamSynchronize(s->stream));
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_octree_layout_read")
 
 // ------------------------------------------------------------------------------------------------
 // Marching cubes
@@ -547,7 +547,7 @@ int mc_extract(const OctBuild& O, const float gridMin[3], float voxelSize, McBui
 } // namespace
 
 extern "C" int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	RtoTriangle** trisOut, size_t* numTris) {
+	RtoTriangle** trisOut, size_t* numTris) try {
 	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_device_mc_mesh: null output");
 	*trisOut = nullptr; *numTris = 0;
 	if (dimX == 0 || dimY == 0 || dimZ == 0) return RTO_OK;
@@ -574,7 +574,7 @@ extern "C" int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 	if (rc) return rc;
 	*trisOut = host; *numTris = M.numTris;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_device_mc_mesh")
 
 // ------------------------------------------------------------------------------------------------
 // BVH build on the device: the fast, NON-reference-shaped mode.
@@ -714,6 +714,7 @@ __global__ void k_lbvh_fit(int numLeaves, const float* __restrict__ leafBox, flo
 		lbvh_store_child_box(n16, slot, lo, hi);
 		__threadfence();
 		if (atomicAdd(arrived + node, 1) == 0) return;          // the sibling subtree is not finished yet: its thread will continue
+		__threadfence();                                        // acquire side: the sibling's box (stored before ITS fence + atomic) is read after our atomic
 		volatile float* other = n16 + (slot ^ 1);
 #pragma unroll
 		for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], other[2 * a]); hi[a] = fmaxf(hi[a], other[6 + 2 * a]); }
@@ -813,7 +814,7 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 
 } // namespace
 
-extern "C" int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTris, RtoScene** out) {
+extern "C" int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTris, RtoScene** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_device: null output");
 	*out = nullptr;
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_device: null triangles");
@@ -829,10 +830,10 @@ extern "C" int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTr
 	if (rc) { rto_scene_destroy(s); return rc; }
 	*out = s;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_create_bvh_device")
 
 extern "C" int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	RtoScene** out) {
+	RtoScene** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid: null output");
 	*out = nullptr;
 	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid: empty grid");
@@ -850,13 +851,13 @@ extern "C" int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, i
 	if (rc) { rto_scene_destroy(s); return rc; }
 	*out = s;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_create_bvh_from_grid")
 
 // The pipeline configuration C4 names, entirely on the device: grid -> octree -> Adaptive Dual Contouring mesh (rto_dc.cu: the reference's
 // triangles in the reference's order) -> linear BVH.  Hit ids index the soup rto_device_dc_mesh / rto_host_dc_mesh return for the
 // same arguments.
 extern "C" int rto_scene_create_bvh_from_grid_dc(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const float* viewProj16, float extraMargin, RtoScene** out) {
+	const float* viewProj16, float extraMargin, RtoScene** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid_dc: null output");
 	*out = nullptr;
 	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid_dc: empty grid");
@@ -878,7 +879,7 @@ extern "C" int rto_scene_create_bvh_from_grid_dc(const uint8_t* voxels, int dimX
 	if (rc) { rto_scene_destroy(s); return rc; }
 	*out = s;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_create_bvh_from_grid_dc")
 
 
 // ------------------------------------------------------------------------------------------------
@@ -906,7 +907,7 @@ __global__ void k_voxelize(const RtoTriangle* __restrict__ tris, size_t numFaces
 }
 } // namespace
 
-extern "C" int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) {
+extern "C" int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) try {
 	if (!dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_device_csv_voxelize: null output");
 	*voxelsOut = nullptr; dims[0] = dims[1] = dims[2] = 0;
 	int rc = rto_require_device(); if (rc) return rc;
@@ -938,7 +939,7 @@ extern "C" int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCs
 	if (e != cudaSuccess) { std::free(host); return rto_fail(RTO_ERR_CUDA, "rto_device_csv_voxelize: %s", cudaGetErrorString(e)); }
 	*voxelsOut = host;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_device_csv_voxelize")
 
 
 // ------------------------------------------------------------------------------------------------
@@ -969,7 +970,7 @@ __global__ void k_cull_emit(const RtoGpuNode* __restrict__ nodes, size_t n, cons
 } // namespace
 
 extern "C" int rto_device_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, const float viewProj16[16],
-	float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut) {
+	float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut) try {
 	if (!culledOut || !numCulled) return rto_fail(RTO_ERR_INVALID, "rto_device_frustum_cull: null output");
 	*culledOut = nullptr; *numCulled = 0;
 	if (newToOldOut) *newToOldOut = nullptr;
@@ -1015,4 +1016,4 @@ extern "C" int rto_device_frustum_cull(const RtoGpuNode* nodes, size_t numNodes,
 	*culledOut = host; *numCulled = visible;
 	if (newToOldOut) *newToOldOut = back; else std::free(back);
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_device_frustum_cull")

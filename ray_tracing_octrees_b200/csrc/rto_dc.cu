@@ -264,7 +264,7 @@ int rto_dc_extract_device(const uint8_t* dVox, int dimX, int dimY, int dimZ, con
 }
 
 extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
-	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) {
+	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) try {
 	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_device_dc_mesh: null output");
 	*trisOut = nullptr; *numTris = 0;
 	if (numNodes == 0) return RTO_OK;
@@ -301,4 +301,4 @@ extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int
 	}
 	*trisOut = host; *numTris = total;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_device_dc_mesh")

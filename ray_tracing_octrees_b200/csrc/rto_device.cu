@@ -41,7 +41,7 @@ int rto_require_device() {
 	return RTO_OK;
 }
 
-extern "C" int rto_init(int device) {
+extern "C" int rto_init(int device) try {
 	{	// constants whose exact bit patterns the traversal code relies on
 		float a = kMissT, b = kBelowMissT, c = kMinPositive; uint32_t ua, ub, uc;
 		std::memcpy(&ua, &a, 4); std::memcpy(&ub, &b, 4); std::memcpy(&uc, &c, 4);
@@ -53,9 +53,9 @@ extern "C" int rto_init(int device) {
 	CUDA_TRY(cudaGetDeviceProperties(&p, device));
 	if (p.major != 10) return rto_fail(RTO_ERR_NO_DEVICE, "device %d is sm_%d%d; librto is built for sm_100a only", device, p.major, p.minor);
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_init")
 
-extern "C" int rto_device_info(int* smCount, int* ccMajor, int* ccMinor, size_t* l2Bytes, size_t* totalMem) {
+extern "C" int rto_device_info(int* smCount, int* ccMajor, int* ccMinor, size_t* l2Bytes, size_t* totalMem) try {
 	int rc = require_device(); if (rc) return rc;
 	int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
 	cudaDeviceProp p; CUDA_TRY(cudaGetDeviceProperties(&p, dev));
@@ -65,7 +65,7 @@ extern "C" int rto_device_info(int* smCount, int* ccMajor, int* ccMinor, size_t*
 	if (l2Bytes) *l2Bytes = (size_t)p.l2CacheSize;
 	if (totalMem) *totalMem = p.totalGlobalMem;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_device_info")
 
 // ------------------------------------------------------------------------------------------------
 // scene (struct in rto_scene.cuh)
@@ -131,7 +131,7 @@ extern "C" void rto_scene_destroy(RtoScene* s) {
 	delete s;
 }
 
-extern "C" int rto_scene_info(const RtoScene* s, int* kind, size_t* numPrims, size_t* numNodes, size_t* deviceBytes, int* compactLayout) {
+extern "C" int rto_scene_info(const RtoScene* s, int* kind, size_t* numPrims, size_t* numNodes, size_t* deviceBytes, int* compactLayout) try {
 	if (!s) return rto_fail(RTO_ERR_INVALID, "rto_scene_info: null scene");
 	if (kind) *kind = s->kind;
 	if (numPrims) *numPrims = s->numPrims;
@@ -139,26 +139,26 @@ extern "C" int rto_scene_info(const RtoScene* s, int* kind, size_t* numPrims, si
 	if (deviceBytes) *deviceBytes = s->deviceBytes;
 	if (compactLayout) *compactLayout = (s->kind == RTO_MODE_BVH) ? 0 : s->oct.compact;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_info")
 extern "C" void* rto_scene_stream(const RtoScene* s) { return s ? (void*)s->stream : nullptr; }
 extern "C" uint64_t rto_scene_launch_count(const RtoScene* s) { return s ? s->launches : 0; }
-extern "C" int rto_scene_sync(RtoScene* s) {
+extern "C" int rto_scene_sync(RtoScene* s) try {
 	if (!s) return rto_fail(RTO_ERR_INVALID, "rto_scene_sync: null scene");
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	return RTO_OK;
-}
-extern "C" int rto_scene_last_kernel_ms(RtoScene* s, float* ms) {
+} RTO_CATCH_ALL("rto_scene_sync")
+extern "C" int rto_scene_last_kernel_ms(RtoScene* s, float* ms) try {
 	if (!s || !ms) return rto_fail(RTO_ERR_INVALID, "rto_scene_last_kernel_ms: null argument");
 	if (!s->timed) return rto_fail(RTO_ERR_INVALID, "rto_scene_last_kernel_ms: nothing rendered yet");
 	CUDA_TRY(cudaEventSynchronize(s->evStop));
 	CUDA_TRY(cudaEventElapsedTime(ms, s->evStart, s->evStop));
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_last_kernel_ms")
 
 // ------------------------------------------------------------------------------------------------
 // octree upload: RayTracerBVH::setOctree's SSBO (RayTracerBVH.cpp:492-504) -> pointer-free device arrays
 // ------------------------------------------------------------------------------------------------
-extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, RtoScene** out) {
+extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, RtoScene** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: null output");
 	*out = nullptr;
 	if (!nodes || numNodes == 0 || !gridMin) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: empty octree (the reference's setOctree(nullptr) clears the scene; nothing to trace)");
@@ -172,6 +172,7 @@ extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes,
 	D.numNodes = (int)numNodes; D.rootSize = nodes[0].size;
 	D.gmin[0] = gridMin[0]; D.gmin[1] = gridMin[1]; D.gmin[2] = gridMin[2]; D.voxel = voxelSize;
 	D.compact = L.compact ? 1 : 0;
+	s->octIsTree = L.isTree;
 	auto up = [&](const void* src, size_t bytes, void** dst) -> int {
 		int r = scene_alloc(s, dst, bytes); if (r) return r;
 		cudaError_t e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s->stream);
@@ -190,7 +191,7 @@ extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes,
 	if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "octree upload failed: %s", cudaGetErrorString(e)); }
 	*out = s;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_scene_create_octree")
 
 // ------------------------------------------------------------------------------------------------
 // BVH upload: reference-shaped host tree -> child-boxes-in-parent nodes + leaf-ordered triangles
@@ -235,7 +236,7 @@ int rto_bvh_layout_from_tris(const RtoTriangle* tris, size_t numTris, const RtoH
 	return rc;
 }
 
-extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, RtoScene** out) {
+extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, RtoScene** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null output");
 	*out = nullptr;
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null triangles");
@@ -243,7 +244,7 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 	BvhLayout L; size_t numRefNodes = 0;
 	if ((rc = rto_bvh_layout_from_tris(tris, numTris, prebuilt, L, &numRefNodes))) return rc;
 	return rto_scene_from_bvh_layout(L, numTris, numRefNodes, out);
-}
+} RTO_CATCH_ALL("rto_scene_create_bvh")
 
 // ------------------------------------------------------------------------------------------------
 // rendering
@@ -251,6 +252,8 @@ extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, con
 static int check_mode(const RtoScene* s, int mode) {
 	if (s->kind == RTO_MODE_BVH) { if (mode != RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "scene is a BVH; mode must be RTO_MODE_BVH"); }
 	else if (mode != RTO_MODE_OCTREE_SKIP && mode != RTO_MODE_OCTREE_GLSL) return rto_fail(RTO_ERR_INVALID, "scene is an octree; mode must be RTO_MODE_OCTREE_SKIP or RTO_MODE_OCTREE_GLSL");
+	else if (mode == RTO_MODE_OCTREE_SKIP && !s->octIsTree)
+		return rto_fail(RTO_ERR_INVALID, "RTO_MODE_OCTREE_SKIP: the node array's child graph is not a tree (a node is shared or lies on a cycle); octreeRaySkip is a recursion over a pointer tree");
 	return RTO_OK;
 }
 
@@ -302,7 +305,7 @@ static int release_cameras(RtoScene* s, int slot, cudaStream_t st) {
 }
 
 extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams, int mode, uint32_t flags, float shadowBias,
-	int y0, int y1, const RtoFrame* frame) {
+	int y0, int y1, const RtoFrame* frame) try {
 	if (!s || !cams || !frame || numCams <= 0) return rto_fail(RTO_ERR_INVALID, "rto_render: null argument");
 	int rc = check_mode(s, mode); if (rc) return rc;
 	const int W = cams[0].width, H = cams[0].height;
@@ -359,7 +362,7 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 		CUDA_TRY(cudaStreamSynchronize(s->stream));
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_render_batch")
 
 // ------------------------------------------------------------------------------------------------
 // hit codes: 4 bytes per pixel out of the trace kernel, planes rebuilt where they are wanted (rto_c.h "compact frames")
@@ -409,7 +412,7 @@ extern "C" size_t rto_codes_frame_words(int width, int height) {
 }
 
 extern "C" int rto_render_codes(RtoScene* s, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, int y0, int y1,
-	uint32_t* codes, size_t firstFrame, void* stream) {
+	uint32_t* codes, size_t firstFrame, void* stream) try {
 	if (!s || !codes) return rto_fail(RTO_ERR_INVALID, "rto_render_codes: null argument");
 	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render_codes: hit codes exist for BVH scenes only");
 	int rc = check_rows("rto_render_codes", cams, numCams, y0, y1, true); if (rc) return rc;
@@ -420,10 +423,10 @@ extern "C" int rto_render_codes(RtoScene* s, const RtoCamera* cams, int numCams,
 	if ((rc = rto_enqueue_render(s, cams, numCams, RTO_MODE_BVH, flags, shadowBias, y0, y1, nullptr, nullptr, nullptr, codes, firstFrame, st))) return rc;
 	if (!stream) { CUDA_TRY(cudaEventRecord(s->evStop, st)); s->timed = true; }
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_render_codes")
 
 extern "C" int rto_resolve_codes(RtoScene* s, const RtoCamera* cams, int numCams, int y0, int y1, const uint32_t* codes, size_t firstFrame,
-	const RtoFrame* frame, void* stream) {
+	const RtoFrame* frame, void* stream) try {
 	if (!s || !codes || !frame) return rto_fail(RTO_ERR_INVALID, "rto_resolve_codes: null argument");
 	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_resolve_codes: hit codes exist for BVH scenes only");
 	int rc = check_rows("rto_resolve_codes", cams, numCams, y0, y1, true); if (rc) return rc;
@@ -449,14 +452,14 @@ extern "C" int rto_resolve_codes(RtoScene* s, const RtoCamera* cams, int numCams
 		CUDA_TRY(cudaStreamSynchronize(st));
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_resolve_codes")
 
 // ------------------------------------------------------------------------------------------------
 // exchange memory: device buffers another GPU of the box writes hit codes into (same process: peer access; other process: CUDA IPC)
 // ------------------------------------------------------------------------------------------------
 static_assert(sizeof(RtoIpcHandle) == sizeof(cudaIpcMemHandle_t), "RtoIpcHandle must hold a cudaIpcMemHandle_t");
 
-extern "C" int rto_exchange_alloc(size_t bytes, void** devPtr, RtoIpcHandle* handleOut) {
+extern "C" int rto_exchange_alloc(size_t bytes, void** devPtr, RtoIpcHandle* handleOut) try {
 	if (!devPtr) return rto_fail(RTO_ERR_INVALID, "rto_exchange_alloc: null output");
 	*devPtr = nullptr;
 	int rc = require_device(); if (rc) return rc;
@@ -471,12 +474,12 @@ extern "C" int rto_exchange_alloc(size_t bytes, void** devPtr, RtoIpcHandle* han
 	}
 	*devPtr = p;
 	return RTO_OK;
-}
-extern "C" int rto_exchange_free(void* devPtr) {
+} RTO_CATCH_ALL("rto_exchange_alloc")
+extern "C" int rto_exchange_free(void* devPtr) try {
 	if (devPtr) CUDA_TRY(cudaFree(devPtr));
 	return RTO_OK;
-}
-extern "C" int rto_exchange_open(const RtoIpcHandle* handle, void** devPtr) {
+} RTO_CATCH_ALL("rto_exchange_free")
+extern "C" int rto_exchange_open(const RtoIpcHandle* handle, void** devPtr) try {
 	if (!handle || !devPtr) return rto_fail(RTO_ERR_INVALID, "rto_exchange_open: null argument");
 	*devPtr = nullptr;
 	int rc = require_device(); if (rc) return rc;
@@ -485,17 +488,17 @@ extern "C" int rto_exchange_open(const RtoIpcHandle* handle, void** devPtr) {
 	cudaError_t e = cudaIpcOpenMemHandle(devPtr, h, cudaIpcMemLazyEnablePeerAccess);
 	if (e != cudaSuccess) { cudaGetLastError(); *devPtr = nullptr; return rto_fail(RTO_ERR_CUDA, "rto_exchange_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); }
 	return RTO_OK;
-}
-extern "C" int rto_exchange_close(void* devPtr) {
+} RTO_CATCH_ALL("rto_exchange_open")
+extern "C" int rto_exchange_close(void* devPtr) try {
 	if (devPtr) CUDA_TRY(cudaIpcCloseMemHandle(devPtr));
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_exchange_close")
 
-extern "C" int rto_render(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, const RtoFrame* frame) {
+extern "C" int rto_render(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, const RtoFrame* frame) try {
 	return rto_render_batch(s, cam, 1, mode, flags, shadowBias, y0, y1, frame);
-}
+} RTO_CATCH_ALL("rto_render")
 
-extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, uint64_t stats[5]) {
+extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, uint64_t stats[5]) try {
 	if (!s || !cam || !stats) return rto_fail(RTO_ERR_INVALID, "rto_render_stats: null argument");
 	int rc = check_mode(s, mode); if (rc) return rc;
 	if (s->deviceBuiltBvh) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render_stats: the scene's BVH was built on the device; the reference's work counters need the reference-shaped tree (rto_scene_create_bvh)");
@@ -514,15 +517,19 @@ extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uin
 	CUDA_TRY(cudaMemcpyAsync(stats, d, 5 * 8, cudaMemcpyDeviceToHost, s->stream));
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_render_stats")
 
 // ------------------------------------------------------------------------------------------------
 // explicit ray lists
 // ------------------------------------------------------------------------------------------------
 extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float* origins, const float* dirs, size_t numRays,
-	float tMin, float tMax, float* tOut, int32_t* idOut, int memory) {
+	float tMin, float tMax, float* tOut, int32_t* idOut, int memory) try {
 	if (!s || !origins || !dirs) return rto_fail(RTO_ERR_INVALID, "rto_trace_rays: null argument");
 	int rc = check_mode(s, mode); if (rc) return rc;
+	if (memory != RTO_MEM_HOST && memory != RTO_MEM_DEVICE) return rto_fail(RTO_ERR_INVALID, "rto_trace_rays: bad memory selector %d", memory);
+	// the closest-hit rule of BVH scenes has no interval (accept t > 1e-4, strict minimum); octree scenes take the caller's
+	if (s->kind == RTO_MODE_BVH && !(tMin == 0.0f && tMax >= 1e30f))
+		return rto_fail(RTO_ERR_INVALID, "rto_trace_rays: BVH scenes take tMin = 0 and tMax >= 1e30 only (the hit rule has no interval)");
 	if (numRays == 0) return RTO_OK;
 	CUDA_TRY(cudaSetDevice(s->device));
 	const bool host = memory == RTO_MEM_HOST;
@@ -569,10 +576,10 @@ extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float
 		CUDA_TRY(cudaStreamSynchronize(s->stream));
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_trace_rays")
 
 extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dirs, size_t numRays,
-	int64_t* offsets, int32_t* ids, size_t idsCapacity, size_t* totalOut) {
+	int64_t* offsets, int32_t* ids, size_t idsCapacity, size_t* totalOut) try {
 	if (!s || !origins || !dirs || !offsets) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: null argument");
 	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: scene is not a BVH");
 	if (s->deviceBuiltBvh) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_bvh_query: the scene's BVH was built on the device; BVH::query's candidate order needs the reference-shaped tree (rto_scene_create_bvh)");
@@ -611,13 +618,13 @@ extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dir
 	CUDA_TRY(cudaMemcpyAsync(ids, dIds, (size_t)total * 4, cudaMemcpyDeviceToHost, s->stream));
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_bvh_query")
 
 // ------------------------------------------------------------------------------------------------
 // VolumeRaycastRenderer's per-frame use of octreeRaySkip (VolumeRaycastRenderer.cpp:1598-1664): 49 probe rays -> one start distance
 // ------------------------------------------------------------------------------------------------
 extern "C" int rto_octree_skip_distance(RtoScene* s, const float view16[16], const float camPos[3], float aspect, float lastSkipDistance,
-	float* skipDistanceOut, float* probeT /* 49 floats, may be NULL */) {
+	float* skipDistanceOut, float* probeT /* 49 floats, may be NULL */) try {
 	if (!s || !skipDistanceOut) return rto_fail(RTO_ERR_INVALID, "rto_octree_skip_distance: null argument");
 	if (s->kind == RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "rto_octree_skip_distance: scene is not an octree");
 	float o[49 * 3], d[49 * 3], t[49];
@@ -626,4 +633,4 @@ extern "C" int rto_octree_skip_distance(RtoScene* s, const float view16[16], con
 	if (probeT) std::memcpy(probeT, t, sizeof(t));
 	*skipDistanceOut = rto_host_skip_distance_from_probes(t, 49, lastSkipDistance);
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_octree_skip_distance")

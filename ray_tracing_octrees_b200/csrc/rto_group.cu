@@ -58,7 +58,7 @@ struct RtoGroup {
 
 static int group_fail_cleanup(RtoGroup* g, int rc) { rto_group_destroy(g); return rc; }
 
-extern "C" int rto_group_create(const int* devices, int numDevices, RtoGroup** out) {
+extern "C" int rto_group_create(const int* devices, int numDevices, RtoGroup** out) try {
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_group_create: null output");
 	*out = nullptr;
 	if (!devices || numDevices <= 0 || numDevices > 64) return rto_fail(RTO_ERR_INVALID, "rto_group_create: 1 to 64 devices");
@@ -94,7 +94,7 @@ extern "C" int rto_group_create(const int* devices, int numDevices, RtoGroup** o
 	if (e != cudaSuccess) return group_fail_cleanup(g, rto_fail(RTO_ERR_CUDA, "rto_group_create: %s", cudaGetErrorString(e)));
 	*out = g;
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_group_create")
 
 extern "C" void rto_group_destroy(RtoGroup* g) {
 	if (!g) return;
@@ -117,7 +117,7 @@ extern "C" void rto_group_destroy(RtoGroup* g) {
 
 extern "C" int rto_group_size(const RtoGroup* g) { return g ? (int)g->m.size() : 0; }
 
-extern "C" int rto_group_scene_bvh(RtoGroup* g, const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt) {
+extern "C" int rto_group_scene_bvh(RtoGroup* g, const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt) try {
 	if (!g) return rto_fail(RTO_ERR_INVALID, "rto_group_scene_bvh: null group");
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_group_scene_bvh: null triangles");
 	BvhLayout L; size_t numRefNodes = 0;
@@ -128,13 +128,13 @@ extern "C" int rto_group_scene_bvh(RtoGroup* g, const RtoTriangle* tris, size_t 
 		if ((rc = rto_scene_from_bvh_layout(L, numTris, numRefNodes, &M.scene))) return rc;                 // ... uploaded to every device
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_group_scene_bvh")
 
 extern "C" RtoScene* rto_group_scene(RtoGroup* g, int member) {
 	return (g && member >= 0 && member < (int)g->m.size()) ? g->m[member].scene : nullptr;
 }
 
-extern "C" int rto_group_set_balancing(RtoGroup* g, int enabled, const float* weights, int chunks) {
+extern "C" int rto_group_set_balancing(RtoGroup* g, int enabled, const float* weights, int chunks) try {
 	if (!g) return rto_fail(RTO_ERR_INVALID, "rto_group_set_balancing: null group");
 	if (chunks < 0 || chunks > 64) return rto_fail(RTO_ERR_INVALID, "rto_group_set_balancing: 1 to 64 chunks (0 keeps the setting)");
 	if (chunks) g->chunks = chunks;
@@ -144,9 +144,9 @@ extern "C" int rto_group_set_balancing(RtoGroup* g, int enabled, const float* we
 		g->m[i].weight = weights[i];
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_group_set_balancing")
 
-extern "C" int rto_group_last_ms(RtoGroup* g, float* msPerDevice) {
+extern "C" int rto_group_last_ms(RtoGroup* g, float* msPerDevice) try {
 	if (!g || !msPerDevice) return rto_fail(RTO_ERR_INVALID, "rto_group_last_ms: null argument");
 	for (size_t i = 0; i < g->m.size(); i++) {
 		Member& M = g->m[i];
@@ -157,9 +157,9 @@ extern "C" int rto_group_last_ms(RtoGroup* g, float* msPerDevice) {
 		CUDA_TRY(cudaEventElapsedTime(&msPerDevice[i], M.evBegin, M.evEnd));
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_group_last_ms")
 
-extern "C" int rto_group_sync(RtoGroup* g) {
+extern "C" int rto_group_sync(RtoGroup* g) try {
 	if (!g) return rto_fail(RTO_ERR_INVALID, "rto_group_sync: null group");
 	for (Member& M : g->m) if (M.scene) {
 		CUDA_TRY(cudaSetDevice(M.device));
@@ -168,7 +168,7 @@ extern "C" int rto_group_sync(RtoGroup* g) {
 	CUDA_TRY(cudaSetDevice(g->m[0].device));
 	CUDA_TRY(cudaStreamSynchronize(g->resolveStream));
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_group_sync")
 
 // shares from the measured times of the previous batch, if that batch has finished (never waits)
 static void rebalance(RtoGroup* g) {
@@ -189,7 +189,7 @@ static void rebalance(RtoGroup* g) {
 	for (size_t i = 0; i < n; i++) { g->m[i].weight = g->m[i].weight * n / sum; if (g->m[i].weight < 0.02) g->m[i].weight = 0.02; }
 }
 
-extern "C" int rto_group_render_batch(RtoGroup* g, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, const RtoFrame* frame) {
+extern "C" int rto_group_render_batch(RtoGroup* g, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, const RtoFrame* frame) try {
 	if (!g || !cams || !frame || numCams <= 0) return rto_fail(RTO_ERR_INVALID, "rto_group_render_batch: null argument");
 	const size_t n = g->m.size();
 	for (Member& M : g->m) if (!M.scene) return rto_fail(RTO_ERR_INVALID, "rto_group_render_batch: no scene (rto_group_scene_bvh first)");
@@ -310,6 +310,6 @@ extern "C" int rto_group_render_batch(RtoGroup* g, const RtoCamera* cams, int nu
 		CUDA_TRY(cudaStreamSynchronize(ls));
 	}
 	return RTO_OK;
-}
+} RTO_CATCH_ALL("rto_group_render_batch")
 
 extern "C" void* rto_group_stream(const RtoGroup* g) { return (g && !g->m.empty() && g->m[0].scene) ? (void*)g->m[0].scene->stream : nullptr; }

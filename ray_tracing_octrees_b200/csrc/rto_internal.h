@@ -3,10 +3,51 @@
 #include "../../include/rto_c.h"
 #include "rto_math.h"
 #include <cstdint>
+#include <exception>
+#include <new>
+#include <system_error>
+#include <thread>
 #include <vector>
 
 // Records a thread-local message for rto_last_error() and returns `code`.
 int rto_fail(int code, const char* fmt, ...);
+
+// Nothing may throw across the C ABI: every extern "C" entry point that allocates or starts threads is a function-try-block ending in this.
+#define RTO_CATCH_ALL(name) \
+	catch (const std::bad_alloc&) { return rto_fail(RTO_ERR_ALLOC, name ": out of host memory"); } \
+	catch (const std::exception& e_) { return rto_fail(RTO_ERR_ALLOC, name ": %s", e_.what()); } \
+	catch (...) { return rto_fail(RTO_ERR_ALLOC, name ": unknown failure"); }
+
+// The two halves of a divide-and-conquer step, the first on a new thread when `parallel` and a thread can be had (otherwise both on
+// the calling thread).  An exception on either side surfaces on the calling thread after BOTH halves have finished -- never through
+// the destructor of a joinable std::thread.
+template <class A, class B> void rto_fork_join(bool parallel, A&& a, B&& b) {
+	if (!parallel) { a(); b(); return; }
+	std::exception_ptr ea, eb;
+	std::thread th;
+	bool started = false;
+	try { th = std::thread([&] { try { a(); } catch (...) { ea = std::current_exception(); } }); started = true; }
+	catch (const std::system_error&) {}
+	try { if (!started) a(); b(); } catch (...) { eb = std::current_exception(); }
+	if (started) th.join();
+	if (ea) std::rethrow_exception(ea);
+	if (eb) std::rethrow_exception(eb);
+}
+// fn(t) for t in [0, n) on n threads (the last one is the caller); threads that cannot be created run on the caller, exceptions are
+// rethrown after every thread has been joined.
+template <class F> void rto_run_threads(int n, F&& fn) {
+	std::vector<std::thread> th;
+	std::vector<std::exception_ptr> err((size_t)(n > 0 ? n : 0));
+	int started = 0;
+	for (; started + 1 < n; started++) {
+		const int t = started;
+		try { th.emplace_back([&, t] { try { fn(t); } catch (...) { err[t] = std::current_exception(); } }); }
+		catch (const std::system_error&) { break; }
+	}
+	for (int t = started; t < n; t++) { try { fn(t); } catch (...) { err[t] = std::current_exception(); } }
+	for (auto& x : th) x.join();
+	for (auto& e : err) if (e) std::rethrow_exception(e);
+}
 
 // ---- host BVH (shape of the reference's BVHNode tree, BVH.h:37-42, stored as a pre-order array) -------------
 struct HostBvhNode {
@@ -40,6 +81,8 @@ void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, i
 // ---- device layouts, built on the host (host_layouts.cpp) and uploaded verbatim by rto_device.cu --------------
 struct OctLayout {
 	bool compact = false;
+	bool isTree = false;            // every node but the root is the child of exactly one node (what createOctreeFromVoxelGrid and the frustum
+	                                // cull produce); the octreeRaySkip walk, a recursion over a pointer TREE in the reference, is defined only then
 	size_t numLeaves = 0;
 	std::vector<uint32_t> desc;     // compact: 7 pad words + one word per node (bit31 leaf, bit30 solid, else first child)
 	std::vector<int32_t>  up;       // compact: parent node of sibling group (node - 1) >> 3

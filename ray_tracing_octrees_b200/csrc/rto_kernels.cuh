@@ -672,7 +672,9 @@ RTO_DEV OctHit octA_general(const OctDev& S, V3 o, V3 d, float tMin, float tMax)
 	int cur = 0; float curMin = tMin, curMax = tMax;
 	while (true) {
 		if (cur >= 0 && cur < S.numNodes) {
-			visits++;
+			// a walk over a tree visits no node twice; arrays whose child graph is not a tree are refused for this mode before any launch
+			// (rto_device.cu check_mode), the budget keeps even a corrupted device array from walking forever
+			if (++visits > (unsigned)S.numNodes) break;
 			const int4* n = S.nodes16 + 4 * (size_t)cur;
 			int4 a = RTO_LDG(n), f = RTO_LDG(n + 1);
 			OctBox b = oct_box(S, a.x, a.y, a.z, a.w);

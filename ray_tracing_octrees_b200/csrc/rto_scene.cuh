@@ -31,6 +31,7 @@ struct RtoScene {
 	static constexpr int kCamSlots = 16;
 	CamSlot camRing[kCamSlots];
 	int camNext = 0;
+	bool octIsTree = true;            // octree scenes: the uploaded child graph is a tree (OctLayout::isTree)
 	bool deviceBuiltBvh = false;      // linear BVH built on the device: the reference-shaped tree (BVH::query replay, work counters) does not exist
 };
 

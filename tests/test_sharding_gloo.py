@@ -88,3 +88,36 @@ def test_shards_tile_exactly_once(world):
         assert allf == list(range(F))
         sizes = [len(sharding.shard_frames(F, world, r)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_weighted_row_ranges_tile_the_batch_exactly_once():
+    """The pure host logic of the gathered renderer (sharding.py; csrc/rto_group.cu does the same in C++): weighted contiguous ranges
+    of 8-row tiles, each cut into at most three launches, cover every row of every frame once, on tile boundaries."""
+    rng = np.random.default_rng(5)
+    for H in (1080, 2160, 203, 8, 1):
+        tpf = (H + 7) // 8
+        for n, w in ((16, [0.5, 1, 1, 1]), (1, [1, 1]), (3, [0.02, 1, 5]), (128, [0.55] + [1] * 7), (5, list(rng.uniform(0.05, 3, 8)))):
+            cuts = sharding.deal_tiles(tpf * n, w)
+            assert cuts[0] == 0 and cuts[-1] == tpf * n and all(a <= b for a, b in zip(cuts, cuts[1:]))
+            rows = [sharding.tile_row_to_row(c, H) for c in cuts]
+            assert rows[-1] == n * H
+            done = {}
+            for r in range(len(w)):
+                parts = sharding.split_rows(rows[r], rows[r + 1], H)
+                assert len(parts) <= 3
+                for (f, k, y0, y1) in parts:
+                    assert y0 % 8 == 0 and (y1 % 8 == 0 or y1 == H) and 0 <= y0 < y1 <= H and (k == 1 or (y0 == 0 and y1 == H))
+                    for ff in range(f, f + k):
+                        assert done.get(ff, 0) == y0, "gap or overlap in frame %d" % ff
+                        done[ff] = y1
+            assert len(done) == n and all(v == H for v in done.values())
+
+
+def test_rebalance_moves_work_away_from_slow_ranks():
+    w = [1.0, 1.0, 1.0, 1.0]
+    speed = [0.5, 1.0, 1.0, 1.25]                       # rank 0 is half as fast (it also expands everyone's codes)
+    for _ in range(12):
+        t = [wi / sum(w) / si for wi, si in zip(w, speed)]
+        w = sharding.rebalance(w, t)
+    t = [wi / sum(w) / si for wi, si in zip(w, speed)]
+    assert max(t) / min(t) < 1.02 and w[0] < w[1] < w[3]
