@@ -175,10 +175,16 @@ def run_ours(args, rank, world, local_rank):
     cam_cache = {}
 
     def cam_array(start, n):
-        """ctypes array of the n orbit cameras from global frame index `start` (built once per distinct phase: nothing per step)."""
+        """ctypes array of the n orbit cameras from global frame index `start` (built once per distinct phase: nothing per step).
+        The frames of a batch are listed in a strided order (j -> start + j * s mod n, s odd ~ 0.38 n, a permutation because n is a
+        multiple of 16 and a power of two here): the cost of a frame varies smoothly along the orbit, and with this order every
+        contiguous share of a batch samples the whole arc, so the shares of the ranks cost the same in EVERY batch."""
         key = (start % ORBIT, n)
         if key not in cam_cache:
-            cam_cache[key] = (rto.RtoCamera * n)(*[orbit[(start + j) % ORBIT] for j in range(n)])
+            s = max(1, int(0.382 * n)) | 1
+            while np.gcd(s, n) != 1:
+                s += 2
+            cam_cache[key] = (rto.RtoCamera * n)(*[orbit[(start + (j * s) % n) % ORBIT] for j in range(n)])
         return cam_cache[key]
 
     def sync_all():
@@ -190,7 +196,7 @@ def run_ours(args, rank, world, local_rank):
     tmp_id = torch.empty((BATCH, H, W), dtype=torch.int32, device=dev)
     hits_of = []
     for k0 in range(0, ORBIT, BATCH):
-        scene.render_device(cam_array(k0, BATCH), rto.MODE_BVH, flags, bias, 0, H, None, tmp_id.data_ptr(), None)
+        scene.render_device((rto.RtoCamera * BATCH)(*orbit[k0:k0 + BATCH]), rto.MODE_BVH, flags, bias, 0, H, None, tmp_id.data_ptr(), None)
         torch.cuda.synchronize()
         hits_of += [int(x) for x in (tmp_id >= 0).flatten(1).sum(1).tolist()]
     del tmp_id
@@ -272,8 +278,10 @@ def run_ours(args, rank, world, local_rank):
             got = ring[(chunks - 1) & 1]
             ref = dict(rgba=torch.empty_like(got["rgba"][:BATCH]), id=torch.empty_like(got["id"][:BATCH]), t=torch.empty_like(got["t"][:BATCH]))
             same = True
+            batch_cams = cam_array(last, BATCH * world)
             for j in range(0, BATCH * world, BATCH):
-                scene.render_device(cam_array(last + j, BATCH), rto.MODE_BVH, flags, bias, 0, H, ref["rgba"].data_ptr(), ref["id"].data_ptr(), ref["t"].data_ptr())
+                sub = (rto.RtoCamera * BATCH).from_buffer(batch_cams, j * ctypes.sizeof(rto.RtoCamera))
+                scene.render_device(sub, rto.MODE_BVH, flags, bias, 0, H, ref["rgba"].data_ptr(), ref["id"].data_ptr(), ref["t"].data_ptr())
                 torch.cuda.synchronize()
                 for key in ("rgba", "id", "t"):
                     same = same and bool(torch.equal(got[key][j:j + BATCH].view(torch.int32), ref[key].view(torch.int32)))

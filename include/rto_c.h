@@ -273,7 +273,7 @@ RTO_API int rto_render_batch(RtoScene* scene, const RtoCamera* cams, int numCams
 /* ---- compact frames: 4 bytes per pixel out of the trace kernel ---------------------------------------------------------------------
  * Colour, hit id and t of a pixel of a BVH scene are pure functions of (camera, pixel, hit triangle, shadow bit).  rto_render_codes
  * writes only that: one 32-bit word per pixel (0 = miss, else (position of the hit triangle in the scene's leaf order + 1) |
- * shadowed << 31), in the kernel's TILE order (the 128 pixels of a 16 x 8 block are consecutive: a warp writes one full 128-byte line,
+ * normal flipped << 30 | shadowed << 31), in the kernel's TILE order (the 128 pixels of a 16 x 8 block are consecutive: a warp writes one full 128-byte line,
  * which is what makes the destination usable across NVLink), and rto_resolve_codes rebuilds the three planes of RtoFrame from the
  * words with the same ray generation, the same Moller-Trumbore arithmetic on the same triangle record and the same shading: the planes
  * equal those of rto_render_batch bit for bit (tests/test_gpu_codes.py).  The words are meaningful to any scene built from the same

@@ -126,6 +126,7 @@ extern "C" void rto_scene_destroy(RtoScene* s) {
 	if (s->evStart) cudaEventDestroy(s->evStart);
 	if (s->evStop) cudaEventDestroy(s->evStop);
 	if (s->evFrame) cudaEventDestroy(s->evFrame);
+	if (s->evTable) cudaEventDestroy(s->evTable);
 	if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
@@ -399,8 +400,21 @@ int rto_enqueue_resolve(RtoScene* s, const RtoCamera* cams, int numCams, int y0,
 	A.codes = const_cast<uint32_t*>(codes); A.codeFrame0 = (unsigned)codeFrame0; A.codeTilesY = (unsigned)((cams[0].height + 7) / 8);
 	int slot = -1, rc;
 	if (numCams > 1 && (rc = stage_cameras(s, cams, numCams, st, &slot, &A.cams))) return rc;
+	if (!s->shadeTable) {
+		// once per scene, on the stream this first expansion runs on (later ones on other streams come after it in host order and
+		// are ordered behind it by the event below)
+		void* p = nullptr;
+		if ((rc = scene_alloc(s, &p, (s->numPrims ? s->numPrims : 1) * sizeof(float)))) return rc;
+		if (s->numPrims) k_shade_table<<<(unsigned)((s->numPrims + 255) / 256), 256, 0, st>>>(s->bvhFast.tris, (int)s->numPrims, (float*)p);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventCreateWithFlags(&s->evTable, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventRecord(s->evTable, st));
+		s->shadeTable = (float*)p;
+		s->launches++;
+	}
+	CUDA_TRY(cudaStreamWaitEvent(st, s->evTable, 0));
 	dim3 block(128), grid((cams[0].width + 15) / 16, (y1 - y0 + 7) / 8, numCams);
-	k_resolve_bvh<<<grid, block, 0, st>>>(s->bvhFast, A);
+	k_resolve_bvh<<<grid, block, 0, st>>>(s->bvhFast, A, s->shadeTable);
 	s->launches++;
 	CUDA_TRY(cudaGetLastError());
 	return release_cameras(s, slot, st);

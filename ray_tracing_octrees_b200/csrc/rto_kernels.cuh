@@ -57,6 +57,16 @@ RTO_DEV int ffs32(unsigned v) {
 #endif
 }
 
+// Loop form of the BVH walks (measured on B200, 16 x 1080p per launch, single loop -> while-while: closest hit C2 2.909 -> 2.829 ms,
+// primary only 2.021 -> 1.940, 512^3 city mesh 5.025 -> 4.826, sphere 0.901 -> 0.875; any-hit in the same form: C2 +1 % slower, city
+// 2 % faster -- left in the single-loop form).  profiles/README.md, round 2.
+#ifndef RTO_BVH_WHILE_WHILE
+#define RTO_BVH_WHILE_WHILE 1
+#endif
+#ifndef RTO_BVH_ANY_WHILE_WHILE
+#define RTO_BVH_ANY_WHILE_WHILE 0
+#endif
+
 struct Ray { V3 o, d; };
 struct alignas(8) StackEnt { int ref; float t; };     // postponed far child of the ordered BVH traversal and its box entry distance
 
@@ -278,6 +288,61 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 	int cur = S.rootRef;
 	const RayBox2 rb2 = make_raybox2(rb);
 	float tcut = kMissT * kPruneSlack;
+#if RTO_BVH_WHILE_WHILE
+	// while-while form: the lanes of a warp walk inner nodes until each of them stands at a leaf (or is done) and re-join at the end of
+	// the inner loop, so that the Moller-Trumbore block below runs once for all of them instead of once per lane that happens to reach
+	// a leaf (in the single-loop form that block ran with 4-7 of 32 lanes and took a third of all issue slots).  No votes: the
+	// re-joining is the hardware's own convergence barrier at the loop exit.  A lane that waits has nothing to catch up with -- its
+	// pruning distance only changes at its own leaves -- so the visit pattern, and with it every result, is the same.
+	constexpr int kDone = (int)0x80000000;        // never a leaf reference: ~kDone >> 1 is beyond the 2^30 triangles a scene can have
+	for (;;) {
+		while (cur >= 0) {
+			const float4* n = S.nodes + 4 * (size_t)cur;
+			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
+			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
+			float e0, e1;
+			bool h0, h1;
+			node_boxes<OCT>(rb, rb2, S.paired, a, b, c, PRUNE ? tcut : FLT_MAX, h0, h1, e0, e1);
+			int r0 = f2i(r.x), r1 = f2i(r.y);
+			if (h0 && h1) {
+				bool swap = PRUNE && (e1 < e0);
+				int farRef = swap ? r0 : r1;
+				float farT = swap ? e0 : e1;
+				if (sp < kBvhStack) { StackEnt e; e.ref = farRef; e.t = farT; stack[sp++] = e; }
+				cur = swap ? r1 : r0;
+			}
+			else if (h0) cur = r0;
+			else if (h1) cur = r1;
+			else {
+				cur = kDone;
+				while (sp > 0) {
+					StackEnt e = stack[--sp];
+					if (!PRUNE || e.t <= tcut) { cur = e.ref; break; }
+				}
+			}
+		}
+		if (cur == kDone) break;
+		{
+			int ref = ~cur;
+			int pos = ref >> 1, cnt = (ref & 1) + 1;
+			for (int k = 0; k < cnt; k++) {
+				TriV tri = load_tri(S.tris, pos + k);
+				float t;
+				if (moller_trumbore(tri, o, d, t)) {
+					if ((t < bestT || (t == bestT && pos + k < bestPos)) && (!S.leafBox || ref_leaf_box_passes<OCT>(S, rb, pos + k, FLT_MAX))) {
+						bestT = t; bestPos = pos + k; tcut = t * kPruneSlack;
+					}
+				}
+			}
+		}
+		cur = kDone;
+		while (sp > 0) {
+			StackEnt e = stack[--sp];
+			if (!PRUNE || e.t <= tcut) { cur = e.ref; break; }
+		}
+		if (cur == kDone) break;
+	}
+#else
 	// (a per-step warp vote that re-joins the lanes, the change that made the octree mode-A walk 2x faster, costs 5-9 % here)
 	{
 		for (;;) {
@@ -325,6 +390,7 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 			}
 		}
 	}
+#endif
 }
 
 template <bool PRUNE>
@@ -359,6 +425,40 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 	int sp = 0;
 	int cur = S.rootRef;
 	const RayBox2 rb2 = make_raybox2(rb);
+#if RTO_BVH_ANY_WHILE_WHILE
+	constexpr int kDone = (int)0x80000000;
+	for (;;) {
+		while (cur >= 0) {
+			const float4* n = S.nodes + 4 * (size_t)cur;
+			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
+			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
+			float e0, e1;
+			bool h0, h1;
+			node_boxes<OCT>(rb, rb2, S.paired, a, b, c, FLT_MAX, h0, h1, e0, e1);
+			int r0 = f2i(r.x), r1 = f2i(r.y);
+			if (h0 && h1) {
+				bool swap = e1 < e0;
+				if (sp < kBvhStack) stackRef[sp++] = swap ? r0 : r1;
+				cur = swap ? r1 : r0;
+			}
+			else if (h0) cur = r0;
+			else if (h1) cur = r1;
+			else cur = sp > 0 ? stackRef[--sp] : kDone;
+		}
+		if (cur == kDone) return false;
+		{
+			int ref = ~cur;
+			int pos = ref >> 1, cnt = (ref & 1) + 1;
+			for (int k = 0; k < cnt; k++) {
+				TriV tri = load_tri(S.tris, pos + k);
+				float t;
+				if (moller_trumbore(tri, o, d, t) && (!S.leafBox || ref_leaf_box_passes<OCT>(S, rb, pos + k, FLT_MAX))) return true;
+			}
+		}
+		if (sp == 0) return false;
+		cur = stackRef[--sp];
+	}
+#else
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
@@ -390,6 +490,7 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 		cur = stackRef[--sp];
 	}
 	return false;
+#endif
 }
 
 RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
@@ -1029,8 +1130,8 @@ struct RenderArgs {
 	unsigned codeTilesY;          // blocks per image column = (height + 7) / 8
 };
 
-// word of one pixel: 0 = miss, else (position of the hit triangle in the scene's leaf order + 1) | (shadowed << 31)
-constexpr uint32_t kCodeShadowBit = 0x80000000u;
+// word of one pixel: 0 = miss, else (position of the hit triangle in the scene's leaf order + 1) | (normal flipped << 30) | (shadowed << 31)
+constexpr uint32_t kCodeShadowBit = 0x80000000u, kCodeFlipBit = 0x40000000u;
 __device__ __forceinline__ size_t code_index(const RenderArgs& A) {
 	const size_t tile = ((size_t)(A.codeFrame0 + blockIdx.z) * A.codeTilesY + (size_t)(A.y0 >> 3) + blockIdx.y) * gridDim.x + blockIdx.x;
 	return tile * 128 + threadIdx.x;
@@ -1080,7 +1181,8 @@ __global__ void __launch_bounds__(128, RTO_BVH_MIN_BLOCKS) k_render_bvh(BvhDev S
 		TriV tri = load_tri(S.tris, bestPos);
 		id = tri.id;
 		V3 n = normalize3(cross3(tri.e1, tri.e2));
-		if (dot3(n, ray.d) > 0.0f) n = -n;
+		const bool flip = dot3(n, ray.d) > 0.0f;
+		if (flip) n = -n;
 		V3 hit = ray.o + ray.d * bestT;
 		bool shadowed = false;
 		if (SHADOWS) {
@@ -1089,16 +1191,37 @@ __global__ void __launch_bounds__(128, RTO_BVH_MIN_BLOCKS) k_render_bvh(BvhDev S
 			shadowed = bvh_any(S, so, sd);
 		}
 		color = shadowed ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
-		if (A.codes) __stcs(A.codes + code_index(A), (uint32_t)(bestPos + 1) | (shadowed ? kCodeShadowBit : 0u));
+		if (A.codes) __stcs(A.codes + code_index(A), (uint32_t)(bestPos + 1) | (flip ? kCodeFlipBit : 0u) | (shadowed ? kCodeShadowBit : 0u));
 	}
 	else if (A.codes) __stcs(A.codes + code_index(A), 0u);
 	store_pixel(A, pix, color, id, bestT);
 }
 
-// The frame planes from the hit codes: colour, hit id and t of a pixel are pure functions of (camera, pixel, hit triangle, shadow
-// bit) -- the same ray generation, the same Moller-Trumbore arithmetic on the same record and the same shading as k_render_bvh, so
-// the planes equal a direct render bit for bit.  Memory-bound: 4 bytes in, 24 bytes out per pixel.
-__global__ void __launch_bounds__(128) k_resolve_bvh(BvhDev S, RenderArgs A) {
+// The frame planes from the hit codes: colour, hit id and t of a pixel are pure functions of (camera, pixel, hit triangle, flip and
+// shadow bits) -- the same ray generation, the Moller-Trumbore distance computed by the same operations on the same record (the u / v
+// tests decided nothing about its value), and the Lambert term of the triangle's normal, which is the same number for every pixel
+// that sees the triangle and is therefore tabulated once per scene (k_shade_table; the flipped normal's term is its exact negation,
+// products and sums of negated operands being negated results).  The planes equal a direct render bit for bit.
+// 4 bytes in, 24 bytes out per pixel; about 170 instructions per hit pixel, most of them the IEEE divisions and square roots of the ray.
+__global__ void __launch_bounds__(256) k_shade_table(const float4* __restrict__ tris, int numTris, float* __restrict__ ndotl) {
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pos >= numTris) return;
+	TriV tri = load_tri(tris, pos);
+	V3 n = normalize3(cross3(tri.e1, tri.e2));
+	V3 lightDir = normalize3(mk3(-1.0f, -1.0f, -1.0f));
+	ndotl[pos] = dot3(n, -lightDir);                  // shade_lambert(n) = (1, .8, .6) * max(0, this) + .1
+}
+
+RTO_DEV float mt_distance(const TriV& tri, V3 o, V3 d) {      // moller_trumbore()'s t, operation for operation
+	V3 p = cross3(d, tri.e2);
+	float det = dot3(tri.e1, p);
+	float inv = 1.0f / det;
+	V3 s = o - tri.v0;
+	V3 q = cross3(s, tri.e1);
+	return dot3(tri.e2, q) * inv;
+}
+
+__global__ void __launch_bounds__(128) k_resolve_bvh(BvhDev S, RenderArgs A, const float* __restrict__ ndotl) {
 	RtoCamera cam = A.cam0;
 	if (A.cams) cam = A.cams[blockIdx.z];
 	int px, py; size_t pix;
@@ -1107,15 +1230,15 @@ __global__ void __launch_bounds__(128) k_resolve_bvh(BvhDev S, RenderArgs A) {
 	V3 color = mk3(0.0f, 0.0f, 0.0f);
 	int id = -1;
 	float t = kMissT;
-	const int pos = (int)(code & ~kCodeShadowBit) - 1;
+	const int pos = (int)(code & ~(kCodeShadowBit | kCodeFlipBit)) - 1;
 	if (pos >= 0 && pos < S.numTris) {
 		Ray ray = gen_ray(cam, px, py);
 		TriV tri = load_tri(S.tris, pos);
 		id = tri.id;
-		if (!moller_trumbore(tri, ray.o, ray.d, t)) t = kMissT;      // cannot happen for a code this scene produced for this camera
-		V3 n = normalize3(cross3(tri.e1, tri.e2));
-		if (dot3(n, ray.d) > 0.0f) n = -n;
-		color = (code & kCodeShadowBit) ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
+		t = mt_distance(tri, ray.o, ray.d);
+		const float nl = RTO_LDG(ndotl + pos);
+		const float k = maxf(0.0f, (code & kCodeFlipBit) ? -nl : nl);
+		color = (code & kCodeShadowBit) ? mk3(0.1f, 0.1f, 0.1f) : mk3(1.0f, 0.8f, 0.6f) * k + mk3(0.1f, 0.1f, 0.1f);
 	}
 	store_pixel(A, pix, color, id, t);
 }

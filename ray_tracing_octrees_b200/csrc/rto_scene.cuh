@@ -31,6 +31,8 @@ struct RtoScene {
 	static constexpr int kCamSlots = 16;
 	CamSlot camRing[kCamSlots];
 	int camNext = 0;
+	cudaEvent_t evTable = nullptr;    // "the table below is filled"
+	float* shadeTable = nullptr;      // BVH scenes: Lambert term of every triangle's normal in leaf order (rto_resolve_codes; built on first use)
 	bool octIsTree = true;            // octree scenes: the uploaded child graph is a tree (OctLayout::isTree)
 	bool deviceBuiltBvh = false;      // linear BVH built on the device: the reference-shaped tree (BVH::query replay, work counters) does not exist
 };

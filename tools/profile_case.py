@@ -62,7 +62,17 @@ def main():
     hid = torch.empty((F, H, W), dtype=torch.int32, device="cuda")
     tt = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
     ms = []
-    for r in range(a.reps):
+    if a.case.endswith("-resolve"):
+        # the expansion of hit codes into planes (k_resolve_bvh): what the gathering GPU pays per frame it did not trace itself
+        buf = rto.ExchangeBuffer(rto.codes_frame_words(W, H) * 4 * F)
+        arr = (rto.RtoCamera * F)(*cams)
+        sc.render_codes(arr, flags, bias, buf.ptr)
+        cms = sc.last_kernel_ms()
+        for r in range(a.reps):
+            sc.resolve_codes(arr, buf.ptr, rgba_ptr=rgba.data_ptr(), id_ptr=hid.data_ptr(), t_ptr=tt.data_ptr())
+            ms.append(sc.last_kernel_ms())
+        print("%s: trace into codes %.3f ms for %d frames; expansion %.3f ms = %.1f us per frame" % (a.case, cms, F, float(np.median(ms[2:])), 1e3 * float(np.median(ms[2:])) / F))
+    for r in range(0 if a.case.endswith("-resolve") else a.reps):
         sc.render_device(cams, mode, flags, bias, 0, H, rgba.data_ptr(), hid.data_ptr(), tt.data_ptr())
         ms.append(sc.last_kernel_ms())
     hits = int((hid >= 0).sum().item())
