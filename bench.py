@@ -320,17 +320,38 @@ def run_ours(args, rank, world, local_rank):
     e2e_rays = sum(rays_in(((args.warmup + k) * world + rank) * F, F) for k in range(e2e_steps))
     lastb = ((args.warmup + e2e_steps - 1) * world + rank) * F + F - EB
     assert int((h_id >= 0).sum().item()) == sum(hits_of[(lastb + j) % ORBIT] for j in range(EB)), "host planes differ from device planes"
+    # the same call asking for hit id + t only (8 B/pixel): what a caller that shades on its own side, or only needs visibility, moves
+    def step_host_idt(k):
+        base = (k * world + rank) * F
+        for c in range(F // EB):
+            scene.render_host_ptrs(cam_array(base + c * EB, EB), rto.MODE_BVH, flags, bias, 0, H, None, h_id.data_ptr(), h_t.data_ptr())
+    sync_all()
+    te = time.perf_counter()
+    step_host_idt(args.warmup)
+    torch.cuda.synchronize()
+    e2e_idt_s = time.perf_counter() - te
+    e2e_idt_rays = rays_in((args.warmup * world + rank) * F, F)
+    # the ceiling of the link: all ranks copy device -> pinned host at the same time, nothing else running
+    d_src = ring[0]["rgba"].view(-1)[:h_rgba.numel()]
+    sync_all()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(6):
+        h_rgba.view(-1).copy_(d_src, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    d2h_gbps = 6 * h_rgba.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
     if world > 1:
         dist.barrier()
 
     # ---- reduce over ranks: max time, sum rays ---------------------------------------------------------------
-    tvec = torch.tensor([dev_ms, e2e_s, kern_ms_avg, comm_free[0] if comm_free else 0.0], dtype=torch.float64, device=dev)
-    rvec = torch.tensor([0 if gathered else rays_main, e2e_rays, launches, comm_free[1] if comm_free else 0.0], dtype=torch.float64, device=dev)
+    tvec = torch.tensor([dev_ms, e2e_s, kern_ms_avg, comm_free[0] if comm_free else 0.0, e2e_idt_s], dtype=torch.float64, device=dev)
+    rvec = torch.tensor([0 if gathered else rays_main, e2e_rays, launches, comm_free[1] if comm_free else 0.0, e2e_idt_rays, d2h_gbps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
         dist.all_reduce(rvec, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, kern_ms_max, cf_ms_max = [float(x) for x in tvec.tolist()]
-    rays_all, e2e_rays_all, launches_all, cf_rays_all = [float(x) for x in rvec.tolist()]
+    dev_ms_max, e2e_s_max, kern_ms_max, cf_ms_max, e2e_idt_s_max = [float(x) for x in tvec.tolist()]
+    rays_all, e2e_rays_all, launches_all, cf_rays_all, e2e_idt_rays_all, d2h_gbps_all = [float(x) for x in rvec.tolist()]
     if gathered:
         rays_all = float(rays_main)                     # every rank counted the same global frames
 
@@ -413,7 +434,11 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": dev_ms_max / args.steps, "ms_per_step_median": float(np.median(per_step)), "timed_region_s": dev_ms_max * 1e-3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA, "config": CONFIG, "run": run, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": F * ctypes.sizeof(rto.RtoCamera), "d2h_bytes_per_step": F * W * H * 24,
-                    "steps": e2e_steps, "api": "rto_render_batch(RTO_MEM_HOST), %d frames per call into pinned host planes; per-frame D2H overlaps the next frame's kernel" % EB},
+                    "steps": e2e_steps, "api": "rto_render_batch(RTO_MEM_HOST), %d frames per call into pinned host planes; per-frame D2H overlaps the next frame's kernel" % EB,
+                    "d2h_GBps": world * e2e_steps * F * W * H * 24 / e2e_s_max / 1e9,
+                    "d2h_ceiling_GBps": d2h_gbps_all, "ceiling": "all %d rank(s) copying 530 MB device -> pinned host six times concurrently, nothing else running (sum over ranks)" % world,
+                    "id_t_only": {"value": e2e_idt_rays_all / e2e_idt_s_max / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": F * W * H * 8, "steps": 1,
+                                  "what": "the same call with rgba = NULL: hit id + t planes only (8 B/pixel)"}},
             "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu}
     if gathered:
         line["gather"] = {"what": "every frame delivered as rgba32f + id + t planes in rank 0's HBM inside the timed region", "transport": gr.transport,

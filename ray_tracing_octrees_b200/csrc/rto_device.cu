@@ -122,7 +122,12 @@ extern "C" void rto_scene_destroy(RtoScene* s) {
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (void* p : s->owned) cudaFree(p);
 	for (void* p : s->scratch) if (p) cudaFree(p);
-	for (auto& c : s->camRing) { if (c.host) cudaFreeHost(c.host); if (c.dev) cudaFree(c.dev); if (c.done) cudaEventDestroy(c.done); }
+	for (auto& c : s->camRing) {
+		if (c.host) cudaFreeHost(c.host);
+		if (c.dev) cudaFree(c.dev);
+		if (c.uploaded) cudaEventDestroy(c.uploaded);
+		for (cudaEvent_t e : c.readerDone) if (e) cudaEventDestroy(e);
+	}
 	if (s->evStart) cudaEventDestroy(s->evStart);
 	if (s->evStop) cudaEventDestroy(s->evStop);
 	if (s->evFrame) cudaEventDestroy(s->evFrame);
@@ -264,7 +269,7 @@ static int check_mode(const RtoScene* s, int mode) {
 // persistent per-lane refill kernel, a warp-phased while-while kernel and a per-step warp vote; for the octree walks a persistent
 // kernel refilling idle lanes from a pixel counter; see profiles/README.md.)
 static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCams, int mode, cudaStream_t st) {
-	dim3 block(128), grid((width + 15) / 16, (A.y1 - A.y0 + 7) / 8, numCams);
+	dim3 block(kRenderThreads), grid((width + kRenderBlockW - 1) / kRenderBlockW, (A.y1 - A.y0 + 7) / 8, numCams);
 	if (s->kind == RTO_MODE_BVH) {
 		bool sh = (A.flags & RTO_FLAG_SHADOWS) != 0, prune = (A.flags & RTO_FLAG_NO_PRUNE) == 0;
 		if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, st>>>(s->bvhFast, A);
@@ -281,11 +286,22 @@ static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCam
 // Camera array of a batched call: copied into a pinned slot of the scene's ring and from there to the device on `st`, so the call
 // returns without waiting for anything.  A slot is reused only after the kernel that read it has finished (release_cameras).
 static int stage_cameras(RtoScene* s, const RtoCamera* cams, int n, cudaStream_t st, int* slotOut, const RtoCamera** devOut) {
+	// the same camera array again (an orbit traced batch after batch, the sub-ranges of a sharded batch): the copy that is already on the
+	// device is read-only and still valid -- no copy, no wait
+	for (int k = 0; k < RtoScene::kCamSlots; k++) {
+		RtoScene::CamSlot& c = s->camRing[k];
+		if (c.count == n && c.host && std::memcmp(c.host, cams, sizeof(RtoCamera) * n) == 0) {
+			CUDA_TRY(cudaStreamWaitEvent(st, c.uploaded, 0));          // (another stream may have staged it)
+			*slotOut = k; *devOut = c.dev;
+			return RTO_OK;
+		}
+	}
 	const int slot = s->camNext;
 	s->camNext = (s->camNext + 1) % RtoScene::kCamSlots;
 	RtoScene::CamSlot& c = s->camRing[slot];
-	if (!c.done) CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
-	else CUDA_TRY(cudaEventSynchronize(c.done));
+	if (!c.uploaded) CUDA_TRY(cudaEventCreateWithFlags(&c.uploaded, cudaEventDisableTiming));
+	for (int k = 0; k < 4; k++) if (c.readerDone[k]) CUDA_TRY(cudaEventSynchronize(c.readerDone[k]));      // every kernel that read this slot has finished
+	c.count = 0;
 	if (c.cap < n) {
 		if (c.host) cudaFreeHost(c.host);
 		if (c.dev) cudaFree(c.dev);
@@ -297,11 +313,20 @@ static int stage_cameras(RtoScene* s, const RtoCamera* cams, int n, cudaStream_t
 	}
 	std::memcpy(c.host, cams, sizeof(RtoCamera) * n);
 	CUDA_TRY(cudaMemcpyAsync(c.dev, c.host, sizeof(RtoCamera) * n, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaEventRecord(c.uploaded, st));
+	c.count = n;
 	*slotOut = slot; *devOut = c.dev;
 	return RTO_OK;
 }
 static int release_cameras(RtoScene* s, int slot, cudaStream_t st) {
-	if (slot >= 0) CUDA_TRY(cudaEventRecord(s->camRing[slot].done, st));
+	if (slot < 0) return RTO_OK;
+	RtoScene::CamSlot& c = s->camRing[slot];
+	int k = 0;
+	while (k < 4 && c.readerDone[k] && c.readerStream[k] != st) k++;
+	if (k == 4) { k = 0; CUDA_TRY(cudaEventSynchronize(c.readerDone[0])); }      // a fifth stream: take over the first entry once its reader is done
+	if (!c.readerDone[k]) CUDA_TRY(cudaEventCreateWithFlags(&c.readerDone[k], cudaEventDisableTiming));
+	c.readerStream[k] = st;
+	CUDA_TRY(cudaEventRecord(c.readerDone[k], st));
 	return RTO_OK;
 }
 
@@ -413,7 +438,7 @@ int rto_enqueue_resolve(RtoScene* s, const RtoCamera* cams, int numCams, int y0,
 		s->launches++;
 	}
 	CUDA_TRY(cudaStreamWaitEvent(st, s->evTable, 0));
-	dim3 block(128), grid((cams[0].width + 15) / 16, (y1 - y0 + 7) / 8, numCams);
+	dim3 block(kRenderThreads), grid((cams[0].width + kRenderBlockW - 1) / kRenderBlockW, (y1 - y0 + 7) / 8, numCams);
 	k_resolve_bvh<<<grid, block, 0, st>>>(s->bvhFast, A, s->shadeTable);
 	s->launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -422,7 +447,7 @@ int rto_enqueue_resolve(RtoScene* s, const RtoCamera* cams, int numCams, int y0,
 
 extern "C" size_t rto_codes_frame_words(int width, int height) {
 	if (width <= 0 || height <= 0) return 0;
-	return (size_t)((width + 15) / 16) * (size_t)((height + 7) / 8) * 128;
+	return (size_t)((width + kRenderBlockW - 1) / kRenderBlockW) * (size_t)((height + 7) / 8) * kRenderThreads;
 }
 
 extern "C" int rto_render_codes(RtoScene* s, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, int y0, int y1,
@@ -523,7 +548,7 @@ extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uin
 	CUDA_TRY(cudaMemsetAsync(d, 0, 5 * 8, s->stream));
 	RenderArgs A{};
 	A.cam0 = *cam; A.y0 = y0; A.y1 = y1; A.shadowBias = shadowBias; A.flags = flags;
-	dim3 block(128), grid((cam->width + 15) / 16, (y1 - y0 + 7) / 8, 1);
+	dim3 block(kRenderThreads), grid((cam->width + kRenderBlockW - 1) / kRenderBlockW, (y1 - y0 + 7) / 8, 1);
 	if (s->kind == RTO_MODE_BVH) k_stats_bvh<<<grid, block, 0, s->stream>>>(s->bvh, A, (unsigned long long*)d);
 	else k_stats_octree<<<grid, block, 0, s->stream>>>(s->oct, A, mode, (unsigned long long*)d);
 	s->launches++;

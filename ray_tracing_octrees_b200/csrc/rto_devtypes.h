@@ -43,6 +43,12 @@ struct OctDev {
 	float voxel;
 };
 
+// render kernels: one warp = one 4 x 8 pixel tile, a block = kRenderThreads / 32 tiles side by side (16 x 8 pixels at 128 threads)
+#ifndef RTO_RENDER_THREADS
+#define RTO_RENDER_THREADS 128
+#endif
+constexpr int kRenderThreads = RTO_RENDER_THREADS;
+constexpr int kRenderBlockW = kRenderThreads / 8;      // pixels per block row
 constexpr uint32_t kOctLeaf = 0x80000000u;
 constexpr uint32_t kOctSolid = 0x40000000u;
 constexpr int kMaxOctDepth = 32;

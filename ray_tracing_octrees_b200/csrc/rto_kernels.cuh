@@ -63,9 +63,18 @@ RTO_DEV int ffs32(unsigned v) {
 #ifndef RTO_BVH_WHILE_WHILE
 #define RTO_BVH_WHILE_WHILE 1
 #endif
+#ifndef RTO_RESOLVE_HOIST_RAY
+#define RTO_RESOLVE_HOIST_RAY 0
+#endif
 #ifndef RTO_BVH_ANY_WHILE_WHILE
 #define RTO_BVH_ANY_WHILE_WHILE 0
 #endif
+
+__device__ __host__ __forceinline__ void load_node(const float4* __restrict__ n, float4& a, float4& b, float4& c, float2& r) {
+	// (two 256-bit loads -- LDG.E.256, new on sm_100 -- instead of these four were measured 1-4 % slower: profiles/README.md, round 2)
+	a = RTO_LDG(n); b = RTO_LDG(n + 1); c = RTO_LDG(n + 2);
+	r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
+}
 
 struct Ray { V3 o, d; };
 struct alignas(8) StackEnt { int ref; float t; };     // postponed far child of the ordered BVH traversal and its box entry distance
@@ -298,8 +307,8 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 	for (;;) {
 		while (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
-			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
+			float4 a, b, c; float2 r;
+			load_node(n, a, b, c, r);
 			float e0, e1;
 			bool h0, h1;
 			node_boxes<OCT>(rb, rb2, S.paired, a, b, c, PRUNE ? tcut : FLT_MAX, h0, h1, e0, e1);
@@ -349,8 +358,8 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 			bool pop = true;
 			if (cur >= 0) {
 				const float4* n = S.nodes + 4 * (size_t)cur;
-				float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
-				float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
+				float4 a, b, c; float2 r;
+				load_node(n, a, b, c, r);
 				float e0, e1;
 				bool h0, h1;
 				node_boxes<OCT>(rb, rb2, S.paired, a, b, c, PRUNE ? tcut : FLT_MAX, h0, h1, e0, e1);
@@ -430,8 +439,8 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 	for (;;) {
 		while (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
-			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
+			float4 a, b, c; float2 r;
+			load_node(n, a, b, c, r);
 			float e0, e1;
 			bool h0, h1;
 			node_boxes<OCT>(rb, rb2, S.paired, a, b, c, FLT_MAX, h0, h1, e0, e1);
@@ -462,8 +471,8 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 	while (true) {
 		if (cur >= 0) {
 			const float4* n = S.nodes + 4 * (size_t)cur;
-			float4 a = RTO_LDG(n), b = RTO_LDG(n + 1), c = RTO_LDG(n + 2);
-			float2 r = RTO_LDG(reinterpret_cast<const float2*>(n + 3));
+			float4 a, b, c; float2 r;
+			load_node(n, a, b, c, r);
 			float e0, e1;
 			bool h0, h1;
 			node_boxes<OCT>(rb, rb2, S.paired, a, b, c, FLT_MAX, h0, h1, e0, e1);
@@ -1134,13 +1143,13 @@ struct RenderArgs {
 constexpr uint32_t kCodeShadowBit = 0x80000000u, kCodeFlipBit = 0x40000000u;
 __device__ __forceinline__ size_t code_index(const RenderArgs& A) {
 	const size_t tile = ((size_t)(A.codeFrame0 + blockIdx.z) * A.codeTilesY + (size_t)(A.y0 >> 3) + blockIdx.y) * gridDim.x + blockIdx.x;
-	return tile * 128 + threadIdx.x;
+	return tile * kRenderThreads + threadIdx.x;
 }
 
 __device__ __forceinline__ bool pixel_of_thread(const RenderArgs& A, const RtoCamera& cam, int& px, int& py, size_t& pix) {
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	// 4 wide x 8 tall per warp: measured 1-4 % faster than 8 x 4 on every kernel (16 x 2: 5-7 % slower)
-	px = blockIdx.x * 16 + (warp & 3) * 4 + (lane & 3);
+	px = blockIdx.x * kRenderBlockW + warp * 4 + (lane & 3);
 	py = A.y0 + blockIdx.y * 8 + (lane >> 2);
 	if (px >= cam.width || py >= A.y1) return false;
 	pix = (size_t)blockIdx.z * (size_t)(A.y1 - A.y0) * cam.width + (size_t)(py - A.y0) * cam.width + px;
@@ -1167,7 +1176,7 @@ RTO_DEV void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, floa
                                   // spills) 1.838 / 1.224 / 2.857 / 0.503; 14-16 blocks (32 registers) is slower still
 #endif
 template <bool SHADOWS, bool PRUNE>
-__global__ void __launch_bounds__(128, RTO_BVH_MIN_BLOCKS) k_render_bvh(BvhDev S, RenderArgs A) {
+__global__ void __launch_bounds__(kRenderThreads, RTO_BVH_MIN_BLOCKS * 128 / kRenderThreads) k_render_bvh(BvhDev S, RenderArgs A) {
 	RtoCamera cam = A.cam0;
 	if (A.cams) cam = A.cams[blockIdx.z];
 	int px, py; size_t pix;
@@ -1221,18 +1230,26 @@ RTO_DEV float mt_distance(const TriV& tri, V3 o, V3 d) {      // moller_trumbore
 	return dot3(tri.e2, q) * inv;
 }
 
-__global__ void __launch_bounds__(128) k_resolve_bvh(BvhDev S, RenderArgs A, const float* __restrict__ ndotl) {
+#ifndef RTO_RESOLVE_MIN_BLOCKS
+#define RTO_RESOLVE_MIN_BLOCKS 12
+#endif
+__global__ void __launch_bounds__(kRenderThreads, RTO_RESOLVE_MIN_BLOCKS * 128 / kRenderThreads) k_resolve_bvh(BvhDev S, RenderArgs A, const float* __restrict__ ndotl) {
 	RtoCamera cam = A.cam0;
 	if (A.cams) cam = A.cams[blockIdx.z];
 	int px, py; size_t pix;
 	if (!pixel_of_thread(A, cam, px, py, pix)) return;
 	const uint32_t code = __ldcs(A.codes + code_index(A));
+#if RTO_RESOLVE_HOIST_RAY
+	Ray ray = gen_ray(cam, px, py);              // independent of the code word: its divisions and square roots run while that load is in flight
+#endif
 	V3 color = mk3(0.0f, 0.0f, 0.0f);
 	int id = -1;
 	float t = kMissT;
 	const int pos = (int)(code & ~(kCodeShadowBit | kCodeFlipBit)) - 1;
 	if (pos >= 0 && pos < S.numTris) {
+#if !RTO_RESOLVE_HOIST_RAY
 		Ray ray = gen_ray(cam, px, py);
+#endif
 		TriV tri = load_tri(S.tris, pos);
 		id = tri.id;
 		t = mt_distance(tri, ray.o, ray.d);
@@ -1252,7 +1269,7 @@ __global__ void __launch_bounds__(128) k_resolve_bvh(BvhDev S, RenderArgs A, con
 #define RTO_OCT_A_MIN_BLOCKS 8     // re-measured (DT / 512^3 city, 8 x 1080p): 8 blocks 2.60 / 4.14 ms, 6 blocks 2.66 / 4.25, 10 blocks 2.62 / 4.17, 4-5 and 12 slower
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(128, MODE == RTO_MODE_OCTREE_SKIP ? RTO_OCT_A_MIN_BLOCKS : RTO_OCT_B_MIN_BLOCKS) k_render_octree(OctDev S, RenderArgs A) {
+__global__ void __launch_bounds__(kRenderThreads, (MODE == RTO_MODE_OCTREE_SKIP ? RTO_OCT_A_MIN_BLOCKS : RTO_OCT_B_MIN_BLOCKS) * 128 / kRenderThreads) k_render_octree(OctDev S, RenderArgs A) {
 	const int mode = MODE;
 	RtoCamera cam = A.cam0;
 	if (A.cams) cam = A.cams[blockIdx.z];
@@ -1339,7 +1356,7 @@ __device__ __forceinline__ void warp_add(unsigned long long* dst, unsigned long 
 	if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
 }
 
-__global__ void __launch_bounds__(128) k_stats_bvh(BvhDev S, RenderArgs A, unsigned long long* stats) {
+__global__ void __launch_bounds__(kRenderThreads) k_stats_bvh(BvhDev S, RenderArgs A, unsigned long long* stats) {
 	const RtoCamera& cam = A.cam0;
 	int px, py; size_t pix;
 	bool active = pixel_of_thread(A, cam, px, py, pix);
@@ -1364,7 +1381,7 @@ __global__ void __launch_bounds__(128) k_stats_bvh(BvhDev S, RenderArgs A, unsig
 	warp_add(stats + 0, B); warp_add(stats + 1, C); warp_add(stats + 2, Bs); warp_add(stats + 3, Cs); warp_add(stats + 4, nS);
 }
 
-__global__ void __launch_bounds__(128) k_stats_octree(OctDev S, RenderArgs A, int mode, unsigned long long* stats) {
+__global__ void __launch_bounds__(kRenderThreads) k_stats_octree(OctDev S, RenderArgs A, int mode, unsigned long long* stats) {
 	const RtoCamera& cam = A.cam0;
 	int px, py; size_t pix;
 	bool active = pixel_of_thread(A, cam, px, py, pix);

@@ -27,8 +27,14 @@ struct RtoScene {
 	size_t scratchBytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	int smCount = 0;
 	// camera arrays of batched calls: pinned host slot -> device slot, a ring so that a call never waits for the previous one's kernel
-	struct CamSlot { RtoCamera* host = nullptr; RtoCamera* dev = nullptr; int cap = 0; cudaEvent_t done = nullptr; };
-	static constexpr int kCamSlots = 16;
+	struct CamSlot {
+		RtoCamera* host = nullptr; RtoCamera* dev = nullptr; int cap = 0, count = 0;
+		cudaEvent_t uploaded = nullptr;
+		cudaStream_t readerStream[4] = { nullptr, nullptr, nullptr, nullptr };      // last kernel that read the slot, per stream that ever did
+		cudaEvent_t readerDone[4] = { nullptr, nullptr, nullptr, nullptr };
+		bool used = false;
+	};
+	static constexpr int kCamSlots = 64;
 	CamSlot camRing[kCamSlots];
 	int camNext = 0;
 	cudaEvent_t evTable = nullptr;    // "the table below is filled"

@@ -4,12 +4,31 @@
 #pragma once
 #include "../../../include/rto_c.h"
 #include "rto_shim_math.h"
+#include <limits>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 struct Triangle { rto_shim::vec3 v0, v1, v2; };                            // BVH.h:7-11 (36 bytes)
 static_assert(sizeof(Triangle) == sizeof(RtoTriangle), "Triangle must be 9 packed floats");
+
+struct AABB {                                                              // BVH.h:14-34
+	rto_shim::vec3 min, max;
+	AABB() : min(std::numeric_limits<float>::max()), max(-std::numeric_limits<float>::max()) {}
+	void expand(const rto_shim::vec3& p) {                                 // glm::min / glm::max: (b < a) ? b : a, (a < b) ? b : a
+		min = rto_shim::vec3(p.x < min.x ? p.x : min.x, p.y < min.y ? p.y : min.y, p.z < min.z ? p.z : min.z);
+		max = rto_shim::vec3(max.x < p.x ? p.x : max.x, max.y < p.y ? p.y : max.y, max.z < p.z ? p.z : max.z);
+	}
+	void expand(const AABB& other) { expand(other.min); expand(other.max); }
+};
+
+struct BVHNode {                                                           // BVH.h:37-42
+	AABB bounds;
+	BVHNode* left = nullptr;
+	BVHNode* right = nullptr;
+	std::vector<const Triangle*> triangles;                                // non-empty for leaf nodes
+};
 
 class BVH {
 public:
@@ -42,6 +61,30 @@ public:
 	}
 	RtoScene* scene() const { ensureScene(); return m_scene; }
 	const RtoHostBvh* host() const { return m_host; }
+	const std::vector<Triangle>& triangles() const { return *m_tris; }
+	// the pointer tree the reference keeps in its private `root` (BVH.h:54), for callers that walk it themselves: same shape, same
+	// boxes, same leaves, materialised on first use from the pre-order export of the host tree
+	const BVHNode* root() const {
+		if (m_nodes) return m_nodes->empty() ? nullptr : m_nodes->data();
+		const size_t n = rto_host_bvh_num_nodes(m_host);
+		std::vector<float> boxes(n * 6); std::vector<int32_t> meta(n * 4);
+		check(rto_host_bvh_export(m_host, boxes.data(), meta.data(), n));
+		m_nodes.reset(new std::vector<BVHNode>(n));
+		// pre-order, left subtree first: the left child of node i is i + 1, the right child follows the left subtree
+		std::vector<size_t> stack;                                          // inner nodes whose right child is still to come
+		for (size_t i = 0; i < n; i++) {
+			BVHNode& nd = (*m_nodes)[i];
+			nd.bounds.min = rto_shim::vec3(boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]);
+			nd.bounds.max = rto_shim::vec3(boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]);
+			if (i > 0) {
+				BVHNode& parent = (*m_nodes)[stack.back()];
+				if (!parent.left) parent.left = &nd; else { parent.right = &nd; stack.pop_back(); }
+			}
+			if (meta[4 * i]) for (int k = 0; k < meta[4 * i + 1]; k++) nd.triangles.push_back(&(*m_tris)[meta[4 * i + 2 + k]]);
+			else stack.push_back(i);
+		}
+		return m_nodes->empty() ? nullptr : m_nodes->data();
+	}
 
 private:
 	void ensureScene() const {
@@ -52,4 +95,5 @@ private:
 	const std::vector<Triangle>* m_tris;
 	RtoHostBvh* m_host = nullptr;
 	mutable RtoScene* m_scene = nullptr;
+	mutable std::unique_ptr<std::vector<BVHNode>> m_nodes;
 };

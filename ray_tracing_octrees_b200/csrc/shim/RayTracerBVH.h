@@ -23,7 +23,7 @@ struct Framebuffer {                       // host copy of one frame: row 0 = to
 class RayTracerBVH {
 public:
 	RayTracerBVH() = default;
-	~RayTracerBVH() { rto_scene_destroy(m_scene); rto_scene_destroy(m_culled); }
+	~RayTracerBVH() { rto_scene_destroy(m_scene); rto_scene_destroy(m_culled); rto_group_destroy(m_group); }
 	RayTracerBVH(const RayTracerBVH&) = delete;
 	RayTracerBVH& operator=(const RayTracerBVH&) = delete;
 
@@ -54,7 +54,46 @@ public:
 			std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error());
 	}
 	// extension: ray cast a triangle soup through the reference-shaped BVH
-	void setMesh(const BVH& bvh, float sceneScale) { rto_scene_destroy(m_scene); m_scene = nullptr; rto_scene_destroy(m_culled); m_culled = nullptr; m_culledEmpty = false; m_external = bvh.scene(); m_mode = RTO_MODE_BVH; m_shadowBias = 1e-3f * sceneScale; }
+	void setMesh(const BVH& bvh, float sceneScale) {
+		rto_scene_destroy(m_scene); m_scene = nullptr; rto_scene_destroy(m_culled); m_culled = nullptr; m_culledEmpty = false;
+		m_external = bvh.scene(); m_mode = RTO_MODE_BVH; m_shadowBias = 1e-3f * sceneScale; m_bvh = &bvh; m_groupHasMesh = false;
+	}
+	// extension: use several GPUs of the box for renderBatch (rto_group_*: scene replicated, frames dealt to the devices, hit codes
+	// gathered on devices[0] over NVLink and expanded there).  An empty list goes back to one device.
+	bool setDevices(const std::vector<int>& devices) {
+		rto_group_destroy(m_group); m_group = nullptr; m_groupHasMesh = false;
+		if (devices.empty()) return true;
+		if (rto_group_create(devices.data(), (int)devices.size(), &m_group) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
+		return true;
+	}
+	// extension: many cameras in one submission (a camera orbit, main.cpp's per-frame loop unrolled): mesh scenes only
+	bool renderBatch(const std::vector<Camera>& cameras, int width, int height, float aspect, float fovDeg, std::vector<Framebuffer>& out) {
+		if (!m_inited || m_mode != RTO_MODE_BVH || !m_bvh || cameras.empty()) return false;
+		std::vector<RtoCamera> cams(cameras.size());
+		for (size_t i = 0; i < cameras.size(); i++) if (cameras[i].consts(fovDeg, aspect, width, height, cams[i], nullptr) != RTO_OK) return false;
+		const size_t npix = (size_t)width * height, n = cameras.size();
+		std::vector<float> rgba(n * npix * 4), t(n * npix); std::vector<int32_t> ids(n * npix);
+		RtoFrame fr{ rgba.data(), ids.data(), t.data(), RTO_MEM_HOST };
+		int rc;
+		if (m_group) {
+			if (!m_groupHasMesh) {
+				const std::vector<Triangle>& tris = m_bvh->triangles();
+				if (rto_group_scene_bvh(m_group, reinterpret_cast<const RtoTriangle*>(tris.data()), tris.size(), m_bvh->host()) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
+				m_groupHasMesh = true;
+			}
+			rc = rto_group_render_batch(m_group, cams.data(), (int)n, m_flags, m_shadowBias, &fr);
+		}
+		else rc = rto_render_batch(m_external, cams.data(), (int)n, RTO_MODE_BVH, m_flags, m_shadowBias, 0, height, &fr);
+		if (rc != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
+		out.resize(n);
+		for (size_t i = 0; i < n; i++) {
+			out[i].width = width; out[i].height = height;
+			out[i].rgba.assign(rgba.begin() + i * npix * 4, rgba.begin() + (i + 1) * npix * 4);
+			out[i].hitId.assign(ids.begin() + i * npix, ids.begin() + (i + 1) * npix);
+			out[i].t.assign(t.begin() + i * npix, t.begin() + (i + 1) * npix);
+		}
+		return true;
+	}
 
 	void ensureComputeInitialized() { if (!m_inited && rto_init(0) == RTO_OK) m_inited = true; else if (!m_inited) std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); }
 	void setFrustumCullingEnabled(bool on) { m_cullingEnabled = on; }       // RayTracerBVH.h:44 (stored, like the reference; the culling call below does not consult it either)
@@ -107,6 +146,9 @@ private:
 	float m_gridMin[3] = { 0, 0, 0 }, m_voxelSize = 1.0f;
 	bool m_cullingEnabled = false, m_culledEmpty = false;
 	RtoScene* m_external = nullptr;       // owned by a BVH (setMesh)
+	const BVH* m_bvh = nullptr;
+	RtoGroup* m_group = nullptr;          // setDevices
+	bool m_groupHasMesh = false;
 	int m_mode = RTO_MODE_OCTREE_GLSL;
 	unsigned m_flags = 0;
 	float m_shadowBias = 0.0f;

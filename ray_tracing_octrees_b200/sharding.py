@@ -141,7 +141,7 @@ class GatheredRenderer:
         self.words_per_tile_row = self.words // self.tiles_per_frame
         self.device = device
         self.main = torch.cuda.ExternalStream(scene.stream, device=device)
-        self.side = torch.cuda.Stream(device=device)
+        self.side = torch.cuda.Stream(device=device, priority=-1)       # the expansion gets SM slots as they free up, ahead of the next trace
         self.weights = [0.55 if (r == 0 and self.world > 1) else 1.0 for r in range(self.world)]
         self.flag = torch.zeros(1, dtype=torch.int32, device=device)
         nbytes = self.words * 4 * max_frames

@@ -32,7 +32,7 @@ def cams_orbit(theta, radius, W, H, n, phi0=40.0, target=(0, 0, 0)):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_configs.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_configs.json"))
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One named case rendered a few times -- the target of `ncu -k regex:k_render -s 2 -c 1` captures and of quick A/B timing.
-    python tools/profile_case.py CASE [--reps N]      CASE in dt-bvh, dt-bvh-primary, dt-dcbvh, dt-octA, dt-octB, c3-octA, c3-octB, c3-dcbvh, c1-bvh, c3-dcbuild, c4-dcbuild"""
+    python tools/profile_case.py CASE [--reps N]      CASE in dt-bvh, dt-bvh-primary, dt-dcbvh, dt-octA, dt-octB, c3-octA, c3-octB, c3-dcbvh, c4-dcbvh, c1-bvh, c3-dcbuild, c4-dcbuild, dt-bvh-resolve"""
 import argparse, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,6 +27,9 @@ def main():
     elif a.case.startswith("c3"):
         g = rto.city_block_grid(512, 1234, 32)
         radius, theta = 0.9 * 512, 35
+    elif a.case.startswith("c4"):
+        g = rto.city_block_grid(1024, 4321, 64)
+        radius, theta, W, H = 0.9 * 1024, 35, 3840, 2160
     else:
         g = rto.generate_test_volume(128)
         radius, theta, W, H = 1.2, 30, 1024, 768
@@ -40,14 +43,14 @@ def main():
             print("%s: scene from grid in %.3f s, %d triangles" % (a.case, dt, sc.info()["prims"]))
             del sc
         return
-    nodes = rto.create_octree_from_voxel_grid(g)
+    nodes = rto.create_octree_on_device(g) if a.case.startswith("c4") else rto.create_octree_from_voxel_grid(g)
     if "devbvh" in a.case:          # the device-built tree over the Marching-Cubes soup 
         import time
-        tris = rto.marching_cubes_mesh(g, nodes)
+        tris = rto.marching_cubes_mesh_on_device(g) if a.case.startswith("c4") else rto.marching_cubes_mesh(g, nodes)
         t0 = time.time(); sc = rto.Scene.bvh_device(tris); print("device BVH over %d triangles built in %.3f s" % (len(tris), time.time() - t0))
         mode, flags, bias = rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3 * g.voxel_size
     elif "dcbvh" in a.case:
-        sc = rto.Scene.bvh(rto.dual_contouring_mesh(g, nodes))
+        sc = rto.Scene.bvh(rto.dual_contouring_mesh(g, nodes, algo="device" if a.case.startswith("c4") else "default"))
         mode, flags, bias = rto.MODE_BVH, rto.FLAG_SHADOWS, 1e-3 * g.voxel_size
     elif "bvh" in a.case:
         sc = rto.Scene.bvh(rto.marching_cubes_mesh(g, nodes))
