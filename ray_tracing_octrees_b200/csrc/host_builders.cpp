@@ -442,6 +442,80 @@ void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, i
 	}
 }
 
+// 4-wide collapse of the fast topology with 16-bit quantised boxes (rto_internal.h)
+namespace {
+struct WideBuilder {
+	const float* bin; std::vector<uint32_t>* out;
+	double lo[3], step, margin;
+	int maxNeed = 0;
+	bool offGrid = false;            // a box did not fit on the grid (cannot happen for trees of rto_build_fast_topology; checked, not assumed)
+	struct Cand { int32_t ref; float mn[3], mx[3]; };
+	static void childBox(const float* d, int k, Cand& c) {        // paired layout: plane p of child k at d[2 * p + k], p = lo xyz, hi xyz
+		for (int a = 0; a < 3; a++) { c.mn[a] = d[2 * a + k]; c.mx[a] = d[6 + 2 * a + k]; }
+		std::memcpy(&c.ref, &d[12 + k], 4);
+	}
+	static float area(const Cand& c) { float dx = c.mx[0] - c.mn[0], dy = c.mx[1] - c.mn[1], dz = c.mx[2] - c.mn[2]; return dx * dy + dy * dz + dz * dx; }
+	// returns the wide index of binary node b; need = postponed entries a walk below it can hold at once
+	int32_t build(int32_t b, int& need) {
+		Cand c[4]; int n = 2;
+		childBox(bin + (size_t)b * 16, 0, c[0]); childBox(bin + (size_t)b * 16, 1, c[1]);
+		while (n < 4) {                                             // open the inner child with the largest box until four children or only leaves
+			int pick = -1; float best = -1.0f;
+			for (int i = 0; i < n; i++) if (c[i].ref >= 0 && area(c[i]) > best) { best = area(c[i]); pick = i; }
+			if (pick < 0) break;
+			const float* d = bin + (size_t)c[pick].ref * 16;
+			childBox(d, 0, c[pick]); childBox(d, 1, c[n]); n++;
+		}
+		const size_t idx = out->size() / 16;
+		out->resize(out->size() + 16);
+		uint32_t w[16];
+		int deepest = 0;
+		for (int k = 0; k < 4; k++) {
+			if (k >= n) { for (int a = 0; a < 3; a++) w[4 * a + k] = 0x0000ffffu; w[12 + k] = (uint32_t)kWideEmpty; continue; }      // lo = 65535, hi = 0: never hit
+			for (int a = 0; a < 3; a++) {
+				double ql = std::floor(((double)c[k].mn[a] - lo[a]) / step) - margin, qh = std::ceil(((double)c[k].mx[a] - lo[a]) / step) + margin;
+				if (ql < 0.0 || qh > 65535.0) { offGrid = true; ql = std::max(0.0, ql); qh = std::min(65535.0, qh); }
+				w[4 * a + k] = (uint32_t)ql | ((uint32_t)qh << 16);
+			}
+			int32_t ref = c[k].ref;
+			if (ref >= 0) { int sub = 0; ref = build(ref, sub); deepest = std::max(deepest, sub); }
+			w[12 + k] = (uint32_t)ref;
+		}
+		std::memcpy(&(*out)[idx * 16], w, sizeof(w));
+		need = (n - 1) + deepest;
+		maxNeed = std::max(maxNeed, need);
+		return (int32_t)idx;
+	}
+};
+} // namespace
+
+bool rto_build_wide_topology(const std::vector<float>& fastNodes, int32_t fastRoot, const float rootLo[3], const float rootHi[3], float grow,
+	std::vector<uint32_t>& wide, int32_t& wideRoot, float wideLo[3], float& wideStep) {
+	wide.clear(); wideRoot = -1;
+	if (fastRoot < 0 || fastNodes.empty()) return false;          // empty scene or a single triangle: nothing to collapse
+	float ext = 0.0f;
+	for (int a = 0; a < 3; a++) ext = std::max(ext, rootHi[a] - rootLo[a]);
+	if (!(ext > 0.0f) || !(ext < 1e30f)) return false;
+	// One grid for the whole scene: 65 536 positions along the longest side of the root box (whose corners are those of exact boxes)
+	// widened by the growth of the leaf boxes and by the margin every quantised box gets on top of rounding outwards.  The margin has
+	// to cover what the kernels' dequantising test (rto_kernels.cuh wide_test: t = fma(2^23 + q, step/d, ((lo - o)/d - 2^23 step/d)))
+	// and the leaf-level test it must not contradict can be off by, for the rays admitted to the fused tests (|o| <= 16 e, e the largest
+	// coordinate of the scene, grow = 64 e 2^-24): half a step from rounding the per-ray constant (2^23 step/d dominates it), and at
+	// most (2 x 17 + 17 + 16 + 17) e 2^-24 = 1.31 grow from the roundings of (lo - o), of the products and of the leaf test.
+	// (half a `grow` of slack at either end absorbs the rounding of wideLo itself: grow is 32 ulps of the largest coordinate)
+	wideStep = (ext + 6.0f * grow) / 65400.0f;
+	const double margin = 1.0 + std::ceil(1.5 * (double)grow / (double)wideStep);
+	for (int a = 0; a < 3; a++) wideLo[a] = rootLo[a] - 3.0f * grow - 8.0f * wideStep;
+	WideBuilder b; b.bin = fastNodes.data(); b.out = &wide; b.step = (double)wideStep; b.margin = margin;
+	for (int a = 0; a < 3; a++) b.lo[a] = (double)wideLo[a];
+	wide.reserve(fastNodes.size() / 2 + 16);
+	int need = 0;
+	wideRoot = b.build(fastRoot, need);
+	if (getenv("RTO_DEBUG_WIDE")) fprintf(stderr, "[wide] ext %g grow %g step %g margin %g lo %g %g %g nodes %zu need %d offGrid %d\n", ext, grow, wideStep, margin, wideLo[0], wideLo[1], wideLo[2], wide.size() / 16, b.maxNeed, (int)b.offGrid);
+	if (b.maxNeed > kWideStack - 4 || b.offGrid) { wide.clear(); wide.shrink_to_fit(); wideRoot = -1; return false; }
+	return true;
+}
+
 // =================================================================================================
 // Camera constants
 // =================================================================================================

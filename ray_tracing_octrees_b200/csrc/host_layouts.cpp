@@ -5,6 +5,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef RTO_BVH_WIDE_DEFAULT
+#define RTO_BVH_WIDE_DEFAULT false
+#endif
+
 // The compact layout needs the shape the reference builder always produces: every internal node has 8 children
 // with consecutive indices, child boxes are the 8 octants of the parent, leaf <=> uniform.
 static bool octree_is_compactable(const RtoGpuNode* n, size_t count) {
@@ -114,4 +118,10 @@ void rto_build_bvh_layout(const RtoHostBvh& h, BvhLayout& L) {
 	}
 	const HostBvhNode& root = h.nodes[0];
 	for (int k = 0; k < 3; k++) { L.rootLo[k] = root.mn[k]; L.rootHi[k] = root.mx[k]; }
+	// the 4-wide quantised form of the production tree (RTO_BVH_WIDE=0 keeps the binary form only)
+	const char* we = getenv("RTO_BVH_WIDE");
+	const bool wantWide = we ? (atoi(we) != 0) : RTO_BVH_WIDE_DEFAULT;
+	if (wantWide && !L.fastNodes.empty() && L.fastRoot >= 0) {
+		rto_build_wide_topology(L.fastNodes, L.fastRoot, L.rootLo, L.rootHi, L.fastGrow, L.wideNodes, L.wideRoot, L.wideLo, L.wideStep);
+	}
 }

@@ -225,6 +225,15 @@ int rto_scene_from_bvh_layout(const BvhLayout& L, size_t numTris, size_t numRefN
 	s->bvh = D;
 	s->bvhFast = D;
 	if (dF) { s->bvhFast.nodes = (const float4*)dF; s->bvhFast.rootRef = L.fastRoot; s->bvhFast.leafBox = 1; s->bvhFast.grow = L.fastGrow; s->bvhFast.paired = 1; }
+	if (dF && !L.wideNodes.empty() && L.wideRoot >= 0) {
+		void* dW = nullptr;
+		if ((rc = scene_alloc(s, &dW, L.wideNodes.size() * 4))) { rto_scene_destroy(s); return rc; }
+		e = cudaMemcpyAsync(dW, L.wideNodes.data(), L.wideNodes.size() * 4, cudaMemcpyHostToDevice, s->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+		if (e != cudaSuccess) { rto_scene_destroy(s); return rto_fail(RTO_ERR_CUDA, "BVH upload failed: %s", cudaGetErrorString(e)); }
+		s->bvhFast.wide = (const uint4*)dW; s->bvhFast.wideRoot = L.wideRoot; s->bvhFast.wideStep = L.wideStep;
+		for (int k = 0; k < 3; k++) s->bvhFast.wideLo[k] = L.wideLo[k];
+	}
 	*out = s;
 	return RTO_OK;
 }
@@ -272,7 +281,10 @@ static int launch_render(RtoScene* s, const RenderArgs& A, int width, int numCam
 	dim3 block(kRenderThreads), grid((width + kRenderBlockW - 1) / kRenderBlockW, (A.y1 - A.y0 + 7) / 8, numCams);
 	if (s->kind == RTO_MODE_BVH) {
 		bool sh = (A.flags & RTO_FLAG_SHADOWS) != 0, prune = (A.flags & RTO_FLAG_NO_PRUNE) == 0;
-		if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, st>>>(s->bvhFast, A);
+		const bool wide = s->bvhFast.wide != nullptr;
+		if (sh && prune && wide) k_render_bvh<true, true, true><<<grid, block, 0, st>>>(s->bvhFast, A);
+		else if (prune && wide) k_render_bvh<false, true, true><<<grid, block, 0, st>>>(s->bvhFast, A);
+		else if (sh && prune) k_render_bvh<true, true><<<grid, block, 0, st>>>(s->bvhFast, A);
 		else if (prune) k_render_bvh<false, true><<<grid, block, 0, st>>>(s->bvhFast, A);
 		else if (sh) k_render_bvh<true, false><<<grid, block, 0, st>>>(s->bvh, A);
 		else k_render_bvh<false, false><<<grid, block, 0, st>>>(s->bvh, A);

@@ -28,6 +28,11 @@ struct BvhDev {
 	                         // interleaved plane by plane ([lo0.x lo1.x lo0.y lo1.y][lo0.z lo1.z hi0.x hi1.x][hi0.y hi1.y hi0.z hi1.z]), so that the same plane of both
 	                         // children sits in one 64-bit register pair and one packed FFMA2 (fma.rn.f32x2, sm_100) tests it for both
 	int   exactPaired;       // the same for `exactNodes`
+	// the production tree once more, collapsed into 4-wide nodes with 16-bit boxes on one grid (rto_internal.h rto_build_wide_topology):
+	// 4 x uint4 per node [x0..x3][y0..y3][z0..z3][ref0..ref3], plane = wideLo[axis] + q * wideStep.  Null: the scene has no wide form.
+	const uint4* wide;
+	int   wideRoot;
+	float wideLo[3], wideStep;
 };
 
 struct OctDev {
@@ -52,6 +57,7 @@ constexpr int kRenderBlockW = kRenderThreads / 8;      // pixels per block row
 constexpr uint32_t kOctLeaf = 0x80000000u;
 constexpr uint32_t kOctSolid = 0x40000000u;
 constexpr int kMaxOctDepth = 32;
+constexpr int kWideStackDev = 144;  // == kWideStack (rto_internal.h): the builder refuses trees whose walks could need more
 constexpr int kBvhStack = 96;       // deepest tree the builders hand out: 92 levels (host SAH falls back to a balanced tree, device LBVH refuses)
 constexpr float kMissT = 1e30f;
 constexpr float kBelowMissT = 9.99999940e29f;    // the largest float below 1e30f (rto_init checks the bit pattern)

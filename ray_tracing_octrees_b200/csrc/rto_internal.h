@@ -77,6 +77,17 @@ struct RtoHostBvh {
 //                       per-triangle boxes cut the Moller-Trumbore tests (the block that runs with the fewest lanes) by a third.
 void rto_build_reference_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef);
 void rto_build_fast_topology(const RtoHostBvh& h, std::vector<float>& nodeBuf, int32_t& rootRef, float& grow);
+// The fast topology collapsed into 4-wide nodes with boxes quantised to 16 bits per plane on ONE grid for the whole scene:
+// 64 bytes per node instead of 64 bytes per PAIR of children, half as many dependent fetches per ray.  Node layout (16 words):
+// [x0 x1 x2 x3][y0 y1 y2 y3][z0 z1 z2 z3][ref0 ref1 ref2 ref3], word k of an axis = lo | hi << 16 of child k in grid units
+// (plane = lo[axis] + q * step); refs as in the binary arrays, an unused slot holds an inverted box and kWideEmpty.  Every quantised box
+// contains the (already grown) box it stands for with two grid steps to spare on every side, which covers the rounding of the
+// kernels' dequantising node test (rto_kernels.cuh wide_test).  Returns false (no wide tree) when the tree is a
+// single leaf or when a walk could need more postponed entries than the kernels' stack holds.
+bool rto_build_wide_topology(const std::vector<float>& fastNodes, int32_t fastRoot, const float rootLo[3], const float rootHi[3], float grow,
+	std::vector<uint32_t>& wide, int32_t& wideRoot, float wideLo[3], float& wideStep);
+constexpr int32_t kWideEmpty = (int32_t)0x80000000;   // ref of an unused child slot (never a leaf reference: ~it >> 1 is beyond 2^30 triangles)
+constexpr int kWideStack = 144;
 
 // ---- device layouts, built on the host (host_layouts.cpp) and uploaded verbatim by rto_device.cu --------------
 struct OctLayout {
@@ -93,6 +104,9 @@ struct OctLayout {
 int rto_build_octree_layout(const RtoGpuNode* nodes, size_t numNodes, OctLayout& out);
 
 struct BvhLayout {
+	std::vector<uint32_t> wideNodes;                  // 16 words per 4-wide node (rto_build_wide_topology); empty: no wide tree
+	int32_t wideRoot = -1;
+	float wideLo[3] = { 0, 0, 0 }, wideStep = 0.0f;
 	std::vector<float> refNodes, fastNodes, tris;     // 16 floats per inner node; 16 floats per triangle in leaf order: v0, v1 - v0, v2 - v0, id in [9], box of its reference leaf in [10..15]
 	int32_t refRoot = -1, fastRoot = -1;
 	float fastGrow = 0.0f;                             // how far the fast topology's leaf boxes were grown (BvhDev::grow)

@@ -287,6 +287,192 @@ RTO_DEV bool ref_leaf_box_passes(const BvhDev& S, const RayBox& rb, int pos, flo
 	return slab_ref(rb, c.x, c.y, d.x, d.y, d.z, d.w, e) && (e <= tcap);       // the reference's own arithmetic: this one decides
 }
 
+// ------------------------------------------------------------------------------------------------
+// 4-wide quantised form of the production tree (BvhDev::wide)
+// ------------------------------------------------------------------------------------------------
+// A plane of a child box is a 16-bit grid position q: plane = wideLo + q * step.  Its distance along the ray,
+// (plane - o) / d = q * (step / d) + (wideLo - o) / d, is ONE fused multiply-add per plane once q is a float, and q becomes a float
+// without a conversion instruction: the bit pattern 0x4B000000 | q is the float 2^23 + q (one PRMT / LOP3), and the 2^23 is taken out
+// again inside the per-ray constant, b' = (wideLo - o)/d - 2^23 * (step/d).  The quantised boxes were rounded outwards and widened
+// by what this arithmetic and the leaf-level test can be off by (host_builders.cpp rto_build_wide_topology), so a ray that passes
+// the test of a triangle's own box passes the test of every wide node above it: candidates are decided at the leaves, exactly as
+// with the binary form, and every result is the same bit for bit.  Per node: 64 bytes instead of 64 bytes per pair of children,
+// and half as many dependent fetches on the way down.
+struct WideRay { float2 sx, sy, sz, bx, by, bz; };
+RTO_DEV bool make_wideray(const BvhDev& S, const RayBox& rb, WideRay& w) {
+	const float sx = S.wideStep * rb.inv.x, sy = S.wideStep * rb.inv.y, sz = S.wideStep * rb.inv.z;
+	const float bx = fmaf(-8388608.0f, sx, (S.wideLo[0] - rb.o.x) * rb.inv.x);
+	const float by = fmaf(-8388608.0f, sy, (S.wideLo[1] - rb.o.y) * rb.inv.y);
+	const float bz = fmaf(-8388608.0f, sz, (S.wideLo[2] - rb.o.z) * rb.inv.z);
+	w.sx = make_float2(sx, sx); w.sy = make_float2(sy, sy); w.sz = make_float2(sz, sz);
+	w.bx = make_float2(bx, bx); w.by = make_float2(by, by); w.bz = make_float2(bz, bz);
+	// 2^23 * step / d must not overflow (a direction component below ~1e-30): such rays stay on the binary form
+	return fabsf(bx) <= FLT_MAX && fabsf(by) <= FLT_MAX && fabsf(bz) <= FLT_MAX &&
+		fabsf(sx) <= 1e30f && fabsf(sy) <= 1e30f && fabsf(sz) <= 1e30f;
+}
+RTO_DEV float i2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(u);
+#else
+	float f; std::memcpy(&f, &u, 4); return f;
+#endif
+}
+// (inline PTX with the selector as an immediate and 0x4B000000 in a register: left to itself the compiler builds the low half from two
+// LOP3 and re-materialises the selector of the high half over and over -- 44 instructions per node for 24 conversions)
+RTO_DEV float wide_lo(uint32_t w) {                                                  // 2^23 + low half
+#if defined(__CUDA_ARCH__)
+	uint32_t r; asm("prmt.b32 %0, %1, %2, 0x7610;" : "=r"(r) : "r"(w), "r"(0x4B000000u)); return __uint_as_float(r);
+#else
+	return i2f(0x4B000000u | (w & 0xffffu));
+#endif
+}
+RTO_DEV float wide_hi(uint32_t w) {                                                  // 2^23 + high half
+#if defined(__CUDA_ARCH__)
+	uint32_t r; asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(w), "r"(0x4B000000u)); return __uint_as_float(r);
+#else
+	return i2f(0x4B000000u | (w >> 16));
+#endif
+}
+// entry distances of the four children (clamped at 0) and the mask of those whose box is hit no later than tcap
+template <int OCT>
+RTO_DEV unsigned wide_test(const WideRay& R, uint4 X, uint4 Y, uint4 Z, float tcap, float tn[4]) {
+	const uint32_t xs[4] = { X.x, X.y, X.z, X.w }, ys[4] = { Y.x, Y.y, Y.z, Y.w }, zs[4] = { Z.x, Z.y, Z.z, Z.w };
+	unsigned mask = 0;
+#pragma unroll
+	for (int p = 0; p < 4; p += 2) {          // two children per packed fused multiply-add
+		const float2 nx = fma2(make_float2((OCT & 1) ? wide_hi(xs[p]) : wide_lo(xs[p]), (OCT & 1) ? wide_hi(xs[p + 1]) : wide_lo(xs[p + 1])), R.sx, R.bx);
+		const float2 fx = fma2(make_float2((OCT & 1) ? wide_lo(xs[p]) : wide_hi(xs[p]), (OCT & 1) ? wide_lo(xs[p + 1]) : wide_hi(xs[p + 1])), R.sx, R.bx);
+		const float2 ny = fma2(make_float2((OCT & 2) ? wide_hi(ys[p]) : wide_lo(ys[p]), (OCT & 2) ? wide_hi(ys[p + 1]) : wide_lo(ys[p + 1])), R.sy, R.by);
+		const float2 fy = fma2(make_float2((OCT & 2) ? wide_lo(ys[p]) : wide_hi(ys[p]), (OCT & 2) ? wide_lo(ys[p + 1]) : wide_hi(ys[p + 1])), R.sy, R.by);
+		const float2 nz = fma2(make_float2((OCT & 4) ? wide_hi(zs[p]) : wide_lo(zs[p]), (OCT & 4) ? wide_hi(zs[p + 1]) : wide_lo(zs[p + 1])), R.sz, R.bz);
+		const float2 fz = fma2(make_float2((OCT & 4) ? wide_lo(zs[p]) : wide_hi(zs[p]), (OCT & 4) ? wide_lo(zs[p + 1]) : wide_hi(zs[p + 1])), R.sz, R.bz);
+		const float e0 = fmaxf(fmax3f(nx.x, ny.x, nz.x), 0.0f), e1 = fmaxf(fmax3f(nx.y, ny.y, nz.y), 0.0f);
+		const float x0 = fminf(fmin3f(fx.x, fy.x, fz.x), tcap), x1 = fminf(fmin3f(fx.y, fy.y, fz.y), tcap);
+		tn[p] = e0; tn[p + 1] = e1;
+		if (!(x0 < e0)) mask |= 1u << p;
+		if (!(x1 < e1)) mask |= 2u << p;
+	}
+	return mask;
+}
+
+constexpr int kWideDone = (int)0x80000000;        // == kWideEmpty: never pushed (an empty slot is never hit), never a leaf reference
+
+// closest hit on the wide form: same rule, same leaves, same results as bvh_closest_loop<true, OCT>
+template <int OCT>
+RTO_DEV void bvh_closest_wide_loop(const BvhDev& S, const RayBox& rb, const WideRay& wr, V3 o, V3 d, float& bestT, int& bestPos) {
+	StackEnt stack[kWideStackDev];
+	int sp = 0;
+	int cur = S.wideRoot;
+	float tcut = kMissT * kPruneSlack;
+	for (;;) {
+		while (cur >= 0) {
+			const uint4* n = S.wide + 4 * (size_t)cur;
+			const uint4 X = RTO_LDG(n), Y = RTO_LDG(n + 1), Z = RTO_LDG(n + 2), R = RTO_LDG(n + 3);
+			float tn[4];
+			const unsigned mask = wide_test<OCT>(wr, X, Y, Z, tcut, tn);
+			const int refs[4] = { (int)R.x, (int)R.y, (int)R.z, (int)R.w };
+			// on to the nearest child that is hit, the others wait with their entry distances (selects only: no array is indexed at run time)
+			int best = -1, bestRef = kWideDone; float bt = FLT_MAX;
+#pragma unroll
+			for (int k = 0; k < 4; k++) { const bool nearer = ((mask >> k) & 1u) && tn[k] < bt; bt = nearer ? tn[k] : bt; best = nearer ? k : best; bestRef = nearer ? refs[k] : bestRef; }
+#pragma unroll
+			for (int k = 0; k < 4; k++) if (((mask >> k) & 1u) && k != best && sp < kWideStackDev) { StackEnt e; e.ref = refs[k]; e.t = tn[k]; stack[sp++] = e; }
+			if (best >= 0) cur = bestRef;
+			else {
+				cur = kWideDone;
+				while (sp > 0) {
+					StackEnt e = stack[--sp];
+					if (e.t <= tcut) { cur = e.ref; break; }
+				}
+			}
+		}
+		if (cur == kWideDone) break;
+		{
+			const int pos = (~cur) >> 1;                  // single-triangle leaves
+			TriV tri = load_tri(S.tris, pos);
+			float t;
+			if (moller_trumbore(tri, o, d, t)) {
+				if ((t < bestT || (t == bestT && pos < bestPos)) && ref_leaf_box_passes<OCT>(S, rb, pos, FLT_MAX)) {
+					bestT = t; bestPos = pos; tcut = t * kPruneSlack;
+				}
+			}
+		}
+		cur = kWideDone;
+		while (sp > 0) {
+			StackEnt e = stack[--sp];
+			if (e.t <= tcut) { cur = e.ref; break; }
+		}
+		if (cur == kWideDone) break;
+	}
+}
+
+template <int OCT>
+RTO_DEV bool bvh_any_wide_loop(const BvhDev& S, const RayBox& rb, const WideRay& wr, V3 o, V3 d) {
+	int stackRef[kWideStackDev];
+	int sp = 0;
+	int cur = S.wideRoot;
+	while (true) {
+		if (cur >= 0) {
+			const uint4* n = S.wide + 4 * (size_t)cur;
+			const uint4 X = RTO_LDG(n), Y = RTO_LDG(n + 1), Z = RTO_LDG(n + 2), R = RTO_LDG(n + 3);
+			float tn[4];
+			const unsigned mask = wide_test<OCT>(wr, X, Y, Z, FLT_MAX, tn);
+			const int refs[4] = { (int)R.x, (int)R.y, (int)R.z, (int)R.w };
+			int best = -1, bestRef = kWideDone; float bt = FLT_MAX;
+#pragma unroll
+			for (int k = 0; k < 4; k++) { const bool nearer = ((mask >> k) & 1u) && tn[k] < bt; bt = nearer ? tn[k] : bt; best = nearer ? k : best; bestRef = nearer ? refs[k] : bestRef; }
+#pragma unroll
+			for (int k = 0; k < 4; k++) if (((mask >> k) & 1u) && k != best && sp < kWideStackDev) stackRef[sp++] = refs[k];
+			if (best >= 0) { cur = bestRef; continue; }
+		}
+		else {
+			const int pos = (~cur) >> 1;
+			TriV tri = load_tri(S.tris, pos);
+			float t;
+			if (moller_trumbore(tri, o, d, t) && ref_leaf_box_passes<OCT>(S, rb, pos, FLT_MAX)) return true;
+		}
+		if (sp == 0) break;
+		cur = stackRef[--sp];
+	}
+	return false;
+}
+
+// rays admitted to the fused tests (oct < 8) whose wide constants are finite walk the wide form; false: the caller goes on with the binary form
+template <bool WIDE>
+RTO_DEV bool bvh_closest_wide(const BvhDev& S, const RayBox& rb, int oct, V3 o, V3 d, float& bestT, int& bestPos) {
+	if (!WIDE || oct >= kOctGeneric || !S.wide) return false;
+	WideRay wr;
+	if (!make_wideray(S, rb, wr)) return false;
+	switch (oct) {
+	case 0: bvh_closest_wide_loop<0>(S, rb, wr, o, d, bestT, bestPos); break;
+	case 1: bvh_closest_wide_loop<1>(S, rb, wr, o, d, bestT, bestPos); break;
+	case 2: bvh_closest_wide_loop<2>(S, rb, wr, o, d, bestT, bestPos); break;
+	case 3: bvh_closest_wide_loop<3>(S, rb, wr, o, d, bestT, bestPos); break;
+	case 4: bvh_closest_wide_loop<4>(S, rb, wr, o, d, bestT, bestPos); break;
+	case 5: bvh_closest_wide_loop<5>(S, rb, wr, o, d, bestT, bestPos); break;
+	case 6: bvh_closest_wide_loop<6>(S, rb, wr, o, d, bestT, bestPos); break;
+	default: bvh_closest_wide_loop<7>(S, rb, wr, o, d, bestT, bestPos); break;
+	}
+	return true;
+}
+template <bool WIDE>
+RTO_DEV bool bvh_any_wide(const BvhDev& S, const RayBox& rb, int oct, V3 o, V3 d, bool& hit) {
+	if (!WIDE || oct >= kOctGeneric || !S.wide) return false;
+	WideRay wr;
+	if (!make_wideray(S, rb, wr)) return false;
+	switch (oct) {
+	case 0: hit = bvh_any_wide_loop<0>(S, rb, wr, o, d); break;
+	case 1: hit = bvh_any_wide_loop<1>(S, rb, wr, o, d); break;
+	case 2: hit = bvh_any_wide_loop<2>(S, rb, wr, o, d); break;
+	case 3: hit = bvh_any_wide_loop<3>(S, rb, wr, o, d); break;
+	case 4: hit = bvh_any_wide_loop<4>(S, rb, wr, o, d); break;
+	case 5: hit = bvh_any_wide_loop<5>(S, rb, wr, o, d); break;
+	case 6: hit = bvh_any_wide_loop<6>(S, rb, wr, o, d); break;
+	default: hit = bvh_any_wide_loop<7>(S, rb, wr, o, d); break;
+	}
+	return true;
+}
+
 // Closest hit.  Result = min over the reference's candidate set of (t, position in candidate order), i.e. the
 // oracle's "strict <, first candidate wins".  PRUNE: near-child-first order and subtrees entered only while their
 // box entry <= best * kPruneSlack.  !PRUNE: every box the reference's queryNode would test is tested.
@@ -402,7 +588,7 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 #endif
 }
 
-template <bool PRUNE>
+template <bool PRUNE, bool WIDE = false>
 RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos) {
 	bestT = kMissT; bestPos = -1;
 	if (S.numTris <= 0) return;
@@ -410,7 +596,9 @@ RTO_DEV void bvh_closest(const BvhDev& S, V3 o, V3 d, float& bestT, int& bestPos
 	float te;
 	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return;
 	if (!PRUNE) { bvh_closest_loop<false, kOctGeneric>(S, rb, o, d, bestT, bestPos); return; }      // verification path: one generic loop
-	switch (ray_octant(S, rb)) {
+	const int oct = ray_octant(S, rb);
+	if (WIDE && PRUNE && bvh_closest_wide<WIDE>(S, rb, oct, o, d, bestT, bestPos)) return;
+	switch (oct) {
 	case 0: bvh_closest_loop<PRUNE, 0>(S, rb, o, d, bestT, bestPos); break;
 	case 1: bvh_closest_loop<PRUNE, 1>(S, rb, o, d, bestT, bestPos); break;
 	case 2: bvh_closest_loop<PRUNE, 2>(S, rb, o, d, bestT, bestPos); break;
@@ -502,12 +690,15 @@ RTO_DEV bool bvh_any_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d) {
 #endif
 }
 
+template <bool WIDE = false>
 RTO_DEV bool bvh_any(const BvhDev& S, V3 o, V3 d) {
 	if (S.numTris <= 0) return false;
 	RayBox rb = make_raybox(o, d);
 	float te;
 	if (!slab_ref(rb, S.rootLo[0], S.rootLo[1], S.rootLo[2], S.rootHi[0], S.rootHi[1], S.rootHi[2], te)) return false;
-	switch (ray_octant(S, rb)) {
+	const int oct = ray_octant(S, rb);
+	if (WIDE) { bool hit; if (bvh_any_wide<WIDE>(S, rb, oct, o, d, hit)) return hit; }
+	switch (oct) {
 	case 0: return bvh_any_loop<0>(S, rb, o, d);
 	case 1: return bvh_any_loop<1>(S, rb, o, d);
 	case 2: return bvh_any_loop<2>(S, rb, o, d);
@@ -1175,7 +1366,7 @@ RTO_DEV void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, floa
                                   // 10 blocks 1.716 / 1.187 / 2.573 / 0.493 ms, 12 blocks (40 registers) 1.732 / 1.217 / 2.570 / 0.506, 8 blocks (58 registers, no
                                   // spills) 1.838 / 1.224 / 2.857 / 0.503; 14-16 blocks (32 registers) is slower still
 #endif
-template <bool SHADOWS, bool PRUNE>
+template <bool SHADOWS, bool PRUNE, bool WIDE = false>
 __global__ void __launch_bounds__(kRenderThreads, RTO_BVH_MIN_BLOCKS * 128 / kRenderThreads) k_render_bvh(BvhDev S, RenderArgs A) {
 	RtoCamera cam = A.cam0;
 	if (A.cams) cam = A.cams[blockIdx.z];
@@ -1183,7 +1374,7 @@ __global__ void __launch_bounds__(kRenderThreads, RTO_BVH_MIN_BLOCKS * 128 / kRe
 	if (!pixel_of_thread(A, cam, px, py, pix)) return;
 	Ray ray = gen_ray(cam, px, py);
 	float bestT; int bestPos;
-	bvh_closest<PRUNE>(S, ray.o, ray.d, bestT, bestPos);
+	bvh_closest<PRUNE, WIDE>(S, ray.o, ray.d, bestT, bestPos);
 	V3 color = mk3(0.0f, 0.0f, 0.0f);
 	int id = -1;
 	if (bestPos >= 0) {
@@ -1197,7 +1388,7 @@ __global__ void __launch_bounds__(kRenderThreads, RTO_BVH_MIN_BLOCKS * 128 / kRe
 		if (SHADOWS) {
 			V3 so = hit + n * A.shadowBias;
 			V3 sd = normalize3(mk3(1.0f, 1.0f, 1.0f));
-			shadowed = bvh_any(S, so, sd);
+			shadowed = bvh_any<WIDE>(S, so, sd);
 		}
 		color = shadowed ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
 		if (A.codes) __stcs(A.codes + code_index(A), (uint32_t)(bestPos + 1) | (flip ? kCodeFlipBit : 0u) | (shadowed ? kCodeShadowBit : 0u));

@@ -39,6 +39,8 @@ def lib():
         L.emu_bvh_create.restype = vp
         L.emu_bvh_create.argtypes = [vp, sz]
         L.emu_bvh_free.argtypes = [vp]
+        L.emu_bvh_wide_nodes.argtypes = [vp]
+        L.emu_bvh_wide_nodes.restype = i32
         L.emu_render_bvh.argtypes = [vp, vp, C.c_uint, f32, i32, i32, vp, vp, vp]
         _lib = L
     return _lib
@@ -79,6 +81,12 @@ class Bvh:
         self.tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
         self.h = lib().emu_bvh_create(_p(self.tris), len(self.tris))
         assert self.h
+
+    WIDE = 0x100            # render(): walk the 4-wide quantised form (present when the Bvh was created with RTO_BVH_WIDE=1)
+
+    @property
+    def wide_nodes(self):
+        return lib().emu_bvh_wide_nodes(self.h)
 
     def render(self, cam, flags=0, bias=0.0, y0=0, y1=None):
         y1 = cam.height if y1 is None else y1

@@ -63,7 +63,7 @@ void* emu_bvh_create(const RtoTriangle* tris, size_t n) {
 	if (rto_host_bvh_build(e->tris.data(), n, &hb) != RTO_OK) { delete e; return nullptr; }
 	rto_build_bvh_layout(*hb, e->L);
 	rto_host_bvh_free(hb);
-	BvhDev D;
+	BvhDev D{};
 	D.numTris = (int)n; D.rootRef = e->L.refRoot;
 	for (int k = 0; k < 3; k++) { D.rootLo[k] = e->L.rootLo[k]; D.rootHi[k] = e->L.rootHi[k]; }
 	D.nodes = (const float4*)e->L.refNodes.data(); D.tris = (const float4*)e->L.tris.data();
@@ -71,9 +71,14 @@ void* emu_bvh_create(const RtoTriangle* tris, size_t n) {
 	D.exactNodes = D.nodes; D.exactRoot = D.rootRef; D.exactLeafBox = 0;
 	e->ref = D; e->fast = D;
 	if (!e->L.fastNodes.empty()) { e->fast.nodes = (const float4*)e->L.fastNodes.data(); e->fast.rootRef = e->L.fastRoot; e->fast.leafBox = 1; e->fast.grow = e->L.fastGrow; e->fast.paired = 1; }
+	if (!e->L.wideNodes.empty() && e->L.wideRoot >= 0) {      // (built when RTO_BVH_WIDE=1 is set at creation)
+		e->fast.wide = (const uint4*)e->L.wideNodes.data(); e->fast.wideRoot = e->L.wideRoot; e->fast.wideStep = e->L.wideStep;
+		for (int k = 0; k < 3; k++) e->fast.wideLo[k] = e->L.wideLo[k];
+	}
 	return e;
 }
 void emu_bvh_free(void* h) { delete (EmuBvh*)h; }
+int emu_bvh_wide_nodes(void* h) { return (int)(((EmuBvh*)h)->L.wideNodes.size() / 16); }
 
 void emu_render_bvh(void* h, const RtoCamera* cam, unsigned flags, float bias, int y0, int y1, float* rgba, int32_t* ids, float* t) {
 	EmuBvh* e = (EmuBvh*)h;
@@ -84,7 +89,9 @@ void emu_render_bvh(void* h, const RtoCamera* cam, unsigned flags, float bias, i
 			size_t pix = (size_t)(py - y0) * cam->width + px;
 			Ray ray = gen_ray(*cam, px, py);
 			float bestT; int bestPos;
-			if (prune) bvh_closest<true>(S, ray.o, ray.d, bestT, bestPos); else bvh_closest<false>(S, ray.o, ray.d, bestT, bestPos);
+			const bool wide = prune && (flags & 0x100u) && S.wide;      // the 4-wide quantised form of the same tree
+			if (wide) bvh_closest<true, true>(S, ray.o, ray.d, bestT, bestPos);
+			else if (prune) bvh_closest<true>(S, ray.o, ray.d, bestT, bestPos); else bvh_closest<false>(S, ray.o, ray.d, bestT, bestPos);
 			V3 color = mk3(0.0f, 0.0f, 0.0f); int id = -1;
 			if (bestPos >= 0) {
 				TriV tri = load_tri(S.tris, bestPos);
@@ -94,7 +101,7 @@ void emu_render_bvh(void* h, const RtoCamera* cam, unsigned flags, float bias, i
 				if (dot3(n, ray.d) > 0.0f) n = -n;
 				V3 hp = ray.o + ray.d * bestT;
 				bool shadowed = false;
-				if (flags & RTO_FLAG_SHADOWS) shadowed = bvh_any(S, hp + n * bias, normalize3(mk3(1.0f, 1.0f, 1.0f)));
+				if (flags & RTO_FLAG_SHADOWS) shadowed = wide ? bvh_any<true>(S, hp + n * bias, normalize3(mk3(1.0f, 1.0f, 1.0f))) : bvh_any(S, hp + n * bias, normalize3(mk3(1.0f, 1.0f, 1.0f)));
 				color = shadowed ? mk3(0.1f, 0.1f, 0.1f) : shade_lambert(n);
 			}
 			if (rgba) { rgba[4 * pix] = color.x; rgba[4 * pix + 1] = color.y; rgba[4 * pix + 2] = color.z; rgba[4 * pix + 3] = 1.0f; }

@@ -105,3 +105,30 @@ def test_emu_axis_parallel_and_zero_direction_rays(rto, emu, checker):
     ta, ia = oc.trace(o, d, rto.MODE_OCTREE_GLSL, count=True)
     tb, ib = oc.trace(o, d, rto.MODE_OCTREE_GLSL, count=False)
     assert_bit_equal(ta, tb, "mode B per-node vs batched"); assert np.array_equal(ia, ib)
+
+
+def test_emu_wide_quantised_tree_gives_the_same_frames(rto, emu, checker, monkeypatch):
+    """The 4-wide form of the production tree (16-bit boxes on one grid, dequantised by one fused multiply-add per plane) decides
+    nothing by itself: candidates are settled at the leaves, so ids, t and colours equal the binary form's -- and the oracle's -- bit
+    for bit, from outside, from inside the mesh, along axes, and for scenes far from the origin (where the margin of the quantised
+    boxes is set by the size of the coordinates, not by the size of the scene)."""
+    monkeypatch.setenv("RTO_BVH_WIDE", "1")
+    for shift, dim in (((0.0, 0.0, 0.0), 24), ((5.0e4, -3.0e4, 7.0e4), 16)):
+        grid = rto.generate_test_volume(dim)
+        gm = tuple(float(np.float32(grid.min[i]) + np.float32(shift[i])) for i in range(3))
+        grid = rto.VoxelGrid(grid.dims, gm, grid.voxel_size, grid.data)
+        nodes = rto.create_octree_from_voxel_grid(grid)
+        tris = rto.marching_cubes_mesh(grid, nodes)
+        bv = emu.Bvh(tris)
+        assert bv.wide_nodes > len(tris) // 8, "no wide tree was built"
+        m_ref = checker.mesh(tris); m_ref.build()
+        tgt = tuple(gm[i] + 0.5 for i in range(3))
+        bias = 1e-3 * grid.voxel_size
+        for (th, ph, r, w, h) in ((30, 40, 1.2, 80, 60), (0, 0, 1.5, 48, 48), (-60, 200, 0.3, 48, 36), (89, 10, 2.0, 40, 40)):
+            cam, _ = rto.Camera.from_degrees(th, ph, r, tgt).consts(45.0, float(np.float32(w) / np.float32(h)), w, h)
+            rcam, _ = checker.camera(th, ph, r, target=tgt, width=w, height=h)
+            for flags in (0, 1):
+                want = m_ref.render(rcam, flags, bias)
+                _same(bv.render(cam, flags, bias), want, "binary form")
+                _same(bv.render(cam, flags | emu.Bvh.WIDE, bias), want, "wide form, shift %s camera %s" % (shift, (th, ph, r)))
+        m_ref.free()
