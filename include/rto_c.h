@@ -289,7 +289,7 @@ RTO_API int rto_render_codes(RtoScene* scene, const RtoCamera* cams, int numCams
 RTO_API int rto_resolve_codes(RtoScene* scene, const RtoCamera* cams, int numCams, int y0, int y1, const uint32_t* codes, size_t firstFrame,
 	const RtoFrame* frame /* planes indexed from (frame 0 of this call, row y0) */, void* stream);
 
-/* Exchange memory: a device buffer GPUs of the same box write hit codes into.  Same process: allocate on the receiving device and let
+/* Exchange memory: a zero-filled device buffer GPUs of the same box write hit codes into.  Same process: allocate on the receiving device and let
  * the senders enable peer access (rto_group_* does).  Other processes (one process per GPU): pass the 64-byte handle over any channel and
  * map it with rto_exchange_open (CUDA IPC; the mapping is an ordinary device pointer for rto_render_codes). */
 typedef struct RtoIpcHandle { unsigned char bytes[64]; } RtoIpcHandle;

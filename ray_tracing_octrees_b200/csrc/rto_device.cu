@@ -517,6 +517,8 @@ extern "C" int rto_exchange_alloc(size_t bytes, void** devPtr, RtoIpcHandle* han
 	void* p = nullptr;
 	cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
 	if (e != cudaSuccess) return rto_fail(RTO_ERR_ALLOC, "rto_exchange_alloc: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	e = cudaMemset(p, 0, bytes ? bytes : 256);                       // signal words start at 0; hit codes at "miss"
+	if (e != cudaSuccess) { cudaFree(p); return rto_fail(RTO_ERR_CUDA, "rto_exchange_alloc: cudaMemset failed: %s", cudaGetErrorString(e)); }
 	if (handleOut) {
 		cudaIpcMemHandle_t h;
 		e = cudaIpcGetMemHandle(&h, p);

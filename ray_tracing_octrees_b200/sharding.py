@@ -217,6 +217,7 @@ class GatheredRenderer:
         if self.timing:
             self.t_begin.record(self.main)
         if self.rank == 0:
+            self.main.wait_event(self.resolved[par])                   # the plane set this batch goes into was last written two batches ago
             for (f, k, y0, y1) in split_rows(g0, g1, H):
                 off = (f * H + y0) * W
                 sub = (rto.RtoCamera * k).from_buffer(cams, f * C_sizeof_cam(rto))
@@ -274,6 +275,8 @@ class GatheredRenderer:
             self.main.wait_event(self.resolved[1])
 
     def close(self):
+        self.torch.cuda.synchronize()
+        self.dist.barrier()                                            # nobody unmaps a buffer a peer may still be writing into
         self.torch.cuda.synchronize()
         for b in list(self.remote) + list(self.local):
             if b is not None:

@@ -1,6 +1,6 @@
 """One process per GPU (torch.distributed over NCCL, as bench.py runs under torchrun): frames traced by all ranks and delivered on
 rank 0 (sharding.GatheredRenderer) equal a local render bit for bit, with hit codes written through CUDA-IPC peer mappings and with
-the NCCL fallback.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a single-GPU box, where tests/test_gpu_codes.py covers the same
+the NCCL send/receive fallback.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a single-GPU box, where tests/test_gpu_codes.py covers the same
 kernels, the IPC mapping between two processes and the device group."""
 import os
 import socket
@@ -61,7 +61,7 @@ def _worker(rank, world, port, transport, q):
                     if not same:
                         msg += "plane set %d %s differs; " % (pi, key)
             ok = ok and float((ref["id"] >= 0).float().mean()) > 0.2
-        want = "nccl" if transport == "nccl" else gr.transport
+        want = transport if transport != "auto" else gr.transport
         ok = ok and gr.transport == want and len(hist) == 2 and len(hist[0]) == world
         q.put((rank, ok, gr.transport, msg))
         gr.close()
