@@ -10,6 +10,7 @@
 //            (-fmad=false), so the triangle array equals rto_host_mc_mesh's bit for bit.
 // Memory traffic, not arithmetic, bounds all of it (bytes in, bytes out, a few passes); see DESIGN.md section 5.
 #include "rto_scene.cuh"
+#include "rto_sahchunk.h"
 #include "mc_tables.h"
 #include "rto_voxelize.h"
 #include "rto_frustum.h"
@@ -659,7 +660,8 @@ __device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ codes, in
 }
 
 // Karras 2012: internal node i of the binary radix tree over the sorted leaves; child refs into the node, parent links for the fit pass
-__global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int perLeaf, int numLeaves, size_t numTris, float4* __restrict__ nodes, int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf) {
+__global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int perLeaf, int numLeaves, size_t numTris, float4* __restrict__ nodes, int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf,
+	int2* __restrict__ rangeOf /* may be null: [first, last] leaf of every internal node */) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= numLeaves - 1) return;
 	const int d = (lbvh_delta(codes, perLeaf, numLeaves, i, i + 1) - lbvh_delta(codes, perLeaf, numLeaves, i, i - 1)) >= 0 ? 1 : -1;
@@ -677,6 +679,7 @@ __global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int perLeaf, int
 	}
 	const int gamma = i + s * d + min(d, 0);
 	const int first = min(i, j), last = max(i, j);
+	if (rangeOf) rangeOf[i] = make_int2(first, last);
 	auto leafRef = [&](int leaf) {
 		const size_t p = perLeaf * (size_t)leaf;
 		const int cnt = (perLeaf == 2 && p + 1 < numTris) ? 2 : 1;
@@ -687,6 +690,26 @@ __global__ void k_lbvh_tree(const uint64_t* __restrict__ codes, int perLeaf, int
 	if (gamma + 1 == last) { r1 = leafRef(gamma + 1); parentOfLeaf[gamma + 1] = 2 * i + 1; } else { r1 = gamma + 1; parentOfInner[gamma + 1] = 2 * i + 1; }
 	nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(r0), __int_as_float(r1), 0.0f, 0.0f);
 	if (i == 0) parentOfInner[0] = -1;
+}
+
+// the subtrees the surface-area rebuild takes (rto_sahchunk.h): at most kSahChunk leaves, and the parent has more
+__global__ void k_sah_select(int numInner, const int2* __restrict__ rangeOf, const int* __restrict__ parentOfInner, int* __restrict__ list, int* __restrict__ count) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= numInner) return;
+	const int2 r = rangeOf[i];
+	const int m = r.y - r.x + 1;
+	if (m < 3 || m > kSahChunk) return;
+	const int link = parentOfInner[i];
+	if (link >= 0) { const int2 pr = rangeOf[link >> 1]; if (pr.y - pr.x + 1 <= kSahChunk) return; }
+	list[atomicAdd(count, 1)] = i;
+}
+__global__ void __launch_bounds__(64) k_sah_rebuild(int count, const int* __restrict__ list, const int2* __restrict__ rangeOf, const float* __restrict__ leafBox, float4* __restrict__ nodes,
+	int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count) return;
+	const int i = list[t];
+	const int2 r = rangeOf[i];
+	sah_rebuild_chunk(leafBox, r.x, r.y, i, nodes, parentOfInner, parentOfLeaf);
 }
 
 __device__ __forceinline__ void lbvh_store_child_box(float* node16, int slot, const float lo[3], const float hi[3]) {
@@ -791,7 +814,22 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 		BUILD_TRY(tmp.alloc(&pInner, numInner)); BUILD_TRY(tmp.alloc(&pLeaf, numLeaves)); BUILD_TRY(tmp.alloc(&arrived, numInner)); BUILD_TRY(tmp.alloc(&dDepth, 1));
 		BUILD_TRY(cudaMemsetAsync(arrived, 0, sizeof(int) * (size_t)numInner, st));
 		BUILD_TRY(cudaMemsetAsync(dDepth, 0, sizeof(int), st));
-		k_lbvh_tree<<<(unsigned)((numInner + 255) / 256), 256, 0, st>>>(codesSorted, perLeaf, numLeaves, numTris, (float4*)dNodes, pInner, pLeaf);
+		// the radix tree's top, surface-area splits below (rto_sahchunk.h); RTO_LBVH_SAH=0 keeps the plain radix tree (tuning aid)
+		static const bool sahBottom = [] { const char* e = getenv("RTO_LBVH_SAH"); return !(e && e[0] == '0'); }();
+		int2* rangeOf = nullptr; int* chunkList = nullptr; int* chunkCount = nullptr;
+		if (sahBottom && perLeaf == 1) {
+			BUILD_TRY(tmp.alloc(&rangeOf, numInner)); BUILD_TRY(tmp.alloc(&chunkList, numInner)); BUILD_TRY(tmp.alloc(&chunkCount, 1));
+			BUILD_TRY(cudaMemsetAsync(chunkCount, 0, sizeof(int), st));
+		}
+		k_lbvh_tree<<<(unsigned)((numInner + 255) / 256), 256, 0, st>>>(codesSorted, perLeaf, numLeaves, numTris, (float4*)dNodes, pInner, pLeaf, rangeOf);
+		if (rangeOf) {
+			k_sah_select<<<(unsigned)((numInner + 255) / 256), 256, 0, st>>>(numInner, rangeOf, pInner, chunkList, chunkCount);
+			int chunks = 0;
+			BUILD_TRY(cudaMemcpyAsync(&chunks, chunkCount, sizeof(int), cudaMemcpyDeviceToHost, st));
+			BUILD_TRY(cudaStreamSynchronize(st));
+			if (chunks > 0) k_sah_rebuild<<<(unsigned)((chunks + 63) / 64), 64, 0, st>>>(chunks, chunkList, rangeOf, leafBox, (float4*)dNodes, pInner, pLeaf);
+			BUILD_TRY(cudaGetLastError());
+		}
 		k_lbvh_fit<<<blocksL, 256, 0, st>>>(numLeaves, leafBox, (float*)dNodes, pInner, pLeaf, arrived, dRoot, dDepth);
 		BUILD_TRY(cudaGetLastError());
 		int depth = 0;

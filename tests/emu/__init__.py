@@ -39,6 +39,8 @@ def lib():
         L.emu_bvh_create.restype = vp
         L.emu_bvh_create.argtypes = [vp, sz]
         L.emu_bvh_free.argtypes = [vp]
+        L.emu_sah_chunk.argtypes = [vp, i32, i32, i32]
+        L.emu_sah_chunk.restype = C.c_double
         L.emu_bvh_wide_nodes.argtypes = [vp]
         L.emu_bvh_wide_nodes.restype = i32
         L.emu_render_bvh.argtypes = [vp, vp, C.c_uint, f32, i32, i32, vp, vp, vp]
@@ -94,3 +96,9 @@ class Bvh:
         out = dict(rgba=np.empty((n, 4), np.float32), id=np.empty(n, np.int32), t=np.empty(n, np.float32))
         lib().emu_render_bvh(self.h, C.byref(cam), flags, bias, y0, y1, _p(out["rgba"]), _p(out["id"]), _p(out["t"]))
         return out
+
+
+def sah_chunk(leaf_boxes, first=0, root_at_end=False):
+    """rto_sahchunk.h on the CPU over (m, 6) leaf boxes -> sum of the half areas of the rebuilt subtree's boxes (negative: broken tree)."""
+    b = np.ascontiguousarray(leaf_boxes, np.float32).reshape(-1, 6)
+    return float(lib().emu_sah_chunk(_p(b), len(b), first, 1 if root_at_end else 0))

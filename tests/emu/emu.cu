@@ -2,7 +2,9 @@
 // on the CPU over the product's own device layouts (host_layouts.cpp), pixel by pixel.  Purpose: find logic errors
 // (wrong links, endless walks, mismatches against the oracle) in this GPU-less container before spending GPU minutes.
 // This is NOT a fallback: it is not part of librto.so and nothing in the package loads it.
+#include <functional>
 #include "../../ray_tracing_octrees_b200/csrc/rto_kernels.cuh"
+#include "../../ray_tracing_octrees_b200/csrc/rto_sahchunk.h"
 #include <cstdarg>
 #include <cstdio>
 #include <vector>
@@ -108,6 +110,59 @@ void emu_render_bvh(void* h, const RtoCamera* cam, unsigned flags, float bias, i
 			if (ids) ids[pix] = id;
 			if (t) t[pix] = bestT;
 		}
+}
+
+// rto_sahchunk.h on the CPU: rebuild one subtree over m leaves placed at leaf offset `first`, with its root on the first or on the
+// last index of its range, and check the result as a tree: every leaf exactly once, every owned slot exactly once, parent links
+// consistent, nothing written outside the owned slots.  Returns the sum of the half areas of all internal boxes (the quantity the
+// splits minimise), or a negative error code.
+double emu_sah_chunk(const float* leafBox6, int m, int first, int rootAtEnd) {
+	const int last = first + m - 1, root = rootAtEnd ? last : first;
+	const int total = last + 8;
+	std::vector<float> boxes((size_t)total * 6, 0.0f);
+	std::memcpy(&boxes[(size_t)first * 6], leafBox6, sizeof(float) * 6 * m);
+	std::vector<float4> nodes((size_t)total * 4, make_float4(-7.0f, -7.0f, -7.0f, -7.0f));
+	std::vector<int> pInner(total, -7), pLeaf(total, -7);
+	sah_rebuild_chunk(boxes.data(), first, last, root, nodes.data(), pInner.data(), pLeaf.data());
+	const int slotLo = rootAtEnd ? first + 1 : first, slotHi = rootAtEnd ? last : last - 1;
+	for (int i = 0; i < total; i++) {
+		const bool owned = i >= slotLo && i <= slotHi;
+		if (!owned && (nodes[4 * (size_t)i + 3].x != -7.0f || (pInner[i] != -7))) return -1;             // wrote outside its slots
+		if (owned && nodes[4 * (size_t)i + 3].x == -7.0f && nodes[4 * (size_t)i + 3].y == -7.0f) return -2;  // a slot was left unused
+		if ((i < first || i > last) && pLeaf[i] != -7) return -3;
+	}
+	if (pInner[root] != -7) return -4;                                                                      // the root's own link belongs to the radix tree above
+	std::vector<int> seenLeaf(total, 0), seenNode(total, 0);
+	double cost = 0;
+	struct Fr { int node; };
+	std::vector<int> st{ root };
+	std::vector<SahBox> box(total);
+	// post-order via explicit recursion
+	std::function<SahBox(int, int, int)> walk = [&](int ref, int parent, int side) -> SahBox {
+		SahBox b; sah_box_reset(b);
+		if (ref < 0) {
+			const int leaf = (~ref) >> 1;
+			if (leaf < first || leaf > last || ((~ref) & 1)) { cost = -5; return b; }
+			if (seenLeaf[leaf]++) { cost = -6; return b; }
+			if (pLeaf[leaf] != 2 * parent + side) { cost = -7; return b; }
+			sah_box_add(b, &boxes[(size_t)leaf * 6]);
+			return b;
+		}
+		if (ref < slotLo || ref > slotHi) { cost = -8; return b; }
+		if (seenNode[ref]++) { cost = -9; return b; }
+		if (ref != root && pInner[ref] != 2 * parent + side) { cost = -10; return b; }
+		int r0, r1; std::memcpy(&r0, &nodes[4 * (size_t)ref + 3].x, 4); std::memcpy(&r1, &nodes[4 * (size_t)ref + 3].y, 4);
+		SahBox l = walk(r0, ref, 0); if (cost < 0) return b;
+		SahBox r = walk(r1, ref, 1); if (cost < 0) return b;
+		b = l; sah_box_join(b, r);
+		cost += sah_half_area(b);
+		return b;
+	};
+	walk(root, -1, 0);
+	if (cost < 0) return cost;
+	for (int i = first; i <= last; i++) if (seenLeaf[i] != 1) return -11;
+	for (int i = slotLo; i <= slotHi; i++) if (seenNode[i] != 1) return -12;
+	return cost;
 }
 
 } // extern "C"

@@ -132,3 +132,33 @@ def test_emu_wide_quantised_tree_gives_the_same_frames(rto, emu, checker, monkey
                 _same(bv.render(cam, flags, bias), want, "binary form")
                 _same(bv.render(cam, flags | emu.Bvh.WIDE, bias), want, "wide form, shift %s camera %s" % (shift, (th, ph, r)))
         m_ref.free()
+
+
+def test_emu_surface_area_rebuild_of_radix_subtrees(rto, emu):
+    """rto_sahchunk.h, the per-thread surface-area rebuild of the bottom of the device-built BVH, on the CPU: for every size and for both
+    places the subtree's root can sit, the result is a binary tree over exactly the given leaves inside exactly the slots the radix
+    subtree owned (checked by emu_sah_chunk), and its boxes are smaller in total than those of halving the Morton-sorted list."""
+    rng = np.random.default_rng(3)
+
+    def halving_cost(boxes):
+        if len(boxes) == 1:
+            return 0.0
+        lo, hi = boxes[:, :3].min(0), boxes[:, 3:].max(0)
+        d = (hi - lo).astype(np.float64)
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0] + halving_cost(boxes[:len(boxes) // 2]) + halving_cost(boxes[len(boxes) // 2:])
+    for m in (2, 3, 4, 5, 7, 16, 33, 100, 255, 256, 1000, 4096):
+        for kind in ("random", "plane", "identical", "line"):
+            c = rng.random((m, 3)).astype(np.float32)
+            if kind == "plane":
+                c[:, 1] = 0.25
+            elif kind == "identical":
+                c[:] = 0.5
+            elif kind == "line":
+                c[:, 1:] = c[:, :1]
+            h = (rng.random((m, 3)) * 0.02).astype(np.float32)
+            boxes = np.concatenate([c - h, c + h], 1).astype(np.float32)
+            for end in (False, True):
+                cost = emu.sah_chunk(boxes, first=int(rng.integers(0, 50)), root_at_end=end)
+                assert cost >= 0, "broken tree (code %g) for m=%d %s root_at_end=%s" % (cost, m, kind, end)
+                if kind == "random" and m >= 16:
+                    assert cost < 0.9 * halving_cost(boxes), "surface-area splits no better than halving a random list (m=%d)" % m
