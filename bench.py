@@ -395,8 +395,11 @@ def run_ours(args, rank, world, local_rank):
         "definition": "algorithmic flops of the REFERENCE's structures (SURVEY.md 8d) per launch / kernel time; the production tree does fewer box and triangle tests than counted",
         "hbm": {"achieved_GBps": (traffic / ksec / 1e9) if traffic else None, "peak_GBps": hbm_peak, "frac": (traffic / ksec / 1e9 / hbm_peak) if traffic else None,
                 "peak_source": peak_src, "compulsory_bytes_per_launch": prim * 24, "source": "profiles/r02_bvh_counters.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None},
-        "ncu": {k: counters.get(k) for k in ("issue_active_pct", "lanes_per_instruction", "alu_pipe_pct", "fma_pipe_pct", "l1_hit_pct", "l2_hit_pct",
-                                             "l2_throughput_pct", "dram_throughput_pct", "warp_instructions", "source")} if counters else None,
+        # utilisations ncu measured for this kernel (percent of each unit's own peak): the two highest -- L1/TEX throughput and issue slots --
+        # are what the kernel is bound by; L2 and DRAM are far from theirs
+        "ncu": {k: counters.get(k) for k in ("l1_throughput_pct", "issue_active_pct", "alu_pipe_pct", "fma_pipe_pct", "lsu_pipe_pct", "lanes_per_instruction",
+                                             "long_scoreboard_warps_per_issue", "l1_hit_pct", "l2_hit_pct", "l2_throughput_pct", "dram_throughput_pct",
+                                             "warp_instructions", "source")} if counters else None,
         "algorithmic_intensity": {"bytes_per_launch": alg_bytes, "GBps": alg_bytes / ksec / 1e9, "flops_per_launch": alg_flops,
                                   "note": "reference-defined bytes, served from L1/L2; not a fraction of any limit"},
         "per_primary_ray": {"box_tests": st[0] / prim, "candidates": st[1] / prim}, "shadow_rays_per_launch": st[4]}

@@ -68,7 +68,17 @@ def summarise(rep):
         traffic = to_bytes(*got["dram__bytes_read.sum"]) + to_bytes(*got["dram__bytes_write.sum"])
         lines.append("")
         lines.append("DRAM traffic per launch: %.1f MB (read + write)" % (traffic / 1e6))
-    return "\n".join(lines) + "\n", traffic
+    def num(key):
+        return float(got[key][0].replace(",", "")) if key in got else None
+    counters = {"kernel": vals[hdr.index("Kernel Name")], "grid": vals[hdr.index("Grid Size")], "ncu_ms": num("gpu__time_duration.sum"),
+                "dram_bytes_per_launch": int(traffic) if traffic else None, "warp_instructions": num("smsp__inst_executed.sum"),
+                "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"), "lanes_per_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "alu_pipe_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "lsu_pipe_pct": num("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"), "l1_hit_pct": num("l1tex__t_sector_hit_rate.pct"),
+                "l1_throughput_pct": num("l1tex__throughput.avg.pct_of_peak_sustained_active"), "l2_hit_pct": num("lts__t_sector_hit_rate.pct"),
+                "l2_throughput_pct": num("lts__throughput.avg.pct_of_peak_sustained_elapsed"), "dram_throughput_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "long_scoreboard_warps_per_issue": num("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio")}
+    return "\n".join(lines) + "\n", traffic, counters
 
 
 def main():
@@ -81,10 +91,13 @@ def main():
         name = os.path.basename(rep)[5:-8]
         if name in ("bvh_pt", "bvh_warp", "bvh_r1", "oct_A_fast", "oct_B"):
             continue                                         # captures of variants that were removed; summarised by hand in README.md
-        text, traffic = summarise(rep)
+        text, traffic, counters = summarise(rep)
         out = os.path.join(ROOT, "profiles", "%s_%s_%s_full.txt" % (a.round, name, a.tag))
         open(out, "w").write(text)
         print("wrote", out)
+        if name == "bvh":
+            counters["source"] = "profiles/" + os.path.basename(out) + " (ncu --set full --clock-control none of one k_render_bvh<shadows,pruned> launch under bench.py)"
+            json.dump(counters, open(os.path.join(ROOT, "profiles", "%s_bvh_counters.json" % a.round), "w"), indent=1)
         if name == "bvh" and traffic:
             json.dump({"k_render_bvh_bytes_per_launch": int(traffic), "source": os.path.basename(out),
                        "what": "dram__bytes_read.sum + dram__bytes_write.sum of one k_render_bvh<shadows,pruned> launch (8 x 1080p frames), ncu --set full"},
