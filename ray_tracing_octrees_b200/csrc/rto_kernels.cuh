@@ -66,6 +66,17 @@ RTO_DEV int ffs32(unsigned v) {
 #ifndef RTO_RESOLVE_HOIST_RAY
 #define RTO_RESOLVE_HOIST_RAY 0
 #endif
+// Octree walks: a node whose children are used up hands back to its parent inside the same step instead of in a step of its own.
+// Measured on B200 (16 x 1080p per launch): mode A 512^3 city 8.377 -> 6.437 ms, DT 5.350 -> 4.357 (profiles/README.md, round 2).
+#ifndef RTO_OCTA_FOLD_ASCEND
+#define RTO_OCTA_FOLD_ASCEND 1
+#endif
+#ifndef RTO_OCTA_VOTE
+#define RTO_OCTA_VOTE 1
+#endif
+#ifndef RTO_OCTB_FOLD_ASCEND
+#define RTO_OCTB_FOLD_ASCEND 0
+#endif
 #ifndef RTO_BVH_ANY_WHILE_WHILE
 #define RTO_BVH_ANY_WHILE_WHILE 0
 #endif
@@ -1103,9 +1114,10 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 	bool entering = true;
 	unsigned M = 0;
 	while (true) {
-		const int h = size >> 1;
-		const unsigned leafMask = (unsigned)e.w & 0xffu, solidMask = ((unsigned)e.w >> 8) & 0xffu;
+		int h = size >> 1;
+		unsigned leafMask = (unsigned)e.w & 0xffu;
 		if (entering) {
+			const unsigned solidMask = ((unsigned)e.w >> 8) & 0xffu;
 			ChildPlanes P = oct_child_planes<OCT>(S, o, inv, x, y, z, h);
 			// "tNear < closestT" (closestT stays 1e30 until the hit that ends the walk) is folded into the far distance of one axis:
 			// tn <= tf && tf > 0 && tn < 1e30  <=>  tn <= min(tf, kBelowMissT) && min(tf, kBelowMissT) > 0
@@ -1124,6 +1136,25 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 			pos = 8;
 		}
 		unsigned below = M & ((1u << pos) - 1u);
+#if RTO_OCTB_FOLD_ASCEND
+		// climbs happen inside the iteration (see octA_step): the lanes of a warp run this loop in lockstep, and a lane that hands back
+		// through k levels would otherwise pay k iterations, each as long as the classification some other lane runs in it
+		bool out = false;
+		while (below == 0u) {                                  // the remaining `pos` children are popped, tested and dropped
+			steps += pos;
+			if (steps >= 512 || level == 0) { out = true; break; }
+			pos = ((unsigned)e.w >> 16) & 7u;
+			rank = e.z;
+			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
+			level--;
+			M = maskS[level];
+			e = RTO_LDG(S.inner + rank);
+			below = M & ((1u << pos) - 1u);
+		}
+		if (out) break;
+		h = size >> 1;
+		leafMask = (unsigned)e.w & 0xffu;
+#else
 		if (below == 0u) {                                     // the remaining `pos` children are popped, tested and dropped
 			steps += pos;
 			if (steps >= 512 || level == 0) break;
@@ -1136,6 +1167,7 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 			entering = false;
 			continue;
 		}
+#endif
 		const int j = 31 - clz32(below);
 		steps += pos - 1 - j;
 		if (steps >= 512) break;
@@ -1209,9 +1241,10 @@ RTO_DEV bool octA_step(const OctDev& S, V3 o, V3 d, float tMin, float tMax, cons
 	// exactly-zero direction component, where the two differ, run with OCT == 8)
 	const uint32_t order = (OCT < 8) ? skip_order((~OCT) & 7) : r.order;
 	const uint32_t rnk = (OCT < 8) ? skip_rank((~OCT) & 7) : r.rank;
-	const int h = w.size >> 1;
-	const unsigned leafMask = (unsigned)w.e.w & 0xffu, solidMask = ((unsigned)w.e.w >> 8) & 0xffu;
+	int h = w.size >> 1;
+	unsigned leafMask = (unsigned)w.e.w & 0xffu;
 	if (w.entering) {
+		const unsigned solidMask = ((unsigned)w.e.w >> 8) & 0xffu;
 		ChildPlanes P = oct_child_planes<OCT>(S, r.o, r.inv, w.x, w.y, w.z, h);
 		const unsigned skipMask = leafMask & ~solidMask;       // empty leaves return 1e30f whatever their box test says
 		// the parent's clamps (tMin, tMax of the recursive call) enter every child's max/min once: fold them into one axis
@@ -1231,6 +1264,23 @@ RTO_DEV bool octA_step(const OctDev& S, V3 o, V3 d, float tMin, float tMax, cons
 		w.entering = false;
 	}
 	unsigned rem = (w.pos < 0) ? w.M : (w.M & ~((2u << w.pos) - 1u));     // order positions after the last consumed one
+#if RTO_OCTA_FOLD_ASCEND
+	// a node whose children are used up hands back to its parent, and the parent to its own, inside this step: the lanes of a warp step
+	// together (octA_fast), and a lane that climbs k levels would otherwise spend k of the warp's steps on a dozen instructions each
+	while (rem == 0u) {
+		if (w.level == 0) return true;
+		w.pos = (int)((rnk >> (4 * (((unsigned)w.e.w >> 16) & 7u))) & 7u);
+		w.rank = w.e.z;
+		w.x &= ~w.size; w.y &= ~w.size; w.z &= ~w.size; w.size <<= 1;
+		w.level--;
+		w.M = cs.mask[w.level];
+		w.curMin = cs.mn[w.level]; w.curMax = cs.mx[w.level];
+		w.e = RTO_LDG(S.inner + w.rank);
+		rem = w.M & ~((2u << w.pos) - 1u);
+	}
+	h = w.size >> 1;
+	leafMask = (unsigned)w.e.w & 0xffu;
+#else
 	if (rem == 0u) {
 		if (w.level == 0) return true;
 		w.pos = (int)((rnk >> (4 * (((unsigned)w.e.w >> 16) & 7u))) & 7u);
@@ -1242,6 +1292,7 @@ RTO_DEV bool octA_step(const OctDev& S, V3 o, V3 d, float tMin, float tMax, cons
 		w.e = RTO_LDG(S.inner + w.rank);
 		return false;
 	}
+#endif
 	const int jO = ffs32(rem) - 1;
 	const int k = (int)((order >> (4 * jO)) & 7u);
 	w.pos = jO;
@@ -1285,7 +1336,7 @@ RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 	const int oct = octA_octant(S, r, d);
 	OctWalk w; OctClamps cs; OctHit hit;
 	if (octA_init(S, o, d, tMin, tMax, r, w, hit)) return hit;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && RTO_OCTA_VOTE
 	// The lanes of the warp that walk with this octant instantiation vote once per step.  Without it the lanes drift apart after
 	// the first divergent branch inside a step and never re-join: ncu showed 7 (512^3 city) to 15 (DT grid) of 32 lanes active in
 	// EVERY instruction of the loop; with it the kernel is 1.5x (DT) to 2.4x (city) faster (profiles/README.md).  (The same vote

@@ -8,7 +8,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "ray_tracing_octrees_b200", "csrc")
-SO = os.path.join(HERE, "_build", "libemu.so")
+# RTO_EMU_DEFINES="-DNAME=1 ...": the emulator of a kernel variant (its own .so), to check a variant on the CPU before it costs GPU time
+EXTRA = os.environ.get("RTO_EMU_DEFINES", "").split()
+SO = os.path.join(HERE, "_build", "libemu%s.so" % ("_" + "".join(c if c.isalnum() else "_" for c in "".join(EXTRA)) if EXTRA else ""))
 SRCS = [os.path.join(HERE, "emu.cu"), os.path.join(CSRC, "host_builders.cpp"), os.path.join(CSRC, "host_layouts.cpp")]
 DEPS = SRCS + [os.path.join(CSRC, f) for f in ("rto_kernels.cuh", "rto_internal.h", "rto_math.h")]
 
@@ -19,7 +21,7 @@ def build():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.check_call(["nvcc", "-ccbin", ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false",
-                           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-o", SO, *SRCS, "-lpthread"])
+                           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", *EXTRA, "-o", SO, *SRCS, "-lpthread"])
     return SO
 
 
