@@ -66,17 +66,6 @@ RTO_DEV int ffs32(unsigned v) {
 #ifndef RTO_RESOLVE_HOIST_RAY
 #define RTO_RESOLVE_HOIST_RAY 0
 #endif
-// Octree walks: a node whose children are used up hands back to its parent inside the same step instead of in a step of its own.
-// Measured on B200 (16 x 1080p per launch): mode A 512^3 city 8.377 -> 6.437 ms, DT 5.350 -> 4.357 (profiles/README.md, round 2).
-#ifndef RTO_OCTA_FOLD_ASCEND
-#define RTO_OCTA_FOLD_ASCEND 1
-#endif
-#ifndef RTO_OCTA_VOTE
-#define RTO_OCTA_VOTE 1
-#endif
-#ifndef RTO_OCTB_FOLD_ASCEND
-#define RTO_OCTB_FOLD_ASCEND 0
-#endif
 #ifndef RTO_BVH_ANY_WHILE_WHILE
 #define RTO_BVH_ANY_WHILE_WHILE 0
 #endif
@@ -549,7 +538,7 @@ RTO_DEV void bvh_closest_loop(const BvhDev& S, const RayBox& rb, V3 o, V3 d, flo
 		if (cur == kDone) break;
 	}
 #else
-	// (a per-step warp vote that re-joins the lanes, the change that made the octree mode-A walk 2x faster, costs 5-9 % here)
+	// (a per-step warp vote that re-joins the lanes costs 5-9 % here)
 	{
 		for (;;) {
 			bool pop = true;
@@ -1073,24 +1062,11 @@ RTO_DEV void oct_child_coords(int k, int h, int& x, int& y, int& z) {
 	x += (k & 1) ? h : 0; y += (k & 2) ? h : 0; z += (k & 4) ? h : 0;
 }
 
-// The fast walks are written as explicit state machines (init + step) so that one ray can be advanced a step at a time: the
-// persistent kernel below refills idle lanes with new pixels between steps, everything else just steps until done.
-struct OctWalk {
-	int x, y, z, size;              // current internal node
-	int level, rank, pos;           // depth below the root, rank of the node's 16-byte record, position among its children
-	int4 e;                         // the record
-	unsigned M;                     // children still to visit, in visit-order space
-	bool entering;                  // the node was just entered: classify its 8 children first
-	int steps;                      // mode B: nodes popped so far (512-step budget)
-	float curMin, curMax;           // mode A: (enterT, exitT) of the current node = clamps of its children
-};
-// mode A: clamps of the ancestors (kept apart from OctWalk so that the scalars above stay in registers while this dynamically
-// indexed array lives in local memory)
+// mode A: clamps of the ancestors (dynamically indexed: local memory)
 struct OctClamps { float mn[16], mx[16]; unsigned char mask[16]; };     // + M of the ancestors
 
 // ---- mode B ------------------------------------------------------------------------------------------------------
-// One loop, state in plain locals: the init/step form used for mode A below (which needs a warp vote between steps) costs this
-// lighter walk 10-25 % (measured: 512^3 city 4.16 -> 5.27 ms, sphere 0.76 -> 0.92 ms per 8 frames), so it keeps the plain loop.
+// One loop, state in plain locals (an init/step form with a warp vote between steps, tried in round 1, costs this walk 10-25 %).
 template <int OCT>
 RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 	OctHit hit; hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
@@ -1136,9 +1112,9 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 			pos = 8;
 		}
 		unsigned below = M & ((1u << pos) - 1u);
-#if RTO_OCTB_FOLD_ASCEND
-		// climbs happen inside the iteration (see octA_step): the lanes of a warp run this loop in lockstep, and a lane that hands back
-		// through k levels would otherwise pay k iterations, each as long as the classification some other lane runs in it
+		// climbs happen inside the iteration: the lanes of a warp run this loop in lockstep, and a lane that hands back through k levels
+		// would otherwise pay k iterations, each as long as the classification some other lane runs in it (measured, 16 x 1080p: 512^3
+		// city 6.44 -> 5.43 ms, DT 3.96 -> 3.46)
 		bool out = false;
 		while (below == 0u) {                                  // the remaining `pos` children are popped, tested and dropped
 			steps += pos;
@@ -1154,20 +1130,6 @@ RTO_DEV OctHit octB_fast_loop(const OctDev& S, V3 o, V3 d, V3 inv) {
 		if (out) break;
 		h = size >> 1;
 		leafMask = (unsigned)e.w & 0xffu;
-#else
-		if (below == 0u) {                                     // the remaining `pos` children are popped, tested and dropped
-			steps += pos;
-			if (steps >= 512 || level == 0) break;
-			pos = ((unsigned)e.w >> 16) & 7u;
-			rank = e.z;
-			x &= ~size; y &= ~size; z &= ~size; size <<= 1;
-			level--;
-			M = maskS[level];
-			e = RTO_LDG(S.inner + rank);
-			entering = false;
-			continue;
-		}
-#endif
 		const int j = 31 - clz32(below);
 		steps += pos - 1 - j;
 		if (steps >= 512) break;
@@ -1219,107 +1181,102 @@ RTO_DEV OctHit octB_fast(const OctDev& S, V3 o, V3 d) {
 }
 
 // ---- mode A ------------------------------------------------------------------------------------------------------
-RTO_DEV bool octA_init(const OctDev& S, V3 o, V3 d, float tMin, float tMax, const SkipRay& r, OctWalk& w, OctHit& hit) {
-	hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
-	w.x = 0; w.y = 0; w.z = 0; w.size = S.rootSize;
-	OctBox b = oct_box(S, 0, 0, 0, w.size);
-	if (!skip_box(b, r, tMin, tMax, w.curMin, w.curMax)) return true;
-	uint32_t dsc = RTO_LDG(S.desc);
-	if (dsc & kOctLeaf) {
-		if ((dsc & kOctSolid) && w.curMin < 1e30f) { hit.t = w.curMin; hit.id = 0; hit.normal = box_normal(b, o, d, w.curMin); }
-		return true;
-	}
-	w.level = 0; w.rank = 0; w.pos = -1; w.M = 0; w.steps = 0;
-	w.e = RTO_LDG(S.inner);
-	w.entering = true;
-	return false;
-}
-
+// One loop with its state in plain locals.  Every trip of the outer loop starts with the classification of the 8 children of the node
+// just entered -- the expensive part, which all lanes of the warp that are still walking run together -- and the inner loop does the
+// cheap rest per lane: hand back to the parent while a node's children are used up, test a solid leaf, until the lane has a node to
+// descend into (or is done).  The lanes re-join at the exit of the inner loop, the hardware's own convergence point; no votes.
+// History (B200, 16 x 1080p per launch, 512^3 city / DT): init + step form with one warp vote per step, climbs as steps of their own
+// 8.38 / 5.35 ms (round 1: the vote had made it 1.5-2.4x faster than lanes drifting apart); climbs folded into the step 6.44 / 4.36;
+// without the vote 6.14 / 4.16; this loop 6.06 / 4.12, at 10 resident blocks per SM 5.75 / 3.97.  Same operations per ray in the same
+// order throughout: same bits.
 template <int OCT>
-RTO_DEV bool octA_step(const OctDev& S, V3 o, V3 d, float tMin, float tMax, const SkipRay& r, OctWalk& w, OctClamps& cs, OctHit& hit) {
-	// visit order of the octants: a compile-time table when the octant of 1/d is (then dirMask == ~OCT & 7: rays with an
-	// exactly-zero direction component, where the two differ, run with OCT == 8)
+RTO_DEV OctHit octA_fast_loop(const OctDev& S, V3 o, V3 d, float tMin, float tMax, const SkipRay& r) {
+	OctHit hit; hit.t = kMissT; hit.id = -1; hit.normal = mk3(0.0f, 0.0f, 0.0f); hit.visits = 0;
 	const uint32_t order = (OCT < 8) ? skip_order((~OCT) & 7) : r.order;
 	const uint32_t rnk = (OCT < 8) ? skip_rank((~OCT) & 7) : r.rank;
-	int h = w.size >> 1;
-	unsigned leafMask = (unsigned)w.e.w & 0xffu;
-	if (w.entering) {
-		const unsigned solidMask = ((unsigned)w.e.w >> 8) & 0xffu;
-		ChildPlanes P = oct_child_planes<OCT>(S, r.o, r.inv, w.x, w.y, w.z, h);
-		const unsigned skipMask = leafMask & ~solidMask;       // empty leaves return 1e30f whatever their box test says
-		// the parent's clamps (tMin, tMax of the recursive call) enter every child's max/min once: fold them into one axis
-		P.n0[2] = fmaxf(P.n0[2], w.curMin); P.n1[2] = fmaxf(P.n1[2], w.curMin);
-		P.f0[2] = fminf(P.f0[2], w.curMax); P.f1[2] = fminf(P.f1[2], w.curMax);
-		unsigned Mo = 0, skipO = 0;                            // bit j = j-th child in VISIT order (octant `order` nibble j)
+	int x = 0, y = 0, z = 0, size = S.rootSize;
+	float curMin, curMax;
+	{
+		OctBox b = oct_box(S, 0, 0, 0, size);
+		if (!skip_box(b, r, tMin, tMax, curMin, curMax)) return hit;
+		uint32_t dsc = RTO_LDG(S.desc);
+		if (dsc & kOctLeaf) {
+			if ((dsc & kOctSolid) && curMin < 1e30f) { hit.t = curMin; hit.id = 0; hit.normal = box_normal(b, o, d, curMin); }
+			return hit;
+		}
+	}
+	OctClamps cs;
+	int level = 0, rank = 0, steps = 0;
+	int4 e = RTO_LDG(S.inner);
+	for (;;) {
+		int h = size >> 1;
+		unsigned leafMask = (unsigned)e.w & 0xffu;
+		unsigned M;
+		{
+			const unsigned solidMask = ((unsigned)e.w >> 8) & 0xffu;
+			ChildPlanes P = oct_child_planes<OCT>(S, r.o, r.inv, x, y, z, h);
+			const unsigned skipMask = leafMask & ~solidMask;       // empty leaves return 1e30f whatever their box test says
+			P.n0[2] = fmaxf(P.n0[2], curMin); P.n1[2] = fmaxf(P.n1[2], curMin);
+			P.f0[2] = fminf(P.f0[2], curMax); P.f1[2] = fminf(P.f1[2], curMax);
+			unsigned Mo = 0, skipO = 0;                            // bit j = j-th child in VISIT order
 #pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const int k = (int)((order >> (4 * j)) & 7u);      // a compile-time constant when the octant is (OCT < 8)
-			float tn = fmax3f((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1], (k & 4) ? P.n1[2] : P.n0[2]);
-			float tf = fmin3f((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1], (k & 4) ? P.f1[2] : P.f0[2]);
-			Mo |= !(tn > tf) ? (1u << j) : 0u;
-			skipO |= ((skipMask >> k) & 1u) << j;
+			for (int j = 0; j < 8; j++) {
+				const int k = (int)((order >> (4 * j)) & 7u);
+				float tn = fmax3f((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1], (k & 4) ? P.n1[2] : P.n0[2]);
+				float tf = fmin3f((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1], (k & 4) ? P.f1[2] : P.f0[2]);
+				Mo |= !(tn > tf) ? (1u << j) : 0u;
+				skipO |= ((skipMask >> k) & 1u) << j;
+			}
+			M = Mo & ~skipO;
 		}
-		w.M = Mo & ~skipO;
-		w.pos = -1;
-		w.entering = false;
-	}
-	unsigned rem = (w.pos < 0) ? w.M : (w.M & ~((2u << w.pos) - 1u));     // order positions after the last consumed one
-#if RTO_OCTA_FOLD_ASCEND
-	// a node whose children are used up hands back to its parent, and the parent to its own, inside this step: the lanes of a warp step
-	// together (octA_fast), and a lane that climbs k levels would otherwise spend k of the warp's steps on a dozen instructions each
-	while (rem == 0u) {
-		if (w.level == 0) return true;
-		w.pos = (int)((rnk >> (4 * (((unsigned)w.e.w >> 16) & 7u))) & 7u);
-		w.rank = w.e.z;
-		w.x &= ~w.size; w.y &= ~w.size; w.z &= ~w.size; w.size <<= 1;
-		w.level--;
-		w.M = cs.mask[w.level];
-		w.curMin = cs.mn[w.level]; w.curMax = cs.mx[w.level];
-		w.e = RTO_LDG(S.inner + w.rank);
-		rem = w.M & ~((2u << w.pos) - 1u);
-	}
-	h = w.size >> 1;
-	leafMask = (unsigned)w.e.w & 0xffu;
-#else
-	if (rem == 0u) {
-		if (w.level == 0) return true;
-		w.pos = (int)((rnk >> (4 * (((unsigned)w.e.w >> 16) & 7u))) & 7u);
-		w.rank = w.e.z;
-		w.x &= ~w.size; w.y &= ~w.size; w.z &= ~w.size; w.size <<= 1;
-		w.level--;
-		w.M = cs.mask[w.level];
-		w.curMin = cs.mn[w.level]; w.curMax = cs.mx[w.level];
-		w.e = RTO_LDG(S.inner + w.rank);
-		return false;
-	}
-#endif
-	const int jO = ffs32(rem) - 1;
-	const int k = (int)((order >> (4 * jO)) & 7u);
-	w.pos = jO;
-	int cx = w.x, cy = w.y, cz = w.z;
-	oct_child_coords(k, h, cx, cy, cz);
-	OctBox b = oct_box(S, cx, cy, cz, h);
-	float enterT, exitT;
-	bool ok = skip_box_oct<OCT>(b, r, w.curMin, w.curMax, enterT, exitT);
-	if ((leafMask >> k) & 1u) {                                // solid leaf
-		if (ok && enterT < 1e30f) {
-			if (enterT == 0.0f) { hit = octA_compact(S, o, d, tMin, tMax); return true; }      // zero of either sign: take the reference's select forms
-			hit.t = enterT; hit.id = w.e.x + k; hit.normal = box_normal(b, o, d, enterT);
-			return true;
+		unsigned rem = M;                                          // order positions still to visit in the current node
+		bool done = false;
+		for (;;) {
+			while (rem == 0u) {                                    // children used up: back to the parent, after the child we came from
+				if (level == 0) { done = true; break; }
+				const int pos = (int)((rnk >> (4 * (((unsigned)e.w >> 16) & 7u))) & 7u);
+				rank = e.z;
+				x &= ~size; y &= ~size; z &= ~size; size <<= 1;
+				level--;
+				M = cs.mask[level];
+				curMin = cs.mn[level]; curMax = cs.mx[level];
+				e = RTO_LDG(S.inner + rank);
+				rem = M & ~((2u << pos) - 1u);
+			}
+			if (done) break;
+			h = size >> 1;
+			leafMask = (unsigned)e.w & 0xffu;
+			const int jO = ffs32(rem) - 1;
+			const int k = (int)((order >> (4 * jO)) & 7u);
+			rem &= rem - 1u;                                       // consumed
+			int cx = x, cy = y, cz = z;
+			oct_child_coords(k, h, cx, cy, cz);
+			OctBox b = oct_box(S, cx, cy, cz, h);
+			float enterT, exitT;
+			const bool ok = skip_box_oct<OCT>(b, r, curMin, curMax, enterT, exitT);
+			if ((leafMask >> k) & 1u) {                            // solid leaf
+				if (ok && enterT < 1e30f) {
+					if (enterT == 0.0f) return octA_compact(S, o, d, tMin, tMax);      // zero of either sign: take the reference's select forms
+					hit.t = enterT; hit.id = e.x + k; hit.normal = box_normal(b, o, d, enterT);
+					done = true; break;
+				}
+				continue;
+			}
+			if (!ok) continue;                                     // (cannot happen: same values as the batch test)
+			cs.mask[level] = (unsigned char)M;
+			cs.mn[level] = curMin; cs.mx[level] = curMax;
+			level++;
+			curMin = enterT; curMax = exitT;
+			rank = e.y + popc32(~leafMask & ((1u << k) - 1u) & 0xffu);
+			x = cx; y = cy; z = cz; size = h;
+			e = RTO_LDG(S.inner + rank);
+			// (a finite walk enters < nodes internal nodes; the bound only keeps a corrupted array from hanging the GPU)
+			if (++steps >= (1 << 24)) done = true;
+			break;
 		}
-		return false;
+		if (done) break;
 	}
-	if (!ok) return false;                                     // (cannot happen: same values as the batch test)
-	cs.mask[w.level] = (unsigned char)w.M;
-	cs.mn[w.level] = w.curMin; cs.mx[w.level] = w.curMax;
-	w.level++;
-	w.curMin = enterT; w.curMax = exitT;
-	w.rank = w.e.y + popc32(~leafMask & ((1u << k) - 1u) & 0xffu);
-	w.x = cx; w.y = cy; w.z = cz; w.size = h;
-	w.e = RTO_LDG(S.inner + w.rank);
-	w.entering = true;
-	// (a finite walk visits < 2 * nodes steps; the bound only keeps a corrupted array from hanging the GPU)
-	return ++w.steps >= (1 << 24);
+	return hit;
 }
 
 RTO_DEV bool octA_is_fast(const OctDev& S, const SkipRay& r, float tMin, float tMax) {
@@ -1334,19 +1291,8 @@ RTO_DEV OctHit octA_fast(const OctDev& S, V3 o, V3 d, float tMin, float tMax) {
 	SkipRay r = make_skipray(o, d);
 	if (!octA_is_fast(S, r, tMin, tMax)) return octA_compact(S, o, d, tMin, tMax);
 	const int oct = octA_octant(S, r, d);
-	OctWalk w; OctClamps cs; OctHit hit;
-	if (octA_init(S, o, d, tMin, tMax, r, w, hit)) return hit;
-#if defined(__CUDA_ARCH__) && RTO_OCTA_VOTE
-	// The lanes of the warp that walk with this octant instantiation vote once per step.  Without it the lanes drift apart after
-	// the first divergent branch inside a step and never re-join: ncu showed 7 (512^3 city) to 15 (DT grid) of 32 lanes active in
-	// EVERY instruction of the loop; with it the kernel is 1.5x (DT) to 2.4x (city) faster (profiles/README.md).  (The same vote
-	// around a single hand-inlined loop instead of init/step measured 3 % slower.)
-	const unsigned arm = __match_any_sync(__activemask(), oct);
-	bool fin = false;
-#define RTO_CALL_A(K) for (;;) { if (!fin) fin = octA_step<K>(S, o, d, tMin, tMax, r, w, cs, hit); if (__ballot_sync(arm, !fin) == 0u) break; }
-#else
-#define RTO_CALL_A(K) while (!octA_step<K>(S, o, d, tMin, tMax, r, w, cs, hit)) {}
-#endif
+	OctHit hit;
+#define RTO_CALL_A(K) hit = octA_fast_loop<K>(S, o, d, tMin, tMax, r)
 	RTO_OCT_DISPATCH(oct, RTO_CALL_A)
 #undef RTO_CALL_A
 	return hit;
@@ -1502,13 +1448,12 @@ __global__ void __launch_bounds__(kRenderThreads, RTO_RESOLVE_MIN_BLOCKS * 128 /
 	store_pixel(A, pix, color, id, t);
 }
 
-// One instantiation per traversal mode so that each gets its own register budget: the mode-A walk wants ~80 registers (it
-// spills at 64), the lighter mode-B walk runs better with 8 resident blocks per SM (64 registers).
+// One instantiation per traversal mode so that each gets its own register budget (mode A: 48 registers, mode B: 40).
 #ifndef RTO_OCT_B_MIN_BLOCKS
 #define RTO_OCT_B_MIN_BLOCKS 12    // re-measured: 12 blocks 2.12 / 3.31 ms, 8 blocks 2.20 / 3.45, 10 blocks 2.15 / 3.38, 14-16 blocks 2.18 / 3.41
 #endif
 #ifndef RTO_OCT_A_MIN_BLOCKS
-#define RTO_OCT_A_MIN_BLOCKS 8     // re-measured (DT / 512^3 city, 8 x 1080p): 8 blocks 2.60 / 4.14 ms, 6 blocks 2.66 / 4.25, 10 blocks 2.62 / 4.17, 4-5 and 12 slower
+#define RTO_OCT_A_MIN_BLOCKS 10    // re-measured on the one-loop walk (DT / 512^3 city, 16 x 1080p): 10 blocks (48 registers) 3.97 / 5.75 ms, 8 blocks 4.12 / 6.06, 6 blocks 4.16 / 6.21, 12 blocks 4.10 / 5.91
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(kRenderThreads, (MODE == RTO_MODE_OCTREE_SKIP ? RTO_OCT_A_MIN_BLOCKS : RTO_OCT_B_MIN_BLOCKS) * 128 / kRenderThreads) k_render_octree(OctDev S, RenderArgs A) {
