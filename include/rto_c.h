@@ -250,6 +250,15 @@ RTO_API int rto_scene_create_bvh_from_grid_dc(const uint8_t* voxels, int dimX, i
  * inner: 4 words per internal node); any pointer may be NULL.  Lets tests compare the two construction routes. */
 RTO_API int rto_scene_octree_layout_read(RtoScene* scene, uint32_t* desc, int32_t* up, int32_t* inner4, size_t* numInner);
 
+/* A device scene as one file, and back: the flattened arrays the kernels walk (BVH: production and reference-shaped nodes, triangle
+ * records, wide form; octree: compact or general arrays), whatever route built them.  The reference rebuilds octree, flatten and BVH at
+ * every start (main.cpp:1127-1131) and caches only what comes before them -- sceneCache.bin (CacheUtils.cpp:5-59, rto_host_grid_*) and the
+ * Dual-Contouring triangle cache (main.cpp:27-92, rto_host_tricache_*); this is the cache of what comes after.
+ * rto_scene_load gives a scene that renders the same bits as the one saved.  A file written by another version of the library is refused
+ * with RTO_ERR_UNSUPPORTED, a truncated or damaged one (checksum) with RTO_ERR_IO. */
+RTO_API int rto_scene_save(RtoScene* scene, const char* path);
+RTO_API int rto_scene_load(const char* path, RtoScene** out);
+
 RTO_API void rto_scene_destroy(RtoScene* scene);
 RTO_API int rto_scene_info(const RtoScene* scene, int* kind /* RtoMode of a BVH or octree scene */,
 	size_t* numPrims, size_t* numNodes, size_t* deviceBytes, int* compactLayout);

@@ -70,6 +70,8 @@ SIGNATURES = {
     "rto_scene_create_bvh_from_grid": (_i, [_vp, _i, _i, _i, _vp, _f, _pp]),
     "rto_scene_create_bvh_from_grid_dc": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _f, _pp]),
     "rto_scene_octree_layout_read": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_sz)]),
+    "rto_scene_save": (_i, [_vp, C.c_char_p]),
+    "rto_scene_load": (_i, [C.c_char_p, _vp]),
     "rto_scene_destroy": (None, [_vp]),
     "rto_scene_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "rto_scene_stream": (_vp, [_vp]),

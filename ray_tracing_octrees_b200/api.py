@@ -322,6 +322,17 @@ class Scene:
         check(lib().rto_octree_skip_distance(self.h, _p(v), _p(p), float(aspect), float(last), C.byref(out), _p(probes)))
         return out.value, probes
 
+    def save(self, path):
+        """The device layout of this scene as one file (rto_scene_save)."""
+        check(lib().rto_scene_save(self.h, os.fsencode(path)))
+
+    @staticmethod
+    def load(path):
+        """A scene from a file written by save(): one read, one upload, no builder runs (rto_scene_load)."""
+        h = C.c_void_p()
+        check(lib().rto_scene_load(os.fsencode(path), C.byref(h)))
+        return Scene(h)
+
     def info(self):
         kind, compact = C.c_int(), C.c_int()
         prims, nodes, nbytes = C.c_size_t(), C.c_size_t(), C.c_size_t()

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librto.so")
-SOURCES = ["rto_device.cu", "rto_group.cu", "rto_build.cu", "rto_dc.cu", "host_builders.cpp", "host_layouts.cpp", "host_dc.cpp"]
-DEPS = SOURCES + ["rto_kernels.cuh", "rto_scene.cuh", "rto_devtypes.h", "rto_voxelize.h", "rto_frustum.h", "rto_dc.h", "rto_sahchunk.h", "rto_internal.h", "rto_math.h", "mc_tables.h", "../../include/rto_c.h"]
+SOURCES = ["rto_device.cu", "rto_group.cu", "rto_build.cu", "rto_dc.cu", "rto_blob.cu", "host_builders.cpp", "host_layouts.cpp", "host_dc.cpp"]
+DEPS = SOURCES + ["rto_kernels.cuh", "rto_scene.cuh", "rto_devtypes.h", "rto_voxelize.h", "rto_frustum.h", "rto_dc.h", "rto_sahchunk.h", "rto_internal.h", "rto_nvtx.h", "rto_math.h", "mc_tables.h", "../../include/rto_c.h"]
 
 
 def nvcc_cmd(extra=(), out=None):
@@ -21,7 +21,7 @@ def nvcc_cmd(extra=(), out=None):
     return ["nvcc", "-ccbin", ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
             "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
             "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2", "-shared",
-            *extra, "-o", out or OUT, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
+            *extra, "-o", out or OUT, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread", "-ldl"]
 
 
 def needs_build():

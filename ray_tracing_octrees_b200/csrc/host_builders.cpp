@@ -14,6 +14,7 @@
 //   rto_host_camera_orbit  == Camera::getView/getPos (Camera.cpp:11-29) + glm::lookAtRH + glm::inverse.
 // Compiled with -ffp-contract=off; arithmetic follows rto_math.h (glm operation order).
 #include "rto_internal.h"
+#include "rto_nvtx.h"
 #include "mc_tables.h"
 #include "rto_voxelize.h"
 #include "rto_frustum.h"
@@ -92,6 +93,7 @@ void buildPyramid(const uint8_t* vox, int dx, int dy, int dz, int levels, Pyrami
 } // namespace
 
 extern "C" int rto_host_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ, RtoGpuNode** nodesOut, size_t* numNodes) try {
+	RTO_RANGE("rto_host_octree_build");
 	if (!nodesOut || !numNodes) return rto_fail(RTO_ERR_INVALID, "rto_host_octree_build: null output");
 	*nodesOut = nullptr; *numNodes = 0;
 	// createOctreeFromVoxelGrid returns nullptr for an empty grid (OctreeVoxel.cpp:766): zero nodes, still RTO_OK
@@ -183,6 +185,7 @@ inline void mcCell(const McGrid& g, int x, int y, int z, std::vector<RtoTriangle
 
 extern "C" int rto_host_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	const RtoGpuNode* nodes, size_t numNodes, RtoTriangle** trisOut, size_t* numTris) try {
+	RTO_RANGE("rto_host_mc_mesh");
 	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_host_mc_mesh: null output");
 	*trisOut = nullptr; *numTris = 0;
 	if (numNodes == 0) return RTO_OK;
@@ -258,6 +261,7 @@ struct Builder {
 } // namespace
 
 extern "C" int rto_host_bvh_build(const RtoTriangle* tris, size_t numTris, RtoHostBvh** out) try {
+	RTO_RANGE("rto_host_bvh_build");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_build: null output");
 	*out = nullptr;
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_host_bvh_build: null triangles");
@@ -712,6 +716,7 @@ int rto_csv_load(const char* vertsCsv, const char* facesCsv, float voxelSize, Cs
 }
 
 extern "C" int rto_host_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) try {
+	RTO_RANGE("rto_host_csv_voxelize");
 	if (!dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_host_csv_voxelize: null output");
 	*voxelsOut = nullptr; dims[0] = dims[1] = dims[2] = 0;
 	CsvScene S;

@@ -18,6 +18,7 @@
 // a replay of the cache protocol in visit order (rto_host_dc_mesh_replay).  See the comments above each.
 // Limits: the reference's keys are (x << 20 | y << 10 | z), which alias beyond 1024 voxels per axis; larger octrees are refused.
 #include "rto_internal.h"
+#include "rto_nvtx.h"
 #include "rto_dc.h"
 
 #include <algorithm>
@@ -254,6 +255,7 @@ static int dcMeshOrderFree(const uint8_t* voxels, int dimX, int dimY, int dimZ, 
 
 extern "C" int rto_host_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) try {
+	RTO_RANGE("rto_host_dc_mesh");
 	return dcMeshOrderFree(voxels, dimX, dimY, dimZ, gridMin, voxelSize, nodes, numNodes, viewProj16, extraMargin, trisOut, nullptr, numTris);
 } RTO_CATCH_ALL("rto_host_dc_mesh")
 
@@ -332,6 +334,7 @@ extern "C" int rto_host_tricache_load(const char* path, RtoTriangle** trisOut, f
 // =================================================================================================================================
 extern "C" int rto_host_dc_mesh_replay(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) try {
+	RTO_RANGE("rto_host_dc_mesh_replay");
 	int rc = checkArgs("rto_host_dc_mesh_replay", voxels, gridMin, nodes, numNodes, trisOut, numTris);
 	if (rc || numNodes == 0) return rc;
 	const Grid g{ voxels, dimX, dimY, dimZ, gridMin[0], gridMin[1], gridMin[2], voxelSize };

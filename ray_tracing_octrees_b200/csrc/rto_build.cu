@@ -10,6 +10,7 @@
 //            (-fmad=false), so the triangle array equals rto_host_mc_mesh's bit for bit.
 // Memory traffic, not arithmetic, bounds all of it (bytes in, bytes out, a few passes); see DESIGN.md section 5.
 #include "rto_scene.cuh"
+#include "rto_nvtx.h"
 #include "rto_sahchunk.h"
 #include "mc_tables.h"
 #include "rto_voxelize.h"
@@ -291,6 +292,7 @@ int oct_emit(OctBuild& B, bool wantCompact, bool wantNodes, cudaStream_t st) {
 // C ABI: octree
 // ------------------------------------------------------------------------------------------------
 extern "C" int rto_device_octree_build(const uint8_t* voxels, int dimX, int dimY, int dimZ, RtoGpuNode** nodesOut, size_t* numNodes) try {
+	RTO_RANGE("rto_device_octree_build");
 	if (!nodesOut || !numNodes) return rto_fail(RTO_ERR_INVALID, "rto_device_octree_build: null output");
 	*nodesOut = nullptr; *numNodes = 0;
 	if (dimX == 0 || dimY == 0 || dimZ == 0) return RTO_OK;        // createOctreeFromVoxelGrid returns nullptr (OctreeVoxel.cpp:766)
@@ -320,6 +322,7 @@ extern "C" int rto_device_octree_build(const uint8_t* voxels, int dimX, int dimY
 
 extern "C" int rto_scene_create_octree_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	RtoScene** out) try {
+	RTO_RANGE("rto_scene_create_octree_from_grid");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree_from_grid: null output");
 	*out = nullptr;
 	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree_from_grid: empty grid (nothing to trace)");
@@ -549,6 +552,7 @@ int mc_extract(const OctBuild& O, const float gridMin[3], float voxelSize, McBui
 
 extern "C" int rto_device_mc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	RtoTriangle** trisOut, size_t* numTris) try {
+	RTO_RANGE("rto_device_mc_mesh");
 	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_device_mc_mesh: null output");
 	*trisOut = nullptr; *numTris = 0;
 	if (dimX == 0 || dimY == 0 || dimZ == 0) return RTO_OK;
@@ -853,6 +857,7 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 } // namespace
 
 extern "C" int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTris, RtoScene** out) try {
+	RTO_RANGE("rto_scene_create_bvh_device");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_device: null output");
 	*out = nullptr;
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_device: null triangles");
@@ -872,6 +877,7 @@ extern "C" int rto_scene_create_bvh_device(const RtoTriangle* tris, size_t numTr
 
 extern "C" int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	RtoScene** out) try {
+	RTO_RANGE("rto_scene_create_bvh_from_grid");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid: null output");
 	*out = nullptr;
 	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid: empty grid");
@@ -896,6 +902,7 @@ extern "C" int rto_scene_create_bvh_from_grid(const uint8_t* voxels, int dimX, i
 // same arguments.
 extern "C" int rto_scene_create_bvh_from_grid_dc(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	const float* viewProj16, float extraMargin, RtoScene** out) try {
+	RTO_RANGE("rto_scene_create_bvh_from_grid_dc");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid_dc: null output");
 	*out = nullptr;
 	if (!voxels || !gridMin || dimX <= 0 || dimY <= 0 || dimZ <= 0) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh_from_grid_dc: empty grid");
@@ -946,6 +953,7 @@ __global__ void k_voxelize(const RtoTriangle* __restrict__ tris, size_t numFaces
 } // namespace
 
 extern "C" int rto_device_csv_voxelize(const char* vertsCsv, const char* facesCsv, float voxelSize, int dims[3], float minAndVoxel[4], uint8_t** voxelsOut) try {
+	RTO_RANGE("rto_device_csv_voxelize");
 	if (!dims || !minAndVoxel || !voxelsOut) return rto_fail(RTO_ERR_INVALID, "rto_device_csv_voxelize: null output");
 	*voxelsOut = nullptr; dims[0] = dims[1] = dims[2] = 0;
 	int rc = rto_require_device(); if (rc) return rc;
@@ -1009,6 +1017,7 @@ __global__ void k_cull_emit(const RtoGpuNode* __restrict__ nodes, size_t n, cons
 
 extern "C" int rto_device_frustum_cull(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, const float viewProj16[16],
 	float margin, RtoGpuNode** culledOut, size_t* numCulled, int32_t** newToOldOut) try {
+	RTO_RANGE("rto_device_frustum_cull");
 	if (!culledOut || !numCulled) return rto_fail(RTO_ERR_INVALID, "rto_device_frustum_cull: null output");
 	*culledOut = nullptr; *numCulled = 0;
 	if (newToOldOut) *newToOldOut = nullptr;

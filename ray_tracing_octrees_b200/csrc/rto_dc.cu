@@ -13,6 +13,7 @@
 // Per-cell arithmetic comes from rto_dc.h (shared with the host), compiled -fmad=false -prec-div=true -prec-sqrt=true.
 // One thread per cell: Hermite sums are sequential float sums in the reference's order and cannot be split across threads.
 #include "rto_scene.cuh"
+#include "rto_nvtx.h"
 #include "rto_dc.h"
 
 #include <cub/cub.cuh>
@@ -265,6 +266,7 @@ int rto_dc_extract_device(const uint8_t* dVox, int dimX, int dimY, int dimZ, con
 
 extern "C" int rto_device_dc_mesh(const uint8_t* voxels, int dimX, int dimY, int dimZ, const float gridMin[3], float voxelSize,
 	const RtoGpuNode* nodes, size_t numNodes, const float* viewProj16, float extraMargin, RtoTriangle** trisOut, size_t* numTris) try {
+	RTO_RANGE("rto_device_dc_mesh");
 	if (!trisOut || !numTris) return rto_fail(RTO_ERR_INVALID, "rto_device_dc_mesh: null output");
 	*trisOut = nullptr; *numTris = 0;
 	if (numNodes == 0) return RTO_OK;

@@ -3,6 +3,7 @@
 // Built for sm_100a only with -fmad=false (exact parity with the CPU oracle needs unfused multiply/add).
 // There is no CPU fallback in this file: every entry point that traces rays requires a CUDA device.
 #include "rto_scene.cuh"
+#include "rto_nvtx.h"
 #include "rto_kernels.cuh"
 #include <cub/cub.cuh>
 
@@ -74,12 +75,12 @@ int rto_scene_alloc(RtoScene* s, void** p, size_t bytes) {
 	*p = nullptr;
 	cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
 	if (e != cudaSuccess) return rto_fail(RTO_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-	s->owned.push_back(*p);
+	s->owned.push_back(*p); s->ownedBytes.push_back(bytes ? bytes : 16);
 	s->deviceBytes += bytes;
 	return RTO_OK;
 }
 int rto_scene_adopt(RtoScene* s, void* p, size_t bytes) {
-	s->owned.push_back(p);
+	s->owned.push_back(p); s->ownedBytes.push_back(bytes);
 	s->deviceBytes += bytes;
 	return RTO_OK;
 }
@@ -165,6 +166,7 @@ extern "C" int rto_scene_last_kernel_ms(RtoScene* s, float* ms) try {
 // octree upload: RayTracerBVH::setOctree's SSBO (RayTracerBVH.cpp:492-504) -> pointer-free device arrays
 // ------------------------------------------------------------------------------------------------
 extern "C" int rto_scene_create_octree(const RtoGpuNode* nodes, size_t numNodes, const float gridMin[3], float voxelSize, RtoScene** out) try {
+	RTO_RANGE("rto_scene_create_octree");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: null output");
 	*out = nullptr;
 	if (!nodes || numNodes == 0 || !gridMin) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_octree: empty octree (the reference's setOctree(nullptr) clears the scene; nothing to trace)");
@@ -252,6 +254,7 @@ int rto_bvh_layout_from_tris(const RtoTriangle* tris, size_t numTris, const RtoH
 }
 
 extern "C" int rto_scene_create_bvh(const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt, RtoScene** out) try {
+	RTO_RANGE("rto_scene_create_bvh");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null output");
 	*out = nullptr;
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_scene_create_bvh: null triangles");
@@ -344,6 +347,7 @@ static int release_cameras(RtoScene* s, int slot, cudaStream_t st) {
 
 extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams, int mode, uint32_t flags, float shadowBias,
 	int y0, int y1, const RtoFrame* frame) try {
+	RTO_RANGE("rto_render_batch");
 	if (!s || !cams || !frame || numCams <= 0) return rto_fail(RTO_ERR_INVALID, "rto_render: null argument");
 	int rc = check_mode(s, mode); if (rc) return rc;
 	const int W = cams[0].width, H = cams[0].height;
@@ -464,6 +468,7 @@ extern "C" size_t rto_codes_frame_words(int width, int height) {
 
 extern "C" int rto_render_codes(RtoScene* s, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, int y0, int y1,
 	uint32_t* codes, size_t firstFrame, void* stream) try {
+	RTO_RANGE("rto_render_codes");
 	if (!s || !codes) return rto_fail(RTO_ERR_INVALID, "rto_render_codes: null argument");
 	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render_codes: hit codes exist for BVH scenes only");
 	int rc = check_rows("rto_render_codes", cams, numCams, y0, y1, true); if (rc) return rc;
@@ -478,6 +483,7 @@ extern "C" int rto_render_codes(RtoScene* s, const RtoCamera* cams, int numCams,
 
 extern "C" int rto_resolve_codes(RtoScene* s, const RtoCamera* cams, int numCams, int y0, int y1, const uint32_t* codes, size_t firstFrame,
 	const RtoFrame* frame, void* stream) try {
+	RTO_RANGE("rto_resolve_codes");
 	if (!s || !codes || !frame) return rto_fail(RTO_ERR_INVALID, "rto_resolve_codes: null argument");
 	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_resolve_codes: hit codes exist for BVH scenes only");
 	int rc = check_rows("rto_resolve_codes", cams, numCams, y0, y1, true); if (rc) return rc;
@@ -552,6 +558,7 @@ extern "C" int rto_render(RtoScene* s, const RtoCamera* cam, int mode, uint32_t 
 } RTO_CATCH_ALL("rto_render")
 
 extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias, int y0, int y1, uint64_t stats[5]) try {
+	RTO_RANGE("rto_render_stats");
 	if (!s || !cam || !stats) return rto_fail(RTO_ERR_INVALID, "rto_render_stats: null argument");
 	int rc = check_mode(s, mode); if (rc) return rc;
 	if (s->deviceBuiltBvh) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render_stats: the scene's BVH was built on the device; the reference's work counters need the reference-shaped tree (rto_scene_create_bvh)");
@@ -577,6 +584,7 @@ extern "C" int rto_render_stats(RtoScene* s, const RtoCamera* cam, int mode, uin
 // ------------------------------------------------------------------------------------------------
 extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float* origins, const float* dirs, size_t numRays,
 	float tMin, float tMax, float* tOut, int32_t* idOut, int memory) try {
+	RTO_RANGE("rto_trace_rays");
 	if (!s || !origins || !dirs) return rto_fail(RTO_ERR_INVALID, "rto_trace_rays: null argument");
 	int rc = check_mode(s, mode); if (rc) return rc;
 	if (memory != RTO_MEM_HOST && memory != RTO_MEM_DEVICE) return rto_fail(RTO_ERR_INVALID, "rto_trace_rays: bad memory selector %d", memory);
@@ -633,6 +641,7 @@ extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float
 
 extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dirs, size_t numRays,
 	int64_t* offsets, int32_t* ids, size_t idsCapacity, size_t* totalOut) try {
+	RTO_RANGE("rto_bvh_query");
 	if (!s || !origins || !dirs || !offsets) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: null argument");
 	if (s->kind != RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "rto_bvh_query: scene is not a BVH");
 	if (s->deviceBuiltBvh) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_bvh_query: the scene's BVH was built on the device; BVH::query's candidate order needs the reference-shaped tree (rto_scene_create_bvh)");
@@ -678,6 +687,7 @@ extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dir
 // ------------------------------------------------------------------------------------------------
 extern "C" int rto_octree_skip_distance(RtoScene* s, const float view16[16], const float camPos[3], float aspect, float lastSkipDistance,
 	float* skipDistanceOut, float* probeT /* 49 floats, may be NULL */) try {
+	RTO_RANGE("rto_octree_skip_distance");
 	if (!s || !skipDistanceOut) return rto_fail(RTO_ERR_INVALID, "rto_octree_skip_distance: null argument");
 	if (s->kind == RTO_MODE_BVH) return rto_fail(RTO_ERR_INVALID, "rto_octree_skip_distance: scene is not an octree");
 	float o[49 * 3], d[49 * 3], t[49];

@@ -9,6 +9,7 @@
 //
 // One host thread drives all devices; nothing here blocks except rto_group_sync and host-memory frames.
 #include "rto_scene.cuh"
+#include "rto_nvtx.h"
 
 #include <cmath>
 #include <cstring>
@@ -59,6 +60,7 @@ struct RtoGroup {
 static int group_fail_cleanup(RtoGroup* g, int rc) { rto_group_destroy(g); return rc; }
 
 extern "C" int rto_group_create(const int* devices, int numDevices, RtoGroup** out) try {
+	RTO_RANGE("rto_group_create");
 	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_group_create: null output");
 	*out = nullptr;
 	if (!devices || numDevices <= 0 || numDevices > 64) return rto_fail(RTO_ERR_INVALID, "rto_group_create: 1 to 64 devices");
@@ -118,6 +120,7 @@ extern "C" void rto_group_destroy(RtoGroup* g) {
 extern "C" int rto_group_size(const RtoGroup* g) { return g ? (int)g->m.size() : 0; }
 
 extern "C" int rto_group_scene_bvh(RtoGroup* g, const RtoTriangle* tris, size_t numTris, const RtoHostBvh* prebuilt) try {
+	RTO_RANGE("rto_group_scene_bvh");
 	if (!g) return rto_fail(RTO_ERR_INVALID, "rto_group_scene_bvh: null group");
 	if (numTris && !tris) return rto_fail(RTO_ERR_INVALID, "rto_group_scene_bvh: null triangles");
 	BvhLayout L; size_t numRefNodes = 0;
@@ -190,6 +193,7 @@ static void rebalance(RtoGroup* g) {
 }
 
 extern "C" int rto_group_render_batch(RtoGroup* g, const RtoCamera* cams, int numCams, uint32_t flags, float shadowBias, const RtoFrame* frame) try {
+	RTO_RANGE("rto_group_render_batch");
 	if (!g || !cams || !frame || numCams <= 0) return rto_fail(RTO_ERR_INVALID, "rto_group_render_batch: null argument");
 	const size_t n = g->m.size();
 	for (Member& M : g->m) if (!M.scene) return rto_fail(RTO_ERR_INVALID, "rto_group_render_batch: no scene (rto_group_scene_bvh first)");

@@ -22,6 +22,7 @@ struct RtoScene {
 	rto::BvhDev bvhFast{};            // SAH topology over the same leaves (production closest-hit / shadow rays)
 	rto::OctDev oct{};
 	std::vector<void*> owned;         // device allocations of the scene
+	std::vector<size_t> ownedBytes;   // and their sizes (rto_scene_save writes the ones the descriptors point into)
 	// growable scratch (device outputs for RTO_MEM_HOST calls, cameras, ray lists)
 	void* scratch[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	size_t scratchBytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };

@@ -135,6 +135,26 @@ public:
 		if (rto_render(sc, &cam, m_mode, m_flags, m_shadowBias, 0, height, &fr) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
 		return true;
 	}
+	// extension: the uploaded scene as a file and back (rto_scene_save / rto_scene_load) -- the cache of what the reference rebuilds at
+	// every start (octree flatten, main.cpp:1127-1131), next to its own sceneCache.bin and triangle cache.  A loaded octree scene renders
+	// at once; flatNodes() stays empty, so renderSceneComputeWithCulling(.., updateFrustum = true) needs a setOctree() first.
+	bool saveSceneCache(const char* path) const {
+		RtoScene* sc = m_scene ? m_scene : m_external;
+		if (!sc || rto_scene_save(sc, path) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", sc ? rto_last_error() : "no scene to save"); return false; }
+		return true;
+	}
+	bool loadSceneCache(const char* path, const VoxelGrid& grid) {
+		RtoScene* sc = nullptr;
+		if (rto_scene_load(path, &sc) != RTO_OK) { std::fprintf(stderr, "[RayTracerBVH] %s\n", rto_last_error()); return false; }
+		int kind = 0;
+		rto_scene_info(sc, &kind, nullptr, nullptr, nullptr, nullptr);
+		if (kind == RTO_MODE_BVH) { rto_scene_destroy(sc); std::fprintf(stderr, "[RayTracerBVH] %s holds a mesh scene; setOctree's cache is an octree scene\n", path); return false; }
+		m_flatNodes.clear(); m_visibleToFlat.clear();
+		rto_scene_destroy(m_scene); m_scene = sc; m_mode = RTO_MODE_OCTREE_GLSL;
+		rto_scene_destroy(m_culled); m_culled = nullptr; m_culledEmpty = false;
+		m_gridMin[0] = grid.minX; m_gridMin[1] = grid.minY; m_gridMin[2] = grid.minZ; m_voxelSize = grid.voxelSize;
+		return true;
+	}
 	const Framebuffer& frame() const { return m_frame; }
 	const std::vector<GPUNodes>& flatNodes() const { return m_flatNodes; }
 

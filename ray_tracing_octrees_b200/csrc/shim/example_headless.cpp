@@ -6,6 +6,8 @@
 #include "VolumeRaycastRenderer.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <string>
 
 // FNV-1a over the three planes of a frame (tests/test_shim_cpp.py computes the same over the Python binding's render)
 static unsigned long long frameHash(const Framebuffer& fb) {
@@ -57,6 +59,15 @@ int main() {
 		size_t hits = 0; for (int id : fb.hitId) hits += id >= 0;
 		std::printf("octree frame: %zu of %zu pixels hit\n", hits, fb.hitId.size());
 		std::printf("octree frame hash %016llx\n", frameHash(fb));
+		{	// the uploaded scene as a file and back: a second tracer starts from the cache instead of createOctreeFromVoxelGrid + setOctree
+			const char* tmpdir = std::getenv("TMPDIR");
+			const std::string cache = std::string(tmpdir ? tmpdir : "/tmp") + "/rto_example_octree.rtoscene";
+			RayTracerBVH cached; Framebuffer fb2;
+			cached.ensureComputeInitialized();
+			if (tracer.saveSceneCache(cache.c_str()) && cached.loadSceneCache(cache.c_str(), grid) && cached.render(cam, 160, 120, 160.f / 120.f, 45.f, fb2))
+				std::printf("scene cache: frame hash %016llx\n", frameHash(fb2));
+			std::remove(cache.c_str());
+		}
 		{	// the single-ray call VolumeRaycastRenderer makes 49 times per frame (VolumeRaycastRenderer.cpp:1630), through the centre pixel's ray
 			rto_shim::vec3 ro = cam.getPos(), rd(-ro.x, -ro.y, -ro.z);
 			float len = std::sqrt(rd.x * rd.x + rd.y * rd.y + rd.z * rd.z); rd = rto_shim::vec3(rd.x / len, rd.y / len, rd.z / len);

@@ -63,6 +63,9 @@ def test_no_cpu_fallback_without_gpu(rto):
     with pytest.raises(rto.RtoError) as e:
         rto.Scene.octree(nodes, g.min, g.voxel_size)
     assert e.value.code == 2
+    with pytest.raises(rto.RtoError) as e:
+        rto.Scene.load("/nonexistent/scene.rtoscene")      # a cached scene is a DEVICE layout: nothing to do with it without one
+    assert e.value.code == 2
 
 
 def test_missing_library_fails_loudly(rto, monkeypatch):

@@ -68,6 +68,7 @@ def test_shim_renders_on_gpu(rto, tmp_path):
     cam, _ = rto.Camera(f32(0.5235988), f32(0.6981317), f32(1.2)).consts(45.0, f32(np.float32(160.0) / np.float32(120.0)), 160, 120)
     oc = rto.Scene.octree(nodes, grid.min, grid.voxel_size).render(cam, rto.MODE_OCTREE_GLSL)
     assert "octree frame hash " + fnv(oc["id"], oc["t"], oc["rgba"]) in out.stdout
+    assert "scene cache: frame hash " + fnv(oc["id"], oc["t"], oc["rgba"]) in out.stdout      # saveSceneCache -> loadSceneCache -> same frame
     tris = rto.marching_cubes_mesh(grid, nodes)
     sc = rto.Scene.bvh(tris)
     bias = f32(np.float32(1e-3) * np.float32(grid.voxel_size))
