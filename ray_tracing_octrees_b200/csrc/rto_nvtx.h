@@ -2,6 +2,11 @@
 // attached a range is one load and a branch; under Nsight Systems / Compute every C-ABI call shows up as a named range with the kernels,
 // copies and host work it caused underneath.  RTO_NO_NVTX compiles them out.
 #pragma once
+#if !defined(RTO_NO_NVTX) && defined(__has_include)
+#if !__has_include(<nvtx3/nvToolsExt.h>)
+#define RTO_NO_NVTX 1      // host files compiled on their own with a plain g++ (tests/dc_asan): no CUDA include path, no ranges
+#endif
+#endif
 #if !defined(RTO_NO_NVTX)
 #include <nvtx3/nvToolsExt.h>
 struct RtoRange {
