@@ -9,7 +9,7 @@ from the reference checkout, so its own voxel grid -> octree -> Marching-Cubes m
 8d) -- ray cast through the reference-shaped BVH at 1920x1080, primary rays plus one shadow ray per primary hit, cameras on the
 64-position orbit (theta 35 deg, radius 0.6 * 4250, phi_k = 40 + 360 k / 64 deg).
 
-One "step" = F orbit frames PER GPU (default 128 = two orbits), traced in launches of 16 frames per GPU.
+One "step" = F orbit frames PER GPU (default 128 = two orbits), traced in launches of BATCH (32) frames per GPU.
   N = 1   the frames are rendered straight into the frame planes (rgba32f + hit id + t, 24 B/pixel) in HBM.
   N > 1   scene replicated, the rows of every 16 x N-frame batch are dealt to the ranks, and EVERY frame is delivered as full planes
           in rank 0's HBM inside the timed region (BASELINE north_star: "only the framebuffer gather uses ... NVLink"): ranks != 0
@@ -45,7 +45,10 @@ CONFIG = {"workload": "C2: DT Calgary mesh (Marching-Cubes soup of the reference
                       "from the checkout), BVH ray cast at 1920x1080, primary + shadow rays, 64-camera orbit",
           "image": "1920x1080", "rays": "primary + one shadow ray per primary hit", "cameras": "orbit theta 35 deg, r 0.6*4250, phi 40 + 360k/64 deg"}
 DATA = "the reference's own voxelised DT Calgary grid (sceneCache.bin, committed gzip-compressed as tests/golden/dt_sceneCache.bin.gz) -> octree -> Marching-Cubes mesh; cameras synthetic"
-BATCH = 16            # frames per GPU per launch
+# frames per GPU per launch.  Measured on one 8-GPU box (third session of round 2; Grays/s at N = 8 with every frame on rank 0 / at N = 1):
+# 16 frames 95.1 / 13.45, 32 frames 99.0 / 13.59, 64 frames 98.1 / 13.60 -- a batch is what the ranks meet for (one 4-byte all-reduce per
+# batch), so fewer, larger batches cost less waiting; beyond 32 the larger plane sets on rank 0 take it back.
+BATCH = int(os.environ.get("RTO_BENCH_BATCH", "32"))
 
 
 def load_peaks():
@@ -205,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
     def rays_in(start, n):
         return sum(rays_of[(start + j) % ORBIT] for j in range(n))
 
-    # ---- planes: a ring of two batches (a batch is 16 frames per GPU; N > 1: all of them on rank 0) --------------------------
+    # ---- planes: a ring of two batches (a batch is BATCH frames per GPU; N > 1: all of them on rank 0) --------------------------
     gathered = world > 1 and not args.comm_free_only
     nb = BATCH * world if (gathered and rank == 0) else BATCH
     ring = [dict(rgba=torch.empty((nb, H, W, 4), dtype=torch.float32, device=dev), id=torch.empty((nb, H, W), dtype=torch.int32, device=dev),
@@ -290,13 +293,13 @@ def run_ours(args, rank, world, local_rank):
         cf_ms, _ = timed(step_local, min(args.steps, 10))
         comm_free = (cf_ms, sum(rays_in(((args.warmup + k) * world + rank) * F, F) for k in range(min(args.steps, 10))))
 
-    # ---- kernel duration for the roofline (CUDA events on the launching stream around one launch of 16 frames) ------------------
+    # ---- kernel duration for the roofline (CUDA events on the launching stream around one launch of BATCH frames) ------------------
     kern_ms = []
     p = ring[0]
     for k in range(7):
         scene.render_device(cam_array(k * BATCH, BATCH), rto.MODE_BVH, flags, bias, 0, H, p["rgba"].data_ptr(), p["id"].data_ptr(), p["t"].data_ptr())
         kern_ms.append(scene.last_kernel_ms())
-    kern_ms_avg = float(np.mean(kern_ms[2:6]))          # launches 2..5 = camera phases 32, 48, 0, 16: the whole orbit once
+    kern_ms_avg = float(np.mean(kern_ms[2:6]))          # launches 2..5: the whole orbit (twice at 32 frames per launch)
 
     # ---- e2e: host API, pinned host buffers, H2D cameras + D2H frame planes inside the timed region ---------------------------
     EB = 8
@@ -362,14 +365,16 @@ def run_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_render_bvh<shadows, pruned>), one launch = 16 frames ------------------------------
+    # ---- roofline of the dominant kernel (k_render_bvh<shadows, pruned>), one launch = BATCH frames ------------------------------
     # Algorithmic bytes/flops per ray are defined on the REFERENCE's structures: B box tests, C candidates, counted on
     # the GPU by replaying the reference's visit pattern (rto_render_stats, checked against the oracle's counters in the tests):
     #   primary ray: 24 B + 36 C + 24 bytes, 18 B + 51 C + 60 flops;  shadow ray: 24 Bs + 36 Cs bytes, 18 Bs + 51 Cs flops.
-    # The orbit's 64 cameras are sampled every 4th (16 of them = the cameras of an average launch).
+    # The orbit's 64 cameras are sampled every 4th and scaled to the BATCH cameras of an average launch.
     st = np.zeros(5, np.float64)
-    for k in range(0, ORBIT, 4):
+    sampled = list(range(0, ORBIT, 4))
+    for k in sampled:
         st += scene.stats(orbit[k], rto.MODE_BVH, flags, bias).astype(np.float64)
+    st *= BATCH / float(len(sampled))              # counters of the BATCH cameras of an average launch
     prim = BATCH * W * H
     alg_bytes = 24 * st[0] + 36 * st[1] + 24 * prim + 24 * st[2] + 36 * st[3]
     alg_flops = 18 * st[0] + 51 * st[1] + 60 * prim + 18 * st[2] + 51 * st[3]
@@ -386,6 +391,8 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             counters = {}
     traffic = counters.get("dram_bytes_per_launch")
+    if traffic and ("%d)" % BATCH) not in str(counters.get("grid", "")).replace(" ", ""):
+        traffic = None                              # the capture was taken with another number of frames per launch: not this launch's traffic
     roofline = {
         # neither HBM nor the tensor cores bound this kernel (scene L1/L2-resident, no contraction): the limit it is nearest to is FP32
         # instruction issue, so that is the one `frac` is quoted against (<= 1 by construction); the other limits are listed beside it.

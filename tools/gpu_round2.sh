@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.jso
 python tools/bench_configs.py --only ${CONFIGS:-C1,C2,C3,C5,C4DC} --out gpurun_out/configs.json > gpurun_out/configs.log 2>&1; echo "configs rc=$?"
 python tools/bench_builders.py --only ${BUILDERS:-c1,dt,c3,c4} --out gpurun_out/builders.json > gpurun_out/builders.log 2>&1; echo "builders rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_render_bvh -s 30 -c 1 -f -o gpurun_out/prof_bvh python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_render_bvh -s 14 -c 1 -f -o gpurun_out/prof_bvh python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
 if [ -n "$CAPTURE_ALL" ]; then
 for c in c3-octA c3-octB dt-octA dt-octB; do
   ncu --set full --clock-control none --import-source on -k regex:k_render_octree -s 2 -c 1 -f -o gpurun_out/prof_$c python tools/profile_case.py $c --reps 4 > gpurun_out/ncu_$c.log 2>&1
