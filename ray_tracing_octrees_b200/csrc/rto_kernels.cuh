@@ -59,7 +59,8 @@ RTO_DEV int ffs32(unsigned v) {
 
 // Loop form of the BVH walks (measured on B200, 16 x 1080p per launch, single loop -> while-while: closest hit C2 2.909 -> 2.829 ms,
 // primary only 2.021 -> 1.940, 512^3 city mesh 5.025 -> 4.826, sphere 0.901 -> 0.875; any-hit in the same form: C2 +1 % slower, city
-// 2 % faster -- left in the single-loop form).  profiles/README.md, round 2.
+// 2 % faster -- left in the single-loop form; parking the leaves of the any-hit walk and testing them behind the loop, where the lanes
+// have re-joined: 8-36 % slower, a shadowed ray that walks on costs more than the fuller Moller-Trumbore block saves).  profiles/README.md, round 2.
 #ifndef RTO_BVH_WHILE_WHILE
 #define RTO_BVH_WHILE_WHILE 1
 #endif
@@ -767,6 +768,40 @@ __host__ __device__ constexpr uint32_t skip_rank(int m) {
 	for (int j = 0; j < 8; j++) r |= (uint32_t)j << (4 * ((ord >> (4 * j)) & 7u));
 	return r;
 }
+// The mask of the children a mode-A walk may skip (empty leaves), re-ordered from octant numbering into VISIT order: bit j of the result
+// = bit skip_order(m)[j] of the mask.  Done with shifts and logic operations this costs 14 instructions per node on the ALU pipe, the
+// pipe that bounds the octree kernels; here it is one byte load from a 2 KB table (the LSU pipe idles in these kernels).
+#ifndef RTO_OCTA_SKIP_LUT
+#define RTO_OCTA_SKIP_LUT 1
+#endif
+#ifndef RTO_OCT_FADD_COORDS
+#define RTO_OCT_FADD_COORDS 1
+#endif
+struct SkipPermTable { unsigned char v[8][256]; };
+constexpr SkipPermTable make_skip_perm() {
+	SkipPermTable t{};
+	for (int m = 0; m < 8; m++) {
+		const uint32_t ord = skip_order(m);
+		for (unsigned k = 0; k < 256; k++) {
+			unsigned r = 0;
+			for (int j = 0; j < 8; j++) r |= ((k >> ((ord >> (4 * j)) & 7u)) & 1u) << j;
+			t.v[m][k] = (unsigned char)r;
+		}
+	}
+	return t;
+}
+constexpr SkipPermTable kSkipPermInit = make_skip_perm();
+#if defined(__CUDACC__)
+static __device__ const SkipPermTable g_skipPermDev = kSkipPermInit;
+#endif
+static const SkipPermTable g_skipPermHost = kSkipPermInit;
+RTO_DEV unsigned skip_perm(int m, unsigned mask) {
+#if defined(__CUDA_ARCH__)
+	return (unsigned)__ldg(&g_skipPermDev.v[m][mask]);
+#else
+	return g_skipPermHost.v[m][mask];
+#endif
+}
 RTO_DEV void skip_tables(int dirMask, uint32_t& order, uint32_t& rank) {
 	constexpr uint32_t ord[8] = { skip_order(0), skip_order(1), skip_order(2), skip_order(3), skip_order(4), skip_order(5), skip_order(6), skip_order(7) };
 	constexpr uint32_t rnk[8] = { skip_rank(0), skip_rank(1), skip_rank(2), skip_rank(3), skip_rank(4), skip_rank(5), skip_rank(6), skip_rank(7) };
@@ -1032,12 +1067,20 @@ struct ChildPlanes { float n0[3], f0[3], n1[3], f1[3]; };     // per axis: near/
 template <int OCT>
 RTO_DEV ChildPlanes oct_child_planes(const OctDev& S, V3 o, V3 inv, int x, int y, int z, int h) {
 	ChildPlanes P;
-	const float w = float(h) * S.voxel;
+	const float fh = float(h);
+	const float w = fh * S.voxel;
 	const int c[3] = { x, y, z };
 	const float oo[3] = { o.x, o.y, o.z }, ii[3] = { inv.x, inv.y, inv.z };
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
+		// float(c + h) == float(c) + float(h): both are integers below 2^24 on the fast paths (rootSize <= 65536), so the sum is exact --
+		// an addition on the FMA pipe instead of a second conversion on the ALU pipe, which is the one that bounds these kernels
+#if RTO_OCT_FADD_COORDS
+		const float fc = float(c[a]);
+		float lo0 = S.gmin[a] + fc * S.voxel, lo1 = S.gmin[a] + (fc + fh) * S.voxel;
+#else
 		float lo0 = S.gmin[a] + float(c[a]) * S.voxel, lo1 = S.gmin[a] + float(c[a] + h) * S.voxel;
+#endif
 		float t1 = (lo0 - oo[a]) * ii[a], t2 = ((lo0 + w) - oo[a]) * ii[a];
 		float u1 = (lo1 - oo[a]) * ii[a], u2 = ((lo1 + w) - oo[a]) * ii[a];
 		if (OCT < 8) {
@@ -1219,13 +1262,15 @@ RTO_DEV OctHit octA_fast_loop(const OctDev& S, V3 o, V3 d, float tMin, float tMa
 			P.n0[2] = fmaxf(P.n0[2], curMin); P.n1[2] = fmaxf(P.n1[2], curMin);
 			P.f0[2] = fminf(P.f0[2], curMax); P.f1[2] = fminf(P.f1[2], curMax);
 			unsigned Mo = 0, skipO = 0;                            // bit j = j-th child in VISIT order
+			constexpr bool kLut = RTO_OCTA_SKIP_LUT && OCT < 8;
+			if (kLut) skipO = skip_perm((~OCT) & 7, skipMask);
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
 				const int k = (int)((order >> (4 * j)) & 7u);
 				float tn = fmax3f((k & 1) ? P.n1[0] : P.n0[0], (k & 2) ? P.n1[1] : P.n0[1], (k & 4) ? P.n1[2] : P.n0[2]);
 				float tf = fmin3f((k & 1) ? P.f1[0] : P.f0[0], (k & 2) ? P.f1[1] : P.f0[1], (k & 4) ? P.f1[2] : P.f0[2]);
 				Mo |= !(tn > tf) ? (1u << j) : 0u;
-				skipO |= ((skipMask >> k) & 1u) << j;
+				if (!kLut) skipO |= ((skipMask >> k) & 1u) << j;
 			}
 			M = Mo & ~skipO;
 		}

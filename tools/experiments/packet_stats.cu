@@ -25,7 +25,7 @@ static void trace_ray(const BvhDev& S, V3 o, V3 d, std::vector<int>& inner, std:
 			const float4* n = S.nodes + 4 * (size_t)cur;
 			float4 a = n[0], b = n[1], c = n[2]; float2 r = *reinterpret_cast<const float2*>(n + 3);
 			float e0, e1; bool h0, h1;
-			node_boxes<kOctGeneric>(rb, a, b, c, tcut, h0, h1, e0, e1);
+			node_boxes<kOctGeneric>(rb, make_raybox2(rb), S.paired, a, b, c, tcut, h0, h1, e0, e1);
 			int r0 = f2i(r.x), r1 = f2i(r.y);
 			if (h0 && h1) { bool sw = e1 < e0; StackEnt e; e.ref = sw ? r0 : r1; e.t = sw ? e0 : e1; stack[sp++] = e; cur = sw ? r1 : r0; pop = false; }
 			else if (h0) { cur = r0; pop = false; } else if (h1) { cur = r1; pop = false; }
@@ -80,7 +80,7 @@ int main(int argc, char** argv) {
 					const float4* nd = S.nodes + 4 * (size_t)cur; float4 a = nd[0], b = nd[1], c = nd[2]; float2 r = *reinterpret_cast<const float2*>(nd + 3);
 					int r0 = f2i(r.x), r1 = f2i(r.y);
 					int any0 = 0, any1 = 0, pref1 = 0; float min0 = 1e38f, min1 = 1e38f;
-					for (int l = 0; l < 32; l++) if (alive[l]) { float e0, e1; bool h0, h1; node_boxes<kOctGeneric>(rb[l], a, b, c, tcut[l], h0, h1, e0, e1); if (h0) { any0++; min0 = std::min(min0, e0); } if (h1) { any1++; min1 = std::min(min1, e1); } if (h0 && h1 && e1 < e0) pref1++; else if (h1 && !h0) pref1++; }
+					for (int l = 0; l < 32; l++) if (alive[l]) { float e0, e1; bool h0, h1; node_boxes<kOctGeneric>(rb[l], make_raybox2(rb[l]), S.paired, a, b, c, tcut[l], h0, h1, e0, e1); if (h0) { any0++; min0 = std::min(min0, e0); } if (h1) { any1++; min1 = std::min(min1, e1); } if (h0 && h1 && e1 < e0) pref1++; else if (h1 && !h0) pref1++; }
 					if (any0 && any1) { bool sw = min1 < min0; st[sp++] = { sw ? r0 : r1, sw ? min0 : min1 }; cur = sw ? r1 : r0; pop = false; }
 					else if (any0) { cur = r0; pop = false; } else if (any1) { cur = r1; pop = false; }
 				} else {
