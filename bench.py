@@ -334,6 +334,16 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_idt_s = time.perf_counter() - te
     e2e_idt_rays = rays_in((args.warmup * world + rank) * F, F)
+    # ... and asking for the framebuffer only: the RGBA32F image is all RayTracerBVH::renderSceneCompute itself produces (16 B/pixel)
+    def step_host_rgba(k):
+        base = (k * world + rank) * F
+        for c in range(F // EB):
+            scene.render_host_ptrs(cam_array(base + c * EB, EB), rto.MODE_BVH, flags, bias, 0, H, h_rgba.data_ptr(), None, None)
+    sync_all()
+    te = time.perf_counter()
+    step_host_rgba(args.warmup)
+    torch.cuda.synchronize()
+    e2e_rgba_s = time.perf_counter() - te
     # the ceiling of the link: all ranks copy device -> pinned host at the same time, nothing else running
     d_src = ring[0]["rgba"].view(-1)[:h_rgba.numel()]
     sync_all()
@@ -348,12 +358,12 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
 
     # ---- reduce over ranks: max time, sum rays ---------------------------------------------------------------
-    tvec = torch.tensor([dev_ms, e2e_s, kern_ms_avg, comm_free[0] if comm_free else 0.0, e2e_idt_s], dtype=torch.float64, device=dev)
+    tvec = torch.tensor([dev_ms, e2e_s, kern_ms_avg, comm_free[0] if comm_free else 0.0, e2e_idt_s, e2e_rgba_s], dtype=torch.float64, device=dev)
     rvec = torch.tensor([0 if gathered else rays_main, e2e_rays, launches, comm_free[1] if comm_free else 0.0, e2e_idt_rays, d2h_gbps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
         dist.all_reduce(rvec, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, kern_ms_max, cf_ms_max, e2e_idt_s_max = [float(x) for x in tvec.tolist()]
+    dev_ms_max, e2e_s_max, kern_ms_max, cf_ms_max, e2e_idt_s_max, e2e_rgba_s_max = [float(x) for x in tvec.tolist()]
     rays_all, e2e_rays_all, launches_all, cf_rays_all, e2e_idt_rays_all, d2h_gbps_all = [float(x) for x in rvec.tolist()]
     if gathered:
         rays_all = float(rays_main)                     # every rank counted the same global frames
@@ -448,7 +458,9 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_GBps": world * e2e_steps * F * W * H * 24 / e2e_s_max / 1e9,
                     "d2h_ceiling_GBps": d2h_gbps_all, "ceiling": "all %d rank(s) copying 530 MB device -> pinned host six times concurrently, nothing else running (sum over ranks)" % world,
                     "id_t_only": {"value": e2e_idt_rays_all / e2e_idt_s_max / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": F * W * H * 8, "steps": 1,
-                                  "what": "the same call with rgba = NULL: hit id + t planes only (8 B/pixel)"}},
+                                  "what": "the same call with rgba = NULL: hit id + t planes only (8 B/pixel)"},
+                    "rgba_only": {"value": e2e_idt_rays_all / e2e_rgba_s_max / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": F * W * H * 16, "steps": 1,
+                                  "what": "the same call with hitId = t = NULL: the RGBA32F framebuffer alone, which is all the reference's renderSceneCompute produces (16 B/pixel)"}},
             "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu}
     if gathered:
         line["gather"] = {"what": "every frame delivered as rgba32f + id + t planes in rank 0's HBM inside the timed region", "transport": gr.transport,
