@@ -302,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
     kern_ms_avg = float(np.mean(kern_ms[2:6]))          # launches 2..5: the whole orbit (twice at 32 frames per launch)
 
     # ---- e2e: host API, pinned host buffers, H2D cameras + D2H frame planes inside the timed region ---------------------------
-    EB = 8
+    EB = min(args.e2e_batch, BATCH) if args.e2e_batch > 0 and F % min(args.e2e_batch, BATCH) == 0 else 8      # frames per host call: the first kernel of a call has no copy to hide behind
     h_rgba = torch.empty((EB, H, W, 4), dtype=torch.float32).pin_memory()
     h_id = torch.empty((EB, H, W), dtype=torch.int32).pin_memory()
     h_t = torch.empty((EB, H, W), dtype=torch.float32).pin_memory()
@@ -484,6 +484,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=128, help="orbit frames per step per GPU (multiple of 16)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-batch", type=int, default=32, help="frames per rto_render_batch(RTO_MEM_HOST) call of the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm-free-only", action="store_true", help="N > 1: skip the gather (round-1 behaviour)")
     args = ap.parse_args()

@@ -707,7 +707,15 @@ __global__ void k_sah_select(int numInner, const int2* __restrict__ rangeOf, con
 	if (link >= 0) { const int2 pr = rangeOf[link >> 1]; if (pr.y - pr.x + 1 <= kSahChunk) return; }
 	list[atomicAdd(count, 1)] = i;
 }
-__global__ void __launch_bounds__(64) k_sah_rebuild(int count, const int* __restrict__ list, const int2* __restrict__ rangeOf, const float* __restrict__ leafBox, float4* __restrict__ nodes,
+// one block per subtree (rto_sahchunk.h, sah_rebuild_chunk_block)
+__global__ void __launch_bounds__(kSahBlock) k_sah_rebuild(const int* __restrict__ list, const int2* __restrict__ rangeOf, const float* __restrict__ leafBox, float4* __restrict__ nodes,
+	int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf) {
+	const int i = list[blockIdx.x];
+	const int2 r = rangeOf[i];
+	sah_rebuild_chunk_block(leafBox, r.x, r.y, i, nodes, parentOfInner, parentOfLeaf);
+}
+// one thread per subtree: the form the CPU emulation checks, kept as a cross-check of the block form (RTO_SAH_SERIAL=1; tests/test_gpu_builders.py)
+__global__ void __launch_bounds__(64) k_sah_rebuild_serial(int count, const int* __restrict__ list, const int2* __restrict__ rangeOf, const float* __restrict__ leafBox, float4* __restrict__ nodes,
 	int* __restrict__ parentOfInner, int* __restrict__ parentOfLeaf) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= count) return;
@@ -831,7 +839,9 @@ int lbvh_build(RtoScene* s, const RtoTriangle* dTris, size_t numTris) {
 			int chunks = 0;
 			BUILD_TRY(cudaMemcpyAsync(&chunks, chunkCount, sizeof(int), cudaMemcpyDeviceToHost, st));
 			BUILD_TRY(cudaStreamSynchronize(st));
-			if (chunks > 0) k_sah_rebuild<<<(unsigned)((chunks + 63) / 64), 64, 0, st>>>(chunks, chunkList, rangeOf, leafBox, (float4*)dNodes, pInner, pLeaf);
+			const char* serial = getenv("RTO_SAH_SERIAL");
+			if (chunks > 0 && serial && serial[0] == '1') k_sah_rebuild_serial<<<(unsigned)((chunks + 63) / 64), 64, 0, st>>>(chunks, chunkList, rangeOf, leafBox, (float4*)dNodes, pInner, pLeaf);
+			else if (chunks > 0) k_sah_rebuild<<<(unsigned)chunks, kSahBlock, 0, st>>>(chunkList, rangeOf, leafBox, (float4*)dNodes, pInner, pLeaf);
 			BUILD_TRY(cudaGetLastError());
 		}
 		k_lbvh_fit<<<blocksL, 256, 0, st>>>(numLeaves, leafBox, (float*)dNodes, pInner, pLeaf, arrived, dRoot, dDepth);

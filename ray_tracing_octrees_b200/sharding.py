@@ -38,6 +38,7 @@ def assemble_rows(height, width, world, parts, band=8, channels=None):
 
 def gather_planes(plane, dst=0, group=None):
     """Framebuffer gather: every rank contributes a tensor of identical shape, rank `dst` gets the list (others None).
+    `dst` is a rank OF `group` (the default group's ranks are the global ones); torch's gather wants the global rank.
     One grouped NCCL/gloo gather; the caller may run it on a side stream to overlap the next batch."""
     import torch
     import torch.distributed as dist
@@ -47,7 +48,7 @@ def gather_planes(plane, dst=0, group=None):
         return [plane]
     if dist.get_backend(group) == "nccl":
         outs = [torch.empty_like(plane) for _ in range(world)] if rank == dst else None
-        dist.gather(plane, outs, dst=dst, group=group)
+        dist.gather(plane, outs, dst=dst if group is None else dist.get_global_rank(group, dst), group=group)
         return outs
     outs = [torch.empty_like(plane) for _ in range(world)]     # gloo: all_gather is the portable primitive
     dist.all_gather(outs, plane, group=group)

@@ -129,6 +129,35 @@ def test_device_bvh_hits_equal_reference_tree_hits_except_near_ties(rto, grids, 
         assert n_diff <= 1e-4 * w * h, "%s: %d of %d hit ids differ from the reference-shaped tree" % (name, n_diff, w * h)
 
 
+@pytest.mark.parametrize("name,theta,phi,radius", [("sphere32", 30, 40, 1.2), ("ragged_noise", 20, 70, 30.0), ("city128", 35, 40, 115.0), ("dt", 35, 40, 0.6 * 4250)])
+def test_block_rebuild_of_the_device_tree_equals_the_serial_one(rto, grids, name, theta, phi, radius, tmp_path, monkeypatch):
+    """The surface-area rebuild of the device-built tree runs as one block per subtree (rto_sahchunk.h sah_rebuild_chunk_block); the
+    one-thread form, which tests/test_emu_traversal.py checks on the CPU, is kept behind RTO_SAH_SERIAL=1.  Both choose their splits from the
+    same bins, so they build the same tree: the saved device layouts are compared byte for byte (they may differ only below ranges whose
+    centroids all coincide, where any halving is valid -- then the frames still have to agree up to near-ties), and the frames bit for bit."""
+    g = grids[name]
+    tris = rto.marching_cubes_mesh(g, rto.create_octree_from_voxel_grid(g))
+    block = rto.Scene.bvh_device(tris)
+    monkeypatch.setenv("RTO_SAH_SERIAL", "1")
+    serial = rto.Scene.bvh_device(tris)
+    monkeypatch.delenv("RTO_SAH_SERIAL")
+    pa, pb = str(tmp_path / "block.rtoscene"), str(tmp_path / "serial.rtoscene")
+    block.save(pa); serial.save(pb)
+    same_layout = open(pa, "rb").read() == open(pb, "rb").read()
+    w, h = 480, 270
+    cam, _ = rto.Camera.from_degrees(theta, phi, radius).consts(45.0, float(np.float32(w) / np.float32(h)), w, h)
+    bias = 1e-3 * g.voxel_size
+    for flags in (rto.FLAG_NO_PRUNE, rto.FLAG_SHADOWS):
+        a, b = block.render(cam, rto.MODE_BVH, flags, bias), serial.render(cam, rto.MODE_BVH, flags, bias)
+        if same_layout or flags == rto.FLAG_NO_PRUNE:       # the exact path does not depend on the tree at all
+            assert np.array_equal(a["id"], b["id"]) and np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+            assert np.array_equal(a["rgba"].view(np.uint32), b["rgba"].view(np.uint32))
+        else:
+            assert (a["id"] != b["id"]).mean() <= 1e-4
+    assert (a["id"] >= 0).any()
+    print("%s: block and serial rebuild give %s device layouts" % (name, "byte-identical" if same_layout else "different (ranges whose box centres coincide, e.g. the two triangles of a Marching-Cubes quad)"))
+
+
 def test_device_bvh_edge_cases(rto, grids):
     cam, _ = rto.Camera.from_degrees(30, 40, 6.0).consts(45.0, 1.0, 64, 64)
     # no triangles, one triangle, two, three (one and a half leaves)
