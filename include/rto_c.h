@@ -340,6 +340,10 @@ RTO_API int rto_group_sync(RtoGroup* group);
 RTO_API int rto_trace_rays(RtoScene* scene, int mode, uint32_t flags, const float* origins, const float* dirs, size_t numRays,
 	float tMin, float tMax, float* tOut, int32_t* idOut, int memory);
 
+/* The stable device radix sort behind RTO_FLAG_SORT_RAYS on its own (csrc/rto_sort.cuh; hand-written, no library sort): n pairs of 32-bit
+ * keys and values in host memory, sorted by key in place.  Not in the reference (north-star extension: ray coherence sorting). */
+RTO_API int rto_device_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n);
+
 /* BVH::query for many rays (BVH.cpp:107-113): candidate triangle ids per ray in the reference's order.
  * offsets has numRays+1 entries (host memory).  Call with ids == NULL to get the total in *totalOut first. */
 RTO_API int rto_bvh_query(RtoScene* scene, const float* origins, const float* dirs, size_t numRays,

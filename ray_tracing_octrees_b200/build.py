@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librto.so")
 SOURCES = ["rto_device.cu", "rto_group.cu", "rto_build.cu", "rto_dc.cu", "rto_blob.cu", "host_builders.cpp", "host_layouts.cpp", "host_dc.cpp"]
-DEPS = SOURCES + ["rto_kernels.cuh", "rto_scene.cuh", "rto_devtypes.h", "rto_voxelize.h", "rto_frustum.h", "rto_dc.h", "rto_sahchunk.h", "rto_internal.h", "rto_nvtx.h", "rto_math.h", "mc_tables.h", "../../include/rto_c.h"]
+DEPS = SOURCES + ["rto_kernels.cuh", "rto_scene.cuh", "rto_devtypes.h", "rto_voxelize.h", "rto_frustum.h", "rto_dc.h", "rto_sahchunk.h", "rto_sort.cuh", "rto_internal.h", "rto_nvtx.h", "rto_math.h", "mc_tables.h", "../../include/rto_c.h"]
 
 
 def nvcc_cmd(extra=(), out=None):

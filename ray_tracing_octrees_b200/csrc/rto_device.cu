@@ -5,7 +5,7 @@
 #include "rto_scene.cuh"
 #include "rto_nvtx.h"
 #include "rto_kernels.cuh"
-#include <cub/cub.cuh>
+#include "rto_sort.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -617,13 +617,11 @@ extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float
 		if ((rc = scene_scratch(s, 4, numRays * 8, &k0))) return rc;
 		if ((rc = scene_scratch(s, 5, numRays * 8, &i0))) return rc;
 		k1 = (uint32_t*)k0 + numRays; i1 = (uint32_t*)i0 + numRays;
-		size_t tmpBytes = 0;
-		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (uint32_t*)k0, (uint32_t*)k1, (uint32_t*)i0, (uint32_t*)i1, (int)numRays, 0, 32, s->stream));
-		if ((rc = scene_scratch(s, 6, tmpBytes, &tmp))) return rc;
+		if ((rc = scene_scratch(s, 6, sort_scratch_bytes(numRays), &tmp))) return rc;
 		k_ray_sort_keys<<<(unsigned)((numRays + 255) / 256), 256, 0, s->stream>>>(dO, dD, numRays, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], (uint32_t*)k0, (uint32_t*)i0);
-		CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, (uint32_t*)k0, (uint32_t*)k1, (uint32_t*)i0, (uint32_t*)i1, (int)numRays, 0, 32, s->stream));
-		perm = (const uint32_t*)i1;
-		s->launches += 2;
+		s->launches++;
+		CUDA_TRY(sort_pairs_u32((uint32_t*)k0, (uint32_t*)i0, (uint32_t*)k1, (uint32_t*)i1, numRays, tmp, s->stream, &s->launches));      // rto_sort.cuh
+		perm = (const uint32_t*)i0;
 	}
 	if (s->kind == RTO_MODE_BVH) k_trace_bvh<<<blocks, 128, 0, s->stream>>>((flags & RTO_FLAG_NO_PRUNE) ? s->bvh : s->bvhFast, flags, dO, dD, numRays, dT, dI, perm);
 	else k_trace_octree<<<blocks, 128, 0, s->stream>>>(s->oct, mode, dO, dD, numRays, tMin, tMax, dT, dI, perm);
@@ -638,6 +636,26 @@ extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float
 	}
 	return RTO_OK;
 } RTO_CATCH_ALL("rto_trace_rays")
+
+// The device sort behind RTO_FLAG_SORT_RAYS on its own (rto_sort.cuh): n key / value pairs in host memory, sorted by key in place, stable.
+extern "C" int rto_device_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n) try {
+	RTO_RANGE("rto_device_sort_pairs");
+	if (n && (!keys || !vals)) return rto_fail(RTO_ERR_INVALID, "rto_device_sort_pairs: null argument");
+	if (n >= ((size_t)1 << 31)) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_device_sort_pairs: fewer than 2^31 pairs");
+	int rc = rto_require_device(); if (rc) return rc;
+	if (n < 2) return RTO_OK;
+	uint32_t* d = nullptr; void* tmp = nullptr;
+	cudaError_t e = cudaMalloc((void**)&d, 4 * n * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc(&tmp, sort_scratch_bytes(n));
+	if (e == cudaSuccess) e = cudaMemcpy(d, keys, n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(d + n, vals, n * 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = sort_pairs_u32(d, d + n, d + 2 * n, d + 3 * n, n, tmp, 0);
+	if (e == cudaSuccess) e = cudaMemcpy(keys, d, n * 4, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(vals, d + n, n * 4, cudaMemcpyDeviceToHost);
+	cudaFree(d); cudaFree(tmp);
+	if (e != cudaSuccess) return rto_fail(RTO_ERR_CUDA, "rto_device_sort_pairs: %s", cudaGetErrorString(e));
+	return RTO_OK;
+} RTO_CATCH_ALL("rto_device_sort_pairs")
 
 extern "C" int rto_bvh_query(RtoScene* s, const float* origins, const float* dirs, size_t numRays,
 	int64_t* offsets, int32_t* ids, size_t idsCapacity, size_t* totalOut) try {

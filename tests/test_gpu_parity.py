@@ -453,3 +453,29 @@ def test_ray_coherence_sorting_changes_nothing_but_the_order(gpu, dt_scene):
         assert_bit_equal(t0, t1, "t mode %d" % mode)
     t1, i1 = sc.trace_rays(o[:1], d[:1], rto.MODE_BVH, flags=rto.FLAG_SORT_RAYS)                     # a single ray is not sorted
     assert i1[0] == sc.trace_rays(o[:1], d[:1], rto.MODE_BVH)[1][0]
+
+
+def test_device_radix_sort_is_a_stable_sort(gpu):
+    """csrc/rto_sort.cuh (the hand-written sort behind RTO_FLAG_SORT_RAYS) through rto_device_sort_pairs: keys come back ascending and the
+    values follow them in the order of a STABLE sort -- equal keys keep their input order -- for sizes around the 4096-key tiles and the
+    512-key warp runs, for keys with few distinct values, one value, all 32 bits in use, and already sorted / reversed input."""
+    import ctypes
+    rto = gpu
+    rng = np.random.default_rng(11)
+    cases = []
+    for n in (0, 1, 2, 3, 31, 32, 33, 511, 512, 513, 4095, 4096, 4097, 8192, 12345, 100000, 1 << 20, (1 << 21) + 777):
+        cases.append(rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32))
+    cases.append(rng.integers(0, 3, 50000, dtype=np.uint64).astype(np.uint32))                      # three distinct keys
+    cases.append(np.full(70000, 0xdeadbeef, np.uint32))                                             # one key
+    cases.append((rng.integers(0, 256, 300000, dtype=np.uint64) << 24).astype(np.uint32))           # only the top digit differs
+    cases.append(np.arange(200000, dtype=np.uint32))                                                # sorted
+    cases.append(np.arange(200000, dtype=np.uint32)[::-1].copy())                                   # reversed
+    cases.append((rng.integers(0, 1 << 16, 400000, dtype=np.uint64) * 65537 % (1 << 32)).astype(np.uint32))
+    for keys in cases:
+        n = len(keys)
+        k = keys.copy(); v = np.arange(n, dtype=np.uint32)
+        rc = rto.lib().rto_device_sort_pairs(k.ctypes.data_as(ctypes.c_void_p), v.ctypes.data_as(ctypes.c_void_p), n)
+        assert rc == 0, rto.lib().rto_last_error().decode()
+        order = np.argsort(keys, kind="stable").astype(np.uint32)
+        assert np.array_equal(v, order), "n = %d: permutation differs from a stable sort" % n
+        assert np.array_equal(k, keys[order])
