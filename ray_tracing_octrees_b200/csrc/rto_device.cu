@@ -371,20 +371,30 @@ extern "C" int rto_render_batch(RtoScene* s, const RtoCamera* cams, int numCams,
 	else { A.rgba = (float4*)frame->rgba; A.hitId = frame->hitId; A.t = frame->t; }
 	if ((unsigned long long)npix >= 0xffffffffull) return rto_fail(RTO_ERR_UNSUPPORTED, "rto_render: more than 2^32 pixels in one call");
 	CUDA_TRY(cudaEventRecord(s->evStart, s->stream));
-	if (host && numCams > 1) {
-		// one launch per frame; the planes of frame i travel to the host on the copy stream while frame i+1 is traced
-		const size_t fpix = (size_t)(y1 - y0) * W;
+	// a single frame into host memory is cut into row bands for the same reason (the call renderSceneCompute maps to): the copy of band b
+	// runs while band b + 1 is traced, so the call takes one band's trace plus the copies instead of the whole trace plus the copies
+	const int rows = y1 - y0;
+	int bands = (host && numCams == 1 && rows >= 256) ? 4 : 1;
+	if (bands > 1) if (const char* e = getenv("RTO_HOST_BANDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) bands = v; }      // tuning aid
+	if (host && (numCams > 1 || bands > 1)) {
+		// one launch per frame (or band); the planes of unit i travel to the host on the copy stream while unit i + 1 is traced
+		const size_t fpix = (size_t)rows * W;
+		const int bandRows = ((rows + bands - 1) / bands + 7) & ~7;              // multiples of the kernels' 8-row tiles
 		for (int c = 0; c < numCams; c++) {
-			RenderArgs Ac = A;
-			Ac.cam0 = cams[c]; Ac.cams = nullptr;
-			Ac.rgba = A.rgba ? A.rgba + c * fpix : nullptr; Ac.hitId = A.hitId ? A.hitId + c * fpix : nullptr; Ac.t = A.t ? A.t + c * fpix : nullptr;
-			if ((rc = launch_render(s, Ac, W, 1, mode, s->stream))) return rc;
-			CUDA_TRY(cudaGetLastError());
-			CUDA_TRY(cudaEventRecord(s->evFrame, s->stream));
-			CUDA_TRY(cudaStreamWaitEvent(s->copyStream, s->evFrame, 0));
-			if (frame->rgba) CUDA_TRY(cudaMemcpyAsync(frame->rgba + 4 * c * fpix, Ac.rgba, fpix * 16, cudaMemcpyDeviceToHost, s->copyStream));
-			if (frame->hitId) CUDA_TRY(cudaMemcpyAsync(frame->hitId + c * fpix, Ac.hitId, fpix * 4, cudaMemcpyDeviceToHost, s->copyStream));
-			if (frame->t) CUDA_TRY(cudaMemcpyAsync(frame->t + c * fpix, Ac.t, fpix * 4, cudaMemcpyDeviceToHost, s->copyStream));
+			for (int r0 = 0; r0 < rows; r0 += bandRows) {
+				const int r1 = r0 + bandRows < rows ? r0 + bandRows : rows;
+				const size_t off = c * fpix + (size_t)r0 * W, bpix = (size_t)(r1 - r0) * W;
+				RenderArgs Ac = A;
+				Ac.cam0 = cams[c]; Ac.cams = nullptr; Ac.y0 = y0 + r0; Ac.y1 = y0 + r1;
+				Ac.rgba = A.rgba ? A.rgba + off : nullptr; Ac.hitId = A.hitId ? A.hitId + off : nullptr; Ac.t = A.t ? A.t + off : nullptr;
+				if ((rc = launch_render(s, Ac, W, 1, mode, s->stream))) return rc;
+				CUDA_TRY(cudaGetLastError());
+				CUDA_TRY(cudaEventRecord(s->evFrame, s->stream));
+				CUDA_TRY(cudaStreamWaitEvent(s->copyStream, s->evFrame, 0));
+				if (frame->rgba) CUDA_TRY(cudaMemcpyAsync(frame->rgba + 4 * off, Ac.rgba, bpix * 16, cudaMemcpyDeviceToHost, s->copyStream));
+				if (frame->hitId) CUDA_TRY(cudaMemcpyAsync(frame->hitId + off, Ac.hitId, bpix * 4, cudaMemcpyDeviceToHost, s->copyStream));
+				if (frame->t) CUDA_TRY(cudaMemcpyAsync(frame->t + off, Ac.t, bpix * 4, cudaMemcpyDeviceToHost, s->copyStream));
+			}
 		}
 		CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
 		s->timed = true;
