@@ -340,6 +340,12 @@ RTO_API int rto_group_sync(RtoGroup* group);
 RTO_API int rto_trace_rays(RtoScene* scene, int mode, uint32_t flags, const float* origins, const float* dirs, size_t numRays,
 	float tMin, float tMax, float* tOut, int32_t* idOut, int memory);
 
+/* Page-locked host memory for frame planes (cudaHostAlloc, usable from every device): RTO_MEM_HOST frames are copied at the speed of the
+ * link only into page-locked memory; into ordinary memory the driver stages the copy (measured: profiles/README.md).  The reference never
+ * reads its frame back (a GL texture, RayTracerBVH.cpp:815-887), so there is no counterpart.  RTO_ERR_NO_DEVICE without a CUDA device. */
+RTO_API int rto_host_alloc_pinned(size_t bytes, void** out);
+RTO_API void rto_host_free_pinned(void* p);
+
 /* The stable device radix sort behind RTO_FLAG_SORT_RAYS on its own (csrc/rto_sort.cuh; hand-written, no library sort): n pairs of 32-bit
  * keys and values in host memory, sorted by key in place.  Not in the reference (north-star extension: ray coherence sorting). */
 RTO_API int rto_device_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "rto_render_batch": (_i, [_vp, _vp, _i, _i, _u32, _f, _i, _i, C.POINTER(RtoFrame)]),
     "rto_trace_rays": (_i, [_vp, _i, _u32, _vp, _vp, _sz, _f, _f, _vp, _vp, _i]),
     "rto_device_sort_pairs": (_i, [_vp, _vp, _sz]),
+    "rto_host_alloc_pinned": (_i, [_sz, C.POINTER(_vp)]),
+    "rto_host_free_pinned": (None, [_vp]),
     "rto_bvh_query": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(_sz)]),
     "rto_render_stats": (_i, [_vp, C.POINTER(RtoCamera), _i, _u32, _f, _i, _i, _vp]),
     "rto_octree_skip_distance": (_i, [_vp, _vp, _vp, _f, _f, C.POINTER(_f), _vp]),

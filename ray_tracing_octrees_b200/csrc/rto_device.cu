@@ -647,6 +647,19 @@ extern "C" int rto_trace_rays(RtoScene* s, int mode, uint32_t flags, const float
 	return RTO_OK;
 } RTO_CATCH_ALL("rto_trace_rays")
 
+// Page-locked host memory for frame planes: a device -> host copy into ordinary (pageable) memory is staged by the driver and runs at a
+// fraction of the link's speed; the reference never reads its frame back (a GL texture), so this has no counterpart there.
+extern "C" int rto_host_alloc_pinned(size_t bytes, void** out) try {
+	if (!out) return rto_fail(RTO_ERR_INVALID, "rto_host_alloc_pinned: null output");
+	*out = nullptr;
+	int rc = rto_require_device(); if (rc) return rc;
+	if (bytes == 0) bytes = 1;
+	cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+	if (e != cudaSuccess) { *out = nullptr; return rto_fail(e == cudaErrorMemoryAllocation ? RTO_ERR_ALLOC : RTO_ERR_CUDA, "rto_host_alloc_pinned(%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+	return RTO_OK;
+} RTO_CATCH_ALL("rto_host_alloc_pinned")
+extern "C" void rto_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
 // The device sort behind RTO_FLAG_SORT_RAYS on its own (rto_sort.cuh): n key / value pairs in host memory, sorted by key in place, stable.
 extern "C" int rto_device_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n) try {
 	RTO_RANGE("rto_device_sort_pairs");

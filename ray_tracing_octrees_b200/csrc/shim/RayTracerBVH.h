@@ -6,6 +6,8 @@
 #include "Camera.h"
 #include "OctreeVoxel.h"
 #include <cstdio>
+#include <cstdlib>
+#include <new>
 #include <queue>
 #include <unordered_map>
 
@@ -13,11 +15,35 @@ struct Ray { rto_shim::vec3 origin, direction; };                          // Ra
 struct GPUNodes { int x, y, z, size; int isLeaf, isSolid; int isUniform; int child[8]; };   // RayTracerBVH.h:21-26
 static_assert(sizeof(GPUNodes) == sizeof(RtoGpuNode), "GPUNodes must be 15 x int32");
 
+// Frame planes live in page-locked host memory (rto_host_alloc_pinned): the device -> host copy of a frame then runs at the speed of the
+// link instead of through the driver's staging of pageable memory.  Without a CUDA device (host-only use of the builders) the allocator
+// falls back to ordinary memory; a 64-byte header in front of every block remembers which kind it is.
+template <class T> struct RtoFrameAllocator {
+	using value_type = T;
+	RtoFrameAllocator() = default;
+	template <class U> RtoFrameAllocator(const RtoFrameAllocator<U>&) {}
+	T* allocate(size_t n) {
+		const size_t bytes = n * sizeof(T) + 64;
+		void* p = nullptr; unsigned kind = 1;
+		if (rto_host_alloc_pinned(bytes, &p) != RTO_OK) { p = std::malloc(bytes); kind = 0; }
+		if (!p) throw std::bad_alloc();
+		*static_cast<unsigned*>(p) = kind;
+		return reinterpret_cast<T*>(static_cast<char*>(p) + 64);
+	}
+	void deallocate(T* q, size_t) noexcept {
+		void* p = reinterpret_cast<char*>(q) - 64;
+		if (*static_cast<unsigned*>(p)) rto_host_free_pinned(p); else std::free(p);
+	}
+	template <class U> bool operator==(const RtoFrameAllocator<U>&) const { return true; }
+	template <class U> bool operator!=(const RtoFrameAllocator<U>&) const { return false; }
+};
+template <class T> using RtoFrameVector = std::vector<T, RtoFrameAllocator<T>>;
+
 struct Framebuffer {                       // host copy of one frame: row 0 = top scanline
 	int width = 0, height = 0;
-	std::vector<float> rgba;               // 4 floats per pixel (RGBA32F like the reference's output texture)
-	std::vector<int32_t> hitId;            // octree: node index == leaf id of setOctree's BFS numbering; mesh: triangle index; -1 miss
-	std::vector<float> t;                  // hit distance, 1e30f on miss
+	RtoFrameVector<float> rgba;            // 4 floats per pixel (RGBA32F like the reference's output texture)
+	RtoFrameVector<int32_t> hitId;         // octree: node index == leaf id of setOctree's BFS numbering; mesh: triangle index; -1 miss
+	RtoFrameVector<float> t;               // hit distance, 1e30f on miss
 };
 
 class RayTracerBVH {
@@ -72,7 +98,9 @@ public:
 		std::vector<RtoCamera> cams(cameras.size());
 		for (size_t i = 0; i < cameras.size(); i++) if (cameras[i].consts(fovDeg, aspect, width, height, cams[i], nullptr) != RTO_OK) return false;
 		const size_t npix = (size_t)width * height, n = cameras.size();
-		std::vector<float> rgba(n * npix * 4), t(n * npix); std::vector<int32_t> ids(n * npix);
+		// the batch lands in page-locked planes kept from call to call (pinning memory costs more than the copy it speeds up)
+		RtoFrameVector<float>& rgba = m_batchRgba; RtoFrameVector<float>& t = m_batchT; RtoFrameVector<int32_t>& ids = m_batchIds;
+		if (rgba.size() < n * npix * 4) { rgba.resize(n * npix * 4); t.resize(n * npix); ids.resize(n * npix); }
 		RtoFrame fr{ rgba.data(), ids.data(), t.data(), RTO_MEM_HOST };
 		int rc;
 		if (m_group) {
@@ -161,6 +189,7 @@ public:
 private:
 	std::vector<GPUNodes> m_flatNodes;
 	RtoScene* m_scene = nullptr;
+	RtoFrameVector<float> m_batchRgba, m_batchT; RtoFrameVector<int32_t> m_batchIds;      // renderBatch's landing planes
 	RtoScene* m_culled = nullptr;         // the frustum-culled array of the last renderSceneComputeWithCulling(..., true)
 	std::vector<int32_t> m_visibleToFlat;
 	float m_gridMin[3] = { 0, 0, 0 }, m_voxelSize = 1.0f;
