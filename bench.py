@@ -20,7 +20,7 @@ One "step" = F orbit frames PER GPU (default 128 = two orbits), traced in launch
 metric  Mrays/s = (primary + shadow rays of all frames of the K steps) / (max over ranks of the device time of the K steps).
 value   inputs (scene, cameras) resident, outputs in HBM (N > 1: all in rank 0's HBM).
 e2e     the same metric through the public host API: cameras go host->device and the three frame planes come back device->host
-        into pinned buffers inside the timed region (rto_render_batch(RTO_MEM_HOST), 8 frames per call).
+        into pinned buffers inside the timed region (rto_render_batch(RTO_MEM_HOST), 32 frames per call).
 """
 import argparse
 import ctypes

@@ -1404,9 +1404,11 @@ RTO_DEV void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, floa
 }
 
 #ifndef RTO_BVH_MIN_BLOCKS
-#define RTO_BVH_MIN_BLOCKS 10     // 48 registers, 40 warps per SM.  Re-measured on the final kernel (8 x 1080p, C2 / primary only / 512^3 city / sphere):
-                                  // 10 blocks 1.716 / 1.187 / 2.573 / 0.493 ms, 12 blocks (40 registers) 1.732 / 1.217 / 2.570 / 0.506, 8 blocks (58 registers, no
-                                  // spills) 1.838 / 1.224 / 2.857 / 0.503; 14-16 blocks (32 registers) is slower still
+#define RTO_BVH_MIN_BLOCKS 12     // 40 registers, 48 warps per SM.  Re-measured on the final kernel of round 2 (16 x 1080p, ms; DT primary + shadow / DT primary
+                                  // only / 512^3 city mesh primary + shadow / sphere): 12 blocks 2.762 / 1.897 / 4.648 / 2.225 (11 blocks compiles to the same
+                                  // 40 registers), 10 blocks (48 registers, the setting of rounds 1-2 until then) 2.829 / 1.939 / 4.826 / 2.276, 9 blocks
+                                  // (56 registers) 2.923 / 2.008 / - / 2.343.  On the kernel of round 1 the order was the other way round (10 blocks 1.716
+                                  // against 1.732 per 8 frames): since the while-while loop the node step waits on its loads more than on issue slots.
 #endif
 template <bool SHADOWS, bool PRUNE, bool WIDE = false>
 __global__ void __launch_bounds__(kRenderThreads, RTO_BVH_MIN_BLOCKS * 128 / kRenderThreads) k_render_bvh(BvhDev S, RenderArgs A) {
