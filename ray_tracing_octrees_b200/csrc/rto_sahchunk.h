@@ -12,7 +12,8 @@
 // (child references and parent links); the bottom-up fit that follows computes every box.  Any binary tree over the same leaves is a
 // valid result -- the choice of splits decides speed, never hits.
 //
-// Written host+device: tests/emu runs it on the CPU (tests/test_emu_traversal.py) before the GPU ever sees it.
+// The one-thread form is written host+device: tests/emu runs it on the CPU (tests/test_emu_traversal.py) before the GPU ever sees it, and the
+// block form is compared with it on the GPU (tests/test_gpu_builders.py).
 #pragma once
 #include <cfloat>
 #include <cmath>
