@@ -1407,7 +1407,7 @@ RTO_DEV void store_pixel(const RenderArgs& A, size_t pix, V3 color, int id, floa
 #define RTO_BVH_MIN_BLOCKS 12     // 40 registers, 48 warps per SM.  Re-measured on the final kernel of round 2 (16 x 1080p, ms; DT primary + shadow / DT primary
                                   // only / 512^3 city mesh primary + shadow / sphere): 12 blocks 2.762 / 1.897 / 4.648 / 2.225 (11 blocks compiles to the same
                                   // 40 registers), 10 blocks (48 registers, the setting of rounds 1-2 until then) 2.829 / 1.939 / 4.826 / 2.276, 9 blocks
-                                  // (56 registers) 2.923 / 2.008 / - / 2.343.  On the kernel of round 1 the order was the other way round (10 blocks 1.716
+                                  // (56 registers) 2.923 / 2.008 / - / 2.343, 14 blocks (32 registers, spills) 2.923 / 1.914 on DT.  On the kernel of round 1 the order was the other way round (10 blocks 1.716
                                   // against 1.732 per 8 frames): since the while-while loop the node step waits on its loads more than on issue slots.
 #endif
 template <bool SHADOWS, bool PRUNE, bool WIDE = false>
