@@ -19,3 +19,9 @@ if [ -n "$CAPTURE_ALL" ]; then
 ncu --set full --clock-control none --import-source on -k regex:k_resolve_bvh -s 2 -c 1 -f -o gpurun_out/prof_resolve python tools/profile_case.py dt-bvh-resolve --frames 16 --reps 4 > gpurun_out/ncu_resolve.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_render_bvh -s 2 -c 1 -f -o gpurun_out/prof_c4dc python tools/profile_case.py c4-dcbvh --frames 2 --reps 4 > gpurun_out/ncu_c4dc.log 2>&1
 fi
+# fifth session: ray lists on the library's own sort, one frame per host call (row bands, page-locked against pageable planes)
+if [ -n "$CAPTURE_ALL$EXTRAS" ]; then
+python tools/bench_ray_lists.py --out gpurun_out/ray_lists.json > gpurun_out/ray_lists.log 2>&1
+for b in 1 4; do RTO_HOST_BANDS=$b python tools/experiments/e2e_single_frame.py; done > gpurun_out/e2e_single_frame.txt 2>&1
+E2E_PAGEABLE=1 python tools/experiments/e2e_single_frame.py >> gpurun_out/e2e_single_frame.txt 2>&1
+fi
