@@ -41,6 +41,34 @@ def test_shim_octree_node_has_the_reference_layout(rto, tmp_path):
     subprocess.check_call([cxx, "-std=c++17", "-Wall", "-Wno-invalid-offsetof", "-I" + SHIM, "-fsyntax-only", str(src)])
 
 
+def test_shim_frame_planes_without_a_device(rto, tmp_path):
+    """Framebuffer's planes come from rto_host_alloc_pinned; on a machine without a CUDA device that call says RTO_ERR_NO_DEVICE and the
+    allocator hands out ordinary memory instead (host-only use of the builders): planes can be made, grown, copied and freed."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a CUDA device")
+    src = tmp_path / "planes.cpp"
+    src.write_text('#include "RayTracerBVH.h"\n#include <cstdio>\n'
+                   'int main() {\n'
+                   '  void* p = nullptr; int rc = rto_host_alloc_pinned(64, &p);\n'
+                   '  std::printf("pinned rc %d ptr %d\\n", rc, p != nullptr);\n'
+                   '  Framebuffer fb; fb.rgba.resize(4 * 640 * 480, 0.5f); fb.hitId.resize(640 * 480, -1); fb.t.resize(640 * 480, 1e30f);\n'
+                   '  fb.rgba.resize(4 * 1920 * 1080, 0.25f);\n'
+                   '  Framebuffer copy = fb; double s = 0; for (float v : copy.rgba) s += v;\n'
+                   '  std::printf("sum %.1f ids %zu\\n", s, copy.hitId.size());\n'
+                   '  rto_host_free_pinned(nullptr);\n'
+                   '  return 0; }\n')
+    exe = str(tmp_path / "planes")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.join(ROOT, "ray_tracing_octrees_b200")
+    subprocess.check_call([cxx, "-std=c++17", "-Wall", "-O1", "-I" + SHIM, "-I" + os.path.join(ROOT, "include"), str(src), "-L" + libdir, "-lrto", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "pinned rc 2 ptr 0" in out.stdout                                      # RTO_ERR_NO_DEVICE, nothing allocated
+    want = 0.5 * 4 * 640 * 480 + 0.25 * (4 * 1920 * 1080 - 4 * 640 * 480)
+    assert "sum %.1f ids 307200" % want in out.stdout
+
+
 @pytest.mark.gpu
 def test_shim_renders_on_gpu(rto, tmp_path):
     out = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=120)
