@@ -46,13 +46,9 @@ def gather_planes(plane, dst=0, group=None):
     rank = dist.get_rank(group)
     if world == 1:
         return [plane]
-    if dist.get_backend(group) == "nccl":
-        outs = [torch.empty_like(plane) for _ in range(world)] if rank == dst else None
-        dist.gather(plane, outs, dst=dst if group is None else dist.get_global_rank(group, dst), group=group)
-        return outs
-    outs = [torch.empty_like(plane) for _ in range(world)]     # gloo: all_gather is the portable primitive
-    dist.all_gather(outs, plane, group=group)
-    return outs if rank == dst else None
+    outs = [torch.empty_like(plane) for _ in range(world)] if rank == dst else None
+    dist.gather(plane, outs, dst=dst if group is None else dist.get_global_rank(group, dst), group=group)
+    return outs
 
 
 def interleave_frames(per_rank, num_frames, world):

@@ -75,6 +75,39 @@ def test_world_size_2_gloo():
     assert sorted(res) == [(0, True, True, True), (1, True, True, True)]
 
 
+def _subgroup_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # ranks 1 and 2 form a group of their own; its rank 0 is GLOBAL rank 1: gather_planes takes the group's rank and hands torch the global one
+        group = dist.new_group(ranks=[1, 2])
+        ok = True
+        if rank in (1, 2):
+            got = sharding.gather_planes(torch.full((4, 5), rank, dtype=torch.int32), dst=0, group=group)
+            if rank == 1:
+                ok = got is not None and len(got) == 2 and int(got[0][0, 0]) == 1 and int(got[1][0, 0]) == 2
+            else:
+                ok = got is None
+        dist.barrier()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_inside_a_subgroup_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_subgroup_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True), (2, True)]
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 def test_shards_tile_exactly_once(world):
     for H in (1, 7, 8, 9, 135, 1080, 2160):
