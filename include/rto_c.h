@@ -270,8 +270,9 @@ RTO_API void* rto_scene_stream(const RtoScene* scene);
 /* Trace rows [y0, y1) of the camera's image.  Planes in `frame` are indexed from row y0 (size (y1-y0)*width).
  * mode must match the scene kind (BVH scene: RTO_MODE_BVH; octree scene: either octree mode).
  * shadowBias: offset of the shadow-ray origin along the shading normal (rule: 1e-3f * scene scale).
- * With RTO_MEM_HOST the call copies results to the host and synchronises; with RTO_MEM_DEVICE it only
- * enqueues on rto_scene_stream() (use rto_scene_sync or your own event). */
+ * With RTO_MEM_HOST the call copies results to the host and synchronises -- a frame is traced in four row bands (a batch frame by
+ * frame), each band's copy running while the next is traced; the copies reach the speed of the link only into page-locked planes
+ * (rto_host_alloc_pinned) --; with RTO_MEM_DEVICE it only enqueues on rto_scene_stream() (use rto_scene_sync or your own event). */
 RTO_API int rto_render(RtoScene* scene, const RtoCamera* cam, int mode, uint32_t flags, float shadowBias,
 	int y0, int y1, const RtoFrame* frame);
 
